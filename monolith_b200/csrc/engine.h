@@ -1,0 +1,172 @@
+// engine.h — host-side state of the engine (one mono_mtable = K tables on one device).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace mono {
+
+extern std::atomic<int64_t> g_launches;  // kernels launched by this library
+#define MONO_COUNT_LAUNCH() (::mono::g_launches.fetch_add(1, std::memory_order_relaxed))
+
+struct CudaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+struct ArgError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define MONO_CUDA(expr)                                                                    \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      throw ::mono::CudaError(std::string(#expr) + ": " + cudaGetErrorString(_e));         \
+  } while (0)
+
+#define MONO_CHECK_LAUNCH()                                                                \
+  do {                                                                                     \
+    MONO_COUNT_LAUNCH();                                                                   \
+    cudaError_t _e = cudaGetLastError();                                                   \
+    if (_e != cudaSuccess)                                                                 \
+      throw ::mono::CudaError(std::string("kernel launch: ") + cudaGetErrorString(_e));    \
+  } while (0)
+
+inline int grid_for(int64_t work_items, int items_per_block, int max_blocks = 148 * 8) {
+  int64_t b = (work_items + items_per_block - 1) / items_per_block;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return (int)b;
+}
+
+// growable device scratch buffer (stream-ordered allocation)
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void* get(size_t bytes, cudaStream_t s) {
+    if (bytes > cap) {
+      if (p) MONO_CUDA(cudaFreeAsync(p, s));
+      size_t ncap = bytes + bytes / 2 + 256;
+      MONO_CUDA(cudaMallocAsync(&p, ncap, s));
+      cap = ncap;
+    }
+    return p;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// Ring of pinned host blocks mirrored by device blocks: small per-call descriptors (segments,
+// learning rates) are written to a pinned block and copied H2D on the call's stream.
+struct StageRing {
+  static constexpr int kBlocks = 32;
+  static constexpr size_t kBlockBytes = 128 * 1024;
+  char* host = nullptr;
+  char* dev = nullptr;
+  cudaEvent_t ev[kBlocks];
+  bool used[kBlocks];
+  int next = 0;
+  void init();
+  void destroy();
+  // returns block index; host pointer = host + idx*kBlockBytes
+  int acquire();
+  char* h(int idx) { return host + (size_t)idx * kBlockBytes; }
+  char* d(int idx) { return dev + (size_t)idx * kBlockBytes; }
+  void commit(int idx, size_t bytes, cudaStream_t s);  // H2D + event
+};
+
+struct HostTable {
+  std::string name;
+  std::vector<mono_segment_cfg> segs;
+  int dim = 0, state_dim = 0, slices = 0;
+  TableDev dev{};  // host mirror of the device descriptor
+  std::vector<uint32_t> slot_expire_pairs;
+  int64_t max_update_ts = 0;
+  // conservative host-side bounds (exact values live in dev.ctrs)
+  uint64_t snap_size = 0, snap_bump = 0, snap_free = 0, snap_stash = 0;
+  uint64_t issued_total = 0;        // ids submitted to insert-capable calls so far
+  uint64_t issued_at_snapshot = 0;  // issued_total when the last completed snapshot was requested
+  uint64_t issued_at_pending = 0;
+  bool snapshot_pending = false;
+  uint32_t* h_snap = nullptr;  // pinned [kNumCtrs]
+  cudaEvent_t snap_ev = nullptr;
+};
+
+}  // namespace mono
+
+struct mono_mtable {
+  int device = 0;
+  std::vector<mono::HostTable> tables;
+  mono::TableDev* d_tables = nullptr;  // device array [K]
+  bool tables_dirty = true;
+  mono::StageRing ring;
+  mono::DevBuf ws_miss, ws_a, ws_b, ws_c, ws_d, ws_e, ws_host_in, ws_host_out;
+  void* pinned_in = nullptr;
+  size_t pinned_in_cap = 0;
+  void* pinned_out = nullptr;
+  size_t pinned_out_cap = 0;
+  cudaStream_t own_stream = nullptr;  // used by the *_host entry points
+  uint32_t* h_flag = nullptr;         // pinned scratch for small D2H reads
+};
+
+namespace mono {
+
+// table.cu
+void table_init(mono_mtable* mt, HostTable& t, const mono_table_cfg& cfg, cudaStream_t s);
+void table_free(HostTable& t);
+void upload_tables(mono_mtable* mt, cudaStream_t s);
+// make room for n_new more keys in table k (grows row slabs / rehashes buckets when needed)
+void ensure_capacity(mono_mtable* mt, int k, uint64_t n_new, cudaStream_t s);
+void request_snapshot(mono_mtable* mt, int k, cudaStream_t s);
+void read_counters_sync(mono_mtable* mt, int k, cudaStream_t s, uint32_t* out /*kNumCtrs*/);
+void evict_table(mono_mtable* mt, int k, int64_t max_update_time, cudaStream_t s);
+int64_t export_rows(mono_mtable* mt, int k, int64_t* cursor, int64_t max_n, int64_t* ids_out,
+                    float* entry_out, cudaStream_t s);
+
+// ops.cu
+enum UpsertOp { kOpOptimize = 0, kOpAssign = 1, kOpAssignAdd = 2, kOpReinit = 3, kOpRestore = 4 };
+void launch_lookup(mono_mtable* mt, const CallSeg* h_segs, int nsegs, const int64_t* ids_dev,
+                   int64_t n_total, float* out_dev, cudaStream_t s);
+void launch_lookup_pool(mono_mtable* mt, int k, const int64_t* fids_dev, const int32_t* row_offsets,
+                        int64_t n_rows, int pooling, float* out, int64_t out_stride, int out_col,
+                        cudaStream_t s);
+void launch_contains(mono_mtable* mt, int k, const int64_t* ids, int64_t n, uint8_t* out,
+                     cudaStream_t s);
+void launch_lookup_entry(mono_mtable* mt, int k, const int64_t* ids, int64_t n, float* out,
+                         cudaStream_t s);
+// generic find-or-insert + apply over segments.  ids may contain duplicates unless `unique`.
+void run_upsert(mono_mtable* mt, UpsertOp op, const CallSeg* h_segs, int nsegs,
+                const int64_t* ids_dev, int64_t n_total, const float* vals_dev,
+                const float* lr_host, int n_lr, int64_t update_time, bool unique, bool dedup_sum,
+                int32_t* status_dev, cudaStream_t s);
+
+// dedup.cu
+void run_reorder(int device, const int64_t* ids_dev, const int64_t* id_split_host, int K, int N,
+                 const int32_t* dims_host, int rank0_empty, int64_t* output_dev, int32_t* sizes_dev,
+                 int32_t* fused_emb_offset_dev, int32_t* shard_sizes_host,
+                 int32_t* sharded_slot_sizes_host, int64_t* n_unique_host, int32_t* n_unique_dev,
+                 cudaStream_t s);
+
+// layout.cu
+void launch_gather_pool(const float* fused_emb, const int32_t* emb_offset, const int32_t* row_offsets,
+                        int64_t n_rows, int dim, int pooling, float* out, int64_t out_stride,
+                        int out_col, cudaStream_t s);
+void launch_gather_pool_grad(const float* pooled_grad, int64_t grad_stride, int grad_col,
+                             const int32_t* emb_offset, const int32_t* row_offsets, int64_t n_rows,
+                             int dim, int pooling, float* grad_fused, cudaStream_t s);
+void launch_layout(bool backward, float* const* emb_ptrs_dev, const int32_t* emb_strides_dev,
+                   int n_emb, const uint64_t* fid_offset, int64_t total_fid,
+                   const int32_t* feature_offset, int total_feature, const uint32_t* nfl_offset,
+                   int total_nfl, int batch_size, const mono_slice_task* tasks_host, int n_tasks,
+                   float* const* out_ptrs_dev, cudaStream_t s);
+
+}  // namespace mono

@@ -1,0 +1,169 @@
+"""Dedup / shard / pooling ops around the table — mirror of the hot-path subset of
+monolith/native_training/distribution_ops.py (ref: fused_reorder_by_indices :218-258,
+fused_gather_embeddings_by_input :816-889, fused_embedding_to_layout :528-700).
+All tensors are torch CUDA tensors; the work is done by the kernels in csrc/{dedup,layout}.cu.
+"""
+import ctypes as C
+import dataclasses
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+  return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(device):
+  return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def fused_reorder_by_indices(inputs: Sequence[torch.Tensor], num_of_shards: int, dim_sizes: Sequence[int],
+                             rank0_empty_shard: Optional[bool] = None):
+  """ref: distribution_ops.py:218-258 / FusedReorderByIndices (runtime/ops/fused_reorder_by_indices.cc).
+
+  Returns (output, shard_sizes, sharded_slot_sizes, emb_offset_sz, fused_embedding_offsets); the two
+  size vectors come back as Python lists (they size the all-to-all), the rest stay on the device.
+  """
+  lib = _lib.load()
+  if rank0_empty_shard is None:  # ref: distribution_ops.py:253-256
+    rank0_empty_shard = os.environ.get('MONOLITH_SYNC_EMPTY_RANK0_PS_SHARD', '1') == '1' and num_of_shards > 4
+  if len(inputs) != len(dim_sizes):
+    raise ValueError("inputs and dim_sizes must have the same length")
+  device = inputs[0].device
+  ids = torch.cat([t.reshape(-1).to(torch.int64) for t in inputs]) if inputs else torch.empty(0, dtype=torch.int64)
+  K = len(inputs)
+  splits = [0]
+  for t in inputs:
+    splits.append(splits[-1] + t.numel())
+  M = splits[-1]
+  out = torch.empty(max(M, 1), dtype=torch.int64, device=device)
+  offs = torch.empty(max(M, 1), dtype=torch.int32, device=device)
+  c_split = (C.c_int64 * (K + 1))(*splits)
+  c_dims = (C.c_int32 * K)(*[int(d) for d in dim_sizes])
+  shard_sizes = (C.c_int32 * num_of_shards)()
+  slot_sizes = (C.c_int32 * (num_of_shards * K))()
+  n_unique = C.c_int64(0)
+  _lib.check(lib.mono_reorder_by_indices(device.index, _ptr(ids), c_split, K, num_of_shards, c_dims,
+                                         1 if rank0_empty_shard else 0, _ptr(out), None, _ptr(offs), shard_sizes,
+                                         slot_sizes, C.byref(n_unique), _stream(device)))
+  emb_offset_sz = [t.numel() for t in inputs]
+  return out[:n_unique.value], list(shard_sizes), list(slot_sizes), emb_offset_sz, offs[:M]
+
+
+def unique_with_inverse(ids: torch.Tensor, sync: bool = True):
+  """First-occurrence dedup of one id list (tf.unique order).  Returns (unique, inverse[, n_unique])."""
+  lib = _lib.load()
+  ids = ids.reshape(-1).to(torch.int64).contiguous()
+  n = ids.numel()
+  uniq = torch.empty(max(n, 1), dtype=torch.int64, device=ids.device)
+  inv = torch.empty(max(n, 1), dtype=torch.int32, device=ids.device)
+  n_dev = torch.zeros(1, dtype=torch.int32, device=ids.device)
+  n_host = C.c_int64(0)
+  _lib.check(lib.mono_dedup(ids.device.index, _ptr(ids), n, _ptr(uniq), _ptr(inv), _ptr(n_dev),
+                            C.byref(n_host) if sync else None, _stream(ids.device)))
+  if sync:
+    return uniq[:n_host.value], inv[:n]
+  return uniq, inv[:n], n_dev
+
+
+def gather_pool(fused_embeddings: torch.Tensor, fused_embedding_offsets: torch.Tensor, dim: int,
+                row_offsets: Optional[torch.Tensor] = None, pooling: str = "sum",
+                out: Optional[torch.Tensor] = None, out_col: int = 0) -> torch.Tensor:
+  """out[r] = pool_{m in row r} fused_embeddings[offsets[m]:offsets[m]+dim]
+  (ref: FusedGatherKernel, runtime/ops/map_id_to_embedding.cu.cc:30-74, + per-row pool)."""
+  lib = _lib.load()
+  dev = fused_embeddings.device
+  offs = fused_embedding_offsets.to(torch.int32).contiguous()
+  n_rows = offs.numel() if row_offsets is None else row_offsets.numel() - 1
+  if row_offsets is not None:
+    row_offsets = row_offsets.to(torch.int32).contiguous()
+  if out is None:
+    out = torch.empty(n_rows, dim, dtype=torch.float32, device=dev)
+  pool = {"sum": _lib.POOL_SUM, "mean": _lib.POOL_MEAN}[pooling]
+  _lib.check(lib.mono_gather_pool(dev.index, _ptr(fused_embeddings), _ptr(offs), _ptr(row_offsets), n_rows, dim,
+                                  pool, _ptr(out), out.stride(0), out_col, _stream(dev)))
+  return out
+
+
+def gather_pool_grad(pooled_grad: torch.Tensor, fused_embedding_offsets: torch.Tensor, dim: int, total_floats: int,
+                     row_offsets: Optional[torch.Tensor] = None, pooling: str = "sum", grad_col: int = 0):
+  """Backward of gather_pool: scatter-add pooled grads to the fused row buffer
+  (ref: FusedGatherGradKernel, map_id_to_embedding.cu.cc:75-118)."""
+  lib = _lib.load()
+  dev = pooled_grad.device
+  offs = fused_embedding_offsets.to(torch.int32).contiguous()
+  n_rows = offs.numel() if row_offsets is None else row_offsets.numel() - 1
+  if row_offsets is not None:
+    row_offsets = row_offsets.to(torch.int32).contiguous()
+  grad = torch.zeros(total_floats, dtype=torch.float32, device=dev)
+  pool = {"sum": _lib.POOL_SUM, "mean": _lib.POOL_MEAN}[pooling]
+  _lib.check(lib.mono_gather_pool_grad(dev.index, _ptr(pooled_grad), pooled_grad.stride(0), grad_col, _ptr(offs),
+                                       _ptr(row_offsets), n_rows, dim, pool, _ptr(grad), _stream(dev)))
+  return grad
+
+
+# ---- generic fused layout op ------------------------------------------------------------------
+@dataclasses.dataclass
+class SliceTask:
+  """One (layout, slice_config) pair of the reference's FeatureConfigs, flattened
+  (ref: idl/matrix/proto/example.proto:177-220; runtime/ops/fused_embedding_to_layout.cc:229-286)."""
+  nfl_idx: int
+  slice_start: int
+  dim: int
+  pooling: int  # _lib.POOL_*
+  max_seq_len: int
+  out_tensor: int
+  out_row_stride: int
+  out_col: int
+  accumulate: int
+
+
+def _tasks_arr(tasks: Sequence[SliceTask]):
+  arr = (_lib.SliceTask * len(tasks))()
+  for i, t in enumerate(tasks):
+    for f, _ in _lib.SliceTask._fields_:
+      setattr(arr[i], f, int(getattr(t, f)))
+  return arr
+
+
+def _ptr_table(tensors: Sequence[torch.Tensor], device):
+  return torch.tensor([t.data_ptr() for t in tensors], dtype=torch.int64, device=device)
+
+
+def fused_embedding_to_layout(embeddings_list: Sequence[torch.Tensor], emb_strides: Sequence[int],
+                              fid_offset: torch.Tensor, feature_offset: torch.Tensor, nfl_offset: torch.Tensor,
+                              batch_size: int, tasks: Sequence[SliceTask], out_shapes: Sequence[Sequence[int]]):
+  """ref: distribution_ops.fused_embedding_to_layout (versions 3/4/5) -> MonolithEmbeddingToLayoutV*.
+  fid_offset: uint64 viewed as int64 tensor; nfl_offset: uint32 viewed as int32 tensor."""
+  lib = _lib.load()
+  dev = fid_offset.device
+  outs = [torch.zeros(*s, dtype=torch.float32, device=dev) for s in out_shapes]
+  embs = [e.contiguous() for e in embeddings_list]
+  ep, op = _ptr_table(embs, dev), _ptr_table(outs, dev)
+  st = torch.tensor(list(emb_strides), dtype=torch.int32, device=dev)
+  _lib.check(lib.mono_embedding_to_layout(dev.index, _ptr(ep), _ptr(st), len(embs), _ptr(fid_offset),
+                                          fid_offset.numel(), _ptr(feature_offset), feature_offset.numel(),
+                                          _ptr(nfl_offset), nfl_offset.numel(), batch_size, _tasks_arr(tasks),
+                                          len(tasks), _ptr(op), _stream(dev)))
+  return outs
+
+
+def fused_embedding_to_layout_grad(emb_sizes: Sequence[int], emb_strides: Sequence[int], fid_offset: torch.Tensor,
+                                   feature_offset: torch.Tensor, nfl_offset: torch.Tensor, batch_size: int,
+                                   tasks: Sequence[SliceTask], out_grads: Sequence[torch.Tensor]):
+  """ref: MonolithEmbeddingToLayoutGradV* (fused_embedding_to_layout.cc:697-948)."""
+  lib = _lib.load()
+  dev = fid_offset.device
+  grads = [torch.zeros(n, dtype=torch.float32, device=dev) for n in emb_sizes]
+  og = [g.contiguous() for g in out_grads]
+  gp, op = _ptr_table(grads, dev), _ptr_table(og, dev)
+  st = torch.tensor(list(emb_strides), dtype=torch.int32, device=dev)
+  _lib.check(lib.mono_embedding_to_layout_grad(dev.index, _ptr(gp), _ptr(st), len(grads), _ptr(fid_offset),
+                                               fid_offset.numel(), _ptr(feature_offset), feature_offset.numel(),
+                                               _ptr(nfl_offset), nfl_offset.numel(), batch_size, _tasks_arr(tasks),
+                                               len(tasks), _ptr(op), _stream(dev)))
+  return grads
