@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""bench.py — FID lookups/s of the embedding hot path on synthetic MovieLens-shaped batches.
+
+Workload (BASELINE.json configs[1]): one table, dim 32, 10 M resident keys,
+Adagrad(lr .05, init_acc .1); a batch = B samples x 2 slots (uid, movie), one FID per slot,
+FID = (slot << 48) | rank, rank ~ truncated Zipf(1.05) over 5 M ids per slot.
+
+One "step" = the whole sparse part of one training step for one batch:
+    forward : fused probe + row gather + per-slot pool of the M = 2B FID occurrences -> pooled [B, 2*32]
+    backward: FID dedup (first-occurrence order) + scatter of the pooled grads to the U unique rows
+              + fused Adagrad update + expiry-timestamp bump (upsert)
+`value`  = FID occurrences (lookups) per second over all ranks, inputs resident in HBM.
+`e2e`    = same step through the public Python API with pinned HOST inputs (FIDs, pooled grads) copied
+           H2D and the pooled embeddings copied D2H inside the timed region.
+`--impl reference` times the CPU restatement of the reference's parameter-server path (oracle port;
+the reference itself needs bazel + TensorFlow and cannot be built here) on the host cores.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DIM = 32
+SLOTS = 2
+LR = 0.05
+INIT_ACC = 0.1
+ZIPF_S = 1.05
+METRIC = "fid_lookups_per_sec"
+UNIT = "lookups/s"
+
+
+def parse():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=20)
+  ap.add_argument("--warmup", type=int, default=5)
+  ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+  ap.add_argument("--batch", type=int, default=1 << 20, help="samples per GPU per step")
+  ap.add_argument("--keys", type=int, default=10_000_000, help="resident keys per GPU-shard set (total at N=1)")
+  ap.add_argument("--cpu-batch", type=int, default=1 << 16, help="samples per step of the CPU arm / cpu_baseline")
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--no-e2e", action="store_true")
+  return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic inputs
+# ---------------------------------------------------------------------------------------------
+class Zipf:
+  """Truncated Zipf(s) over ranks [0, n) by inverse CDF."""
+
+  def __init__(self, n, s):
+    w = np.arange(1, n + 1, dtype=np.float64)**(-s)
+    self.cdf = np.cumsum(w)
+    self.cdf /= self.cdf[-1]
+
+  def sample(self, rng, size):
+    return np.searchsorted(self.cdf, rng.random(size), side="left").astype(np.int64)
+
+
+def make_batches(n_batches, batch, keys_per_slot, seed):
+  rng = np.random.default_rng(seed)
+  z = Zipf(keys_per_slot, ZIPF_S)
+  # rank -> id via a fixed permutation-free affine map so that hot ids are spread over the table
+  out = []
+  for _ in range(n_batches):
+    cols = []
+    for s in range(1, SLOTS + 1):
+      rank = z.sample(rng, batch)
+      ident = (rank * 2654435761) % keys_per_slot  # bijection on [0, keys_per_slot) only if coprime; fine: stays in range
+      cols.append((np.int64(s) << np.int64(48)) | ident)
+    out.append(np.stack(cols, 1).reshape(-1))  # sample-major: fid index = b * SLOTS + slot
+  return out
+
+
+def fwd_bytes(M, U, D=DIM):
+  """8*M (FIDs) + U*(32 (bucket sector) + 4D (row)) + 4*D*R (pooled rows), R == M here."""
+  return 8 * M + U * (32 + 4 * D) + 4 * D * M
+
+
+def bwd_bytes(M, U, D=DIM):
+  """SURVEY.md §8(d) backward (scatter + Adagrad): 4*D*R + U*(32 + 16*D + 8)."""
+  return 4 * D * M + U * (32 + 16 * D + 8)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler
+# ---------------------------------------------------------------------------------------------
+class Clocks:
+
+  def __init__(self, index):
+    self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+    self.ok = False
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      self.nv = pynvml
+      self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+      self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+      self.ok = True
+    except Exception:
+      pass
+
+  def _run(self):
+    nv = self.nv
+    names = {
+        getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+        getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+        getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+        getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+    }
+    while not self._stop.is_set():
+      try:
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        try:
+          r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+          r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for bit, name in names.items():
+          if r & bit:
+            self.reasons.add(name)
+      except Exception:
+        pass
+      self._stop.wait(0.05)
+
+  def __enter__(self):
+    if self.ok:
+      self.t = threading.Thread(target=self._run, daemon=True)
+      self.t.start()
+    return self
+
+  def __exit__(self, *a):
+    if self.ok:
+      self._stop.set()
+      self.t.join()
+
+  def summary(self):
+    if not self.samples:
+      return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+    return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm (reference PS path, oracle port)
+# ---------------------------------------------------------------------------------------------
+def cpu_arm(keys, batch, steps, warmup, cores):
+  """Times orc_ps_train_step (see oracle/oracle.cc) with `cores` PS shards / threads."""
+  import ctypes as C
+  from monolith_b200 import entry
+  from tests import orc
+  lib = orc.lib()
+  lib.orc_ps_train_step.restype = C.c_int64
+  seg = entry.CombineAsSegment(DIM, entry.RandomUniformInitializer(-0.05, 0.05),
+                               entry.AdagradOptimizer(LR, INIT_ACC))
+  cfg = {"item": entry.HashTableConfigInstance(entry.TableConfig([seg], initial_capacity=keys, init_seed=1), [LR])}
+  arr, keep = entry.to_c_table_cfgs(cfg)
+  ps = C.c_void_p()
+  lib.orc_ps_create(arr, cores, C.byref(ps))
+  keys_per_slot = keys // SLOTS
+  t0 = time.time()
+  lib.orc_ps_fill_slots(ps, SLOTS, C.c_int64(keys_per_slot))
+  fill_s = time.time() - t0
+  batches = make_batches(4, batch, keys_per_slot, seed=2)
+  M = batch * SLOTS
+  rng = np.random.default_rng(5)
+  pg = rng.standard_normal((M, DIM)).astype(np.float32)
+  out = np.zeros((M, DIM), np.float32)
+  lr = np.array([LR], np.float32)
+  times, uniq = [], []
+  for i in range(warmup + steps):
+    f = batches[i % len(batches)]
+    t0 = time.perf_counter()
+    u = lib.orc_ps_train_step(ps, orc.p(f), C.c_int64(M), None, C.c_int64(M), 0, orc.p(pg), orc.p(out), orc.p(lr),
+                              C.c_int64(1000 + i))
+    dt = time.perf_counter() - t0
+    if i >= warmup:
+      times.append(dt)
+      uniq.append(u)
+  lib.orc_ps_destroy(ps)
+  total = float(np.sum(times))
+  return {"value": M * steps / total, "ms_per_step": 1e3 * total / steps, "fill_s": fill_s, "batch": batch,
+          "M": M, "U_mean": float(np.mean(uniq))}
+
+
+def run_reference(args):
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return
+  cores = os.cpu_count() or 1
+  r = cpu_arm(args.keys, args.cpu_batch, args.steps, args.warmup, cores)
+  line = {
+      "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+      "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+      "config": workload_config(args, args.cpu_batch),
+      "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": cores, "kind": "port",
+                       "sample": f"{args.steps} steps x {r['M']} FIDs (batch {args.cpu_batch} samples) on a {args.keys}-key "
+                                 f"table; CPU restatement of the reference PS path (reference build unavailable: no bazel/TF)"},
+      "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+      "gpu_launches": 0,
+  }
+  print(json.dumps(line), flush=True)
+
+
+def workload_config(args, batch):
+  return {
+      "workload": "C2 MovieLens-shaped DSSM sparse step: 1 table dim 32 Adagrad, 10M resident keys, 2 slots/sample, "
+                  "Zipf(1.05) FIDs; step = fused lookup+pool fwd + dedup + grad scatter + fused Adagrad upsert bwd",
+      "keys": args.keys, "dim": DIM, "slots": SLOTS, "batch_per_gpu": batch, "fids_per_step_per_gpu": batch * SLOTS,
+      "l2_hygiene": "inputs larger than L2: 2.6 GB table + 4 rotating batches, 268 MB pooled output per step",
+      "parallelism": f"fid-hash sharding x{args.gpus}" if args.gpus > 1 else "single GPU",
+  }
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+  import torch
+  import torch.distributed as dist
+  from monolith_b200 import MultiHashTable, _lib, distribution_ops as dops, entry
+
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  if world != args.gpus:
+    raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+  torch.cuda.set_device(local)
+  dev = torch.device("cuda", local)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+  lib = _lib.load()
+
+  if world > 1:
+    from monolith_b200.distributed_ps import ShardedStep
+  keys_per_slot = args.keys // SLOTS
+  seg = entry.CombineAsSegment(DIM, entry.RandomUniformInitializer(-0.05, 0.05), entry.AdagradOptimizer(LR, INIT_ACC))
+  # weak scaling: every GPU owns args.keys keys (global table = N * keys), FID ranks span the global range
+  gkeys_per_slot = keys_per_slot * world
+  cap = int(args.keys * 1.05)
+  table = MultiHashTable({"item": entry.HashTableConfigInstance(
+      entry.TableConfig([seg], initial_capacity=cap, init_seed=1), [LR])}, device=dev)
+
+  # prefill this rank's shard: keys with fid % world == rank
+  for s in range(1, SLOTS + 1):
+    for lo in range(0, gkeys_per_slot, 1 << 22):
+      hi = min(gkeys_per_slot, lo + (1 << 22))
+      ids = (torch.arange(lo, hi, device=dev, dtype=torch.int64)) | (s << 48)
+      if world > 1:
+        ids = ids[(ids % world) == rank]
+      table.assign_add({"item": (ids, torch.zeros(ids.numel(), DIM, device=dev))}, req_time=1, ids_unique=True)
+  torch.cuda.synchronize()
+
+  NB = 4
+  M = args.batch * SLOTS
+  batches_np = make_batches(NB, args.batch, gkeys_per_slot, seed=2 + rank)
+  fids_dev = [torch.from_numpy(b).to(dev) for b in batches_np]
+  gen = torch.Generator(device=dev)
+  gen.manual_seed(5 + rank)
+  pgrad_dev = torch.randn(M, DIM, device=dev, generator=gen)
+  pooled = torch.empty(M, DIM, device=dev)
+  uniq_counts = []
+
+  if world > 1:
+    sharded = ShardedStep(table, "item", DIM, world, rank, dev)
+
+  def step(i, fids, pgrad, out):
+    if world == 1:
+      table.lookup_pool("item", fids, None, "sum", out=out)
+      uniq, shard_sizes, _, _, offs = dops.fused_reorder_by_indices([fids], 1, [DIM], rank0_empty_shard=False)
+      ugrad = dops.gather_pool_grad(pgrad, offs, DIM, uniq.numel() * DIM)
+      table.apply_gradients({"item": (uniq, ugrad)}, req_time=1000 + i, ids_unique=True)
+      return uniq.numel()
+    return sharded.step(fids, pgrad, out, 1000 + i)
+
+  def timed(fn, steps, warmup):
+    for i in range(warmup):
+      fn(i)
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = lib.mono_kernel_launch_count()
+    e0.record()
+    for i in range(steps):
+      fn(warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = lib.mono_kernel_launch_count() - l0
+    if world > 1:
+      t = torch.tensor([ms], device=dev)
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+      ms = float(t.item())
+    return ms, launches
+
+  def dev_step(i):
+    uniq_counts.append(step(i, fids_dev[i % NB], pgrad_dev, pooled))
+
+  with Clocks(local) as clk:
+    ms, launches = timed(dev_step, args.steps, args.warmup)
+  U_mean = float(np.mean(uniq_counts[-args.steps:]))
+  value = M * world * args.steps / (ms * 1e-3)
+
+  # ---- e2e: pinned host inputs, H2D + D2H inside the timed region, public API --------------
+  e2e = None
+  if not args.no_e2e:
+    fids_pin = [torch.from_numpy(b).pin_memory() for b in batches_np]
+    pgrad_pin = pgrad_dev.cpu().pin_memory()
+    pooled_pin = torch.empty(M, DIM).pin_memory()
+    d_f, d_g = torch.empty(M, dtype=torch.int64, device=dev), torch.empty(M, DIM, device=dev)
+
+    def e2e_step(i):
+      d_f.copy_(fids_pin[i % NB], non_blocking=True)
+      d_g.copy_(pgrad_pin, non_blocking=True)
+      step(i, d_f, d_g, pooled)
+      pooled_pin.copy_(pooled, non_blocking=True)
+      torch.cuda.current_stream().synchronize()  # the caller consumes the pooled rows on the host
+
+    es, ew = max(3, args.steps // 4), 2
+    ems, _ = timed(e2e_step, es, ew)
+    e2e = {"value": M * world * es / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * M + 4 * M * DIM,
+           "d2h_bytes_per_step": 4 * M * DIM, "ms_per_step": ems / es}
+
+  # ---- per-kernel timing for the roofline (dominant kernel: fused lookup+pool forward) --------
+  roof = None
+  if world == 1:
+    peaks = {}
+    try:
+      peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+      pass
+    peak, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
+
+    def only_fwd(i):
+      table.lookup_pool("item", fids_dev[i % NB], None, "sum", out=pooled)
+
+    fms, _ = timed(only_fwd, 20, 5)
+    fwd_s = fms * 1e-3 / 20
+    A = fwd_bytes(M, U_mean) / fwd_s / 1e9
+    traffic = None
+    try:
+      traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("lookup_pool_dram_bytes_per_launch")
+    except Exception:
+      pass
+    # backward pieces (reported for context)
+    uniq, _, _, _, offs = dops.fused_reorder_by_indices([fids_dev[0]], 1, [DIM], rank0_empty_shard=False)
+    ugrad = dops.gather_pool_grad(pgrad_dev, offs, DIM, uniq.numel() * DIM)
+
+    def only_opt(i):
+      table.apply_gradients({"item": (uniq, ugrad)}, req_time=5000 + i, ids_unique=True)
+
+    oms, _ = timed(only_opt, 20, 5)
+
+    def only_dedup(i):
+      dops.fused_reorder_by_indices([fids_dev[i % NB]], 1, [DIM], rank0_empty_shard=False)
+
+    dms, _ = timed(only_dedup, 20, 5)
+
+    def only_scatter(i):
+      dops.gather_pool_grad(pgrad_dev, offs, DIM, uniq.numel() * DIM)
+
+    sms, _ = timed(only_scatter, 20, 5)
+    Uo = uniq.numel()
+    roof = {
+        "bound": "hbm", "kernel": "lookup_pool_kernel<8,1> (fused probe+gather+pool forward)", "achieved": A,
+        "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": A / peak, "frac_of_nominal_8000": A / 8000.0,
+        "traffic": traffic, "algorithmic_bytes_per_launch": fwd_bytes(M, U_mean), "launch_ms": fwd_s * 1e3,
+        "lookups_per_s_fwd_only": M / fwd_s,
+        "others": {
+            "optimize_ms": oms / 20, "optimize_GBps": (Uo * (32 + 16 * DIM + 8) + 4 * DIM * Uo) / (oms * 1e-3 / 20) / 1e9,
+            "dedup_ms": dms / 20, "scatter_ms": sms / 20, "U": Uo
+        },
+    }
+
+  cpu = None
+  if world == 1 and rank == 0 and not args.no_cpu_baseline:
+    cores = os.cpu_count() or 1
+    r = cpu_arm(args.keys, args.cpu_batch, 6, 2, cores)
+    cpu = {"value": r["value"], "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": f"6 steps x {r['M']} FIDs (batch {args.cpu_batch} samples) on the full {args.keys}-key table, "
+                     f"{cores} PS shards/threads; CPU restatement of the reference PS path (reference build unavailable)",
+           "ms_per_step": r["ms_per_step"]}
+
+  if rank == 0:
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args, args.batch),
+        "samples_per_sec": args.batch * world * args.steps / (ms * 1e-3), "unique_fids_per_step": U_mean,
+        "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def main():
+  args = parse()
+  if args.impl == "reference":
+    run_reference(args)
+  else:
+    run_ours(args)
+
+
+if __name__ == "__main__":
+  main()

@@ -162,19 +162,22 @@ class MultiHashTable:
     emb = self.get_embeddings(splits, flat)
     return {k: v for k, v in emb.items() if k in slot_to_id}
 
-  def assign(self, slot_to_id_and_value: Dict[str, Tuple[torch.Tensor, torch.Tensor]], req_time: int = 0):
+  def assign(self, slot_to_id_and_value: Dict[str, Tuple[torch.Tensor, torch.Tensor]], req_time: int = 0,
+             ids_unique: bool = False):
     """ref: multi_hash_table_ops.py:349-357."""
     values, splits = self.get_ragged_id({k: v[0] for k, v in slot_to_id_and_value.items()})
     flat = self.get_flat_value({k: v[1] for k, v in slot_to_id_and_value.items()})
-    return self.raw_assign(values, splits, flat, req_time)
+    return self.raw_assign(values, splits, flat, req_time, ids_unique)
 
-  def assign_add(self, slot_to_id_and_value: Dict[str, Tuple[torch.Tensor, torch.Tensor]], req_time: int = 0):
+  def assign_add(self, slot_to_id_and_value: Dict[str, Tuple[torch.Tensor, torch.Tensor]], req_time: int = 0,
+                 ids_unique: bool = False):
     """ref: multi_hash_table_ops.py:359-374 (per-id serial semantics for duplicate ids)."""
     values, splits = self.get_ragged_id({k: v[0] for k, v in slot_to_id_and_value.items()})
     flat = self.get_flat_value({k: v[1] for k, v in slot_to_id_and_value.items()})
     self._check_values(values, splits, flat)
     _lib.check(self._lib.mono_mtable_assign_add(self._h, _ptr(values), self._split_arr(splits), _ptr(flat),
-                                                int(req_time), 0, _stream(self._device)))
+                                                int(req_time), _lib.FLAG_IDS_UNIQUE if ids_unique else 0,
+                                                _stream(self._device)))
     return self
 
   def reinitialize(self, slot: str, ids: torch.Tensor):
@@ -228,11 +231,13 @@ class MultiHashTable:
                                               _stream(self._device)))
     return self
 
-  def raw_assign(self, ids: torch.Tensor, id_split: Sequence[int], flat_value: torch.Tensor, req_time: int = 0):
+  def raw_assign(self, ids: torch.Tensor, id_split: Sequence[int], flat_value: torch.Tensor, req_time: int = 0,
+                 ids_unique: bool = False):
     ids, flat_value = _ids(ids, self._device), _f32(flat_value, self._device).reshape(-1)
     self._check_values(ids, id_split, flat_value)
     _lib.check(self._lib.mono_mtable_assign(self._h, _ptr(ids), self._split_arr(id_split), _ptr(flat_value),
-                                            int(req_time), 0, _stream(self._device)))
+                                            int(req_time), _lib.FLAG_IDS_UNIQUE if ids_unique else 0,
+                                            _stream(self._device)))
     return self
 
   # ---- fused ops for sync training (ref: multi_hash_table_ops.py:438-483) ----------------------

