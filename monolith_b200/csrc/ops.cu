@@ -777,7 +777,23 @@ void run_upsert(mono_mtable* mt, UpsertOp op, const CallSeg* h_segs, int nsegs,
                 const int64_t* ids_dev, int64_t n_total, const float* vals_dev,
                 const float* lr_host, int n_lr, int64_t update_time, bool unique, bool dedup_sum,
                 int32_t* status_dev, cudaStream_t s) {
-  if (n_total <= 0) return;
+  if (n_total <= 0 || nsegs <= 0) return;
+  // The kernels walk positions [0, n): rebase the call on the id range its segments cover
+  // (fused_optimize passes one shard's segments of a larger id array).
+  std::vector<CallSeg> rebased(h_segs, h_segs + nsegs);
+  {
+    const int64_t i0 = rebased.front().id_begin;
+    for (int i = 0; i < nsegs; ++i) {
+      if (i > 0 && rebased[i].id_begin != h_segs[i - 1].id_end)
+        throw ArgError("call segments must be contiguous");
+      rebased[i].id_begin -= i0;
+      rebased[i].id_end -= i0;
+    }
+    ids_dev += i0;
+    if (status_dev) status_dev += i0;
+    n_total = rebased.back().id_end;
+    h_segs = rebased.data();
+  }
   if (n_total >= (int64_t)1 << 31) throw ArgError("more than 2^31 ids in one call");
   // capacity first (may rehash / grow and dirty the table descriptors)
   std::vector<uint64_t> per_table(mt->tables.size(), 0);
