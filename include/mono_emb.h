@@ -157,6 +157,23 @@ int mono_mtable_lookup_pool(mono_mtable_t* t, int32_t k, const int64_t* fids_dev
                             int32_t pooling, float* out_dev, int64_t out_stride, int32_t out_col,
                             void* stream);
 
+/* ---- fused backward of lookup_pool ----------------------------------------------------------
+ * Scatter of the pooled-row gradients to the unique FIDs + sparse optimizer step + expiry bump for
+ * table k, in one call and without materialising the per-unique-FID gradient buffer.  Replaces
+ *   ScatterGrad / BackwardBatchKernel (ref: RT/ops/fused_embedding_to_layout.h:286-347,
+ *   fused_embedding_to_layout.cu.cc:337-381: float atomicAdd per occurrence) followed by
+ *   MonolithMultiHashTableOptimize (ref: RT/ops/multi_hash_table_update_op.cc:47-100)
+ * for the occurrences fids_dev[row_offsets[r]:row_offsets[r+1]] of pooled row r (row_offsets NULL:
+ * one FID per row).  Every distinct FID receives ONE optimizer step with the sum (SUM) or the sum
+ * of g/n (MEAN) of its occurrences' pooled-row gradients, accumulated in occurrence order without
+ * float atomics (run-to-run bit-stable); absent FIDs are inserted (upsert) exactly like optimize.
+ * Needs dim(k) % 4 == 0, dim(k) <= 128 and 16-byte aligned gradient rows.  No host sync. */
+int mono_mtable_pool_backward(mono_mtable_t* t, int32_t k, const int64_t* fids_dev, int64_t n_fids,
+                              const int32_t* row_offsets_dev, int64_t n_rows, int32_t pooling,
+                              const float* pooled_grad_dev, int64_t grad_stride, int32_t grad_col,
+                              const float* learning_rate_host /*[slice_size(k)]*/,
+                              int64_t update_time, int64_t global_step, void* stream);
+
 /* ---- updates ----------------------------------------------------------------------------- */
 
 #define MONO_FLAG_IDS_UNIQUE 1u      /* caller guarantees ids unique per table within this call   */

@@ -270,6 +270,21 @@ int mono_mtable_lookup_pool(mono_mtable_t* t, int32_t k, const int64_t* fids_dev
   });
 }
 
+int mono_mtable_pool_backward(mono_mtable_t* t, int32_t k, const int64_t* fids_dev, int64_t n_fids,
+                              const int32_t* row_offsets_dev, int64_t n_rows, int32_t pooling,
+                              const float* pooled_grad_dev, int64_t grad_stride, int32_t grad_col,
+                              const float* learning_rate_host, int64_t update_time,
+                              int64_t /*global_step*/, void* stream) {
+  return guarded([&] {
+    require(k >= 0 && k < (int)t->tables.size(), "bad table index");
+    require(fids_dev && pooled_grad_dev && learning_rate_host, "pool_backward: null argument");
+    require(row_offsets_dev != nullptr || n_rows == n_fids, "pool_backward: n_rows must equal n_fids without offsets");
+    use_device(t);
+    run_pool_backward(t, k, fids_dev, n_fids, row_offsets_dev, n_rows, pooling, pooled_grad_dev, grad_stride,
+                      grad_col, learning_rate_host, update_time, (cudaStream_t)stream);
+  });
+}
+
 int mono_mtable_optimize(mono_mtable_t* t, const int64_t* ids_dev, const int64_t* id_split_host,
                          const float* grads_dev, const float* learning_rate_host,
                          int64_t update_time, int64_t /*global_step*/, uint32_t flags, void* stream) {

@@ -326,6 +326,84 @@ __device__ __forceinline__ void cuckoo_insert(const TableDev* __restrict__ t, En
   atomicOr(t->ctrs + kCtrError, 1u);
 }
 
+// Batched probe: U independent keys per lane group.  All U bucket loads are issued back to back
+// before the first ballot consumes one, so a group keeps U random 64-byte reads in flight instead
+// of one (the kernels are latency-bound on dependent HBM round trips, not on bytes).
+template <int G, int LD, int U>
+__device__ __forceinline__ void probe_keys(const TableDev* __restrict__ t, const int64_t (&key)[U],
+                                           const bool (&active)[U], uint32_t stash_count,
+                                           uint32_t (&row)[U], Entry* (&slot)[U]) {
+  const int gl = Group<G>::gl();
+  Entry* buckets = t->buckets;
+  const uint32_t nb = t->num_buckets;
+  uint32_t b1[U], b2[U];
+  bool pending[U];
+#pragma unroll
+  for (int q = 0; q < U; ++q) {
+    b1[q] = b2[q] = 0;
+    if (active[q]) bucket_pair(key[q], nb, b1[q], b2[q]);
+    pending[q] = active[q];
+    row[q] = kEmptyRow;
+    slot[q] = nullptr;
+  }
+#pragma unroll
+  for (int round = 0; round < 2; ++round) {
+    if (round == 1) {
+      bool any = false;
+#pragma unroll
+      for (int q = 0; q < U; ++q) any |= pending[q];
+      if (!__any_sync(0xffffffffu, any)) break;
+    }
+    Entry e[U];
+    Entry* p[U];
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      const uint32_t b = round == 0 ? b1[q] : b2[q];
+      p[q] = buckets + (size_t)b * kBucketSlots + (gl & 3);
+      e[q].row = kEmptyRow;
+      e[q].key = 0;
+      if (pending[q] && gl < kBucketSlots) e[q] = LD == 0 ? ld_entry_nc(p[q]) : ld_entry(p[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      const bool hit = pending[q] && gl < kBucketSlots && e[q].key == key[q] && e[q].row < kTombRow;
+      const uint32_t bal = Group<G>::bits(__ballot_sync(0xffffffffu, hit));
+      const int src = Group<G>::base() + (bal ? (__ffs(bal) - 1) : 0);
+      const uint32_t r = __shfl_sync(0xffffffffu, e[q].row, src);
+      const unsigned long long pp = __shfl_sync(0xffffffffu, (unsigned long long)p[q], src);
+      if (pending[q] && bal) {
+        row[q] = r;
+        slot[q] = reinterpret_cast<Entry*>(pp);
+        pending[q] = false;
+      }
+    }
+  }
+  if (stash_count != 0) {
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      if (!__any_sync(0xffffffffu, pending[q])) continue;
+      uint32_t r = kEmptyRow;
+      Entry* sp = nullptr;
+      if (pending[q] && gl == 0) {
+        const uint32_t mask = t->stash_cap - 1;
+        const uint32_t s = (uint32_t)(mix64((uint64_t)key[q]) >> 17) & mask;
+        for (uint32_t i = 0; i <= mask; ++i) {
+          Entry* pq = t->stash + ((s + i) & mask);
+          Entry e = ld_entry_cg(pq);
+          if (e.row == kEmptyRow) break;
+          if (e.key == key[q] && e.row < kTombRow) { r = e.row; sp = pq; break; }
+        }
+      }
+      r = __shfl_sync(0xffffffffu, r, Group<G>::base());
+      const unsigned long long pp = __shfl_sync(0xffffffffu, (unsigned long long)sp, Group<G>::base());
+      if (pending[q] && r != kEmptyRow) {
+        row[q] = r;
+        slot[q] = reinterpret_cast<Entry*>(pp);
+      }
+    }
+  }
+}
+
 // binary search: last segment with id_begin <= i (segments are sorted, non-overlapping)
 __device__ __forceinline__ int find_seg(const CallSeg* __restrict__ segs, int nsegs, int64_t i) {
   int lo = 0, hi = nsegs - 1;

@@ -67,7 +67,9 @@ dd_claim_kernel(const int64_t* __restrict__ ids, int64_t M, const int64_t* __res
         continue;
       }
       if (e.key == key && (int32_t)e.row == m) {
-        atomicMin(&set[s].first_pos, (int32_t)i);
+        // first_pos only ever decreases: skip the atomic when the value just read is already
+        // lower (this removes the same-address atomic storm of hot keys in Zipf batches)
+        if ((int32_t)e.ts > (int32_t)i) atomicMin(&set[s].first_pos, (int32_t)i);
         break;
       }
       s = (s + 1) & mask;

@@ -3,7 +3,10 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
+#include <map>
+#include <mutex>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -43,6 +46,35 @@ inline int grid_for(int64_t work_items, int items_per_block, int max_blocks = 14
   if (b < 1) b = 1;
   if (b > max_blocks) b = max_blocks;
   return (int)b;
+}
+
+// Persistent-style grid: exactly one resident wave (SMs x occupancy), never a partial second wave;
+// the kernels are grid-stride loops.  The occupancy query is cached per kernel.
+template <class Kernel>
+inline int resident_grid(Kernel kernel, int64_t work_items, int items_per_block, int threads = kThreads,
+                         size_t smem = 0) {
+  static std::mutex mu;
+  static std::map<const void*, int> cache;  // keyed by kernel address
+  int cached_blocks = 0;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(reinterpret_cast<const void*>(kernel));
+    if (it != cache.end()) cached_blocks = it->second;
+  }
+  if (cached_blocks == 0) {
+    int per_sm = 0, sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess ||
+        per_sm < 1)
+      per_sm = 1;
+    cached_blocks = std::max(1, sms) * per_sm;
+    std::lock_guard<std::mutex> lk(mu);
+    cache[reinterpret_cast<const void*>(kernel)] = cached_blocks;
+  }
+  int64_t b = (work_items + items_per_block - 1) / items_per_block;
+  if (b < 1) b = 1;
+  return (int)std::min<int64_t>(b, cached_blocks);
 }
 
 // growable device scratch buffer (stream-ordered allocation)
@@ -148,6 +180,11 @@ void run_upsert(mono_mtable* mt, UpsertOp op, const CallSeg* h_segs, int nsegs,
                 const int64_t* ids_dev, int64_t n_total, const float* vals_dev,
                 const float* lr_host, int n_lr, int64_t update_time, bool unique, bool dedup_sum,
                 int32_t* status_dev, cudaStream_t s);
+
+void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t n_fids,
+                       const int32_t* row_offsets, int64_t n_rows, int pooling,
+                       const float* pooled_grad, int64_t grad_stride, int grad_col,
+                       const float* lr_host, int64_t update_time, cudaStream_t s);
 
 // dedup.cu
 void run_reorder(int device, const int64_t* ids_dev, const int64_t* id_split_host, int K, int N,

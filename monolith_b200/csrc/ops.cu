@@ -55,61 +55,64 @@ __device__ __forceinline__ float init_state_value(const SegDev& s, int lj) {
 // (Adagrad: a = norm; FTRL: a = norm, b = zero; Adam: a = m, b = v).  `lr` is the slice learning rate
 // (for Adam: the bias-corrected lr_t of the row).  `avx_form` selects the reference's AVX-path
 // arithmetic for Adagrad (first floor(dim/8)*8 lanes, ref: avx_utils.h:96-119) vs the baseline form.
+template <int OPT>
+__device__ __forceinline__ void opt_elem_t(const float* __restrict__ p, bool avx_form, float lr, float g,
+                                           float& w, float& a, float& b) {
+  if (OPT == MONO_OPT_SGD) {  // sgd_optimizer.cc:46-48
+    w = __fsub_rn(w, __fmul_rn(lr, g));
+  } else if (OPT == MONO_OPT_ADAGRAD) {
+    const float wd = p[1];
+    if (avx_form) {  // avx_utils.h:106-113
+      float ug = __fmaf_rn(wd, w, g);
+      float nn = __fmaf_rn(ug, ug, a);
+      a = nn;
+      float eff = __fdiv_rn(lr, __fsqrt_rn(nn));
+      w = __fmaf_rn(-eff, g, w);
+    } else {  // avx_utils.h:31-37
+      float gg = __fadd_rn(g, __fmul_rn(wd, w));
+      a = __fadd_rn(a, __fmul_rn(gg, gg));
+      float eff = __fdiv_rn(lr, __fsqrt_rn(a));
+      w = __fsub_rn(w, __fmul_rn(eff, gg));
+    }
+  } else if (OPT == MONO_OPT_FTRL) {  // ftrl_optimizer.cc:62-75
+    const float beta = p[1], l1 = p[2], l2 = p[3];
+    float norm_new = __fadd_rn(a, __fmul_rn(g, g));
+    float sigma = __fdiv_rn(__fsub_rn(__fsqrt_rn(norm_new), __fsqrt_rn(a)), lr);
+    b = __fadd_rn(b, __fsub_rn(g, __fmul_rn(sigma, w)));
+    a = norm_new;
+    if (fabsf(b) > l1) {
+      float sb = signbit(b) ? 1.0f : 0.0f;
+      float num = __fmul_rn(lr, __fsub_rn(__fmul_rn(sb, l1), b));
+      float den = __fadd_rn(__fadd_rn(__fsqrt_rn(a), beta), __fmul_rn(l2, lr));
+      w = __fdiv_rn(num, den);
+    } else {
+      w = 0.0f;
+    }
+  } else if (OPT == MONO_OPT_ADAM) {  // adam_optimizer.cc:65-80
+    const float beta1 = p[0], beta2 = p[1], eps = p[2], wd = p[3];
+    const bool nesterov = p[4] != 0.0f;
+    float cur = __fadd_rn(g, __fmul_rn(wd, w));
+    float new_m = __fadd_rn(a, __fmul_rn(__fsub_rn(cur, a), __fsub_rn(1.0f, beta1)));
+    float new_v = __fadd_rn(b, __fmul_rn(__fsub_rn(__fmul_rn(cur, cur), b), __fsub_rn(1.0f, beta2)));
+    float den = __fadd_rn(__fsqrt_rn(new_v), eps);
+    if (nesterov) {
+      float t1 = __fadd_rn(__fmul_rn(cur, __fsub_rn(1.0f, beta1)), __fmul_rn(beta1, new_m));
+      w = __fsub_rn(w, __fdiv_rn(__fmul_rn(t1, lr), den));
+    } else {
+      w = __fsub_rn(w, __fdiv_rn(__fmul_rn(new_m, lr), den));
+    }
+    a = new_m;
+    b = new_v;
+  }
+}
+
 __device__ __forceinline__ void opt_elem(const SegDev& s, bool avx_form, float lr, float g, float& w,
                                          float& a, float& b) {
   switch (s.opt_type) {
-    case MONO_OPT_SGD:  // sgd_optimizer.cc:46-48
-      w = __fsub_rn(w, __fmul_rn(lr, g));
-      break;
-    case MONO_OPT_ADAGRAD: {
-      const float wd = s.p[1];
-      if (avx_form) {  // avx_utils.h:106-113
-        float ug = __fmaf_rn(wd, w, g);
-        float nn = __fmaf_rn(ug, ug, a);
-        a = nn;
-        float eff = __fdiv_rn(lr, __fsqrt_rn(nn));
-        w = __fmaf_rn(-eff, g, w);
-      } else {  // avx_utils.h:31-37
-        float gg = __fadd_rn(g, __fmul_rn(wd, w));
-        a = __fadd_rn(a, __fmul_rn(gg, gg));
-        float eff = __fdiv_rn(lr, __fsqrt_rn(a));
-        w = __fsub_rn(w, __fmul_rn(eff, gg));
-      }
-      break;
-    }
-    case MONO_OPT_FTRL: {  // ftrl_optimizer.cc:62-75
-      const float beta = s.p[1], l1 = s.p[2], l2 = s.p[3];
-      float norm_new = __fadd_rn(a, __fmul_rn(g, g));
-      float sigma = __fdiv_rn(__fsub_rn(__fsqrt_rn(norm_new), __fsqrt_rn(a)), lr);
-      b = __fadd_rn(b, __fsub_rn(g, __fmul_rn(sigma, w)));
-      a = norm_new;
-      if (fabsf(b) > l1) {
-        float sb = signbit(b) ? 1.0f : 0.0f;
-        float num = __fmul_rn(lr, __fsub_rn(__fmul_rn(sb, l1), b));
-        float den = __fadd_rn(__fadd_rn(__fsqrt_rn(a), beta), __fmul_rn(l2, lr));
-        w = __fdiv_rn(num, den);
-      } else {
-        w = 0.0f;
-      }
-      break;
-    }
-    case MONO_OPT_ADAM: {  // adam_optimizer.cc:65-80
-      const float beta1 = s.p[0], beta2 = s.p[1], eps = s.p[2], wd = s.p[3];
-      const bool nesterov = s.p[4] != 0.0f;
-      float cur = __fadd_rn(g, __fmul_rn(wd, w));
-      float new_m = __fadd_rn(a, __fmul_rn(__fsub_rn(cur, a), __fsub_rn(1.0f, beta1)));
-      float new_v = __fadd_rn(b, __fmul_rn(__fsub_rn(__fmul_rn(cur, cur), b), __fsub_rn(1.0f, beta2)));
-      float den = __fadd_rn(__fsqrt_rn(new_v), eps);
-      if (nesterov) {
-        float t1 = __fadd_rn(__fmul_rn(cur, __fsub_rn(1.0f, beta1)), __fmul_rn(beta1, new_m));
-        w = __fsub_rn(w, __fdiv_rn(__fmul_rn(t1, lr), den));
-      } else {
-        w = __fsub_rn(w, __fdiv_rn(__fmul_rn(new_m, lr), den));
-      }
-      a = new_m;
-      b = new_v;
-      break;
-    }
+    case MONO_OPT_SGD: opt_elem_t<MONO_OPT_SGD>(s.p, avx_form, lr, g, w, a, b); break;
+    case MONO_OPT_ADAGRAD: opt_elem_t<MONO_OPT_ADAGRAD>(s.p, avx_form, lr, g, w, a, b); break;
+    case MONO_OPT_FTRL: opt_elem_t<MONO_OPT_FTRL>(s.p, avx_form, lr, g, w, a, b); break;
+    case MONO_OPT_ADAM: opt_elem_t<MONO_OPT_ADAM>(s.p, avx_form, lr, g, w, a, b); break;
   }
 }
 
@@ -261,41 +264,148 @@ __device__ __forceinline__ void apply_row(const TableDev* __restrict__ t, uint32
 // ------------------------------------------------------------------------------------------
 // ref: MultiHashTableLookupOp::Compute / FusedLookupOp (multi_hash_table_lookup_op.cc:37-88,143-197)
 // One launch serves every (shard, table) segment of the call.
-template <int G>
-__global__ void __launch_bounds__(kThreads)
-lookup_kernel(const TableDev* __restrict__ tables, const CallSeg* __restrict__ segs, int nsegs,
-              const int64_t* __restrict__ ids, int64_t n_total, float* __restrict__ out) {
-  constexpr int GPW = 32 / G;
-  const int lane = threadIdx.x & 31, gl = Group<G>::gl();
-  const int64_t wstride = (int64_t)gridDim.x * (kThreads / 32) * GPW;
-  for (int64_t wbase = ((int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * GPW;
-       wbase < n_total; wbase += wstride) {
-    const int64_t i = wbase + lane / G;
-    const bool active = i < n_total;
-    int si = 0;
-    const TableDev* t = tables;
-    int64_t key = 0;
-    uint32_t stash = 0;
-    if (active) {
-      si = nsegs > 1 ? find_seg(segs, nsegs, i) : 0;
-      t = tables + segs[si].table;
-      key = __ldg(ids + i);
-      stash = t->ctrs[kCtrStash];
-    }
-    Probe pr = probe_key<G, 0>(t, key, active, stash);
-    if (!active) continue;
-    const int D = t->dim;
-    float* dst = out + segs[si].val_off + (i - segs[si].id_begin) * D;
-    const float* src = t->emb + (size_t)pr.row * t->emb_stride;
-    const bool hit = pr.row != kEmptyRow;
-    if ((D & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-      for (int c = gl * 4; c < D; c += G * 4) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (hit) v = __ldg(reinterpret_cast<const float4*>(src + c));
-        *reinterpret_cast<float4*>(dst + c) = v;
+//
+// Two phases per warp-tile of 32 ids, designed for memory-level parallelism (the op is a chain of
+// dependent random HBM reads: FID -> 64 B bucket -> 128 B row):
+//   A. lane-per-key probe: every lane resolves its own FID (4 x LDG.128 = the whole 64-byte bucket),
+//      so a warp keeps 32 independent bucket reads in flight with ~10 live registers per lane;
+//      the few lanes that miss probe the alternate bucket (and the stash when non-empty).
+//   B. group-per-row copy: row indices are handed around with shuffles; G lanes move one row with
+//      16-byte vectors, kRowsInFlight rows per group issued back to back before the first store.
+// Used by lookup / fused_lookup (multi-segment) and by lookup_pool when every pooled row has exactly
+// one FID (the per-slot case of Criteo/MovieLens/DCN-shaped inputs, where pooling is the identity).
+__device__ __forceinline__ uint32_t probe_lane(const TableDev* __restrict__ t, int64_t key) {
+  const Entry* __restrict__ buckets = t->buckets;
+  uint32_t b1, b2;
+  bucket_pair(key, t->num_buckets, b1, b2);
+  uint32_t row = kEmptyRow;
+  {
+    const Entry* p = buckets + (size_t)b1 * kBucketSlots;
+    Entry e0 = ld_entry_nc(p), e1 = ld_entry_nc(p + 1), e2 = ld_entry_nc(p + 2), e3 = ld_entry_nc(p + 3);
+    if (e0.key == key && e0.row < kTombRow) row = e0.row;
+    if (e1.key == key && e1.row < kTombRow) row = e1.row;
+    if (e2.key == key && e2.row < kTombRow) row = e2.row;
+    if (e3.key == key && e3.row < kTombRow) row = e3.row;
+  }
+  if (row == kEmptyRow) {
+    const Entry* p = buckets + (size_t)b2 * kBucketSlots;
+    Entry e0 = ld_entry_nc(p), e1 = ld_entry_nc(p + 1), e2 = ld_entry_nc(p + 2), e3 = ld_entry_nc(p + 3);
+    if (e0.key == key && e0.row < kTombRow) row = e0.row;
+    if (e1.key == key && e1.row < kTombRow) row = e1.row;
+    if (e2.key == key && e2.row < kTombRow) row = e2.row;
+    if (e3.key == key && e3.row < kTombRow) row = e3.row;
+    if (row == kEmptyRow && t->ctrs[kCtrStash] != 0) {
+      const uint32_t mask = t->stash_cap - 1;
+      const uint32_t s = (uint32_t)(mix64((uint64_t)key) >> 17) & mask;
+      for (uint32_t i = 0; i <= mask; ++i) {
+        Entry e = ld_entry_cg(t->stash + ((s + i) & mask));
+        if (e.row == kEmptyRow) break;
+        if (e.key == key && e.row < kTombRow) { row = e.row; break; }
       }
-    } else {
-      for (int c = gl; c < D; c += G) dst[c] = hit ? __ldg(src + c) : 0.0f;
+    }
+  }
+  return row;
+}
+
+// store one 16-byte vector of a row (vector store when the row base is 16-byte aligned)
+__device__ __forceinline__ void store_vec(float* dst, int c, int D, const float4& x, bool vec_ok) {
+  if (c >= D) return;
+  if (vec_ok) {
+    __stcs(reinterpret_cast<float4*>(dst + c), x);  // streaming: written once, consumed later
+  } else {
+    const float a[4] = {x.x, x.y, x.z, x.w};
+    for (int w = 0; w < 4 && c + w < D; ++w) dst[c + w] = a[w];
+  }
+}
+
+// SINGLE: the call has one segment (one table): table fields and the output base are warp-uniform
+// and hoisted, which keeps the kernel at ~40 registers => 6 resident blocks (48 warps) per SM.
+template <int G, bool SINGLE>
+__global__ void __launch_bounds__(kThreads, SINGLE ? 6 : 4)
+lookup_kernel(const TableDev* __restrict__ tables, const CallSeg* __restrict__ segs, int nsegs,
+              const int64_t* __restrict__ ids, int64_t n_total, float* __restrict__ out,
+              int64_t out_stride /* <= 0: rows packed at dim floats */, int out_col) {
+  constexpr int RPI = 32 / G;   // rows copied per iteration of a warp
+  constexpr int ITERS = G;      // iterations to drain the 32 resolved rows
+  constexpr int UNR = 4;        // row loads in flight per lane
+  const int lane = threadIdx.x & 31, gl = Group<G>::gl(), grp = lane / G;
+  const int c = gl * 4;
+  // SINGLE: hoisted table / output description
+  const TableDev* t0 = tables + segs[0].table;
+  const int D0 = t0->dim;
+  const float* __restrict__ emb0 = t0->emb;
+  const uint32_t stride0 = t0->emb_stride;
+  const int64_t rs0 = out_stride > 0 ? out_stride : D0;
+  float* const base0 = out + segs[0].val_off - segs[0].id_begin * rs0 + out_col;
+  const bool vec0 = (D0 & 3) == 0 && (rs0 & 3) == 0 && (reinterpret_cast<uintptr_t>(base0) & 15) == 0;
+  const int64_t wstride = (int64_t)gridDim.x * (kThreads / 32) * 32;
+  for (int64_t wbase = ((int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * 32;
+       wbase < n_total; wbase += wstride) {
+    // ---- phase A: lane-per-key probe ----
+    const int64_t i = wbase + lane;
+    int si = 0;
+    uint32_t row = kEmptyRow;
+    if (i < n_total) {
+      if (!SINGLE) si = find_seg(segs, nsegs, i);
+      row = probe_lane(SINGLE ? t0 : tables + segs[si].table, __ldg(ids + i));
+    }
+    // ---- phase B: group-per-row copy, UNR rows in flight ----
+#pragma unroll
+    for (int it0 = 0; it0 < ITERS; it0 += UNR) {
+      float4 x[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int src_lane = (it0 + u) * RPI + grp;
+        const uint32_t r = __shfl_sync(0xffffffffu, row, src_lane);
+        x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (SINGLE) {
+          if (r != kEmptyRow && c < D0)
+            x[u] = __ldg(reinterpret_cast<const float4*>(emb0 + (size_t)r * stride0 + c));
+        } else {
+          const int s_r = __shfl_sync(0xffffffffu, si, src_lane);
+          if (r != kEmptyRow) {
+            const TableDev* t = tables + segs[s_r].table;
+            if (c < t->dim) x[u] = __ldg(reinterpret_cast<const float4*>(t->emb + (size_t)r * t->emb_stride + c));
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int src_lane = (it0 + u) * RPI + grp;
+        const int64_t ir = wbase + src_lane;
+        // shuffles read lanes outside the group: all 32 lanes take part, before any divergence
+        const uint32_t r_st = __shfl_sync(0xffffffffu, row, src_lane);
+        const int s_st = SINGLE ? 0 : __shfl_sync(0xffffffffu, si, src_lane);
+        if (ir >= n_total) continue;
+        if (SINGLE) {
+          float* dst = base0 + ir * rs0;
+          store_vec(dst, c, D0, x[u], vec0);
+          if (D0 > 4 * G) {  // wide rows (dim > 128, G == 32): remaining vectors of the row
+            const uint32_t r = r_st;
+            for (int cc = c + 4 * G; cc < D0; cc += 4 * G) {
+              float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (r != kEmptyRow) y = __ldg(reinterpret_cast<const float4*>(emb0 + (size_t)r * stride0 + cc));
+              store_vec(dst, cc, D0, y, vec0);
+            }
+          }
+        } else {
+          const CallSeg sg = segs[s_st];
+          const TableDev* t = tables + sg.table;
+          const int D = t->dim;
+          const int64_t rs = out_stride > 0 ? out_stride : D;
+          float* dst = out + sg.val_off + (ir - sg.id_begin) * rs + out_col;
+          const bool vec_ok = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+          store_vec(dst, c, D, x[u], vec_ok);
+          if (D > 4 * G) {
+            const uint32_t r = r_st;
+            for (int cc = c + 4 * G; cc < D; cc += 4 * G) {
+              float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (r != kEmptyRow) y = __ldg(reinterpret_cast<const float4*>(t->emb + (size_t)r * t->emb_stride + cc));
+              store_vec(dst, cc, D, y, vec_ok);
+            }
+          }
+        }
+      }
     }
   }
 }
@@ -354,7 +464,7 @@ lookup_entry_kernel(const TableDev* __restrict__ t, const int64_t* __restrict__ 
 // vectors of the embedding row and accumulate in registers; one coalesced store per output row.
 // Terms are added in FID order => bit-exact with the CPU reference's pooling
 // (ref: OptimizedSumpooling, fused_embedding_to_layout.cc:26-59; ReduceSumOp, reduce_op.cc:29-51).
-template <int G, int NV>  // NV = 16-byte vectors per lane (dim <= 4*G*NV)
+template <int G, int NV, int U>  // NV = 16-byte vectors per lane (dim <= 4*G*NV); U = rows in flight
 __global__ void __launch_bounds__(kThreads)
 lookup_pool_kernel(const TableDev* __restrict__ t, const int64_t* __restrict__ fids,
                    const int32_t* __restrict__ row_offsets, int64_t n_rows, int pooling,
@@ -365,58 +475,86 @@ lookup_pool_kernel(const TableDev* __restrict__ t, const int64_t* __restrict__ f
   const uint32_t stash = t->ctrs[kCtrStash];
   const float* __restrict__ emb = t->emb;
   const uint32_t stride = t->emb_stride;
-  const int64_t wstride = (int64_t)gridDim.x * (kThreads / 32) * GPW;
-  for (int64_t wbase = ((int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * GPW;
+  // a warp owns GPW*U consecutive pooled rows per iteration; group g takes rows g, g+GPW, ...
+  const int64_t wstride = (int64_t)gridDim.x * (kThreads / 32) * GPW * U;
+  for (int64_t wbase = ((int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * GPW * U;
        wbase < n_rows; wbase += wstride) {
-    const int64_t r = wbase + lane / G;
-    const bool ractive = r < n_rows;
-    int64_t b = 0, e = 0;
-    if (ractive) {
-      b = row_offsets ? row_offsets[r] : r;
-      e = row_offsets ? row_offsets[r + 1] : r + 1;
+    int64_t r[U], b[U];
+    int n[U];
+    int nloc = 0;
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      r[q] = wbase + q * GPW + lane / G;
+      b[q] = 0;
+      n[q] = 0;
+      if (r[q] < n_rows) {
+        b[q] = row_offsets ? row_offsets[r[q]] : r[q];
+        n[q] = row_offsets ? (int)(row_offsets[r[q] + 1] - b[q]) : 1;
+      }
+      nloc = max(nloc, n[q]);
     }
-    const int n = (int)(e - b);
-    const int nmax = __reduce_max_sync(0xffffffffu, n);
-    float4 acc[NV];
+    const int nmax = row_offsets ? __reduce_max_sync(0xffffffffu, nloc) : 1;
+    float4 acc[U][NV];
 #pragma unroll
-    for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float fn = (float)n;
+    for (int q = 0; q < U; ++q)
+#pragma unroll
+      for (int v = 0; v < NV; ++v) acc[q][v] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int j = 0; j < nmax; ++j) {
-      const bool active = j < n;
-      int64_t key = active ? __ldg(fids + b + j) : 0;
-      Probe pr = probe_key<G, 0>(t, key, active, stash);
-      if (!active) continue;
-      const float* src = emb + (size_t)pr.row * stride;
-      const bool hit = pr.row != kEmptyRow;
+      int64_t key[U];
+      bool active[U];
+      uint32_t row[U];
+      Entry* slot[U];
 #pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const int c = (v * G + gl) * 4;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (hit && c < D) x = __ldg(reinterpret_cast<const float4*>(src + c));
-        if (pooling == MONO_POOL_MEAN) {
-          x.x = __fdiv_rn(x.x, fn); x.y = __fdiv_rn(x.y, fn);
-          x.z = __fdiv_rn(x.z, fn); x.w = __fdiv_rn(x.w, fn);
+      for (int q = 0; q < U; ++q) {
+        active[q] = j < n[q];
+        key[q] = active[q] ? __ldg(fids + b[q] + j) : 0;
+      }
+      probe_keys<G, 0, U>(t, key, active, stash, row, slot);
+      float4 x[U][NV];
+#pragma unroll
+      for (int q = 0; q < U; ++q)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int c = (v * G + gl) * 4;
+          x[q][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (active[q] && row[q] != kEmptyRow && c < D)
+            x[q][v] = __ldg(reinterpret_cast<const float4*>(emb + (size_t)row[q] * stride + c));
         }
-        if (j == 0) {
-          acc[v] = x;
-        } else {
-          acc[v].x = __fadd_rn(acc[v].x, x.x); acc[v].y = __fadd_rn(acc[v].y, x.y);
-          acc[v].z = __fadd_rn(acc[v].z, x.z); acc[v].w = __fadd_rn(acc[v].w, x.w);
+#pragma unroll
+      for (int q = 0; q < U; ++q) {
+        if (!active[q]) continue;
+        const float fn = (float)n[q];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          float4 xv = x[q][v];
+          if (pooling == MONO_POOL_MEAN) {
+            xv.x = __fdiv_rn(xv.x, fn); xv.y = __fdiv_rn(xv.y, fn);
+            xv.z = __fdiv_rn(xv.z, fn); xv.w = __fdiv_rn(xv.w, fn);
+          }
+          if (j == 0) {
+            acc[q][v] = xv;
+          } else {
+            acc[q][v].x = __fadd_rn(acc[q][v].x, xv.x); acc[q][v].y = __fadd_rn(acc[q][v].y, xv.y);
+            acc[q][v].z = __fadd_rn(acc[q][v].z, xv.z); acc[q][v].w = __fadd_rn(acc[q][v].w, xv.w);
+          }
         }
       }
     }
-    if (!ractive) continue;
-    float* dst = out + r * out_stride + out_col;
-    const bool vec_ok = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      const int c = (v * G + gl) * 4;
-      if (c >= D) continue;
-      if (vec_ok) {
-        *reinterpret_cast<float4*>(dst + c) = acc[v];
-      } else {
-        const float a[4] = {acc[v].x, acc[v].y, acc[v].z, acc[v].w};
-        for (int q = 0; q < 4 && c + q < D; ++q) dst[c + q] = a[q];
+    for (int q = 0; q < U; ++q) {
+      if (r[q] >= n_rows) continue;
+      float* dst = out + r[q] * out_stride + out_col;
+      const bool vec_ok = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int c = (v * G + gl) * 4;
+        if (c >= D) continue;
+        if (vec_ok) {
+          __stcs(reinterpret_cast<float4*>(dst + c), acc[q][v]);  // streaming: written once, read later
+        } else {
+          const float a[4] = {acc[q][v].x, acc[q][v].y, acc[q][v].z, acc[q][v].w};
+          for (int w = 0; w < 4 && c + w < D; ++w) dst[c + w] = a[w];
+        }
       }
     }
   }
@@ -430,105 +568,116 @@ struct UpsertArgs {
   const CallSeg* segs;
   int nsegs;
   const int64_t* ids;
-  const uint32_t* idx_list;  // optional indirection: process ids[idx_list[j]]
+  const uint32_t* idx_list;  // optional indirection: item j is ids[idx_list[j]]
   int64_t n;                 // number of items to process
   const uint32_t* n_dev;     // optional: item count on device (overrides n when non-null)
   const float* vals;
   const float* lr;           // device copy of the call's learning rates
   uint32_t update_ts;
   uint32_t* miss_ctr;        // global miss counter of the call
-  uint32_t* miss_list;       // positions (into ids) that missed
+  uint32_t* miss_list;       // item indices j that missed
+  uint32_t* rowidx;          // per item j: resolved row (bit 31 = freshly inserted)
   int32_t* status;           // reinitialize only
-  int val_width_extra;       // kOpRestore: row width = dim + state + 2
 };
+constexpr uint32_t kFreshBit = 0x80000000u;
 
-// Pass 1: ids that are present.  Probe, bump the expiry timestamp in the bucket entry, apply the
-// op in place; misses are compacted (warp ballot + one atomic per warp) into miss_list.
-template <int G, int OP>
-__global__ void __launch_bounds__(kThreads) upsert_hit_kernel(UpsertArgs a) {
-  constexpr int GPW = 32 / G;
-  const int lane = threadIdx.x & 31, gl = Group<G>::gl();
-  const int64_t n = a.n_dev ? (int64_t)*a.n_dev : a.n;
-  const int64_t wstride = (int64_t)gridDim.x * (kThreads / 32) * GPW;
-  for (int64_t wbase = ((int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * GPW; wbase < n;
-       wbase += wstride) {
-    const int64_t j = wbase + lane / G;
-    const bool active = j < n;
-    int64_t i = 0, key = 0;
-    int si = 0;
-    const TableDev* t = a.tables;
-    uint32_t stash = 0;
-    if (active) {
-      i = a.idx_list ? (int64_t)a.idx_list[j] : j;
-      si = a.nsegs > 1 ? find_seg(a.segs, a.nsegs, i) : 0;
-      t = a.tables + a.segs[si].table;
-      key = a.ids[i];
-      stash = t->ctrs[kCtrStash];
+// probe that also returns the matching entry's address (for the timestamp bump)
+__device__ __forceinline__ uint32_t probe_lane_slot(const TableDev* __restrict__ t, int64_t key,
+                                                    Entry** slot) {
+  Entry* buckets = t->buckets;
+  uint32_t b1, b2;
+  bucket_pair(key, t->num_buckets, b1, b2);
+  uint32_t row = kEmptyRow;
+#pragma unroll
+  for (int round = 0; round < 2; ++round) {
+    Entry* p = buckets + (size_t)(round == 0 ? b1 : b2) * kBucketSlots;
+    Entry e0 = ld_entry(p), e1 = ld_entry(p + 1), e2 = ld_entry(p + 2), e3 = ld_entry(p + 3);
+    if (e0.key == key && e0.row < kTombRow) { row = e0.row; *slot = p; }
+    if (e1.key == key && e1.row < kTombRow) { row = e1.row; *slot = p + 1; }
+    if (e2.key == key && e2.row < kTombRow) { row = e2.row; *slot = p + 2; }
+    if (e3.key == key && e3.row < kTombRow) { row = e3.row; *slot = p + 3; }
+    if (row != kEmptyRow) return row;
+  }
+  if (t->ctrs[kCtrStash] != 0) {
+    const uint32_t mask = t->stash_cap - 1;
+    const uint32_t s = (uint32_t)(mix64((uint64_t)key) >> 17) & mask;
+    for (uint32_t i = 0; i <= mask; ++i) {
+      Entry* p = t->stash + ((s + i) & mask);
+      Entry e = ld_entry_cg(p);
+      if (e.row == kEmptyRow) break;
+      if (e.key == key && e.row < kTombRow) { *slot = p; return e.row; }
     }
-    Probe pr = probe_key<G, 1>(t, key, active, stash);
-    const bool miss = active && pr.row == kEmptyRow;
-    const uint32_t mbal = __ballot_sync(0xffffffffu, miss && gl == 0);
+  }
+  return kEmptyRow;
+}
+
+__device__ __forceinline__ uint32_t restore_ts(const UpsertArgs& a, const CallSeg& sg, const TableDev* t,
+                                               int64_t i) {
+  const int width = t->dim + t->state_dim + 2;
+  return __float_as_uint(a.vals[sg.val_off + (i - sg.id_begin) * width + t->dim + t->state_dim + 1]);
+}
+
+// Pass 1 — resolve present keys, lane per key (32 independent probe chains per warp): row index to
+// rowidx[j], expiry timestamp bumped in the bucket entry (ref: entry.SetTimestamp(update_time),
+// cuckoo_embedding_hash_table.cc:243); misses are compacted with a warp ballot + one atomic per warp.
+template <bool RESTORE>
+__global__ void __launch_bounds__(kThreads) resolve_hit_kernel(UpsertArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n = a.n_dev ? (int64_t)*a.n_dev : a.n;
+  const int64_t wstride = (int64_t)gridDim.x * (kThreads / 32) * 32;
+  for (int64_t wbase = ((int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * 32; wbase < n;
+       wbase += wstride) {
+    const int64_t j = wbase + lane;
+    bool miss = false;
+    if (j < n) {
+      const int64_t i = a.idx_list ? (int64_t)a.idx_list[j] : j;
+      const CallSeg sg = a.segs[a.nsegs > 1 ? find_seg(a.segs, a.nsegs, i) : 0];
+      const TableDev* t = a.tables + sg.table;
+      Entry* slot = nullptr;
+      const uint32_t row = probe_lane_slot(t, a.ids[i], &slot);
+      if (row == kEmptyRow) {
+        miss = true;
+      } else {
+        slot->ts = RESTORE ? restore_ts(a, sg, t, i) : a.update_ts;
+        a.rowidx[j] = row;
+      }
+    }
+    const uint32_t mbal = __ballot_sync(0xffffffffu, miss);
     if (mbal) {
       uint32_t base = 0;
       if (lane == 0) base = atomicAdd(a.miss_ctr, (uint32_t)__popc(mbal));
       base = __shfl_sync(0xffffffffu, base, 0);
-      if (miss && gl == 0) a.miss_list[base + __popc(mbal & ((1u << lane) - 1u))] = (uint32_t)i;
+      if (miss) a.miss_list[base + __popc(mbal & ((1u << lane) - 1u))] = (uint32_t)j;
     }
-    if (!active || miss) continue;
-    const CallSeg sg = a.segs[si];
-    const int width = OP == kOpRestore ? t->dim + t->state_dim + 2 : t->dim;
-    const float* v = a.vals ? a.vals + sg.val_off + (i - sg.id_begin) * width : nullptr;
-    if (gl == 0) {
-      uint32_t ts = a.update_ts;
-      if (OP == kOpRestore) ts = __float_as_uint(v[t->dim + t->state_dim + 1]);
-      pr.slot->ts = ts;  // ref: entry.SetTimestamp(update_time), cuckoo_embedding_hash_table.cc:243
-      if (OP == kOpReinit) a.status[i] = 1;
-    }
-    apply_row<G, OP>(t, pr.row, key, v, a.lr + sg.lr_off, false);
   }
 }
 
-// Pass 2: absent ids (unique within the call): allocate a row (free list first, then bump),
-// initialise + apply the op, then publish the entry with the lock-free cuckoo insert.
-template <int G, int OP>
-__global__ void __launch_bounds__(kThreads) upsert_miss_kernel(UpsertArgs a) {
-  constexpr int GPW = 32 / G;
-  const int lane = threadIdx.x & 31, gl = Group<G>::gl();
+// Pass 2 — absent keys (unique within the call), thread per key: take a row (free list first, then
+// the bump allocator) and publish {fid, row, ts} with the lock-free cuckoo insert.  The row contents
+// are written by the apply pass (fresh bit set).
+template <bool RESTORE>
+__global__ void __launch_bounds__(kThreads) resolve_miss_kernel(UpsertArgs a) {
   const int64_t n = (int64_t)*a.miss_ctr;
-  const int64_t wstride = (int64_t)gridDim.x * (kThreads / 32) * GPW;
-  for (int64_t wbase = ((int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * GPW; wbase < n;
-       wbase += wstride) {
-    const int64_t j = wbase + lane / G;
-    const bool active = j < n;
-    if (!active) continue;  // no warp-wide votes below
-    const int64_t i = a.miss_list[j];
-    const int si = a.nsegs > 1 ? find_seg(a.segs, a.nsegs, i) : 0;
-    const CallSeg sg = a.segs[si];
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n;
+       q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = a.miss_list[q];
+    const int64_t i = a.idx_list ? (int64_t)a.idx_list[j] : j;
+    const CallSeg sg = a.segs[a.nsegs > 1 ? find_seg(a.segs, a.nsegs, i) : 0];
     const TableDev* t = a.tables + sg.table;
-    const int64_t key = a.ids[i];
-    uint32_t row = 0;
-    if (gl == 0) {
-      const uint32_t ticket = atomicAdd(t->ctrs + kCtrMiss, 1u);
-      const uint32_t fc = t->ctrs[kCtrFree];  // stable during this kernel (finalize updates it)
-      row = ticket < fc ? t->free_list[fc - 1 - ticket] : t->ctrs[kCtrBump] + (ticket - fc);
-      if (row >= t->row_cap) {
-        atomicOr(t->ctrs + kCtrError, 2u);
-        row = kEmptyRow;
-      }
+    const uint32_t ticket = atomicAdd(t->ctrs + kCtrMiss, 1u);
+    const uint32_t fc = t->ctrs[kCtrFree];  // stable during this kernel (finalize updates it)
+    const uint32_t row = ticket < fc ? t->free_list[fc - 1 - ticket] : t->ctrs[kCtrBump] + (ticket - fc);
+    if (row >= t->row_cap) {
+      atomicOr(t->ctrs + kCtrError, 2u);
+      a.rowidx[j] = kEmptyRow;
+      continue;
     }
-    row = __shfl_sync(Group<G>::mask(), row, Group<G>::base());
-    if (row == kEmptyRow) continue;
-    const int width = OP == kOpRestore ? t->dim + t->state_dim + 2 : t->dim;
-    const float* v = a.vals ? a.vals + sg.val_off + (i - sg.id_begin) * width : nullptr;
-    apply_row<G, OP>(t, row, key, v, a.lr + sg.lr_off, true);
-    if (gl == 0) {
-      Entry e;
-      e.key = key;
-      e.row = row;
-      e.ts = OP == kOpRestore ? __float_as_uint(v[t->dim + t->state_dim + 1]) : a.update_ts;
-      cuckoo_insert(t, e);
-      if (OP == kOpReinit) a.status[i] = 0;
-    }
+    Entry e;
+    e.key = a.ids[i];
+    e.row = row;
+    e.ts = RESTORE ? restore_ts(a, sg, t, i) : a.update_ts;
+    cuckoo_insert(t, e);
+    a.rowidx[j] = row | kFreshBit;
   }
 }
 
@@ -550,6 +699,27 @@ __global__ void upsert_finalize_kernel(const TableDev* tables, const int32_t* ta
   t->ctrs[kCtrSize] += m;
   t->ctrs[kCtrMiss] = 0;
   if (update_ts > t->ctrs[kCtrMaxTs]) t->ctrs[kCtrMaxTs] = update_ts;
+}
+
+// Pass 3 — apply the op to the resolved rows, lane group per row (pure streaming over w / state /
+// value rows: no hash logic left here).
+template <int G, int OP>
+__global__ void __launch_bounds__(kThreads) upsert_apply_kernel(UpsertArgs a) {
+  const int gl = Group<G>::gl();
+  const int64_t n = a.n_dev ? (int64_t)*a.n_dev : a.n;
+  const int64_t gstride = (int64_t)gridDim.x * (kThreads / G);
+  for (int64_t j = (int64_t)blockIdx.x * (kThreads / G) + threadIdx.x / G; j < n; j += gstride) {
+    const uint32_t ri = a.rowidx[j];
+    if (ri == kEmptyRow) continue;  // row slab overflow was flagged
+    const int64_t i = a.idx_list ? (int64_t)a.idx_list[j] : j;
+    const CallSeg sg = a.segs[a.nsegs > 1 ? find_seg(a.segs, a.nsegs, i) : 0];
+    const TableDev* t = a.tables + sg.table;
+    const bool fresh = (ri & kFreshBit) != 0;
+    const int width = OP == kOpRestore ? t->dim + t->state_dim + 2 : t->dim;
+    const float* v = a.vals ? a.vals + sg.val_off + (i - sg.id_begin) * width : nullptr;
+    if (OP == kOpReinit && gl == 0) a.status[i] = fresh ? 0 : 1;
+    apply_row<G, OP>(t, ri & ~kFreshBit, a.ids[i], v, a.lr + sg.lr_off, fresh);
+  }
 }
 
 // ---- duplicate handling (ids not guaranteed unique) ------------------------------------------
@@ -591,7 +761,7 @@ dup_claim_kernel(const CallSeg* __restrict__ segs, int nsegs, const int64_t* __r
         continue;  // lost the race: re-read the same slot
       }
       if (e.key == key && (int32_t)e.row == table) {
-        atomicMin(&set[s].first_pos, (int32_t)i);
+        if ((int32_t)e.ts > (int32_t)i) atomicMin(&set[s].first_pos, (int32_t)i);
         break;
       }
       s = (s + 1) & mask;
@@ -686,14 +856,16 @@ static int max_dim_of(mono_mtable* mt, const CallSeg* h_segs, int nsegs) {
   return m;
 }
 
-void launch_lookup(mono_mtable* mt, const CallSeg* h_segs, int nsegs, const int64_t* ids_dev,
-                   int64_t n_total, float* out_dev, cudaStream_t s) {
-  if (n_total <= 0) return;
-  upload_tables(mt, s);
-  CallBlob cb = stage_call(mt, h_segs, nsegs, nullptr, 0, s);
-  const int G = pick_group(max_dim_of(mt, h_segs, nsegs));
-  const int grid = grid_for(n_total, kThreads / G);
-#define L(GG) lookup_kernel<GG><<<grid, kThreads, 0, s>>>(mt->d_tables, cb.segs, nsegs, ids_dev, n_total, out_dev)
+static void launch_lookup_staged(mono_mtable* mt, const CallSeg* d_segs, int nsegs, int G,
+                                 const int64_t* ids_dev, int64_t n_total, float* out_dev,
+                                 int64_t out_stride, int out_col, cudaStream_t s) {
+#define L(GG)                                                                                      \
+  if (nsegs == 1)                                                                                  \
+    lookup_kernel<GG, true><<<resident_grid(lookup_kernel<GG, true>, n_total, kThreads), kThreads, 0, s>>>( \
+        mt->d_tables, d_segs, nsegs, ids_dev, n_total, out_dev, out_stride, out_col);              \
+  else                                                                                             \
+    lookup_kernel<GG, false><<<resident_grid(lookup_kernel<GG, false>, n_total, kThreads), kThreads, 0, s>>>( \
+        mt->d_tables, d_segs, nsegs, ids_dev, n_total, out_dev, out_stride, out_col)
   switch (G) {
     case 4: L(4); break;
     case 8: L(8); break;
@@ -702,6 +874,15 @@ void launch_lookup(mono_mtable* mt, const CallSeg* h_segs, int nsegs, const int6
   }
 #undef L
   MONO_CHECK_LAUNCH();
+}
+
+void launch_lookup(mono_mtable* mt, const CallSeg* h_segs, int nsegs, const int64_t* ids_dev,
+                   int64_t n_total, float* out_dev, cudaStream_t s) {
+  if (n_total <= 0) return;
+  upload_tables(mt, s);
+  CallBlob cb = stage_call(mt, h_segs, nsegs, nullptr, 0, s);
+  launch_lookup_staged(mt, cb.segs, nsegs, pick_group(max_dim_of(mt, h_segs, nsegs)), ids_dev, n_total,
+                       out_dev, 0, 0, s);
 }
 
 void launch_lookup_pool(mono_mtable* mt, int k, const int64_t* fids_dev, const int32_t* row_offsets,
@@ -715,15 +896,30 @@ void launch_lookup_pool(mono_mtable* mt, int k, const int64_t* fids_dev, const i
   if (D > 512) throw ArgError("lookup_pool supports dim <= 512");
   const int G = pick_group(D);
   const int nv = (D + 4 * G - 1) / (4 * G);
-  const int grid = grid_for(n_rows, kThreads / G);
+  if (row_offsets == nullptr) {
+    // one FID per pooled row: SUM and MEAN are the identity (x / 1 == x): probe + gather only
+    CallSeg sg;
+    sg.id_begin = 0;
+    sg.id_end = n_rows;
+    sg.val_off = 0;
+    sg.table = k;
+    sg.lr_off = 0;
+    CallBlob cb = stage_call(mt, &sg, 1, nullptr, 0, s);
+    launch_lookup_staged(mt, cb.segs, 1, G, fids_dev, n_rows, out, out_stride, out_col, s);
+    return;
+  }
   const TableDev* t = mt->d_tables + k;
-#define LP(GG, NV) lookup_pool_kernel<GG, NV><<<grid, kThreads, 0, s>>>(t, fids_dev, row_offsets, n_rows, pooling, out, out_stride, out_col)
-  if (G == 4) LP(4, 1);
-  else if (G == 8) LP(8, 1);
-  else if (G == 16) LP(16, 1);
-  else if (nv == 1) LP(32, 1);
-  else if (nv == 2) LP(32, 2);
-  else LP(32, 4);
+  // U rows in flight per lane group: enough independent HBM round trips per warp to cover latency
+#define LP(GG, NV, UU)                                                                            \
+  lookup_pool_kernel<GG, NV, UU>                                                                   \
+      <<<resident_grid(lookup_pool_kernel<GG, NV, UU>, n_rows, (kThreads / GG) * UU), kThreads, 0, s>>>( \
+          t, fids_dev, row_offsets, n_rows, pooling, out, out_stride, out_col)
+  if (G == 4) LP(4, 1, 4);
+  else if (G == 8) LP(8, 1, 4);
+  else if (G == 16) LP(16, 1, 4);
+  else if (nv == 1) LP(32, 1, 4);
+  else if (nv == 2) LP(32, 2, 2);
+  else LP(32, 4, 1);
 #undef LP
   MONO_CHECK_LAUNCH();
 }
@@ -746,10 +942,13 @@ void launch_lookup_entry(mono_mtable* mt, int k, const int64_t* ids, int64_t n, 
 
 template <int G, int OP>
 static void launch_upsert_pair(const UpsertArgs& a, int64_t n_upper, cudaStream_t s) {
-  const int grid = grid_for(n_upper, kThreads / G);
-  upsert_hit_kernel<G, OP><<<grid, kThreads, 0, s>>>(a);
+  constexpr bool R = OP == kOpRestore;
+  resolve_hit_kernel<R><<<resident_grid(resolve_hit_kernel<R>, n_upper, kThreads), kThreads, 0, s>>>(a);
   MONO_CHECK_LAUNCH();
-  upsert_miss_kernel<G, OP><<<grid, kThreads, 0, s>>>(a);
+  resolve_miss_kernel<R><<<resident_grid(resolve_miss_kernel<R>, n_upper, kThreads), kThreads, 0, s>>>(a);
+  MONO_CHECK_LAUNCH();
+  upsert_apply_kernel<G, OP>
+      <<<resident_grid(upsert_apply_kernel<G, OP>, n_upper, kThreads / G), kThreads, 0, s>>>(a);
   MONO_CHECK_LAUNCH();
 }
 
@@ -805,10 +1004,11 @@ void run_upsert(mono_mtable* mt, UpsertOp op, const CallSeg* h_segs, int nsegs,
   CallBlob cb = stage_call(mt, h_segs, nsegs, lr_host, n_lr, s);
   const int G = pick_group(max_dim_of(mt, h_segs, nsegs));
 
-  // scratch: [miss_ctr (16 B) | miss_list u32[n_total]]
-  char* ws = (char*)mt->ws_miss.get(64 + sizeof(uint32_t) * (size_t)n_total, s);
+  // scratch: [miss_ctr (64 B) | miss_list u32[n_total] | rowidx u32[n_total]]
+  char* ws = (char*)mt->ws_miss.get(64 + 2 * sizeof(uint32_t) * (size_t)n_total, s);
   uint32_t* miss_ctr = reinterpret_cast<uint32_t*>(ws);
   uint32_t* miss_list = reinterpret_cast<uint32_t*>(ws + 64);
+  uint32_t* rowidx = miss_list + n_total;
   MONO_CUDA(cudaMemsetAsync(miss_ctr, 0, 64, s));
 
   UpsertArgs a;
@@ -824,8 +1024,8 @@ void run_upsert(mono_mtable* mt, UpsertOp op, const CallSeg* h_segs, int nsegs,
   a.update_ts = (uint32_t)update_time;
   a.miss_ctr = miss_ctr;
   a.miss_list = miss_list;
+  a.rowidx = rowidx;
   a.status = status_dev;
-  a.val_width_extra = 0;
 
   auto finalize = [&]() {
     upsert_finalize_kernel<<<(cb.ntab + 63) / 64, 64, 0, s>>>(mt->d_tables, cb.table_ids, cb.ntab,
@@ -928,6 +1128,696 @@ void run_upsert(mono_mtable* mt, UpsertOp op, const CallSeg* h_segs, int nsegs,
     t.max_update_ts = std::max<int64_t>(t.max_update_ts, update_time);
     request_snapshot(mt, (int)k, s);
   }
+}
+
+
+// ==========================================================================================
+// Fused backward: pooled-grad scatter + sparse optimizer + expiry bump, deterministic, no float
+// atomics.  Replaces (for one table) the reference's
+//   ScatterGrad / BackwardBatchKernel (fused_embedding_to_layout.h:286-347, .cu.cc:337-381: float
+//   atomicAdd per occurrence into a per-unique-FID grad buffer)  +  MultiHashTableOptimize.
+// Pipeline (all on the caller's stream, no host sync):
+//   1 claim   : occurrences -> scratch-set slot (same slot <=> same FID)
+//   2 sort    : stable LSD radix sort of (slot, position) pairs, 8 bits per pass: occurrences of a
+//               FID become one contiguous run, in position order
+//   3 runs    : run starts -> compact run list (one run per unique FID)
+//   4 resolve : lane-per-key probe of the run's FID (+ insert when absent), timestamp bump
+//   5 reduce+update: a lane group walks a run, sums the pooled-grad rows IN POSITION ORDER (the CPU
+//               reference's order) in registers and applies the optimizer in place: the per-unique
+//               grad buffer is never materialised.  Runs longer than kShortRun (hot FIDs of Zipf
+//               batches) are split into kSubRun-sized pieces reduced by whole blocks, then combined
+//               in piece order (fixed association => run-to-run bit-stable).
+// ==========================================================================================
+constexpr int kSortTile = kThreads * 8;
+constexpr int kShortRun = 64;
+constexpr int kSubRun = 1024;
+
+// MODE 0: per-block digit histogram (+ global digit totals).  MODE 1: stable scatter using the
+// row-scanned histogram and the digit totals.
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+radix_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, int64_t n,
+                  int shift, int32_t* __restrict__ blk_cnt, int32_t* __restrict__ dtot, int nblk,
+                  uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+  __shared__ int32_t wcnt[kThreads / 32][256];
+  __shared__ int32_t bbase[256];
+  __shared__ int32_t dbase[256];
+  __shared__ int32_t wtot[kThreads / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  constexpr int NW = kThreads / 32;
+  constexpr int kPerWarp = kSortTile / NW;
+  if (MODE == 1) {  // exclusive scan of the 256 digit totals (kThreads == 256: one digit per thread)
+    const int v = dtot[threadIdx.x];
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) wtot[w] = x;
+    __syncthreads();
+    int off = 0;
+    for (int ww = 0; ww < w; ++ww) off += wtot[ww];
+    dbase[threadIdx.x] = off + x - v;
+    __syncthreads();
+  }
+  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const int64_t wbeg = (int64_t)blk * kSortTile + (int64_t)w * kPerWarp;
+    for (int d = lane; d < 256; d += 32) wcnt[w][d] = 0;
+    __syncwarp();
+    for (int c = 0; c < kPerWarp; c += 32) {
+      const int64_t i = wbeg + c + lane;
+      const int dg = i < n ? (int)((keys_in[i] >> shift) & 255u) : -1;
+      const uint32_t same = __match_any_sync(0xffffffffu, dg);
+      if (dg >= 0 && lane == (__ffs(same) - 1)) wcnt[w][dg] += __popc(same);
+      __syncwarp();
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < 256; d += blockDim.x) {
+      int run = 0;
+      for (int ww = 0; ww < NW; ++ww) {
+        const int v = wcnt[ww][d];
+        wcnt[ww][d] = run;
+        run += v;
+      }
+      if (MODE == 0) {
+        blk_cnt[(size_t)d * nblk + blk] = run;
+        if (run) atomicAdd(dtot + d, run);
+      } else {
+        bbase[d] = blk_cnt[(size_t)d * nblk + blk] + dbase[d];
+      }
+    }
+    __syncthreads();
+    if (MODE == 1) {
+      for (int c = 0; c < kPerWarp; c += 32) {
+        const int64_t i = wbeg + c + lane;
+        uint32_t key = 0, val = 0;
+        int dg = -1;
+        if (i < n) {
+          key = keys_in[i];
+          val = vals_in ? vals_in[i] : (uint32_t)i;
+          dg = (int)((key >> shift) & 255u);
+        }
+        const uint32_t same = __match_any_sync(0xffffffffu, dg);
+        if (dg >= 0) {
+          const int r = bbase[dg] + wcnt[w][dg] + __popc(same & ((1u << lane) - 1u));
+          keys_out[r] = key;
+          vals_out[r] = val;
+        }
+        __syncwarp();
+        if (dg >= 0 && lane == (__ffs(same) - 1)) wcnt[w][dg] += __popc(same);
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// exclusive scan of every digit row blk_cnt[d][0..nblk): one warp per digit; 1024 elements per
+// step are loaded coalesced into registers up front (32 independent loads), scanned with shuffles,
+// and stored coalesced.
+__global__ void __launch_bounds__(32) radix_rowscan_kernel(int32_t* __restrict__ blk_cnt, int nblk) {
+  const int lane = threadIdx.x;
+  int32_t* row = blk_cnt + (size_t)blockIdx.x * nblk;
+  int carry = 0;
+  for (int base = 0; base < nblk; base += 1024) {
+    int v[32];
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+      const int idx = base + t * 32 + lane;
+      v[t] = idx < nblk ? row[idx] : 0;
+    }
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+      int x = v[t];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      const int excl = carry + x - v[t];
+      carry += __shfl_sync(0xffffffffu, x, 31);
+      v[t] = excl;
+    }
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+      const int idx = base + t * 32 + lane;
+      if (idx < nblk) row[idx] = v[t];
+    }
+  }
+}
+
+// ---- ordered run compaction: run j = j-th distinct slot of the sorted array ----
+__device__ __forceinline__ bool is_run_start(const uint32_t* __restrict__ skeys, int64_t i, int64_t n) {
+  return i < n && (i == 0 || skeys[i] != skeys[i - 1]);
+}
+
+__global__ void __launch_bounds__(kThreads)
+runs_count_kernel(const uint32_t* __restrict__ skeys, int64_t n, int nblk, uint32_t* __restrict__ blk_runs) {
+  __shared__ uint32_t wc[kThreads / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    uint32_t cnt = 0;
+    for (int c = 0; c < kSortTile; c += kThreads)
+      cnt += __popc(__ballot_sync(0xffffffffu, is_run_start(skeys, (int64_t)blk * kSortTile + c + threadIdx.x, n)));
+    if (lane == 0) wc[w] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t t = 0;
+      for (int ww = 0; ww < kThreads / 32; ++ww) t += wc[ww];
+      blk_runs[blk] = t;
+    }
+    __syncthreads();
+  }
+}
+
+// one block: exclusive scan of blk_runs, total -> n_runs, sentinel run_start[n_runs] = n
+__global__ void __launch_bounds__(1024)
+runs_scan_kernel(uint32_t* __restrict__ blk_runs, int nblk, uint32_t* __restrict__ n_runs,
+                 uint32_t* __restrict__ run_start, int64_t n) {
+  __shared__ uint32_t wsum[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int per = (nblk + 1023) / 1024;
+  const int b = min(nblk, (int)threadIdx.x * per), e = min(nblk, b + per);
+  uint32_t sum = 0;
+  for (int i = b; i < e; ++i) sum += blk_runs[i];
+  uint32_t x = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) wsum[w] = x;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t t = wsum[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, t, o);
+      if (lane >= o) t += y;
+    }
+    wsum[lane] = t;
+  }
+  __syncthreads();
+  uint32_t run = (w ? wsum[w - 1] : 0) + x - sum;
+  for (int i = b; i < e; ++i) {
+    const uint32_t v = blk_runs[i];
+    blk_runs[i] = run;
+    run += v;
+  }
+  if (threadIdx.x == 1023) {
+    *n_runs = wsum[31];
+    run_start[wsum[31]] = (uint32_t)n;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+runs_write_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ perm, int64_t n, int nblk,
+                  const uint32_t* __restrict__ blk_runs, uint32_t* __restrict__ run_start,
+                  uint32_t* __restrict__ run_first_pos) {
+  __shared__ uint32_t wc[kThreads / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  constexpr int NW = kThreads / 32;
+  constexpr int kPerWarp = kSortTile / NW;
+  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const int64_t wbeg = (int64_t)blk * kSortTile + (int64_t)w * kPerWarp;
+    uint32_t cnt = 0;
+    for (int c = 0; c < kPerWarp; c += 32)
+      cnt += __popc(__ballot_sync(0xffffffffu, is_run_start(skeys, wbeg + c + lane, n)));
+    if (lane == 0) wc[w] = cnt;
+    __syncthreads();
+    uint32_t base = blk_runs[blk];
+    for (int ww = 0; ww < w; ++ww) base += wc[ww];
+    for (int c = 0; c < kPerWarp; c += 32) {
+      const int64_t i = wbeg + c + lane;
+      const bool st = is_run_start(skeys, i, n);
+      const uint32_t bal = __ballot_sync(0xffffffffu, st);
+      if (st) {
+        const uint32_t j = base + __popc(bal & ((1u << lane) - 1u));
+        run_start[j] = (uint32_t)i;
+        run_first_pos[j] = perm[i];
+      }
+      base += __popc(bal);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+occ_row_kernel(const int32_t* __restrict__ row_offsets, int64_t n_rows, uint32_t* __restrict__ occ_row) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rows;
+       r += (int64_t)gridDim.x * blockDim.x)
+    for (int m = row_offsets[r]; m < row_offsets[r + 1]; ++m) occ_row[m] = (uint32_t)r;
+}
+
+struct BwdArgs {
+  TableDev td;          // by value: lives in the kernel-parameter constant bank (uniform, free reads)
+  const TableDev* t;    // device copy, for the generic apply_row path
+  const int64_t* fids;
+  const uint32_t* skeys;
+  const uint32_t* perm;
+  int64_t n;  // occurrences
+  const uint32_t* n_runs;
+  const uint32_t* run_start;
+  const uint32_t* run_first_pos;
+  const uint32_t* rowidx;       // per run (bit 31 = fresh)
+  const uint32_t* occ_row;      // occurrence -> pooled row (null: identity)
+  const int32_t* row_offsets;   // for MEAN (null: n == 1)
+  int pooling;
+  const float* pooled_grad;
+  int64_t grad_stride;
+  int grad_col;
+  const float* lr;              // device, slice learning rates of the table
+  // long runs
+  uint32_t* n_long;
+  uint32_t* long_list;          // run index j
+  uint32_t* long_len;
+  uint32_t* long_sub_base;      // exclusive prefix of sub-piece counts (+ total at [n_long])
+  float* partial;               // [sub pieces][D]
+  float* scratch;               // [runs][D] summed grads for the generic (multi-segment) apply path
+};
+
+// gradient row of occurrence m, column c..c+3
+__device__ __forceinline__ float4 occ_grad4(const BwdArgs& a, uint32_t m, int c) {
+  const uint32_t r = a.occ_row ? a.occ_row[m] : m;
+  float4 g = __ldg(reinterpret_cast<const float4*>(a.pooled_grad + (size_t)r * a.grad_stride + a.grad_col + c));
+  if (a.pooling == MONO_POOL_MEAN && a.row_offsets) {
+    const float fn = (float)(a.row_offsets[r + 1] - a.row_offsets[r]);
+    g.x = __fdiv_rn(g.x, fn); g.y = __fdiv_rn(g.y, fn); g.z = __fdiv_rn(g.z, fn); g.w = __fdiv_rn(g.w, fn);
+  }
+  return g;
+}
+__device__ __forceinline__ void add4(float4& a, const float4& b) {
+  a.x = __fadd_rn(a.x, b.x); a.y = __fadd_rn(a.y, b.y); a.z = __fadd_rn(a.z, b.z); a.w = __fadd_rn(a.w, b.w);
+}
+
+// Row state prefetched BEFORE the gradient gather so that the w / optimizer-state reads overlap the
+// random gradient-row reads (single-segment fast path).
+struct RowPre {
+  float4 w4, a4, b4;
+  float b1p, b2p;
+};
+
+template <int G, int OPT>
+__device__ __forceinline__ RowPre bwd_prefetch(const BwdArgs& a, uint32_t ri, int c) {
+  RowPre p;
+  p.w4 = p.a4 = p.b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  p.b1p = p.b2p = 0.f;
+  if (OPT < 0 || (ri & kFreshBit)) return p;
+  const int D = a.td.dim;
+  const uint32_t row = ri & ~kFreshBit;
+  const float* __restrict__ w_row = a.td.emb + (size_t)row * a.td.emb_stride;
+  const float* __restrict__ s_row = a.td.state + (size_t)row * a.td.state_stride;
+  if (c < D) {
+    p.w4 = *reinterpret_cast<const float4*>(w_row + c);
+    if (OPT != MONO_OPT_SGD) p.a4 = *reinterpret_cast<const float4*>(s_row + c);
+    if (OPT == MONO_OPT_FTRL || OPT == MONO_OPT_ADAM) p.b4 = *reinterpret_cast<const float4*>(s_row + D + c);
+  }
+  if (OPT == MONO_OPT_ADAM) {
+    p.b1p = s_row[2 * D];
+    p.b2p = s_row[2 * D + 1];
+  }
+  return p;
+}
+
+// Apply the optimizer to row `ri` with the summed gradient held in registers (one float4 per lane,
+// dim <= 4*G).  OPT >= 0: single-segment table with that optimizer (compile-time specialised);
+// OPT < 0: any segment mix, staged through scratch + apply_row.
+template <int G, int OPT>
+__device__ __forceinline__ void bwd_apply(const BwdArgs& a, uint32_t j, uint32_t ri, float4 g4, int c,
+                                          RowPre pre) {
+  const int D = a.td.dim;
+  const uint32_t row = ri & ~kFreshBit;
+  const bool fresh = (ri & kFreshBit) != 0;
+  if (OPT >= 0) {
+    const SegDev& s0 = a.td.segs[0];
+    float* __restrict__ w_row = a.td.emb + (size_t)row * a.td.emb_stride;
+    float* __restrict__ s_row = a.td.state + (size_t)row * a.td.state_stride;
+    float lrt = a.lr[0];
+    float4 w4 = pre.w4, a4 = pre.a4, b4 = pre.b4;
+    float b1p = pre.b1p, b2p = pre.b2p;
+    if (fresh) {  // the key is only needed to initialise a new row
+      const int64_t key = a.fids[a.run_first_pos[j]];
+      w4.x = init_emb_value(&a.td, s0, key, c); w4.y = init_emb_value(&a.td, s0, key, c + 1);
+      w4.z = init_emb_value(&a.td, s0, key, c + 2); w4.w = init_emb_value(&a.td, s0, key, c + 3);
+      a4.x = a4.y = a4.z = a4.w = init_state_value(s0, 0);
+      b4.x = b4.y = b4.z = b4.w = init_state_value(s0, D);
+      b1p = s0.p[0];
+      b2p = s0.p[1];
+    }
+    if (OPT == MONO_OPT_ADAM) lrt = adam_lr(lrt, b1p, b2p);
+    if (c < D) {
+      const bool avx = c < (D & ~7);
+      opt_elem_t<OPT>(s0.p, avx, lrt, g4.x, w4.x, a4.x, b4.x);
+      opt_elem_t<OPT>(s0.p, avx, lrt, g4.y, w4.y, a4.y, b4.y);
+      opt_elem_t<OPT>(s0.p, avx, lrt, g4.z, w4.z, a4.z, b4.z);
+      opt_elem_t<OPT>(s0.p, avx, lrt, g4.w, w4.w, a4.w, b4.w);
+      *reinterpret_cast<float4*>(w_row + c) = w4;
+      if (OPT != MONO_OPT_SGD) *reinterpret_cast<float4*>(s_row + c) = a4;
+      if (OPT == MONO_OPT_FTRL || OPT == MONO_OPT_ADAM) *reinterpret_cast<float4*>(s_row + D + c) = b4;
+    }
+    if (OPT == MONO_OPT_ADAM) {
+      __syncwarp(Group<G>::mask());  // every lane has read the old powers (in the prefetch)
+      if (Group<G>::gl() == 0) {
+        s_row[2 * D] = __fmul_rn(b1p, s0.p[0]);
+        s_row[2 * D + 1] = __fmul_rn(b2p, s0.p[1]);
+      }
+    }
+  } else {
+    float* sc = a.scratch + (size_t)j * D;
+    if (c < D) *reinterpret_cast<float4*>(sc + c) = g4;
+    __syncwarp(Group<G>::mask());
+    apply_row<G, kOpOptimize>(a.t, row, a.fids[a.run_first_pos[j]], sc, a.lr, fresh);
+  }
+}
+
+// sum of the gradient rows of occurrences [s, s+len) of the sorted order, in that order.
+// The group's lanes fetch `perm` cooperatively (one coalesced load per G occurrences) and keep UNR
+// independent gradient-row loads in flight; the adds stay in position order.
+template <int G, int UNR>
+__device__ __forceinline__ float4 sum_grad_rows(const BwdArgs& a, uint32_t s, uint32_t len, int c, bool in) {
+  const int gl = Group<G>::gl(), gb = Group<G>::base();
+  const uint32_t gmask = Group<G>::mask();
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (uint32_t q0 = 0; q0 < len; q0 += G) {
+    const uint32_t m_l = (q0 + gl < len) ? a.perm[s + q0 + gl] : 0u;
+    const int cnt = (int)min((uint32_t)G, len - q0);
+    for (int u0 = 0; u0 < cnt; u0 += UNR) {
+      float4 g[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const uint32_t m = __shfl_sync(gmask, m_l, gb + min(u0 + u, G - 1));
+        g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (u0 + u < cnt && in) g[u] = occ_grad4(a, m, c);
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (u0 + u >= cnt) continue;
+        if (q0 + u0 + u == 0) acc = g[u]; else add4(acc, g[u]);
+      }
+    }
+  }
+  return acc;
+}
+
+// group per run: short runs are reduced and applied here; long runs are queued
+template <int G, int OPT>
+__global__ void __launch_bounds__(kThreads) pool_bwd_short_kernel(BwdArgs a) {
+  const int gl = Group<G>::gl();
+  const int c = gl * 4;
+  const int64_t nr = *a.n_runs;
+  const bool in = c < a.td.dim;
+  const int64_t gstride = (int64_t)gridDim.x * (kThreads / G);
+  for (int64_t j = (int64_t)blockIdx.x * (kThreads / G) + threadIdx.x / G; j < nr; j += gstride) {
+    const uint32_t ri = a.rowidx[j];
+    if (ri == kEmptyRow) continue;
+    const uint32_t s = a.run_start[j];
+    const uint32_t len = a.run_start[j + 1] - s;
+    if (len > kShortRun) {
+      if (gl == 0) a.long_list[atomicAdd(a.n_long, 1u)] = (uint32_t)j;
+      continue;
+    }
+    const RowPre pre = bwd_prefetch<G, OPT>(a, ri, c);
+    const float4 acc = sum_grad_rows<G, 4>(a, s, len, c, in);
+    bwd_apply<G, OPT>(a, (uint32_t)j, ri, acc, c, pre);
+  }
+}
+
+// one block: piece counts of the long runs and their exclusive prefix
+__global__ void __launch_bounds__(1024) long_prep_kernel(BwdArgs a) {
+  __shared__ uint32_t carry;
+  __shared__ uint32_t wsum[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t nl = *a.n_long;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < nl; base += blockDim.x) {
+    const uint32_t q = base + threadIdx.x;
+    uint32_t pieces = 0;
+    if (q < nl) {
+      const uint32_t j = a.long_list[q];
+      const uint32_t len = a.run_start[j + 1] - a.run_start[j];
+      a.long_len[q] = len;
+      pieces = (len + kSubRun - 1) / kSubRun;
+    }
+    uint32_t x = pieces;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      uint32_t t = wsum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += y;
+      }
+      wsum[lane] = t;
+    }
+    __syncthreads();
+    const uint32_t excl = carry + (w ? wsum[w - 1] : 0) + x - pieces;
+    if (q < nl) a.long_sub_base[q] = excl;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = carry + wsum[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) a.long_sub_base[nl] = carry;
+}
+
+// block per piece of a long run: kThreads/G groups reduce contiguous slices in order, then the
+// slices are combined in order (fixed association: deterministic)
+template <int G>
+__global__ void __launch_bounds__(kThreads) pool_bwd_long_partial_kernel(BwdArgs a) {
+  constexpr int NG = kThreads / G;
+  __shared__ float4 sm[NG][G];
+  const int gl = Group<G>::gl(), g = threadIdx.x / G, c = gl * 4;
+  const uint32_t nl = *a.n_long;
+  const uint32_t total = a.long_sub_base[nl];
+  const int D = a.td.dim;
+  const bool in = c < D;
+  for (uint32_t wi = blockIdx.x; wi < total; wi += gridDim.x) {
+    uint32_t lo = 0, hi = nl - 1;  // last q with sub_base[q] <= wi
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi + 1) >> 1;
+      if (a.long_sub_base[mid] <= wi) lo = mid; else hi = mid - 1;
+    }
+    const uint32_t q = lo, piece = wi - a.long_sub_base[q];
+    const uint32_t s = a.run_start[a.long_list[q]] + piece * kSubRun;
+    const uint32_t len = min((uint32_t)kSubRun, a.long_len[q] - piece * kSubRun);
+    const uint32_t per = (len + NG - 1) / NG;
+    const uint32_t b = min(len, g * per), e = min(len, b + per);
+    sm[g][gl] = sum_grad_rows<G, 8>(a, s + b, e - b, c, in);
+    __syncthreads();
+    if (g == 0) {
+      float4 t = sm[0][gl];
+      for (int k = 1; k < NG; ++k)
+        if ((uint32_t)k * per < len) add4(t, sm[k][gl]);
+      if (in) *reinterpret_cast<float4*>(a.partial + (size_t)wi * D + c) = t;
+    }
+    __syncthreads();
+  }
+}
+
+// group per long run: combine its pieces in order, apply the optimizer
+template <int G, int OPT>
+__global__ void __launch_bounds__(kThreads) pool_bwd_long_final_kernel(BwdArgs a) {
+  const int gl = Group<G>::gl(), c = gl * 4;
+  const uint32_t nl = *a.n_long;
+  const int D = a.td.dim;
+  const int64_t gstride = (int64_t)gridDim.x * (kThreads / G);
+  for (int64_t q = (int64_t)blockIdx.x * (kThreads / G) + threadIdx.x / G; q < nl; q += gstride) {
+    const uint32_t j = a.long_list[q];
+    const uint32_t b = a.long_sub_base[q], e = a.long_sub_base[q + 1];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t wi = b; wi < e; ++wi) {
+      float4 p = make_float4(0, 0, 0, 0);
+      if (c < D) p = *reinterpret_cast<const float4*>(a.partial + (size_t)wi * D + c);
+      if (wi == b) acc = p; else add4(acc, p);
+    }
+    const uint32_t ri = a.rowidx[j];
+    if (ri == kEmptyRow) continue;
+    bwd_apply<G, OPT>(a, j, ri, acc, c, bwd_prefetch<G, OPT>(a, ri, c));
+  }
+}
+
+void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t n_fids,
+                       const int32_t* row_offsets, int64_t n_rows, int pooling,
+                       const float* pooled_grad, int64_t grad_stride, int grad_col,
+                       const float* lr_host, int64_t update_time, cudaStream_t s) {
+  if (n_fids <= 0) return;
+  if (n_fids >= ((int64_t)1 << 31)) throw ArgError("more than 2^31 fids in one call");
+  if (pooling != MONO_POOL_SUM && pooling != MONO_POOL_MEAN) throw ArgError("pool_backward: SUM or MEAN");
+  HostTable& ht = mt->tables[k];
+  const int D = ht.dim;
+  if ((D & 3) || D > 128) throw ArgError("pool_backward needs dim % 4 == 0 and dim <= 128");
+  if ((grad_stride & 3) || (grad_col & 3) || (reinterpret_cast<uintptr_t>(pooled_grad) & 15))
+    throw ArgError("pool_backward needs 16-byte aligned gradient rows");
+  const int64_t M = n_fids;
+  ensure_capacity(mt, k, (uint64_t)M, s);
+  upload_tables(mt, s);
+  CallSeg sg;
+  sg.id_begin = 0;
+  sg.id_end = M;
+  sg.val_off = 0;
+  sg.table = k;
+  sg.lr_off = 0;
+  CallBlob cb = stage_call(mt, &sg, 1, lr_host, ht.slices, s);
+  const int G = pick_group(D);
+
+  // ---- scratch layout ----
+  uint32_t cap = 1024;
+  while (cap < 2 * (uint64_t)M) cap <<= 1;
+  int bits = 0;
+  while ((1u << bits) < cap) ++bits;
+  const int passes = (bits + 7) / 8;
+  const int nblk = (int)((M + kSortTile - 1) / kSortTile);
+  const size_t n_long_max = (size_t)M / kShortRun + 2;
+  const size_t max_pieces = (size_t)M / kSubRun + n_long_max + 2;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_set = take(sizeof(SetEntry) * cap);
+  const size_t o_k0 = take(4 * (size_t)M), o_v0 = take(4 * (size_t)M);
+  const size_t o_k1 = take(4 * (size_t)M), o_v1 = take(4 * (size_t)M);
+  const size_t o_blk = take(4 * (size_t)256 * nblk);
+  const size_t o_ctr = take(4096 + 4 * 256 * 4);  // counters + digit totals per pass
+  const size_t o_brun = take(4 * (size_t)nblk);
+  const size_t o_rs = take(4 * ((size_t)M + 1)), o_rfp = take(4 * (size_t)M), o_ridx = take(4 * (size_t)M);
+  const size_t o_miss = take(4 * (size_t)M);
+  const size_t o_occ = take(row_offsets ? 4 * (size_t)M : 0);
+  const size_t o_ll = take(4 * n_long_max), o_llen = take(4 * n_long_max), o_lsb = take(4 * (n_long_max + 1));
+  const size_t o_part = take(sizeof(float) * max_pieces * D);
+  const size_t o_scr = take(ht.segs.size() > 1 ? sizeof(float) * (size_t)M * D : 0);
+  char* ws = (char*)mt->ws_a.get(off, s);
+  SetEntry* set = (SetEntry*)(ws + o_set);
+  uint32_t *k0 = (uint32_t*)(ws + o_k0), *v0 = (uint32_t*)(ws + o_v0);
+  uint32_t *k1 = (uint32_t*)(ws + o_k1), *v1 = (uint32_t*)(ws + o_v1);
+  int32_t* blk_cnt = (int32_t*)(ws + o_blk);
+  uint32_t* ctr = (uint32_t*)(ws + o_ctr);  // [0] n_runs [4] n_long [8] miss_ctr
+  int32_t* dtot = (int32_t*)(ws + o_ctr + 4096);
+  MONO_CUDA(cudaMemsetAsync(set, 0xFF, sizeof(SetEntry) * cap, s));
+  MONO_CUDA(cudaMemsetAsync(ctr, 0, 4096 + 4 * 256 * 4, s));
+
+  // 1 claim: k0[i] = set slot of occurrence i
+  dup_claim_kernel<<<resident_grid(dup_claim_kernel, M, kThreads), kThreads, 0, s>>>(cb.segs, 1, fids_dev, nullptr, M,
+                                                                                    set, cap - 1, k0);
+  MONO_CHECK_LAUNCH();
+  // 2 stable LSD radix sort of (slot, position)
+  const uint32_t* vin = nullptr;  // first pass: value = position
+  uint32_t *kin = k0, *kout = k1, *vout = v1;
+  const int gh = resident_grid(radix_pass_kernel<0>, nblk, 1);
+  const int gs = resident_grid(radix_pass_kernel<1>, nblk, 1);
+  for (int p = 0; p < passes; ++p) {
+    int32_t* dt = dtot + 256 * p;
+    radix_pass_kernel<0><<<gh, kThreads, 0, s>>>(kin, vin, M, 8 * p, blk_cnt, dt, nblk, nullptr, nullptr);
+    MONO_CHECK_LAUNCH();
+    radix_rowscan_kernel<<<256, 32, 0, s>>>(blk_cnt, nblk);
+    MONO_CHECK_LAUNCH();
+    radix_pass_kernel<1><<<gs, kThreads, 0, s>>>(kin, vin, M, 8 * p, blk_cnt, dt, nblk, kout, vout);
+    MONO_CHECK_LAUNCH();
+    vin = vout;
+    std::swap(kin, kout);
+    vout = (vout == v1) ? v0 : v1;
+  }
+  const uint32_t* skeys = kin;
+  const uint32_t* perm = vin;
+  // 3 ordered run list
+  uint32_t* blk_runs = (uint32_t*)(ws + o_brun);
+  uint32_t* run_start = (uint32_t*)(ws + o_rs);
+  uint32_t* run_first_pos = (uint32_t*)(ws + o_rfp);
+  runs_count_kernel<<<resident_grid(runs_count_kernel, nblk, 1), kThreads, 0, s>>>(skeys, M, nblk, blk_runs);
+  MONO_CHECK_LAUNCH();
+  runs_scan_kernel<<<1, 1024, 0, s>>>(blk_runs, nblk, ctr, run_start, M);
+  MONO_CHECK_LAUNCH();
+  runs_write_kernel<<<resident_grid(runs_write_kernel, nblk, 1), kThreads, 0, s>>>(skeys, perm, M, nblk, blk_runs,
+                                                                                  run_start, run_first_pos);
+  MONO_CHECK_LAUNCH();
+  // 4 resolve (+ insert) the run keys
+  UpsertArgs ua;
+  ua.tables = mt->d_tables;
+  ua.segs = cb.segs;
+  ua.nsegs = 1;
+  ua.ids = fids_dev;
+  ua.idx_list = run_first_pos;
+  ua.n = M;
+  ua.n_dev = ctr;
+  ua.vals = nullptr;
+  ua.lr = cb.lr;
+  ua.update_ts = (uint32_t)update_time;
+  ua.miss_ctr = ctr + 8;
+  ua.miss_list = (uint32_t*)(ws + o_miss);
+  ua.rowidx = (uint32_t*)(ws + o_ridx);
+  ua.status = nullptr;
+  resolve_hit_kernel<false><<<resident_grid(resolve_hit_kernel<false>, M, kThreads), kThreads, 0, s>>>(ua);
+  MONO_CHECK_LAUNCH();
+  resolve_miss_kernel<false><<<resident_grid(resolve_miss_kernel<false>, M, kThreads), kThreads, 0, s>>>(ua);
+  MONO_CHECK_LAUNCH();
+  upsert_finalize_kernel<<<1, 64, 0, s>>>(mt->d_tables, cb.table_ids, cb.ntab, ctr + 8, (uint32_t)update_time);
+  MONO_CHECK_LAUNCH();
+  // 5 reduce + update
+  BwdArgs a;
+  a.td = ht.dev;  // descriptor is current: ensure_capacity / upload_tables ran above
+  a.t = mt->d_tables + k;
+  a.fids = fids_dev;
+  a.skeys = skeys;
+  a.perm = perm;
+  a.n = M;
+  a.n_runs = ctr;
+  a.run_start = run_start;
+  a.run_first_pos = run_first_pos;
+  a.rowidx = ua.rowidx;
+  a.occ_row = nullptr;
+  a.row_offsets = row_offsets;
+  a.pooling = pooling;
+  a.pooled_grad = pooled_grad;
+  a.grad_stride = grad_stride;
+  a.grad_col = grad_col;
+  a.lr = cb.lr;
+  a.n_long = ctr + 4;
+  a.long_list = (uint32_t*)(ws + o_ll);
+  a.long_len = (uint32_t*)(ws + o_llen);
+  a.long_sub_base = (uint32_t*)(ws + o_lsb);
+  a.partial = (float*)(ws + o_part);
+  a.scratch = ht.segs.size() > 1 ? (float*)(ws + o_scr) : nullptr;
+  if (row_offsets) {
+    uint32_t* occ = (uint32_t*)(ws + o_occ);
+    occ_row_kernel<<<resident_grid(occ_row_kernel, n_rows, kThreads), kThreads, 0, s>>>(row_offsets, n_rows, occ);
+    MONO_CHECK_LAUNCH();
+    a.occ_row = occ;
+  }
+#define BWD2(GG, OO)                                                                                             \
+  pool_bwd_short_kernel<GG, OO>                                                                                  \
+      <<<resident_grid(pool_bwd_short_kernel<GG, OO>, M, kThreads / GG), kThreads, 0, s>>>(a);                   \
+  MONO_CHECK_LAUNCH();                                                                                           \
+  long_prep_kernel<<<1, 1024, 0, s>>>(a);                                                                        \
+  MONO_CHECK_LAUNCH();                                                                                           \
+  pool_bwd_long_partial_kernel<GG>                                                                               \
+      <<<resident_grid(pool_bwd_long_partial_kernel<GG>, (int64_t)max_pieces, 1), kThreads, 0, s>>>(a);          \
+  MONO_CHECK_LAUNCH();                                                                                           \
+  pool_bwd_long_final_kernel<GG, OO><<<148, kThreads, 0, s>>>(a);                                                \
+  MONO_CHECK_LAUNCH()
+#define BWD(GG)                                                         \
+  switch (opt_sel) {                                                    \
+    case MONO_OPT_SGD: BWD2(GG, MONO_OPT_SGD); break;                   \
+    case MONO_OPT_ADAGRAD: BWD2(GG, MONO_OPT_ADAGRAD); break;           \
+    case MONO_OPT_FTRL: BWD2(GG, MONO_OPT_FTRL); break;                 \
+    case MONO_OPT_ADAM: BWD2(GG, MONO_OPT_ADAM); break;                 \
+    default: BWD2(GG, -1); break;                                       \
+  }
+  const int opt_sel = ht.segs.size() == 1 ? ht.segs[0].opt_type : -1;
+  switch (G) {
+    case 4: BWD(4); break;
+    case 8: BWD(8); break;
+    case 16: BWD(16); break;
+    default: BWD(32); break;
+  }
+#undef BWD2
+#undef BWD
+  ht.issued_total += (uint64_t)M;
+  ht.max_update_ts = std::max<int64_t>(ht.max_update_ts, update_time);
+  request_snapshot(mt, k, s);
 }
 
 }  // namespace mono

@@ -304,6 +304,30 @@ class MultiHashTable:
                                                  _ptr(out), stride, out_col, _stream(self._device)))
     return out
 
+  def pool_backward(self, slot: str, fids: torch.Tensor, pooled_grad: torch.Tensor,
+                    row_offsets: Optional[torch.Tensor] = None, pooling: str = "sum", req_time: int = 0,
+                    global_step: int = 0, grad_col: int = 0):
+    """Fused backward of lookup_pool: scatters the pooled-row gradients to the unique FIDs, applies one
+    sparse optimizer step per FID and bumps the expiry timestamp (upsert), deterministically and without
+    a per-unique gradient buffer.  Equivalent to fused_embedding_to_layout_grad / ScatterGrad followed by
+    apply_gradients on the deduplicated ids (ref: distributed_ps.py:1321-1332,1390-1395)."""
+    k = self._table_names.index(slot)
+    fids = _ids(fids, self._device)
+    pooled_grad = _f32(pooled_grad, self._device)
+    if row_offsets is not None:
+      row_offsets = row_offsets.to(device=self._device, dtype=torch.int32).contiguous()
+      n_rows = row_offsets.numel() - 1
+    else:
+      n_rows = fids.numel()
+    stride = pooled_grad.stride(0) if pooled_grad.dim() == 2 else self._dims[k]
+    lr = self._configs[slot].call_learning_rate_fns()
+    lr_arr = (C.c_float * len(lr))(*lr)
+    pool = {"sum": _lib.POOL_SUM, "mean": _lib.POOL_MEAN}[pooling]
+    _lib.check(self._lib.mono_mtable_pool_backward(self._h, k, _ptr(fids), fids.numel(), _ptr(row_offsets), n_rows,
+                                                   pool, _ptr(pooled_grad), stride, grad_col, lr_arr, int(req_time),
+                                                   int(global_step), _stream(self._device)))
+    return self
+
   def contains(self, slot: str, ids: torch.Tensor) -> torch.Tensor:
     ids = _ids(ids, self._device)
     out = torch.empty(ids.numel(), dtype=torch.uint8, device=self._device)

@@ -563,3 +563,80 @@ def test_full_size_properties(dev):
   t.assign_add({"t": (probe, torch.zeros(probe.numel(), D, device=dev))}, req_time=2)
   assert np.array_equal(t.lookup({"t": probe})["t"].cpu().numpy(), rows)
   assert t.size("t") == n
+
+
+# ------------------------------------------------------------------------------------------------
+# fused backward (sort-based scatter + optimizer) vs oracle: dedup -> ScatterGrad -> Optimize
+# ------------------------------------------------------------------------------------------------
+def _zipfish(rng, n, vocab, hot):
+  """ids with a few very hot keys (long runs) and a long tail."""
+  r = rng.random(n)
+  ids = rng.integers(0, vocab, n)
+  ids[r < 0.30] = 0                      # one key with ~30% of the occurrences (run >> kSubRun)
+  ids[(r >= 0.30) & (r < 0.45)] = rng.integers(1, hot, int(((r >= 0.30) & (r < 0.45)).sum()))
+  return (np.int64(7) << 48) | ids.astype(np.int64)
+
+
+BWD_CASES = [
+    ("adagrad32", [(32, "adagrad", {})], [0.05]),
+    ("sgd8", [(8, "sgd", {})], [0.1]),
+    ("adam64", [(64, "adam", {})], [0.01]),
+    ("ftrl128", [(128, "ftrl", {"beta": 1.0, "l1": 0.001})], [0.05]),
+    ("multiseg16", [(4, "ftrl", {}), (12, "adagrad", {"weight_decay_factor": 0.01})], [0.1, 0.05]),
+]
+
+
+@pytest.mark.parametrize("case", BWD_CASES, ids=lambda c: c[0])
+@pytest.mark.parametrize("n", [3000, 200000])
+def test_pool_backward_vs_oracle(case, n, dev):
+  _, segs, lrs = case
+  D = sum(s[0] for s in segs)
+  rng = np.random.default_rng(n + D)
+  from monolith_b200 import entry
+  cfg = {"t": table(segs, lrs, capacity=256, init=entry.RandomUniformInitializer(-0.1, 0.1), init_seed=5)}
+  gpu, cpu = pair(cfg, dev)
+  for step in range(3):
+    fids = _zipfish(rng, n, 50000, 40)
+    pg = rng.standard_normal((n, D)).astype(np.float32)
+    gpu.pool_backward("t", T(fids, dev), T(pg, dev), None, "sum", req_time=10 + step)
+    u, inv = orc.dedup(fids)
+    ug = orc.gather_pool_grad(pg, inv * D, D, u.size * D).reshape(-1, D)
+    cpu.apply_gradients({"t": (u, ug)}, req_time=10 + step)
+  keys = cpu.keys("t")
+  assert gpu.size("t") == keys.size
+  got, want = gpu_lookup(gpu, {"t": keys}, dev)["t"], cpu.lookup({"t": keys})["t"]
+  # FIDs that occur <= kShortRun (64) times per batch are summed in the reference order; the ~40 hot
+  # FIDs (up to 60 K occurrences) are summed piecewise, i.e. in a different association than the
+  # sequential CPU sum: fp32 reassociation error of a 60 K-term sum (the reference GPU path's float
+  # atomics have the same property, in random order).
+  hot = np.isin(keys, (np.int64(7) << 48) | np.arange(0, 40, dtype=np.int64))
+  np.testing.assert_allclose(got[~hot], want[~hot], rtol=2e-5, atol=1e-6)
+  np.testing.assert_allclose(got[hot], want[hot], rtol=2e-3, atol=2e-3)
+  # rows whose FID occurs at most kShortRun times are summed in the reference order: bit-exact
+  cnt = dict(zip(*np.unique(fids, return_counts=True)))
+  rare = np.array([k for k in keys if cnt.get(k, 0) <= 8][:2000], np.int64)
+  if n == 3000 and case[0] in ("adagrad32", "sgd8"):
+    np.testing.assert_array_equal(gpu_lookup(gpu, {"t": rare}, dev)["t"], cpu.lookup({"t": rare})["t"])
+  e = gpu.lookup_entry("t", T(keys[:100], dev))
+  assert bool((e["last_update_ts_sec"] >= 10).all())
+
+
+def test_pool_backward_csr_mean_and_determinism(dev):
+  D = 16
+  rng = np.random.default_rng(77)
+  cfg = {"t": table([(D, "adagrad", {})], [0.1])}
+  gpu, cpu = pair(cfg, dev)
+  from monolith_b200 import MultiHashTable
+  gpu2 = MultiHashTable(cfg, device=dev)
+  lens = rng.integers(0, 6, 5000)
+  offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+  fids = _zipfish(rng, int(offs[-1]), 3000, 10)
+  pg = rng.standard_normal((lens.size, D)).astype(np.float32)
+  for t in (gpu, gpu2):
+    t.pool_backward("t", T(fids, dev), T(pg, dev), T(offs, dev), "mean", req_time=3)
+  u, inv = orc.dedup(fids)
+  ug = orc.gather_pool_grad(pg, inv * D, D, u.size * D, offs, "mean").reshape(-1, D)
+  cpu.apply_gradients({"t": (u, ug)}, req_time=3)
+  got = gpu_lookup(gpu, {"t": u}, dev)["t"]
+  np.testing.assert_allclose(got, cpu.lookup({"t": u})["t"], rtol=2e-5, atol=1e-6)
+  np.testing.assert_array_equal(got, gpu_lookup(gpu2, {"t": u}, dev)["t"])  # run-to-run bit-stable
