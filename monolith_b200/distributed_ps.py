@@ -1,0 +1,184 @@
+"""FID-hash sharded tables across the GPUs of one box — replacement of the reference's
+distributed_ps path for the embedding hot path.
+
+Mirrors PartitionedHashTable._lookup_gpu / _apply_gradients_gpu (ref: native_training/
+distributed_ps.py:1501-1760, 1762-2001) and DistributedMultiTypeHashTableMpi (ref:
+distributed_ps_sync.py:95-512): owner(fid) = fid mod N (ref: distributed_ps.py:289;
+fused_reorder_by_indices.cc:121-123), and per step
+
+  forward : 1 dedup + bucket FIDs by owner (FusedReorderByIndices layout: shard-major, table-minor)
+            2 all-to-all of the per-(shard, table) counts           int32[N*K]   (ref :1586-1588)
+            3 all-to-all of the deduplicated FIDs                   int64        (ref :1582-1601)
+            4 owner: fused lookup of everything received                        (ref :1619-1621)
+            5 all-to-all of the rows                                float32      (ref :1680-1703)
+            6 requester: gather + per-row pool from the received buffer         (ref :1745-1756)
+  backward: 7 requester: scatter pooled grads to the unique rows                (ref :1792-1805)
+            8 all-to-all of the row grads (reverse splits)                      (ref :1884-1899)
+            9 owner: fused optimizer update, shards applied in order            (ref :1981-1990)
+
+The reference runs these as Horovod/BytePS alltoalls with host staging; here they are NCCL
+all-to-all-v calls (torch.distributed.all_to_all_single) over NVLink/NVSwitch on a dedicated
+communication stream, so that the caller's dense tower can run concurrently on its own stream.
+
+The compute steps come from a `backend` object so that the exchange logic (splits, offsets,
+ordering) is testable on CPU with the gloo backend; the default backend is the CUDA engine.
+"""
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+class CudaBackend:
+  """The engine's kernels behind the five compute steps of the exchange."""
+
+  def __init__(self, table):
+    from . import distribution_ops
+    self.t = table
+    self.dops = distribution_ops
+
+  def reorder(self, fids_list, num_shards, dims):
+    out, shard_sizes, slot_sizes, _, offs = self.dops.fused_reorder_by_indices(fids_list, num_shards, dims,
+                                                                               rank0_empty_shard=False)
+    return out, shard_sizes, slot_sizes, offs
+
+  def fused_lookup(self, ids, slot_sizes, num_shards):
+    return self.t.fused_lookup(ids, slot_sizes, num_shards)[0]
+
+  def fused_apply(self, ids, slot_sizes, grads, num_shards, req_time):
+    _, _, id_off, emb_off = self.t.fused_offsets(slot_sizes, num_shards)
+    self.t.fused_apply_gradient(ids, ids, slot_sizes, grads, id_off, emb_off, 0, req_time, num_shards)
+
+  def gather_pool(self, rows, offs, dim, row_offsets, pooling, out):
+    return self.dops.gather_pool(rows, offs, dim, row_offsets, pooling, out=out)
+
+  def gather_pool_grad_into(self, grad_buf, pooled_grad, offs, dim, row_offsets, pooling):
+    """Accumulates into grad_buf (pre-zeroed, shared by all tables of the step)."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    n_rows = offs.numel() if row_offsets is None else row_offsets.numel() - 1
+    pool = {"sum": _lib.POOL_SUM, "mean": _lib.POOL_MEAN}[pooling]
+    ro = None if row_offsets is None else C.c_void_p(row_offsets.data_ptr())
+    _lib.check(lib.mono_gather_pool_grad(pooled_grad.device.index, C.c_void_p(pooled_grad.data_ptr()),
+                                         pooled_grad.stride(0), 0, C.c_void_p(offs.data_ptr()), ro, n_rows, dim, pool,
+                                         C.c_void_p(grad_buf.data_ptr()),
+                                         C.c_void_p(torch.cuda.current_stream(pooled_grad.device).cuda_stream)))
+
+  def zeros(self, n, like):
+    return torch.zeros(n, dtype=torch.float32, device=like.device)
+
+
+def _a2a(out: torch.Tensor, inp: torch.Tensor, out_splits: Sequence[int], in_splits: Sequence[int], group):
+  dist.all_to_all_single(out, inp, output_split_sizes=list(out_splits), input_split_sizes=list(in_splits), group=group)
+
+
+class StepContext:
+  """What the backward needs from the forward (ref: the tensors _lookup_gpu stashes in auxiliary_bundle)."""
+  __slots__ = ("uniq", "shard_sizes", "slot_sizes", "offs", "recv_ids", "recv_slot", "send_row_splits",
+               "recv_row_splits", "names", "row_offsets", "poolings", "occ_splits", "n_rows_total")
+
+
+class PartitionedHashTable:
+  """Sharded view over one MultiHashTable per rank (ref: PartitionedHashTable, distributed_ps.py:581-2001)."""
+
+  def __init__(self, table, world_size: int, rank: int, group=None, backend=None, dims: Optional[Sequence[int]] = None,
+               names: Optional[Sequence[str]] = None):
+    self.table = table
+    self.N = world_size
+    self.rank = rank
+    self.group = group
+    self.backend = backend if backend is not None else CudaBackend(table)
+    self.names = tuple(names) if names is not None else tuple(table.table_names)
+    self.dims = list(dims) if dims is not None else list(table.get_table_dim_sizes())
+    self.K = len(self.names)
+    self.comm_stream = None
+    if torch.cuda.is_available() and backend is None:
+      self.comm_stream = torch.cuda.Stream(device=table.device)
+
+  # -- helpers ------------------------------------------------------------------------------
+  def _row_splits(self, slot_sizes: Sequence[int]) -> List[int]:
+    """floats exchanged with each peer: sum_k slot[n][k] * D_k (ref: recv_emb_splits, distributed_ps.py:1514-1523)."""
+    return [sum(slot_sizes[n * self.K + k] * self.dims[k] for k in range(self.K)) for n in range(self.N)]
+
+  def lookup(self, slot_to_fids: Dict[str, torch.Tensor], row_offsets: Optional[Dict[str, torch.Tensor]] = None,
+             pooling: Optional[Dict[str, str]] = None, outs: Optional[Dict[str, torch.Tensor]] = None):
+    """Forward steps 1-6.  Returns ({table: pooled [rows, D]}, ctx)."""
+    be, N, K = self.backend, self.N, self.K
+    row_offsets = row_offsets or {}
+    pooling = pooling or {}
+    lists = []
+    for name in self.names:
+      f = slot_to_fids.get(name)
+      lists.append(f.reshape(-1) if f is not None else torch.empty(0, dtype=torch.int64, device=self._dev(slot_to_fids)))
+    dev = lists[0].device
+    # 1 dedup + bucket by owner
+    uniq, shard_sizes, slot_sizes, offs = be.reorder(lists, N, self.dims)
+    # 2 counts
+    send_cnt = torch.tensor(slot_sizes, dtype=torch.int64, device=dev)
+    recv_cnt = torch.empty_like(send_cnt)
+    _a2a(recv_cnt, send_cnt, [K] * N, [K] * N, self.group)
+    recv_slot = [int(x) for x in recv_cnt.cpu().tolist()]  # [requester n][table k]: ids I own
+    recv_id_splits = [sum(recv_slot[n * K:(n + 1) * K]) for n in range(N)]
+    # 3 FIDs
+    recv_ids = torch.empty(sum(recv_id_splits), dtype=torch.int64, device=dev)
+    _a2a(recv_ids, uniq, recv_id_splits, shard_sizes, self.group)
+    # 4 owner-side fused lookup (rows laid out requester-major / table-minor)
+    rows = be.fused_lookup(recv_ids, recv_slot, N)
+    # 5 rows back
+    send_row_splits = self._row_splits(recv_slot)
+    recv_row_splits = self._row_splits(slot_sizes)
+    recv_rows = torch.empty(sum(recv_row_splits), dtype=torch.float32, device=dev)
+    _a2a(recv_rows, rows, recv_row_splits, send_row_splits, self.group)
+    # 6 requester-side gather + pool, table by table (offs covers the occurrences list by list)
+    pooled, occ_splits, pos = {}, [], 0
+    for k, name in enumerate(self.names):
+      n_occ = lists[k].numel()
+      occ_splits.append((pos, pos + n_occ))
+      if name in slot_to_fids:
+        ro = row_offsets.get(name)
+        pooled[name] = be.gather_pool(recv_rows, offs[pos:pos + n_occ], self.dims[k], ro, pooling.get(name, "sum"),
+                                      None if outs is None else outs.get(name))
+      pos += n_occ
+    ctx = StepContext()
+    ctx.uniq, ctx.shard_sizes, ctx.slot_sizes, ctx.offs = uniq, shard_sizes, slot_sizes, offs
+    ctx.recv_ids, ctx.recv_slot = recv_ids, recv_slot
+    ctx.send_row_splits, ctx.recv_row_splits = send_row_splits, recv_row_splits
+    ctx.row_offsets, ctx.poolings, ctx.occ_splits = row_offsets, pooling, occ_splits
+    return pooled, ctx
+
+  def apply_gradients(self, ctx: StepContext, pooled_grads: Dict[str, torch.Tensor], req_time: int = 0):
+    """Backward steps 7-9."""
+    be, N = self.backend, self.N
+    some = next(iter(pooled_grads.values()))
+    # 7 scatter pooled grads to the unique rows, in the layout of the received row buffer
+    grad_rows = be.zeros(sum(ctx.recv_row_splits), some)
+    for k, name in enumerate(self.names):
+      if name not in pooled_grads:
+        continue
+      lo, hi = ctx.occ_splits[k]
+      be.gather_pool_grad_into(grad_rows, pooled_grads[name], ctx.offs[lo:hi], self.dims[k], ctx.row_offsets.get(name),
+                               ctx.poolings.get(name, "sum"))
+    # 8 grads to the owners (reverse of step 5)
+    owner_grads = torch.empty(sum(ctx.send_row_splits), dtype=torch.float32, device=grad_rows.device)
+    _a2a(owner_grads, grad_rows, ctx.send_row_splits, ctx.recv_row_splits, self.group)
+    # 9 owner-side fused optimizer (same FID from several requesters: applied in requester order)
+    be.fused_apply(ctx.recv_ids, ctx.recv_slot, owner_grads, N, req_time)
+
+  @staticmethod
+  def _dev(d):
+    return next(iter(d.values())).device
+
+
+class ShardedStep:
+  """The bench's sparse train step on N GPUs: forward (lookup + pool) and backward through the exchange."""
+
+  def __init__(self, table, name: str, dim: int, world: int, rank: int, device):
+    self.pht = PartitionedHashTable(table, world, rank)
+    self.name = name
+    self.dim = dim
+
+  def step(self, fids: torch.Tensor, pooled_grad: torch.Tensor, out: torch.Tensor, req_time: int):
+    pooled, ctx = self.pht.lookup({self.name: fids}, outs={self.name: out})
+    self.pht.apply_gradients(ctx, {self.name: pooled_grad}, req_time)
+    return ctx.uniq.numel()
