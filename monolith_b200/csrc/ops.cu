@@ -1393,16 +1393,38 @@ struct BwdArgs {
   uint32_t* long_list;          // run index j
   uint32_t* long_len;
   uint32_t* long_sub_base;      // exclusive prefix of sub-piece counts (+ total at [n_long])
+  uint2* piece_desc;            // per piece: {first sorted index, length}
   float* partial;               // [sub pieces][D]
-  float* scratch;               // [runs][D] summed grads for the generic (multi-segment) apply path
+  float* ugrad;                 // [runs][D] summed gradient of every run (= unique FID), run order
+  float* scratch;               // alias of ugrad for the generic (multi-segment) apply path
 };
 
-// gradient row of occurrence m, column c..c+3
-__device__ __forceinline__ float4 occ_grad4(const BwdArgs& a, uint32_t m, int c) {
-  const uint32_t r = a.occ_row ? a.occ_row[m] : m;
-  float4 g = __ldg(reinterpret_cast<const float4*>(a.pooled_grad + (size_t)r * a.grad_stride + a.grad_col + c));
-  if (a.pooling == MONO_POOL_MEAN && a.row_offsets) {
-    const float fn = (float)(a.row_offsets[r + 1] - a.row_offsets[r]);
+// Where the gradient rows come from: copied out of the kernel parameters once per thread so that the
+// inner loops do not re-read the constant bank (ncu showed LDCU stalls inside the unrolled loads).
+struct GradSrc {
+  const float* base;            // pooled_grad + grad_col + lane column
+  int64_t stride;
+  const uint32_t* perm;
+  const uint32_t* occ_row;
+  const int32_t* row_offsets;
+  bool mean;
+};
+__device__ __forceinline__ GradSrc make_grad_src(const BwdArgs& a, int c) {
+  GradSrc g;
+  g.base = a.pooled_grad + a.grad_col + c;
+  g.stride = a.grad_stride;
+  g.perm = a.perm;
+  g.occ_row = a.occ_row;
+  g.row_offsets = a.row_offsets;
+  g.mean = a.pooling == MONO_POOL_MEAN && a.row_offsets != nullptr;
+  return g;
+}
+// gradient row of occurrence m, columns c..c+3
+__device__ __forceinline__ float4 occ_grad4(const GradSrc& gs, uint32_t m) {
+  const uint32_t r = gs.occ_row ? gs.occ_row[m] : m;
+  float4 g = __ldg(reinterpret_cast<const float4*>(gs.base + (size_t)r * gs.stride));
+  if (gs.mean) {
+    const float fn = (float)(gs.row_offsets[r + 1] - gs.row_offsets[r]);
     g.x = __fdiv_rn(g.x, fn); g.y = __fdiv_rn(g.y, fn); g.z = __fdiv_rn(g.z, fn); g.w = __fdiv_rn(g.w, fn);
   }
   return g;
@@ -1495,12 +1517,12 @@ __device__ __forceinline__ void bwd_apply(const BwdArgs& a, uint32_t j, uint32_t
 // The group's lanes fetch `perm` cooperatively (one coalesced load per G occurrences) and keep UNR
 // independent gradient-row loads in flight; the adds stay in position order.
 template <int G, int UNR>
-__device__ __forceinline__ float4 sum_grad_rows(const BwdArgs& a, uint32_t s, uint32_t len, int c, bool in) {
+__device__ __forceinline__ float4 sum_grad_rows(const GradSrc& gs, uint32_t s, uint32_t len, bool in) {
   const int gl = Group<G>::gl(), gb = Group<G>::base();
   const uint32_t gmask = Group<G>::mask();
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (uint32_t q0 = 0; q0 < len; q0 += G) {
-    const uint32_t m_l = (q0 + gl < len) ? a.perm[s + q0 + gl] : 0u;
+    const uint32_t m_l = (q0 + gl < len) ? gs.perm[s + q0 + gl] : 0u;
     const int cnt = (int)min((uint32_t)G, len - q0);
     for (int u0 = 0; u0 < cnt; u0 += UNR) {
       float4 g[UNR];
@@ -1508,7 +1530,7 @@ __device__ __forceinline__ float4 sum_grad_rows(const BwdArgs& a, uint32_t s, ui
       for (int u = 0; u < UNR; ++u) {
         const uint32_t m = __shfl_sync(gmask, m_l, gb + min(u0 + u, G - 1));
         g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (u0 + u < cnt && in) g[u] = occ_grad4(a, m, c);
+        if (u0 + u < cnt && in) g[u] = occ_grad4(gs, m);
       }
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
@@ -1520,26 +1542,47 @@ __device__ __forceinline__ float4 sum_grad_rows(const BwdArgs& a, uint32_t s, ui
   return acc;
 }
 
-// group per run: short runs are reduced and applied here; long runs are queued
-template <int G, int OPT>
-__global__ void __launch_bounds__(kThreads) pool_bwd_short_kernel(BwdArgs a) {
+// Reduce: group per run, short runs are summed (in position order) into ugrad[j]; long runs are
+// queued.  No table access here: few registers, 8 resident blocks per SM, every gradient-row read is
+// independent of the others in flight.  Runs are ordered, so ugrad is written sequentially.
+template <int G>
+__global__ void __launch_bounds__(kThreads, 6) run_sum_kernel(BwdArgs a) {
   const int gl = Group<G>::gl();
   const int c = gl * 4;
   const int64_t nr = *a.n_runs;
-  const bool in = c < a.td.dim;
+  const int D = a.td.dim;
+  const bool in = c < D;
+  const GradSrc gs = make_grad_src(a, c);
+  const uint32_t* __restrict__ run_start = a.run_start;
+  float* __restrict__ ugrad = a.ugrad + c;
   const int64_t gstride = (int64_t)gridDim.x * (kThreads / G);
   for (int64_t j = (int64_t)blockIdx.x * (kThreads / G) + threadIdx.x / G; j < nr; j += gstride) {
-    const uint32_t ri = a.rowidx[j];
-    if (ri == kEmptyRow) continue;
-    const uint32_t s = a.run_start[j];
-    const uint32_t len = a.run_start[j + 1] - s;
+    const uint32_t s = run_start[j];
+    const uint32_t len = run_start[j + 1] - s;
     if (len > kShortRun) {
       if (gl == 0) a.long_list[atomicAdd(a.n_long, 1u)] = (uint32_t)j;
       continue;
     }
+    const float4 acc = sum_grad_rows<G, 4>(gs, s, len, in);
+    if (in) *reinterpret_cast<float4*>(ugrad + (size_t)j * D) = acc;
+  }
+}
+
+// Apply: group per run; rowidx[j], ugrad[j] and the row's w / state are all independent loads.
+template <int G, int OPT>
+__global__ void __launch_bounds__(kThreads) runs_apply_kernel(BwdArgs a) {
+  const int gl = Group<G>::gl();
+  const int c = gl * 4;
+  const int64_t nr = *a.n_runs;
+  const int D = a.td.dim;
+  const int64_t gstride = (int64_t)gridDim.x * (kThreads / G);
+  for (int64_t j = (int64_t)blockIdx.x * (kThreads / G) + threadIdx.x / G; j < nr; j += gstride) {
+    const uint32_t ri = a.rowidx[j];
+    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < D) g4 = __ldcs(reinterpret_cast<const float4*>(a.ugrad + (size_t)j * D + c));
+    if (ri == kEmptyRow) continue;
     const RowPre pre = bwd_prefetch<G, OPT>(a, ri, c);
-    const float4 acc = sum_grad_rows<G, 4>(a, s, len, c, in);
-    bwd_apply<G, OPT>(a, (uint32_t)j, ri, acc, c, pre);
+    bwd_apply<G, OPT>(a, (uint32_t)j, ri, g4, c, pre);
   }
 }
 
@@ -1579,7 +1622,12 @@ __global__ void __launch_bounds__(1024) long_prep_kernel(BwdArgs a) {
     }
     __syncthreads();
     const uint32_t excl = carry + (w ? wsum[w - 1] : 0) + x - pieces;
-    if (q < nl) a.long_sub_base[q] = excl;
+    if (q < nl) {
+      a.long_sub_base[q] = excl;
+      const uint32_t s0 = a.run_start[a.long_list[q]], len = a.long_len[q];
+      for (uint32_t p = 0; p < pieces; ++p)
+        a.piece_desc[excl + p] = make_uint2(s0 + p * kSubRun, min((uint32_t)kSubRun, len - p * kSubRun));
+    }
     __syncthreads();
     if (threadIdx.x == blockDim.x - 1) carry = carry + wsum[31];
     __syncthreads();
@@ -1590,39 +1638,35 @@ __global__ void __launch_bounds__(1024) long_prep_kernel(BwdArgs a) {
 // block per piece of a long run: kThreads/G groups reduce contiguous slices in order, then the
 // slices are combined in order (fixed association: deterministic)
 template <int G>
-__global__ void __launch_bounds__(kThreads) pool_bwd_long_partial_kernel(BwdArgs a) {
+__global__ void __launch_bounds__(kThreads, 6) pool_bwd_long_partial_kernel(BwdArgs a) {
   constexpr int NG = kThreads / G;
   __shared__ float4 sm[NG][G];
   const int gl = Group<G>::gl(), g = threadIdx.x / G, c = gl * 4;
-  const uint32_t nl = *a.n_long;
-  const uint32_t total = a.long_sub_base[nl];
+  const uint32_t total = a.long_sub_base[*a.n_long];
   const int D = a.td.dim;
   const bool in = c < D;
+  const GradSrc gs = make_grad_src(a, c);
+  const uint2* __restrict__ desc = a.piece_desc;
+  float* __restrict__ partial = a.partial + c;
   for (uint32_t wi = blockIdx.x; wi < total; wi += gridDim.x) {
-    uint32_t lo = 0, hi = nl - 1;  // last q with sub_base[q] <= wi
-    while (lo < hi) {
-      const uint32_t mid = (lo + hi + 1) >> 1;
-      if (a.long_sub_base[mid] <= wi) lo = mid; else hi = mid - 1;
-    }
-    const uint32_t q = lo, piece = wi - a.long_sub_base[q];
-    const uint32_t s = a.run_start[a.long_list[q]] + piece * kSubRun;
-    const uint32_t len = min((uint32_t)kSubRun, a.long_len[q] - piece * kSubRun);
+    const uint2 d = desc[wi];
+    const uint32_t len = d.y;
     const uint32_t per = (len + NG - 1) / NG;
     const uint32_t b = min(len, g * per), e = min(len, b + per);
-    sm[g][gl] = sum_grad_rows<G, 8>(a, s + b, e - b, c, in);
+    sm[g][gl] = sum_grad_rows<G, 4>(gs, d.x + b, e - b, in);
     __syncthreads();
     if (g == 0) {
       float4 t = sm[0][gl];
       for (int k = 1; k < NG; ++k)
         if ((uint32_t)k * per < len) add4(t, sm[k][gl]);
-      if (in) *reinterpret_cast<float4*>(a.partial + (size_t)wi * D + c) = t;
+      if (in) *reinterpret_cast<float4*>(partial + (size_t)wi * D) = t;
     }
     __syncthreads();
   }
 }
 
-// group per long run: combine its pieces in order, apply the optimizer
-template <int G, int OPT>
+// group per long run: combine its pieces in order into ugrad[j]
+template <int G>
 __global__ void __launch_bounds__(kThreads) pool_bwd_long_final_kernel(BwdArgs a) {
   const int gl = Group<G>::gl(), c = gl * 4;
   const uint32_t nl = *a.n_long;
@@ -1632,14 +1676,20 @@ __global__ void __launch_bounds__(kThreads) pool_bwd_long_final_kernel(BwdArgs a
     const uint32_t j = a.long_list[q];
     const uint32_t b = a.long_sub_base[q], e = a.long_sub_base[q + 1];
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (uint32_t wi = b; wi < e; ++wi) {
-      float4 p = make_float4(0, 0, 0, 0);
-      if (c < D) p = *reinterpret_cast<const float4*>(a.partial + (size_t)wi * D + c);
-      if (wi == b) acc = p; else add4(acc, p);
+    for (uint32_t w0 = b; w0 < e; w0 += 8) {
+      float4 p[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        p[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (w0 + u < e && c < D) p[u] = *reinterpret_cast<const float4*>(a.partial + (size_t)(w0 + u) * D + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (w0 + u >= e) continue;
+        if (w0 + u == b) acc = p[u]; else add4(acc, p[u]);
+      }
     }
-    const uint32_t ri = a.rowidx[j];
-    if (ri == kEmptyRow) continue;
-    bwd_apply<G, OPT>(a, j, ri, acc, c, bwd_prefetch<G, OPT>(a, ri, c));
+    if (c < D) *reinterpret_cast<float4*>(a.ugrad + (size_t)j * D + c) = acc;
   }
 }
 
@@ -1689,7 +1739,8 @@ void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t 
   const size_t o_occ = take(row_offsets ? 4 * (size_t)M : 0);
   const size_t o_ll = take(4 * n_long_max), o_llen = take(4 * n_long_max), o_lsb = take(4 * (n_long_max + 1));
   const size_t o_part = take(sizeof(float) * max_pieces * D);
-  const size_t o_scr = take(ht.segs.size() > 1 ? sizeof(float) * (size_t)M * D : 0);
+  const size_t o_pd = take(sizeof(uint2) * max_pieces);
+  const size_t o_ug = take(sizeof(float) * (size_t)M * D);
   char* ws = (char*)mt->ws_a.get(off, s);
   SetEntry* set = (SetEntry*)(ws + o_set);
   uint32_t *k0 = (uint32_t*)(ws + o_k0), *v0 = (uint32_t*)(ws + o_v0);
@@ -1780,7 +1831,9 @@ void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t 
   a.long_len = (uint32_t*)(ws + o_llen);
   a.long_sub_base = (uint32_t*)(ws + o_lsb);
   a.partial = (float*)(ws + o_part);
-  a.scratch = ht.segs.size() > 1 ? (float*)(ws + o_scr) : nullptr;
+  a.piece_desc = (uint2*)(ws + o_pd);
+  a.ugrad = (float*)(ws + o_ug);
+  a.scratch = a.ugrad;
   if (row_offsets) {
     uint32_t* occ = (uint32_t*)(ws + o_occ);
     occ_row_kernel<<<resident_grid(occ_row_kernel, n_rows, kThreads), kThreads, 0, s>>>(row_offsets, n_rows, occ);
@@ -1788,15 +1841,16 @@ void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t 
     a.occ_row = occ;
   }
 #define BWD2(GG, OO)                                                                                             \
-  pool_bwd_short_kernel<GG, OO>                                                                                  \
-      <<<resident_grid(pool_bwd_short_kernel<GG, OO>, M, kThreads / GG), kThreads, 0, s>>>(a);                   \
+  run_sum_kernel<GG><<<resident_grid(run_sum_kernel<GG>, M, kThreads / GG), kThreads, 0, s>>>(a);                \
   MONO_CHECK_LAUNCH();                                                                                           \
   long_prep_kernel<<<1, 1024, 0, s>>>(a);                                                                        \
   MONO_CHECK_LAUNCH();                                                                                           \
   pool_bwd_long_partial_kernel<GG>                                                                               \
       <<<resident_grid(pool_bwd_long_partial_kernel<GG>, (int64_t)max_pieces, 1), kThreads, 0, s>>>(a);          \
   MONO_CHECK_LAUNCH();                                                                                           \
-  pool_bwd_long_final_kernel<GG, OO><<<148, kThreads, 0, s>>>(a);                                                \
+  pool_bwd_long_final_kernel<GG><<<148 * 2, kThreads, 0, s>>>(a);                                                \
+  MONO_CHECK_LAUNCH();                                                                                           \
+  runs_apply_kernel<GG, OO><<<resident_grid(runs_apply_kernel<GG, OO>, M, kThreads / GG), kThreads, 0, s>>>(a);  \
   MONO_CHECK_LAUNCH()
 #define BWD(GG)                                                         \
   switch (opt_sel) {                                                    \

@@ -341,6 +341,19 @@ void ensure_capacity(mono_mtable* mt, int k, uint64_t n_new, cudaStream_t s) {
   bool nr, nbk;
   needs(nr, nbk);
   if (!nr && !nbk) return;
+  if (t.snapshot_pending) {
+    // the host ran ahead of the device: wait for the (older) in-flight snapshot only, not for the
+    // whole stream, and re-evaluate with its counters
+    MONO_CUDA(cudaEventSynchronize(t.snap_ev));
+    if (t.h_snap[kCtrError]) {
+      uint32_t tmp[kNumCtrs];
+      read_counters_sync(mt, k, s, tmp);
+    }
+    adopt_snapshot(t, t.h_snap, t.issued_at_pending);
+    t.snapshot_pending = false;
+    needs(nr, nbk);
+    if (!nr && !nbk) return;
+  }
   // exact path (SYNC): read the true counters, then decide
   uint32_t c[kNumCtrs];
   read_counters_sync(mt, k, s, c);
