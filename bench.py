@@ -409,6 +409,8 @@ def run_ours(args):
     }
     print(json.dumps(line), flush=True)
   if world > 1:
+    if rank == 0 and sharded.phases.enabled:
+      print("phase_ms", json.dumps(sharded.phases.report()), file=sys.stderr, flush=True)
     dist.destroy_process_group()
 
 

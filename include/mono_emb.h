@@ -263,6 +263,28 @@ int mono_dedup(int32_t device, const int64_t* ids_dev, int64_t n, int64_t* uniqu
                int32_t* inverse_out_dev, int32_t* n_unique_dev, int64_t* n_unique_host,
                void* stream);
 
+/* ---- owner grouping: one grouping per batch shared by the sharded forward and backward -------
+ * Replaces FusedReorderByIndices (ref: RT/ops/fused_reorder_by_indices.cc:38-123) + the float-atomic
+ * FusedGatherGrad scatter (ref: RT/ops/map_id_to_embedding.cu.cc:75-118) for ONE id list on the
+ * sharded fast path.  build(): the M occurrences are grouped by FID (scratch set + stable radix sort)
+ * and the distinct FIDs are bucketed by owner = (uint64)fid % num_shards.  Outputs on the device:
+ *   uniq_out_dev[<= M]     distinct FIDs, shard-major (order inside a shard is the engine's; use
+ *                          mono_reorder_by_indices when the reference's first-occurrence order is needed)
+ *   occ_offset_out_dev[M]  float offset (index in uniq_out * dim) of every occurrence's row in the
+ *                          post-all-to-all row buffer  (== fused_emb_offset of the reference op)
+ * and on the host (SYNC): shard_counts_host[num_shards], n_unique_host.
+ * reduce(): with the grouping built last, out_rows_dev[u*dim : +dim] = sum (SUM) / sum of g/n (MEAN)
+ * of the pooled-row gradients of FID u's occurrences, in occurrence order, without float atomics. */
+typedef struct mono_grouping mono_grouping_t;
+int mono_grouping_create(int32_t device, mono_grouping_t** out);
+int mono_grouping_destroy(mono_grouping_t* g);
+int mono_grouping_build(mono_grouping_t* g, const int64_t* fids_dev, int64_t n_fids, int32_t num_shards,
+                        int32_t dim, int64_t* uniq_out_dev, int32_t* occ_offset_out_dev,
+                        int32_t* shard_counts_host, int64_t* n_unique_host, void* stream);
+int mono_grouping_reduce(mono_grouping_t* g, const float* pooled_grad_dev, int64_t grad_stride,
+                         int32_t grad_col, const int32_t* row_offsets_dev, int64_t n_rows,
+                         int32_t pooling, float* out_rows_dev, void* stream);
+
 /* ---- pooling from a looked-up buffer (sync all-to-all path) ------------------------------- */
 
 /* ref: FusedGatherKernel, RT/ops/map_id_to_embedding.cu.cc:30-74 (forward) and
@@ -278,6 +300,18 @@ int mono_gather_pool_grad(int32_t device, const float* pooled_grad_dev, int64_t 
                           int32_t grad_col, const int32_t* emb_offset_dev,
                           const int32_t* row_offsets_dev, int64_t n_rows, int32_t dim,
                           int32_t pooling, float* grad_fused_dev, void* stream);
+
+/* Deterministic variant of mono_gather_pool_grad (no float atomics): occurrences are radix-sorted
+ * by destination offset and each destination row is written once with the sum of its occurrences'
+ * pooled-row gradients in occurrence order (run-to-run bit-stable; the reference GPU kernel uses
+ * atomicAdd, map_id_to_embedding.cu.cc:75-118).  emb_offset_dev[m] is the float offset of
+ * occurrence m's row inside grad_fused_dev (multiples of dim; total_floats = buffer length).
+ * Destination rows that no occurrence refers to are left untouched.  dim % 4 == 0, dim <= 128. */
+int mono_scatter_grad_rows(int32_t device, const float* pooled_grad_dev, int64_t grad_stride,
+                           int32_t grad_col, const int32_t* emb_offset_dev, int64_t n_occurrences,
+                           const int32_t* row_offsets_dev, int64_t n_rows, int32_t dim,
+                           int32_t pooling, float* grad_fused_dev, int64_t total_floats,
+                           void* stream);
 
 /* ---- generic fused layout op -------------------------------------------------------------- */
 

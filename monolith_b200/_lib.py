@@ -69,8 +69,13 @@ SIGNATURES = {
     "mono_mtable_restore_rows": (C.c_int, [_p, _i32, _p, _i64, _p, _p]),
     "mono_reorder_by_indices": (C.c_int, [_i32, _p, _p, _i32, _i32, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "mono_dedup": (C.c_int, [_i32, _p, _i64, _p, _p, _p, _p, _p]),
+    "mono_grouping_create": (C.c_int, [_i32, C.POINTER(_p)]),
+    "mono_grouping_destroy": (C.c_int, [_p]),
+    "mono_grouping_build": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p, _p, C.POINTER(_i64), _p]),
+    "mono_grouping_reduce": (C.c_int, [_p, _p, _i64, _i32, _p, _i64, _i32, _p, _p]),
     "mono_gather_pool": (C.c_int, [_i32, _p, _p, _p, _i64, _i32, _i32, _p, _i64, _i32, _p]),
     "mono_gather_pool_grad": (C.c_int, [_i32, _p, _i64, _i32, _p, _p, _i64, _i32, _i32, _p, _p]),
+    "mono_scatter_grad_rows": (C.c_int, [_i32, _p, _i64, _i32, _p, _i64, _p, _i64, _i32, _i32, _p, _i64, _p]),
     "mono_embedding_to_layout": (C.c_int, [_i32, _p, _p, _i32, _p, _i64, _p, _i32, _p, _i32, _i32,
                                            C.POINTER(SliceTask), _i32, _p, _p]),
     "mono_embedding_to_layout_grad": (C.c_int, [_i32, _p, _p, _i32, _p, _i64, _p, _i32, _p, _i32, _i32,

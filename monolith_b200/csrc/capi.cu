@@ -443,6 +443,46 @@ int mono_dedup(int32_t device, const int64_t* ids_dev, int64_t n, int64_t* uniqu
   });
 }
 
+int mono_grouping_create(int32_t device, mono_grouping_t** out) {
+  return guarded([&] {
+    require(out != nullptr, "grouping_create: null out");
+    MONO_CUDA(cudaSetDevice(device));
+    auto g = new mono_grouping();
+    g->device = device;
+    *out = g;
+  });
+}
+
+int mono_grouping_destroy(mono_grouping_t* g) {
+  if (!g) return MONO_OK;
+  cudaSetDevice(g->device);
+  cudaDeviceSynchronize();
+  g->ws.release();
+  if (g->h_counts) cudaFreeHost(g->h_counts);
+  delete g;
+  return MONO_OK;
+}
+
+int mono_grouping_build(mono_grouping_t* g, const int64_t* fids_dev, int64_t n_fids, int32_t num_shards,
+                        int32_t dim, int64_t* uniq_out_dev, int32_t* occ_offset_out_dev,
+                        int32_t* shard_counts_host, int64_t* n_unique_host, void* stream) {
+  return guarded([&] {
+    require(g && fids_dev && uniq_out_dev && occ_offset_out_dev && shard_counts_host, "grouping_build: null argument");
+    grouping_build(g, fids_dev, n_fids, num_shards, dim, uniq_out_dev, occ_offset_out_dev, shard_counts_host,
+                   n_unique_host, (cudaStream_t)stream);
+  });
+}
+
+int mono_grouping_reduce(mono_grouping_t* g, const float* pooled_grad_dev, int64_t grad_stride,
+                         int32_t grad_col, const int32_t* row_offsets_dev, int64_t n_rows,
+                         int32_t pooling, float* out_rows_dev, void* stream) {
+  return guarded([&] {
+    require(g && pooled_grad_dev && out_rows_dev, "grouping_reduce: null argument");
+    grouping_reduce(g, pooled_grad_dev, grad_stride, grad_col, row_offsets_dev, n_rows, pooling, out_rows_dev,
+                    (cudaStream_t)stream);
+  });
+}
+
 int mono_gather_pool(int32_t device, const float* fused_emb_dev, const int32_t* emb_offset_dev,
                      const int32_t* row_offsets_dev, int64_t n_rows, int32_t dim, int32_t pooling,
                      float* out_dev, int64_t out_stride, int32_t out_col, void* stream) {
@@ -463,6 +503,19 @@ int mono_gather_pool_grad(int32_t device, const float* pooled_grad_dev, int64_t 
     require(dim > 0, "dim must be positive");
     launch_gather_pool_grad(pooled_grad_dev, grad_stride, grad_col, emb_offset_dev, row_offsets_dev,
                             n_rows, dim, pooling, grad_fused_dev, (cudaStream_t)stream);
+  });
+}
+
+int mono_scatter_grad_rows(int32_t device, const float* pooled_grad_dev, int64_t grad_stride,
+                           int32_t grad_col, const int32_t* emb_offset_dev, int64_t n_occurrences,
+                           const int32_t* row_offsets_dev, int64_t n_rows, int32_t dim,
+                           int32_t pooling, float* grad_fused_dev, int64_t total_floats,
+                           void* stream) {
+  return guarded([&] {
+    require(pooled_grad_dev && emb_offset_dev && grad_fused_dev, "scatter_grad_rows: null argument");
+    require(row_offsets_dev != nullptr || n_rows == n_occurrences, "scatter_grad_rows: n_rows != n_occurrences");
+    run_scatter_rows(device, emb_offset_dev, n_occurrences, dim, row_offsets_dev, n_rows, pooling,
+                     pooled_grad_dev, grad_stride, grad_col, grad_fused_dev, total_floats, (cudaStream_t)stream);
   });
 }
 

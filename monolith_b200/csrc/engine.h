@@ -150,7 +150,31 @@ struct mono_mtable {
   uint32_t* h_flag = nullptr;         // pinned scratch for small D2H reads
 };
 
+// one reusable grouping of a batch (see ops.cu "Owner grouping")
+struct mono_grouping {
+  int device = 0;
+  mono::DevBuf ws;
+  int64_t M = 0;
+  int dim = 0;
+  // views into ws valid after build()
+  const uint32_t* skeys = nullptr;
+  const uint32_t* perm = nullptr;
+  uint32_t* run_start = nullptr;
+  uint32_t* run_first_pos = nullptr;
+  uint32_t* ord_of_run = nullptr;
+  uint32_t* ctr = nullptr;
+  char* tail = nullptr;      // scratch for reduce()
+  size_t tail_bytes = 0;
+  uint32_t* h_counts = nullptr;  // pinned
+};
+
 namespace mono {
+
+void grouping_build(mono_grouping* g, const int64_t* fids_dev, int64_t M, int N, int dim,
+                    int64_t* uniq_out, int32_t* occ_offset_out, int32_t* shard_counts_host,
+                    int64_t* n_unique_host, cudaStream_t s);
+void grouping_reduce(mono_grouping* g, const float* pooled_grad, int64_t grad_stride, int grad_col,
+                     const int32_t* row_offsets, int64_t n_rows, int pooling, float* out_rows, cudaStream_t s);
 
 // table.cu
 void table_init(mono_mtable* mt, HostTable& t, const mono_table_cfg& cfg, cudaStream_t s);
@@ -185,6 +209,10 @@ void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t 
                        const int32_t* row_offsets, int64_t n_rows, int pooling,
                        const float* pooled_grad, int64_t grad_stride, int grad_col,
                        const float* lr_host, int64_t update_time, cudaStream_t s);
+
+void run_scatter_rows(int device, const int32_t* offs_dev, int64_t M, int dim, const int32_t* row_offsets,
+                      int64_t n_rows, int pooling, const float* pooled_grad, int64_t grad_stride,
+                      int grad_col, float* out_rows, int64_t total_floats, cudaStream_t s);
 
 // dedup.cu
 void run_reorder(int device, const int64_t* ids_dev, const int64_t* id_split_host, int K, int N,

@@ -35,7 +35,15 @@ gather_pool_kernel(const float* __restrict__ fused, const int32_t* __restrict__ 
       for (int c = gl * 4; c < dim; c += G * 4) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int j = 0; j < n; ++j) {
-          float4 x = __ldg(reinterpret_cast<const float4*>(fused + emb_offset[b + j] + c));
+          // rows of a multi-table fused buffer start at arbitrary float offsets when some table's dim
+          // is not a multiple of 4: vector load only when this row is 16-byte aligned
+          const float* src = fused + emb_offset[b + j] + c;
+          float4 x;
+          if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            x = __ldg(reinterpret_cast<const float4*>(src));
+          } else {
+            x.x = __ldg(src); x.y = __ldg(src + 1); x.z = __ldg(src + 2); x.w = __ldg(src + 3);
+          }
           if (pooling == MONO_POOL_MEAN) {
             x.x = __fdiv_rn(x.x, fn); x.y = __fdiv_rn(x.y, fn);
             x.z = __fdiv_rn(x.z, fn); x.w = __fdiv_rn(x.w, fn);

@@ -880,6 +880,23 @@ void launch_lookup(mono_mtable* mt, const CallSeg* h_segs, int nsegs, const int6
                    int64_t n_total, float* out_dev, cudaStream_t s) {
   if (n_total <= 0) return;
   upload_tables(mt, s);
+  // merge adjacent segments of the same table whose ids and output rows are contiguous (fused_lookup
+  // of a single table: N shard segments collapse into one -> hoisted single-table kernel)
+  std::vector<CallSeg> merged;
+  for (int i = 0; i < nsegs; ++i) {
+    if (!merged.empty()) {
+      CallSeg& b = merged.back();
+      const int D = mt->tables[b.table].dim;
+      if (b.table == h_segs[i].table && b.id_end == h_segs[i].id_begin &&
+          b.val_off + (b.id_end - b.id_begin) * D == h_segs[i].val_off) {
+        b.id_end = h_segs[i].id_end;
+        continue;
+      }
+    }
+    merged.push_back(h_segs[i]);
+  }
+  h_segs = merged.data();
+  nsegs = (int)merged.size();
   CallBlob cb = stage_call(mt, h_segs, nsegs, nullptr, 0, s);
   launch_lookup_staged(mt, cb.segs, nsegs, pick_group(max_dim_of(mt, h_segs, nsegs)), ids_dev, n_total,
                        out_dev, 0, 0, s);
@@ -1157,8 +1174,11 @@ constexpr int kSubRun = 1024;
 template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 radix_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, int64_t n,
-                  int shift, int32_t* __restrict__ blk_cnt, int32_t* __restrict__ dtot, int nblk,
-                  uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+                  int shift, int pre_shift /* first pass only: key = raw >> pre_shift */,
+                  int32_t* __restrict__ blk_cnt, int32_t* __restrict__ dtot, int nblk,
+                  uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                  const uint32_t* __restrict__ n_dev /* optional: element count on the device */) {
+  if (n_dev) n = (int64_t)*n_dev;
   __shared__ int32_t wcnt[kThreads / 32][256];
   __shared__ int32_t bbase[256];
   __shared__ int32_t dbase[256];
@@ -1187,7 +1207,7 @@ radix_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restri
     __syncwarp();
     for (int c = 0; c < kPerWarp; c += 32) {
       const int64_t i = wbeg + c + lane;
-      const int dg = i < n ? (int)((keys_in[i] >> shift) & 255u) : -1;
+      const int dg = i < n ? (int)(((keys_in[i] >> pre_shift) >> shift) & 255u) : -1;
       const uint32_t same = __match_any_sync(0xffffffffu, dg);
       if (dg >= 0 && lane == (__ffs(same) - 1)) wcnt[w][dg] += __popc(same);
       __syncwarp();
@@ -1214,7 +1234,7 @@ radix_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restri
         uint32_t key = 0, val = 0;
         int dg = -1;
         if (i < n) {
-          key = keys_in[i];
+          key = keys_in[i] >> pre_shift;
           val = vals_in ? vals_in[i] : (uint32_t)i;
           dg = (int)((key >> shift) & 255u);
         }
@@ -1334,7 +1354,7 @@ runs_scan_kernel(uint32_t* __restrict__ blk_runs, int nblk, uint32_t* __restrict
 __global__ void __launch_bounds__(kThreads)
 runs_write_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ perm, int64_t n, int nblk,
                   const uint32_t* __restrict__ blk_runs, uint32_t* __restrict__ run_start,
-                  uint32_t* __restrict__ run_first_pos) {
+                  uint32_t* __restrict__ run_first_pos, uint32_t* __restrict__ run_of_sorted /* optional */) {
   __shared__ uint32_t wc[kThreads / 32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   constexpr int NW = kThreads / 32;
@@ -1357,6 +1377,7 @@ runs_write_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict
         run_start[j] = (uint32_t)i;
         run_first_pos[j] = perm[i];
       }
+      if (run_of_sorted && i < n) run_of_sorted[i] = base + __popc(bal & (0xffffffffu >> (31 - lane))) - 1;
       base += __popc(bal);
     }
     __syncthreads();
@@ -1693,6 +1714,51 @@ __global__ void __launch_bounds__(kThreads) pool_bwd_long_final_kernel(BwdArgs a
   }
 }
 
+struct SortWs {
+  uint32_t *k0, *v0, *k1, *v1;  // k0 holds the input keys; values are implicit positions
+  int32_t* blk_cnt;             // [256][nblk]
+  int32_t* dtot;                // [passes][256], zeroed
+  uint32_t* blk_runs;           // [nblk]
+  uint32_t* run_start;          // [M + 1]
+  uint32_t* run_first_pos;      // [M]
+  uint32_t* n_runs;             // device counter, zeroed
+  uint32_t* run_of_sorted = nullptr;  // optional [M]: run index of every sorted element
+};
+
+// stable LSD radix sort of (key >> pre_shift, position) over `bits` key bits, then the ordered run
+// list (one run per distinct key).  Everything stays on the stream; counts stay on the device.
+static void sort_and_runs(const SortWs& w, int64_t M, int bits, int pre_shift, const uint32_t** skeys_out,
+                          const uint32_t** perm_out, cudaStream_t s) {
+  const int passes = std::max(1, (bits + 7) / 8);
+  const int nblk = (int)((M + kSortTile - 1) / kSortTile);
+  const uint32_t* vin = nullptr;  // first pass: value = position
+  uint32_t *kin = w.k0, *kout = w.k1, *vout = w.v1;
+  const int gh = resident_grid(radix_pass_kernel<0>, nblk, 1);
+  const int gs = resident_grid(radix_pass_kernel<1>, nblk, 1);
+  for (int p = 0; p < passes; ++p) {
+    int32_t* dt = w.dtot + 256 * p;
+    const int ps = p == 0 ? pre_shift : 0;
+    radix_pass_kernel<0><<<gh, kThreads, 0, s>>>(kin, vin, M, 8 * p, ps, w.blk_cnt, dt, nblk, nullptr, nullptr, nullptr);
+    MONO_CHECK_LAUNCH();
+    radix_rowscan_kernel<<<256, 32, 0, s>>>(w.blk_cnt, nblk);
+    MONO_CHECK_LAUNCH();
+    radix_pass_kernel<1><<<gs, kThreads, 0, s>>>(kin, vin, M, 8 * p, ps, w.blk_cnt, dt, nblk, kout, vout, nullptr);
+    MONO_CHECK_LAUNCH();
+    vin = vout;
+    std::swap(kin, kout);
+    vout = (vout == w.v1) ? w.v0 : w.v1;
+  }
+  runs_count_kernel<<<resident_grid(runs_count_kernel, nblk, 1), kThreads, 0, s>>>(kin, M, nblk, w.blk_runs);
+  MONO_CHECK_LAUNCH();
+  runs_scan_kernel<<<1, 1024, 0, s>>>(w.blk_runs, nblk, w.n_runs, w.run_start, M);
+  MONO_CHECK_LAUNCH();
+  runs_write_kernel<<<resident_grid(runs_write_kernel, nblk, 1), kThreads, 0, s>>>(
+      kin, vin, M, nblk, w.blk_runs, w.run_start, w.run_first_pos, w.run_of_sorted);
+  MONO_CHECK_LAUNCH();
+  *skeys_out = kin;
+  *perm_out = vin;
+}
+
 void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t n_fids,
                        const int32_t* row_offsets, int64_t n_rows, int pooling,
                        const float* pooled_grad, int64_t grad_stride, int grad_col,
@@ -1755,36 +1821,19 @@ void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t 
   dup_claim_kernel<<<resident_grid(dup_claim_kernel, M, kThreads), kThreads, 0, s>>>(cb.segs, 1, fids_dev, nullptr, M,
                                                                                     set, cap - 1, k0);
   MONO_CHECK_LAUNCH();
-  // 2 stable LSD radix sort of (slot, position)
-  const uint32_t* vin = nullptr;  // first pass: value = position
-  uint32_t *kin = k0, *kout = k1, *vout = v1;
-  const int gh = resident_grid(radix_pass_kernel<0>, nblk, 1);
-  const int gs = resident_grid(radix_pass_kernel<1>, nblk, 1);
-  for (int p = 0; p < passes; ++p) {
-    int32_t* dt = dtot + 256 * p;
-    radix_pass_kernel<0><<<gh, kThreads, 0, s>>>(kin, vin, M, 8 * p, blk_cnt, dt, nblk, nullptr, nullptr);
-    MONO_CHECK_LAUNCH();
-    radix_rowscan_kernel<<<256, 32, 0, s>>>(blk_cnt, nblk);
-    MONO_CHECK_LAUNCH();
-    radix_pass_kernel<1><<<gs, kThreads, 0, s>>>(kin, vin, M, 8 * p, blk_cnt, dt, nblk, kout, vout);
-    MONO_CHECK_LAUNCH();
-    vin = vout;
-    std::swap(kin, kout);
-    vout = (vout == v1) ? v0 : v1;
-  }
-  const uint32_t* skeys = kin;
-  const uint32_t* perm = vin;
-  // 3 ordered run list
-  uint32_t* blk_runs = (uint32_t*)(ws + o_brun);
-  uint32_t* run_start = (uint32_t*)(ws + o_rs);
-  uint32_t* run_first_pos = (uint32_t*)(ws + o_rfp);
-  runs_count_kernel<<<resident_grid(runs_count_kernel, nblk, 1), kThreads, 0, s>>>(skeys, M, nblk, blk_runs);
-  MONO_CHECK_LAUNCH();
-  runs_scan_kernel<<<1, 1024, 0, s>>>(blk_runs, nblk, ctr, run_start, M);
-  MONO_CHECK_LAUNCH();
-  runs_write_kernel<<<resident_grid(runs_write_kernel, nblk, 1), kThreads, 0, s>>>(skeys, perm, M, nblk, blk_runs,
-                                                                                  run_start, run_first_pos);
-  MONO_CHECK_LAUNCH();
+  // 2 stable LSD radix sort of (slot, position)  +  3 ordered run list
+  SortWs sw;
+  sw.k0 = k0; sw.v0 = v0; sw.k1 = k1; sw.v1 = v1;
+  sw.blk_cnt = blk_cnt; sw.dtot = dtot;
+  sw.blk_runs = (uint32_t*)(ws + o_brun);
+  sw.run_start = (uint32_t*)(ws + o_rs);
+  sw.run_first_pos = (uint32_t*)(ws + o_rfp);
+  sw.n_runs = ctr;
+  const uint32_t* skeys = nullptr;
+  const uint32_t* perm = nullptr;
+  sort_and_runs(sw, M, bits, 0, &skeys, &perm, s);
+  uint32_t* run_start = sw.run_start;
+  uint32_t* run_first_pos = sw.run_first_pos;
   // 4 resolve (+ insert) the run keys
   UpsertArgs ua;
   ua.tables = mt->d_tables;
@@ -1872,6 +1921,378 @@ void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t 
   ht.issued_total += (uint64_t)M;
   ht.max_update_ts = std::max<int64_t>(ht.max_update_ts, update_time);
   request_snapshot(mt, k, s);
+}
+
+
+// run j of the sorted offsets -> destination row: out_rows + (sorted key << shift)
+template <int G>
+__global__ void __launch_bounds__(kThreads) runs_emit_kernel(BwdArgs a, const uint32_t* __restrict__ skeys,
+                                                             int shift, float* __restrict__ out_rows) {
+  const int gl = Group<G>::gl(), c = gl * 4;
+  const int64_t nr = *a.n_runs;
+  const int D = a.td.dim;
+  const int64_t gstride = (int64_t)gridDim.x * (kThreads / G);
+  for (int64_t j = (int64_t)blockIdx.x * (kThreads / G) + threadIdx.x / G; j < nr; j += gstride) {
+    if (c >= D) continue;
+    const float4 g = __ldcs(reinterpret_cast<const float4*>(a.ugrad + (size_t)j * D + c));
+    *reinterpret_cast<float4*>(out_rows + ((size_t)skeys[a.run_start[j]] << shift) + c) = g;
+  }
+}
+
+// Deterministic replacement of the float-atomic scatter of pooled-row gradients
+// (ref: FusedGatherGradKernel, map_id_to_embedding.cu.cc:75-118; ScatterGrad,
+// fused_embedding_to_layout.h:286-347): out_rows[offs[m] : +dim] = sum over the occurrences m with that
+// offset of pooled_grad[row(m)] (or /n for MEAN), summed in occurrence order.  Rows of out_rows that
+// no occurrence points at are left untouched.
+void run_scatter_rows(int device, const int32_t* offs_dev, int64_t M, int dim, const int32_t* row_offsets,
+                      int64_t n_rows, int pooling, const float* pooled_grad, int64_t grad_stride,
+                      int grad_col, float* out_rows, int64_t total_floats, cudaStream_t s) {
+  MONO_CUDA(cudaSetDevice(device));
+  if (M <= 0) return;
+  if (M >= ((int64_t)1 << 31) || total_floats >= ((int64_t)1 << 31)) throw ArgError("scatter_rows: sizes exceed 2^31");
+  if (pooling != MONO_POOL_SUM && pooling != MONO_POOL_MEAN) throw ArgError("scatter_rows: SUM or MEAN");
+  if ((dim & 3) || dim > 128) throw ArgError("scatter_rows needs dim % 4 == 0 and dim <= 128");
+  if ((grad_stride & 3) || (grad_col & 3) || (reinterpret_cast<uintptr_t>(pooled_grad) & 15) ||
+      (reinterpret_cast<uintptr_t>(out_rows) & 15))
+    throw ArgError("scatter_rows needs 16-byte aligned rows");
+  const int D = dim;
+  // offsets are multiples of 4 floats (16-byte aligned rows; every dim in the fused buffer is a multiple
+  // of 4): drop the two zero bits from the sort key
+  const int shift = 2;
+  int bits = 1;
+  while (((int64_t)1 << bits) < ((total_floats >> shift) + 1)) ++bits;
+  const int passes = std::max(1, (bits + 7) / 8);
+  const int nblk = (int)((M + kSortTile - 1) / kSortTile);
+  const size_t n_long_max = (size_t)M / kShortRun + 2;
+  const size_t max_pieces = (size_t)M / kSubRun + n_long_max + 2;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_v0 = take(4 * (size_t)M), o_k1 = take(4 * (size_t)M), o_v1 = take(4 * (size_t)M);
+  const size_t o_k0b = take(4 * (size_t)M);
+  const size_t o_blk = take(4 * (size_t)256 * nblk);
+  const size_t o_ctr = take(4096 + 4 * 256 * 4);
+  const size_t o_brun = take(4 * (size_t)nblk);
+  const size_t o_rs = take(4 * ((size_t)M + 1)), o_rfp = take(4 * (size_t)M);
+  const size_t o_occ = take(row_offsets ? 4 * (size_t)M : 0);
+  const size_t o_ll = take(4 * n_long_max), o_llen = take(4 * n_long_max), o_lsb = take(4 * (n_long_max + 1));
+  const size_t o_part = take(sizeof(float) * max_pieces * D);
+  const size_t o_pd = take(sizeof(uint2) * max_pieces);
+  const size_t o_ug = take(sizeof(float) * (size_t)M * D);
+  char* ws = nullptr;
+  MONO_CUDA(cudaMallocAsync((void**)&ws, off, s));
+  uint32_t* ctr = (uint32_t*)(ws + o_ctr);
+  MONO_CUDA(cudaMemsetAsync(ctr, 0, 4096 + 4 * 256 * 4, s));
+  SortWs sw;
+  // private copy of the keys: the sort ping-pongs between k0 and k1 and must not touch the caller's offsets
+  sw.k0 = (uint32_t*)(ws + o_k0b);
+  MONO_CUDA(cudaMemcpyAsync(sw.k0, offs_dev, 4 * (size_t)M, cudaMemcpyDeviceToDevice, s));
+  sw.v0 = (uint32_t*)(ws + o_v0);
+  sw.k1 = (uint32_t*)(ws + o_k1);
+  sw.v1 = (uint32_t*)(ws + o_v1);
+  sw.blk_cnt = (int32_t*)(ws + o_blk);
+  sw.dtot = (int32_t*)(ws + o_ctr + 4096);
+  sw.blk_runs = (uint32_t*)(ws + o_brun);
+  sw.run_start = (uint32_t*)(ws + o_rs);
+  sw.run_first_pos = (uint32_t*)(ws + o_rfp);
+  sw.n_runs = ctr;
+  const uint32_t* skeys = nullptr;
+  const uint32_t* perm = nullptr;
+  (void)passes;
+  sort_and_runs(sw, M, bits, shift, &skeys, &perm, s);
+  BwdArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.td.dim = D;
+  a.skeys = skeys;
+  a.perm = perm;
+  a.n = M;
+  a.n_runs = ctr;
+  a.run_start = sw.run_start;
+  a.run_first_pos = sw.run_first_pos;
+  a.row_offsets = row_offsets;
+  a.pooling = pooling;
+  a.pooled_grad = pooled_grad;
+  a.grad_stride = grad_stride;
+  a.grad_col = grad_col;
+  a.n_long = ctr + 4;
+  a.long_list = (uint32_t*)(ws + o_ll);
+  a.long_len = (uint32_t*)(ws + o_llen);
+  a.long_sub_base = (uint32_t*)(ws + o_lsb);
+  a.partial = (float*)(ws + o_part);
+  a.piece_desc = (uint2*)(ws + o_pd);
+  a.ugrad = (float*)(ws + o_ug);
+  if (row_offsets) {
+    uint32_t* occ = (uint32_t*)(ws + o_occ);
+    occ_row_kernel<<<resident_grid(occ_row_kernel, n_rows, kThreads), kThreads, 0, s>>>(row_offsets, n_rows, occ);
+    MONO_CHECK_LAUNCH();
+    a.occ_row = occ;
+  }
+  const int G = pick_group(D);
+#define EMIT(GG)                                                                                              \
+  run_sum_kernel<GG><<<resident_grid(run_sum_kernel<GG>, M, kThreads / GG), kThreads, 0, s>>>(a);             \
+  MONO_CHECK_LAUNCH();                                                                                        \
+  long_prep_kernel<<<1, 1024, 0, s>>>(a);                                                                     \
+  MONO_CHECK_LAUNCH();                                                                                        \
+  pool_bwd_long_partial_kernel<GG>                                                                            \
+      <<<resident_grid(pool_bwd_long_partial_kernel<GG>, (int64_t)max_pieces, 1), kThreads, 0, s>>>(a);       \
+  MONO_CHECK_LAUNCH();                                                                                        \
+  pool_bwd_long_final_kernel<GG><<<148 * 2, kThreads, 0, s>>>(a);                                             \
+  MONO_CHECK_LAUNCH();                                                                                        \
+  runs_emit_kernel<GG><<<resident_grid(runs_emit_kernel<GG>, M, kThreads / GG), kThreads, 0, s>>>(a, skeys, shift, out_rows); \
+  MONO_CHECK_LAUNCH()
+  switch (G) {
+    case 4: EMIT(4); break;
+    case 8: EMIT(8); break;
+    case 16: EMIT(16); break;
+    default: EMIT(32); break;
+  }
+#undef EMIT
+  MONO_CUDA(cudaFreeAsync(ws, s));
+}
+
+
+// ==========================================================================================
+// Owner grouping: ONE grouping of a batch's FID occurrences shared by the forward (dedup + bucket by
+// owner for the all-to-all) and the backward (deterministic per-FID gradient reduction) of the sharded
+// step.  Functionally FusedReorderByIndices (ref: fused_reorder_by_indices.cc:38-123) for a single id
+// list, except that the order of the distinct FIDs inside a shard is the engine's (scratch-set slot
+// order), not first-occurrence order; mono_reorder_by_indices is the bit-exact op.
+// ==========================================================================================
+__global__ void __launch_bounds__(kThreads)
+fid_claim_kernel(const int64_t* __restrict__ fids, int64_t n, SetEntry* set, uint32_t mask,
+                 uint32_t* __restrict__ slot_of) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t key = fids[i];
+    uint32_t s = (uint32_t)(mix64((uint64_t)key) >> 20) & mask;
+    while (true) {
+      Entry e = ld_entry_cg(reinterpret_cast<Entry*>(set + s));
+      if (e.row == kEmptyRow && e.ts == 0xFFFFFFFFu && e.key == -1) {
+        SetEntry ne;
+        ne.key = key;
+        ne.table = 0;
+        ne.first_pos = (int32_t)i;
+        if (cas_set(set + s, ne)) break;
+        continue;
+      }
+      if (e.key == key && e.row == 0u) break;
+      s = (s + 1) & mask;
+    }
+    slot_of[i] = s;
+  }
+}
+
+// key of run j for the owner partition: (uint64)fid % N
+__global__ void __launch_bounds__(kThreads)
+run_owner_kernel(const int64_t* __restrict__ fids, const uint32_t* __restrict__ run_first_pos,
+                 const uint32_t* __restrict__ n_runs, int num_shards, uint32_t* __restrict__ key_out) {
+  const int64_t n = *n_runs;
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
+    key_out[j] = (uint32_t)((uint64_t)fids[run_first_pos[j]] % (uint64_t)num_shards);
+}
+
+// after the owner partition: position p of the partitioned run list holds run j = runs_sorted[p]
+__global__ void __launch_bounds__(kThreads)
+run_ordinal_kernel(const int64_t* __restrict__ fids, const uint32_t* __restrict__ run_first_pos,
+                   const uint32_t* __restrict__ runs_sorted, const uint32_t* __restrict__ n_runs,
+                   uint32_t* __restrict__ ord_of_run, int64_t* __restrict__ uniq_out) {
+  const int64_t n = *n_runs;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t j = runs_sorted[p];
+    ord_of_run[j] = (uint32_t)p;
+    uniq_out[p] = fids[run_first_pos[j]];
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+occ_ordinal_kernel(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ run_of_sorted,
+                   const uint32_t* __restrict__ ord_of_run, int64_t n, int dim, int32_t* __restrict__ occ_offset) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    occ_offset[perm[i]] = (int32_t)(ord_of_run[run_of_sorted[i]] * (uint32_t)dim);
+}
+
+// ugrad[j] (run order) -> out_rows[ord_of_run[j]] (owner-bucketed order)
+template <int G>
+__global__ void __launch_bounds__(kThreads)
+runs_permute_kernel(const float* __restrict__ ugrad, const uint32_t* __restrict__ ord_of_run,
+                    const uint32_t* __restrict__ n_runs, int D, float* __restrict__ out_rows) {
+  const int c = Group<G>::gl() * 4;
+  const int64_t nr = *n_runs;
+  const int64_t gstride = (int64_t)gridDim.x * (kThreads / G);
+  for (int64_t j = (int64_t)blockIdx.x * (kThreads / G) + threadIdx.x / G; j < nr; j += gstride) {
+    if (c >= D) continue;
+    const float4 g = __ldcs(reinterpret_cast<const float4*>(ugrad + (size_t)j * D + c));
+    *reinterpret_cast<float4*>(out_rows + (size_t)ord_of_run[j] * D + c) = g;
+  }
+}
+
+void grouping_build(mono_grouping* g, const int64_t* fids_dev, int64_t M, int N, int dim,
+                    int64_t* uniq_out, int32_t* occ_offset_out, int32_t* shard_counts_host,
+                    int64_t* n_unique_host, cudaStream_t s) {
+  MONO_CUDA(cudaSetDevice(g->device));
+  if (N <= 0 || N > 256) throw ArgError("grouping: num_shards must be in [1, 256]");
+  if (M < 0 || M >= ((int64_t)1 << 31)) throw ArgError("grouping: bad occurrence count");
+  if ((dim & 3) || dim <= 0 || dim > 128) throw ArgError("grouping needs dim % 4 == 0 and dim <= 128");
+  g->M = M;
+  g->dim = dim;
+  if (M == 0) {
+    for (int n = 0; n < N; ++n) shard_counts_host[n] = 0;
+    if (n_unique_host) *n_unique_host = 0;
+    return;
+  }
+  uint32_t cap = 1024;
+  while (cap < 2 * (uint64_t)M) cap <<= 1;
+  int bits = 0;
+  while ((1u << bits) < cap) ++bits;
+  const int nblk = (int)((M + kSortTile - 1) / kSortTile);
+  const size_t n_long_max = (size_t)M / kShortRun + 2;
+  const size_t max_pieces = (size_t)M / kSubRun + n_long_max + 2;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_set = take(sizeof(SetEntry) * cap);
+  const size_t o_k0 = take(4 * (size_t)M), o_v0 = take(4 * (size_t)M), o_k1 = take(4 * (size_t)M), o_v1 = take(4 * (size_t)M);
+  const size_t o_blk = take(4 * (size_t)256 * nblk);
+  const size_t o_ctr = take(4096 + 4 * 256 * 8);
+  const size_t o_brun = take(4 * (size_t)nblk);
+  const size_t o_rs = take(4 * ((size_t)M + 1)), o_rfp = take(4 * (size_t)M), o_ros = take(4 * (size_t)M);
+  const size_t o_rk = take(4 * (size_t)M), o_rk2 = take(4 * (size_t)M), o_rv2 = take(4 * (size_t)M);
+  const size_t o_ord = take(4 * (size_t)M);
+  const size_t o_tail = off;
+  // reduce() scratch
+  const size_t o_occ = take(4 * (size_t)M);
+  const size_t o_ll = take(4 * n_long_max), o_llen = take(4 * n_long_max), o_lsb = take(4 * (n_long_max + 1));
+  const size_t o_part = take(sizeof(float) * max_pieces * dim);
+  const size_t o_pd = take(sizeof(uint2) * max_pieces);
+  const size_t o_ug = take(sizeof(float) * (size_t)M * dim);
+  (void)o_occ; (void)o_ll; (void)o_llen; (void)o_lsb; (void)o_part; (void)o_pd; (void)o_ug;
+  char* ws = (char*)g->ws.get(off, s);
+  g->tail = ws + o_tail;
+  g->tail_bytes = off - o_tail;
+  SetEntry* set = (SetEntry*)(ws + o_set);
+  uint32_t* ctr = (uint32_t*)(ws + o_ctr);
+  int32_t* dtot = (int32_t*)(ws + o_ctr + 4096);
+  MONO_CUDA(cudaMemsetAsync(set, 0xFF, sizeof(SetEntry) * cap, s));
+  MONO_CUDA(cudaMemsetAsync(ctr, 0, 4096 + 4 * 256 * 8, s));
+  SortWs sw;
+  sw.k0 = (uint32_t*)(ws + o_k0); sw.v0 = (uint32_t*)(ws + o_v0);
+  sw.k1 = (uint32_t*)(ws + o_k1); sw.v1 = (uint32_t*)(ws + o_v1);
+  sw.blk_cnt = (int32_t*)(ws + o_blk);
+  sw.dtot = dtot;
+  sw.blk_runs = (uint32_t*)(ws + o_brun);
+  sw.run_start = (uint32_t*)(ws + o_rs);
+  sw.run_first_pos = (uint32_t*)(ws + o_rfp);
+  sw.n_runs = ctr;
+  sw.run_of_sorted = (uint32_t*)(ws + o_ros);
+  fid_claim_kernel<<<resident_grid(fid_claim_kernel, M, kThreads), kThreads, 0, s>>>(fids_dev, M, set, cap - 1, sw.k0);
+  MONO_CHECK_LAUNCH();
+  const uint32_t* skeys = nullptr;
+  const uint32_t* perm = nullptr;
+  sort_and_runs(sw, M, bits, 0, &skeys, &perm, s);
+  // owner partition of the run list: one stable radix pass on key = fid % N (digit totals = shard counts)
+  uint32_t* rk = (uint32_t*)(ws + o_rk);
+  uint32_t* rk2 = (uint32_t*)(ws + o_rk2);
+  uint32_t* rv2 = (uint32_t*)(ws + o_rv2);
+  uint32_t* ord_of_run = (uint32_t*)(ws + o_ord);
+  int32_t* dt_owner = dtot + 256 * 6;
+  run_owner_kernel<<<resident_grid(run_owner_kernel, M, kThreads), kThreads, 0, s>>>(fids_dev, sw.run_first_pos, ctr, N, rk);
+  MONO_CHECK_LAUNCH();
+  const int gh = resident_grid(radix_pass_kernel<0>, nblk, 1), gs = resident_grid(radix_pass_kernel<1>, nblk, 1);
+  radix_pass_kernel<0><<<gh, kThreads, 0, s>>>(rk, nullptr, M, 0, 0, sw.blk_cnt, dt_owner, nblk, nullptr, nullptr, ctr);
+  MONO_CHECK_LAUNCH();
+  radix_rowscan_kernel<<<256, 32, 0, s>>>(sw.blk_cnt, nblk);
+  MONO_CHECK_LAUNCH();
+  radix_pass_kernel<1><<<gs, kThreads, 0, s>>>(rk, nullptr, M, 0, 0, sw.blk_cnt, dt_owner, nblk, rk2, rv2, ctr);
+  MONO_CHECK_LAUNCH();
+  run_ordinal_kernel<<<resident_grid(run_ordinal_kernel, M, kThreads), kThreads, 0, s>>>(fids_dev, sw.run_first_pos, rv2, ctr,
+                                                                                        ord_of_run, uniq_out);
+  MONO_CHECK_LAUNCH();
+  occ_ordinal_kernel<<<resident_grid(occ_ordinal_kernel, M, kThreads), kThreads, 0, s>>>(perm, sw.run_of_sorted, ord_of_run, M,
+                                                                                        dim, occ_offset_out);
+  MONO_CHECK_LAUNCH();
+  // shard counts (= digit totals of the owner pass) and the number of distinct FIDs to the host
+  if (!g->h_counts) MONO_CUDA(cudaHostAlloc((void**)&g->h_counts, 4 * 260, cudaHostAllocDefault));
+  MONO_CUDA(cudaMemcpyAsync(g->h_counts, dt_owner, 4 * 256, cudaMemcpyDeviceToHost, s));
+  MONO_CUDA(cudaMemcpyAsync(g->h_counts + 256, ctr, 4, cudaMemcpyDeviceToHost, s));
+  MONO_CUDA(cudaStreamSynchronize(s));
+  for (int n = 0; n < N; ++n) shard_counts_host[n] = (int32_t)g->h_counts[n];
+  if (n_unique_host) *n_unique_host = g->h_counts[256];
+  g->skeys = skeys;
+  g->perm = perm;
+  g->run_start = sw.run_start;
+  g->run_first_pos = sw.run_first_pos;
+  g->ord_of_run = ord_of_run;
+  g->ctr = ctr;
+}
+
+void grouping_reduce(mono_grouping* g, const float* pooled_grad, int64_t grad_stride, int grad_col,
+                     const int32_t* row_offsets, int64_t n_rows, int pooling, float* out_rows, cudaStream_t s) {
+  MONO_CUDA(cudaSetDevice(g->device));
+  const int64_t M = g->M;
+  const int D = g->dim;
+  if (M <= 0) return;
+  if (!g->skeys) throw ArgError("grouping_reduce before grouping_build");
+  if (pooling != MONO_POOL_SUM && pooling != MONO_POOL_MEAN) throw ArgError("grouping_reduce: SUM or MEAN");
+  if ((grad_stride & 3) || (grad_col & 3) || (reinterpret_cast<uintptr_t>(pooled_grad) & 15) ||
+      (reinterpret_cast<uintptr_t>(out_rows) & 15))
+    throw ArgError("grouping_reduce needs 16-byte aligned rows");
+  const size_t n_long_max = (size_t)M / kShortRun + 2;
+  const size_t max_pieces = (size_t)M / kSubRun + n_long_max + 2;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_occ = take(4 * (size_t)M);
+  const size_t o_ll = take(4 * n_long_max), o_llen = take(4 * n_long_max), o_lsb = take(4 * (n_long_max + 1));
+  const size_t o_part = take(sizeof(float) * max_pieces * D);
+  const size_t o_pd = take(sizeof(uint2) * max_pieces);
+  const size_t o_ug = take(sizeof(float) * (size_t)M * D);
+  if (off > g->tail_bytes) throw ArgError("grouping scratch too small (internal)");
+  char* ws = g->tail;
+  BwdArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.td.dim = D;
+  a.skeys = g->skeys;
+  a.perm = g->perm;
+  a.n = M;
+  a.n_runs = g->ctr;
+  a.run_start = g->run_start;
+  a.run_first_pos = g->run_first_pos;
+  a.row_offsets = row_offsets;
+  a.pooling = pooling;
+  a.pooled_grad = pooled_grad;
+  a.grad_stride = grad_stride;
+  a.grad_col = grad_col;
+  a.n_long = g->ctr + 4;
+  a.long_list = (uint32_t*)(ws + o_ll);
+  a.long_len = (uint32_t*)(ws + o_llen);
+  a.long_sub_base = (uint32_t*)(ws + o_lsb);
+  a.partial = (float*)(ws + o_part);
+  a.piece_desc = (uint2*)(ws + o_pd);
+  a.ugrad = (float*)(ws + o_ug);
+  MONO_CUDA(cudaMemsetAsync(g->ctr + 4, 0, 4, s));  // n_long
+  if (row_offsets) {
+    uint32_t* occ = (uint32_t*)(ws + o_occ);
+    occ_row_kernel<<<resident_grid(occ_row_kernel, n_rows, kThreads), kThreads, 0, s>>>(row_offsets, n_rows, occ);
+    MONO_CHECK_LAUNCH();
+    a.occ_row = occ;
+  }
+  const int G = pick_group(D);
+#define RED(GG)                                                                                               \
+  run_sum_kernel<GG><<<resident_grid(run_sum_kernel<GG>, M, kThreads / GG), kThreads, 0, s>>>(a);             \
+  MONO_CHECK_LAUNCH();                                                                                        \
+  long_prep_kernel<<<1, 1024, 0, s>>>(a);                                                                     \
+  MONO_CHECK_LAUNCH();                                                                                        \
+  pool_bwd_long_partial_kernel<GG>                                                                            \
+      <<<resident_grid(pool_bwd_long_partial_kernel<GG>, (int64_t)max_pieces, 1), kThreads, 0, s>>>(a);       \
+  MONO_CHECK_LAUNCH();                                                                                        \
+  pool_bwd_long_final_kernel<GG><<<148 * 2, kThreads, 0, s>>>(a);                                             \
+  MONO_CHECK_LAUNCH();                                                                                        \
+  runs_permute_kernel<GG><<<resident_grid(runs_permute_kernel<GG>, M, kThreads / GG), kThreads, 0, s>>>(      \
+      a.ugrad, g->ord_of_run, g->ctr, D, out_rows);                                                           \
+  MONO_CHECK_LAUNCH()
+  switch (G) {
+    case 4: RED(4); break;
+    case 8: RED(8); break;
+    case 16: RED(16); break;
+    default: RED(32); break;
+  }
+#undef RED
 }
 
 }  // namespace mono

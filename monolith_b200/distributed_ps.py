@@ -36,6 +36,8 @@ class CudaBackend:
     from . import distribution_ops
     self.t = table
     self.dops = distribution_ops
+    # 16-byte aligned rows everywhere in the fused buffers <=> every table dim is a multiple of 4
+    self.vec_ok = all(d % 4 == 0 for d in table.get_table_dim_sizes())
 
   def reorder(self, fids_list, num_shards, dims):
     out, shard_sizes, slot_sizes, _, offs = self.dops.fused_reorder_by_indices(fids_list, num_shards, dims,
@@ -53,7 +55,11 @@ class CudaBackend:
     return self.dops.gather_pool(rows, offs, dim, row_offsets, pooling, out=out)
 
   def gather_pool_grad_into(self, grad_buf, pooled_grad, offs, dim, row_offsets, pooling):
-    """Accumulates into grad_buf (pre-zeroed, shared by all tables of the step)."""
+    """Fills grad_buf (pre-zeroed, shared by all tables of the step).  dim % 4 == 0 and <= 128: the
+    deterministic sort-based scatter; otherwise the float-atomic kernel (like the reference GPU path)."""
+    if self.vec_ok and dim <= 128:
+      self.dops.scatter_grad_rows(pooled_grad, offs, dim, grad_buf, row_offsets, pooling)
+      return
     import ctypes as C
     from . import _lib
     lib = _lib.load()
@@ -79,6 +85,40 @@ class StepContext:
                "recv_row_splits", "names", "row_offsets", "poolings", "occ_splits", "n_rows_total")
 
 
+class _Phases:
+  """Optional per-phase device timing (MONO_TIMING=1): CUDA events around each step of the exchange."""
+
+  def __init__(self, enabled):
+    import os
+    self.enabled = enabled
+    self.marks = []
+    self.acc = {}
+    self.skip = int(os.environ.get("MONO_TIMING_SKIP", "5"))  # warm-up steps left out of the averages
+
+  def mark(self, name):
+    if self.enabled:
+      e = torch.cuda.Event(enable_timing=True)
+      e.record()
+      self.marks.append((name, e))
+
+  def flush(self):
+    if not self.enabled or len(self.marks) < 2:
+      self.marks = []
+      return
+    torch.cuda.synchronize()
+    if self.skip > 0:
+      self.skip -= 1
+      self.marks = []
+      return
+    for (n0, e0), (n1, e1) in zip(self.marks[:-1], self.marks[1:]):
+      t, c = self.acc.get(n1, (0.0, 0))
+      self.acc[n1] = (t + e0.elapsed_time(e1), c + 1)
+    self.marks = []
+
+  def report(self):
+    return {k: round(t / c, 4) for k, (t, c) in self.acc.items()}
+
+
 class PartitionedHashTable:
   """Sharded view over one MultiHashTable per rank (ref: PartitionedHashTable, distributed_ps.py:581-2001)."""
 
@@ -92,6 +132,8 @@ class PartitionedHashTable:
     self.names = tuple(names) if names is not None else tuple(table.table_names)
     self.dims = list(dims) if dims is not None else list(table.get_table_dim_sizes())
     self.K = len(self.names)
+    import os
+    self.phases = _Phases(os.environ.get("MONO_TIMING", "0") == "1" and backend is None)
     self.comm_stream = None
     if torch.cuda.is_available() and backend is None:
       self.comm_stream = torch.cuda.Stream(device=table.device)
@@ -112,24 +154,31 @@ class PartitionedHashTable:
       f = slot_to_fids.get(name)
       lists.append(f.reshape(-1) if f is not None else torch.empty(0, dtype=torch.int64, device=self._dev(slot_to_fids)))
     dev = lists[0].device
+    ph = self.phases
+    ph.mark("start")
     # 1 dedup + bucket by owner
     uniq, shard_sizes, slot_sizes, offs = be.reorder(lists, N, self.dims)
+    ph.mark("f1_reorder")
     # 2 counts
     send_cnt = torch.tensor(slot_sizes, dtype=torch.int64, device=dev)
     recv_cnt = torch.empty_like(send_cnt)
     _a2a(recv_cnt, send_cnt, [K] * N, [K] * N, self.group)
     recv_slot = [int(x) for x in recv_cnt.cpu().tolist()]  # [requester n][table k]: ids I own
     recv_id_splits = [sum(recv_slot[n * K:(n + 1) * K]) for n in range(N)]
+    ph.mark("f2_a2a_counts")
     # 3 FIDs
     recv_ids = torch.empty(sum(recv_id_splits), dtype=torch.int64, device=dev)
     _a2a(recv_ids, uniq, recv_id_splits, shard_sizes, self.group)
+    ph.mark("f3_a2a_ids")
     # 4 owner-side fused lookup (rows laid out requester-major / table-minor)
     rows = be.fused_lookup(recv_ids, recv_slot, N)
+    ph.mark("f4_owner_lookup")
     # 5 rows back
     send_row_splits = self._row_splits(recv_slot)
     recv_row_splits = self._row_splits(slot_sizes)
     recv_rows = torch.empty(sum(recv_row_splits), dtype=torch.float32, device=dev)
     _a2a(recv_rows, rows, recv_row_splits, send_row_splits, self.group)
+    ph.mark("f5_a2a_rows")
     # 6 requester-side gather + pool, table by table (offs covers the occurrences list by list)
     pooled, occ_splits, pos = {}, [], 0
     for k, name in enumerate(self.names):
@@ -140,6 +189,7 @@ class PartitionedHashTable:
         pooled[name] = be.gather_pool(recv_rows, offs[pos:pos + n_occ], self.dims[k], ro, pooling.get(name, "sum"),
                                       None if outs is None else outs.get(name))
       pos += n_occ
+    ph.mark("f6_gather_pool")
     ctx = StepContext()
     ctx.uniq, ctx.shard_sizes, ctx.slot_sizes, ctx.offs = uniq, shard_sizes, slot_sizes, offs
     ctx.recv_ids, ctx.recv_slot = recv_ids, recv_slot
@@ -151,6 +201,8 @@ class PartitionedHashTable:
     """Backward steps 7-9."""
     be, N = self.backend, self.N
     some = next(iter(pooled_grads.values()))
+    ph = self.phases
+    ph.mark("bwd_start")
     # 7 scatter pooled grads to the unique rows, in the layout of the received row buffer
     grad_rows = be.zeros(sum(ctx.recv_row_splits), some)
     for k, name in enumerate(self.names):
@@ -159,11 +211,15 @@ class PartitionedHashTable:
       lo, hi = ctx.occ_splits[k]
       be.gather_pool_grad_into(grad_rows, pooled_grads[name], ctx.offs[lo:hi], self.dims[k], ctx.row_offsets.get(name),
                                ctx.poolings.get(name, "sum"))
+    ph.mark("b7_scatter_grads")
     # 8 grads to the owners (reverse of step 5)
     owner_grads = torch.empty(sum(ctx.send_row_splits), dtype=torch.float32, device=grad_rows.device)
     _a2a(owner_grads, grad_rows, ctx.send_row_splits, ctx.recv_row_splits, self.group)
+    ph.mark("b8_a2a_grads")
     # 9 owner-side fused optimizer (same FID from several requesters: applied in requester order)
     be.fused_apply(ctx.recv_ids, ctx.recv_slot, owner_grads, N, req_time)
+    ph.mark("b9_owner_apply")
+    ph.flush()
 
   @staticmethod
   def _dev(d):
@@ -171,14 +227,59 @@ class PartitionedHashTable:
 
 
 class ShardedStep:
-  """The bench's sparse train step on N GPUs: forward (lookup + pool) and backward through the exchange."""
+  """Sparse train step of ONE table on N GPUs, fast path: the batch is grouped once
+  (distribution_ops.Grouping) and that grouping serves both the forward (dedup + bucket by owner + pooling
+  offsets) and the backward (deterministic per-FID gradient reduction), around the same 3 + 1 all-to-alls
+  as PartitionedHashTable.  Differences from the reference-layout path: the order of the distinct FIDs
+  inside a shard bucket is the engine's, and no float atomics are used."""
 
-  def __init__(self, table, name: str, dim: int, world: int, rank: int, device):
-    self.pht = PartitionedHashTable(table, world, rank)
-    self.name = name
-    self.dim = dim
+  def __init__(self, table, name: str, dim: int, world: int, rank: int, device, group=None):
+    from . import distribution_ops
+    import os
+    self.table, self.name, self.dim, self.N, self.rank, self.group = table, name, dim, world, rank, group
+    self.dops = distribution_ops
+    self.grouping = distribution_ops.Grouping(device)
+    self.k = table.table_names.index(name)
+    self.K = len(table.table_names)
+    self.phases = _Phases(os.environ.get("MONO_TIMING", "0") == "1")
 
-  def step(self, fids: torch.Tensor, pooled_grad: torch.Tensor, out: torch.Tensor, req_time: int):
-    pooled, ctx = self.pht.lookup({self.name: fids}, outs={self.name: out})
-    self.pht.apply_gradients(ctx, {self.name: pooled_grad}, req_time)
-    return ctx.uniq.numel()
+  def _slot(self, per_shard):
+    """per-(shard, table) sizes with only this table populated."""
+    out = [0] * (self.N * self.K)
+    for n in range(self.N):
+      out[n * self.K + self.k] = int(per_shard[n])
+    return out
+
+  def step(self, fids: torch.Tensor, pooled_grad: torch.Tensor, out: torch.Tensor, req_time: int,
+           row_offsets: Optional[torch.Tensor] = None, pooling: str = "sum"):
+    N, D, dev, ph = self.N, self.dim, fids.device, self.phases
+    ph.mark("start")
+    uniq, offs, shard_sizes = self.grouping.build(fids, N, D)                       # 1
+    ph.mark("f1_group")
+    send_cnt = torch.tensor(shard_sizes, dtype=torch.int64, device=dev)               # 2
+    recv_cnt = torch.empty_like(send_cnt)
+    _a2a(recv_cnt, send_cnt, [1] * N, [1] * N, self.group)
+    recv_sizes = [int(x) for x in recv_cnt.cpu().tolist()]
+    ph.mark("f2_a2a_counts")
+    recv_ids = torch.empty(sum(recv_sizes), dtype=torch.int64, device=dev)            # 3
+    _a2a(recv_ids, uniq, recv_sizes, shard_sizes, self.group)
+    ph.mark("f3_a2a_ids")
+    rows = self.table.fused_lookup(recv_ids, self._slot(recv_sizes), N)[0]            # 4
+    ph.mark("f4_owner_lookup")
+    recv_rows = torch.empty(uniq.numel() * D, dtype=torch.float32, device=dev)        # 5
+    _a2a(recv_rows, rows, [s * D for s in shard_sizes], [s * D for s in recv_sizes], self.group)
+    ph.mark("f5_a2a_rows")
+    self.dops.gather_pool(recv_rows, offs, D, row_offsets, pooling, out=out)          # 6
+    ph.mark("f6_gather_pool")
+    grad_rows = torch.empty(uniq.numel() * D, dtype=torch.float32, device=dev)        # 7
+    self.grouping.reduce(pooled_grad, grad_rows, row_offsets, pooling)
+    ph.mark("b7_reduce_grads")
+    owner_grads = torch.empty(sum(recv_sizes) * D, dtype=torch.float32, device=dev)   # 8
+    _a2a(owner_grads, grad_rows, [s * D for s in recv_sizes], [s * D for s in shard_sizes], self.group)
+    ph.mark("b8_a2a_grads")
+    slot = self._slot(recv_sizes)                                                     # 9
+    _, _, id_off, emb_off = self.table.fused_offsets(slot, N)
+    self.table.fused_apply_gradient(recv_ids, recv_ids, slot, owner_grads, id_off, emb_off, 0, req_time, N)
+    ph.mark("b9_owner_apply")
+    ph.flush()
+    return uniq.numel()

@@ -106,6 +106,70 @@ def gather_pool_grad(pooled_grad: torch.Tensor, fused_embedding_offsets: torch.T
   return grad
 
 
+def scatter_grad_rows(pooled_grad: torch.Tensor, fused_embedding_offsets: torch.Tensor, dim: int,
+                      grad_fused: torch.Tensor, row_offsets: Optional[torch.Tensor] = None, pooling: str = "sum",
+                      grad_col: int = 0):
+  """Deterministic (sort-based, atomics-free) scatter of pooled-row grads into the fused row buffer
+  `grad_fused` (written in place; rows nobody refers to are left as they are)."""
+  lib = _lib.load()
+  dev = pooled_grad.device
+  offs = fused_embedding_offsets.to(torch.int32).contiguous()
+  n_rows = offs.numel() if row_offsets is None else row_offsets.numel() - 1
+  if row_offsets is not None:
+    row_offsets = row_offsets.to(torch.int32).contiguous()
+  pool = {"sum": _lib.POOL_SUM, "mean": _lib.POOL_MEAN}[pooling]
+  _lib.check(lib.mono_scatter_grad_rows(dev.index, _ptr(pooled_grad), pooled_grad.stride(0), grad_col, _ptr(offs),
+                                        offs.numel(), _ptr(row_offsets), n_rows, dim, pool, _ptr(grad_fused),
+                                        grad_fused.numel(), _stream(dev)))
+  return grad_fused
+
+
+class Grouping:
+  """One grouping of a batch's FID occurrences, shared by the sharded forward and backward
+  (mono_grouping_*).  build(): dedup + bucket by owner = fid mod num_shards; reduce(): deterministic
+  per-FID sum of pooled-row gradients in the bucketed order."""
+
+  def __init__(self, device):
+    self._lib = _lib.load()
+    self.device = torch.device(device)
+    h = C.c_void_p()
+    _lib.check(self._lib.mono_grouping_create(self.device.index, C.byref(h)))
+    self._h = h
+    self.dim = 0
+
+  def __del__(self):
+    try:
+      if self._h:
+        self._lib.mono_grouping_destroy(self._h)
+        self._h = None
+    except Exception:
+      pass
+
+  def build(self, fids: torch.Tensor, num_shards: int, dim: int):
+    """Returns (unique fids shard-major, occurrence row offsets int32[M], shard_sizes list)."""
+    fids = fids.reshape(-1).contiguous()
+    M = fids.numel()
+    uniq = torch.empty(max(M, 1), dtype=torch.int64, device=self.device)
+    offs = torch.empty(max(M, 1), dtype=torch.int32, device=self.device)
+    counts = (C.c_int32 * num_shards)()
+    n_u = C.c_int64(0)
+    _lib.check(self._lib.mono_grouping_build(self._h, _ptr(fids), M, num_shards, dim, _ptr(uniq), _ptr(offs), counts,
+                                             C.byref(n_u), _stream(self.device)))
+    self.dim = dim
+    self._keep = fids  # the grouping refers to positions of this tensor until the next build
+    return uniq[:n_u.value], offs[:M], list(counts)
+
+  def reduce(self, pooled_grad: torch.Tensor, out_rows: torch.Tensor, row_offsets: Optional[torch.Tensor] = None,
+             pooling: str = "sum", grad_col: int = 0):
+    n_rows = self._keep.numel() if row_offsets is None else row_offsets.numel() - 1
+    if row_offsets is not None:
+      row_offsets = row_offsets.to(torch.int32).contiguous()
+    pool = {"sum": _lib.POOL_SUM, "mean": _lib.POOL_MEAN}[pooling]
+    _lib.check(self._lib.mono_grouping_reduce(self._h, _ptr(pooled_grad), pooled_grad.stride(0), grad_col,
+                                              _ptr(row_offsets), n_rows, pool, _ptr(out_rows), _stream(self.device)))
+    return out_rows
+
+
 # ---- generic fused layout op ------------------------------------------------------------------
 @dataclasses.dataclass
 class SliceTask:

@@ -355,6 +355,62 @@ def test_gather_pool_fwd_bwd(dim, dev):
     np.testing.assert_allclose(gg, orc.gather_pool_grad(pg, eo, dim, U * dim, offs, pooling), rtol=1e-5, atol=1e-6)
   got = dops.gather_pool(T(fused, dev), T(eo, dev), dim).cpu().numpy()  # pure gather (FusedGatherKernel)
   np.testing.assert_array_equal(got, fused.reshape(U, dim)[eo // dim])
+  # rows at offsets that are not multiples of 4 floats (multi-table fused buffer behind a dim-5 table)
+  fused5 = np.concatenate([np.zeros(5, np.float32), fused])
+  got = dops.gather_pool(T(fused5, dev), T(eo + 5, dev), dim, T(offs, dev), "sum").cpu().numpy()
+  np.testing.assert_array_equal(got, orc.gather_pool(fused, eo, dim, offs, "sum"))
+
+
+@pytest.mark.parametrize("dim", [4, 16, 32, 128])
+def test_scatter_grad_rows_deterministic(dim, dev):
+  """Sort-based scatter == oracle ScatterGrad (sequential order) bit for bit on short runs, 2e-3 on hot rows."""
+  from monolith_b200 import distribution_ops as dops
+  rng = np.random.default_rng(dim * 3)
+  U, R = 3000, 40000
+  lens = rng.integers(0, 4, R)
+  offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+  n = int(offs[-1])
+  u_of = rng.integers(0, U, n)
+  u_of[rng.random(n) < 0.2] = 7                      # hot row: thousands of occurrences
+  u_of[:U] = np.arange(U)                            # every row referenced at least once
+  eo = (u_of * dim).astype(np.int32)
+  pg = rng.standard_normal((R, dim)).astype(np.float32)
+  for pooling in ("sum", "mean"):
+    want = orc.gather_pool_grad(pg, eo, dim, U * dim, offs, pooling).reshape(U, dim)
+    buf = torch.full((U * dim,), 123.0, device=dev)
+    got = dops.scatter_grad_rows(T(pg, dev), T(eo, dev), dim, buf, T(offs, dev), pooling).cpu().numpy().reshape(U, dim)
+    cold = np.ones(U, bool)
+    cold[7] = False
+    np.testing.assert_array_equal(got[cold], want[cold])
+    np.testing.assert_allclose(got[7], want[7], rtol=2e-3, atol=2e-3)
+    again = dops.scatter_grad_rows(T(pg, dev), T(eo, dev), dim, torch.zeros(U * dim, device=dev), T(offs, dev), pooling)
+    np.testing.assert_array_equal(again.cpu().numpy().reshape(U, dim), got)  # bit-stable run to run
+
+
+@pytest.mark.parametrize("N", [1, 2, 8])
+def test_owner_grouping_build_reduce(N, dev):
+  from monolith_b200 import distribution_ops as dops
+  rng = np.random.default_rng(N)
+  D, M = 32, 150000
+  fids = _zipfish(rng, M, 40000, 30)
+  fids[::11] = rng.integers(-2**62, 2**62, fids[::11].size)   # arbitrary 64-bit keys too
+  g = dops.Grouping(dev)
+  uniq, offs, sizes = g.build(T(fids, dev), N, D)
+  u, o = uniq.cpu().numpy(), offs.cpu().numpy()
+  assert np.array_equal(np.sort(u), np.unique(fids))                      # exactly the distinct FIDs
+  shard = (u.view(np.uint64) % np.uint64(N)).astype(np.int64)
+  assert np.all(np.diff(shard) >= 0)                                      # shard-major buckets
+  assert sizes == np.bincount(shard, minlength=N).tolist()
+  assert np.array_equal(u[o // D], fids) and np.all(o % D == 0)           # every occurrence points at its FID
+  pg = rng.standard_normal((M, D)).astype(np.float32)
+  out = g.reduce(T(pg, dev), torch.empty(u.size * D, device=dev)).cpu().numpy().reshape(-1, D)
+  want = orc.gather_pool_grad(pg, o, D, u.size * D).reshape(-1, D)        # oracle ScatterGrad in the same layout
+  cnt = np.bincount(o // D, minlength=u.size)
+  cold = cnt <= 64
+  np.testing.assert_array_equal(out[cold], want[cold])
+  np.testing.assert_allclose(out[~cold], want[~cold], rtol=2e-3, atol=2e-3)
+  out2 = g.reduce(T(pg, dev), torch.empty(u.size * D, device=dev)).cpu().numpy().reshape(-1, D)
+  np.testing.assert_array_equal(out, out2)
 
 
 def _layout_case(rng, B, n_emb_lists, with_shared):
