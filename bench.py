@@ -48,6 +48,9 @@ def parse():
   ap.add_argument("--zipf", type=float, default=ZIPF_S, help="Zipf exponent of the FID ranks (0 = uniform)")
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-e2e", action="store_true")
+  ap.add_argument("--sharded", action="store_true", help="run the sharded step (ShardedStep) even at N=1 (profiling)")
+  ap.add_argument("--exchange", default=None, choices=["peer", "nccl"],
+                  help="exchange of the sharded step: NVLink peer windows (default) or NCCL all-to-all")
   return ap.parse_args()
 
 
@@ -213,10 +216,14 @@ def run_reference(args):
 def workload_config(args, batch):
   return {
       "workload": "C2 MovieLens-shaped DSSM sparse step: 1 table dim 32 Adagrad, 10M resident keys, 2 slots/sample, "
-                  "Zipf(1.05) FIDs; step = fused lookup+pool fwd + dedup + grad scatter + fused Adagrad upsert bwd",
+                  "Zipf(1.05) FIDs; step = fused lookup+pool fwd + fused backward (group FIDs, deterministic per-FID grad "
+                  "reduce, Adagrad upsert with expiry bump)" + (
+                      "; sharded: group by owner, FID/row/grad exchange over NVLink peer windows (fused lookup+send, reduce+send)"
+                      if (args.gpus > 1 or getattr(args, "sharded", False)) else ""),
       "zipf_s": args.zipf, "keys": args.keys, "dim": DIM, "slots": SLOTS, "batch_per_gpu": batch, "fids_per_step_per_gpu": batch * SLOTS,
       "l2_hygiene": "inputs larger than L2: 2.6 GB table + 4 rotating batches, 268 MB pooled output per step",
-      "parallelism": f"fid-hash sharding x{args.gpus}" if args.gpus > 1 else "single GPU",
+      "parallelism": (f"fid-hash sharding x{args.gpus}, exchange={getattr(args, 'exchange', None) or os.environ.get('MONO_EXCHANGE', 'peer')}"
+                      if (args.gpus > 1 or getattr(args, "sharded", False)) else "single GPU"),
   }
 
 
@@ -239,7 +246,8 @@ def run_ours(args):
     dist.init_process_group("nccl", device_id=dev)
   lib = _lib.load()
 
-  if world > 1:
+  use_sharded = world > 1 or args.sharded
+  if use_sharded:
     from monolith_b200.distributed_ps import ShardedStep
   keys_per_slot = args.keys // SLOTS
   seg = entry.CombineAsSegment(DIM, entry.RandomUniformInitializer(-0.05, 0.05), entry.AdagradOptimizer(LR, INIT_ACC))
@@ -269,11 +277,11 @@ def run_ours(args):
   pooled = torch.empty(M, DIM, device=dev)
   uniq_counts = []
 
-  if world > 1:
-    sharded = ShardedStep(table, "item", DIM, world, rank, dev)
+  if use_sharded:
+    sharded = ShardedStep(table, "item", DIM, world, rank, dev, exchange=args.exchange)
 
   def step(i, fids, pgrad, out):
-    if world == 1:
+    if not use_sharded:
       table.lookup_pool("item", fids, None, "sum", out=out)
       table.pool_backward("item", fids, pgrad, None, "sum", req_time=1000 + i)
       return 0
@@ -408,9 +416,9 @@ def run_ours(args):
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
+  if use_sharded and rank == 0 and sharded.phases.enabled:
+    print("phase_ms", json.dumps(sharded.phases.report()), file=sys.stderr, flush=True)
   if world > 1:
-    if rank == 0 and sharded.phases.enabled:
-      print("phase_ms", json.dumps(sharded.phases.report()), file=sys.stderr, flush=True)
     dist.destroy_process_group()
 
 

@@ -349,6 +349,43 @@ int mono_embedding_to_layout_grad(int32_t device, float* const* emb_grad_ptrs_de
                                   int32_t n_tasks, const float* const* out_grad_ptrs_dev,
                                   void* stream);
 
+/* ---- NVLink peer window: the exchange steps of the sharded path as peer stores ---------------
+ * ref: the all-to-alls of the reference's synchronous multi-GPU path (distributed_ps_sync.py:92-118
+ * forward ids + embeddings, :531-573 backward gradients).  One window per rank
+ * (device memory, mapped into every peer process of the node through CUDA IPC); the producing kernel
+ * stores its result where the consuming rank reads it, and a flag barrier orders the ranks.
+ * All offsets are relative to the window's data region; `world` values per array, indexed by rank.
+ *   create  : allocates `bytes` of window on `device` (world <= 16).
+ *   handle  : writes this rank's 64-byte IPC handle; the caller all-gathers the handles ...
+ *   attach  : ... and passes all `world` of them (64 bytes each, rank order).
+ *   detach  : unmaps the peers' windows; teardown = detach on every rank, rank barrier, destroy.
+ *   local   : device pointer of this rank's data region (what the peers write into).
+ *   barrier : stream-ordered; returns immediately.  Every rank must call it the same number of times.
+ *   put     : nbytes[r] bytes from src_dev + src_off[r] into rank r's window at region_off + dst_off[r]
+ *             (multiples of 8 bytes).
+ *   lookup_push       : fused lookup + row exchange.  ids_dev = counts[0] ids of rank 0, then counts[1]
+ *             of rank 1, ...; the row of rank r's i-th id is stored into rank r's window at
+ *             region_off + (dst_row_off[r] + i) * dim * 4.  Absent ids give zero rows.  dim % 4 == 0.
+ *   reduce_push       : mono_grouping_reduce whose output rows (owner-bucketed: shard_counts[r] rows for
+ *             rank r, in mono_grouping_build's order) are stored into rank r's window at
+ *             region_off + dst_row_off[r] * dim * 4. */
+typedef struct mono_peer mono_peer_t;
+int mono_peer_create(int32_t device, int32_t world, int32_t rank, int64_t bytes, mono_peer_t** out);
+int mono_peer_destroy(mono_peer_t* p);
+int mono_peer_detach(mono_peer_t* p);
+int mono_peer_handle(mono_peer_t* p, void* handle_out_64);
+int mono_peer_attach(mono_peer_t* p, const void* handles, int32_t n_handles);
+int mono_peer_local(mono_peer_t* p, void** data_dev_out);
+int mono_peer_barrier(mono_peer_t* p, void* stream);
+int mono_peer_put(mono_peer_t* p, int64_t region_off, const int64_t* dst_off, const void* src_dev,
+                  const int64_t* src_off, const int64_t* nbytes, void* stream);
+int mono_mtable_lookup_push(mono_mtable_t* t, int32_t k, const int64_t* ids_dev, const int64_t* counts,
+                            mono_peer_t* p, int64_t region_off, const int64_t* dst_row_off, void* stream);
+int mono_grouping_reduce_push(mono_grouping_t* g, const float* pooled_grad_dev, int64_t grad_stride,
+                              int32_t grad_col, const int32_t* row_offsets_dev, int64_t n_rows,
+                              int32_t pooling, const int64_t* shard_counts, mono_peer_t* p,
+                              int64_t region_off, const int64_t* dst_row_off, void* stream);
+
 /* ---- host-buffer entry points (what a CPU-resident caller such as the reference's TF op shim
  *      would call: ids / grads in host memory, results back in host memory).  These stage through
  *      pinned memory and include the H2D / D2H copies; they return after the result is on the host.

@@ -73,6 +73,16 @@ SIGNATURES = {
     "mono_grouping_destroy": (C.c_int, [_p]),
     "mono_grouping_build": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p, _p, C.POINTER(_i64), _p]),
     "mono_grouping_reduce": (C.c_int, [_p, _p, _i64, _i32, _p, _i64, _i32, _p, _p]),
+    "mono_peer_create": (C.c_int, [_i32, _i32, _i32, _i64, C.POINTER(_p)]),
+    "mono_peer_destroy": (C.c_int, [_p]),
+    "mono_peer_detach": (C.c_int, [_p]),
+    "mono_peer_handle": (C.c_int, [_p, _p]),
+    "mono_peer_attach": (C.c_int, [_p, _p, _i32]),
+    "mono_peer_local": (C.c_int, [_p, C.POINTER(_p)]),
+    "mono_peer_barrier": (C.c_int, [_p, _p]),
+    "mono_peer_put": (C.c_int, [_p, _i64, _p, _p, _p, _p, _p]),
+    "mono_mtable_lookup_push": (C.c_int, [_p, _i32, _p, _p, _p, _i64, _p, _p]),
+    "mono_grouping_reduce_push": (C.c_int, [_p, _p, _i64, _i32, _p, _i64, _i32, _p, _p, _i64, _p, _p]),
     "mono_gather_pool": (C.c_int, [_i32, _p, _p, _p, _i64, _i32, _i32, _p, _i64, _i32, _p]),
     "mono_gather_pool_grad": (C.c_int, [_i32, _p, _i64, _i32, _p, _p, _i64, _i32, _i32, _p, _p]),
     "mono_scatter_grad_rows": (C.c_int, [_i32, _p, _i64, _i32, _p, _i64, _p, _i64, _i32, _i32, _p, _i64, _p]),

@@ -320,6 +320,20 @@ int mono_mtable_fused_optimize(mono_mtable_t* t, const int64_t* ids_dev,
     }
     int n_lr = 0;
     for (auto& tb : t->tables) n_lr += tb.slices;
+    if ((flags & MONO_FLAG_IDS_UNIQUE) && !(flags & MONO_FLAG_DEDUP_SUM) && num_shards > 1) {
+      // ids unique inside every shard: one resolve pass for the whole call, then the shards' rows are
+      // applied in shard order (same result as the loop below, without per-shard launch trains)
+      int64_t n_total = 0;
+      auto segs = fused_segs(t, fused_slot_size_host, num_shards, 0, num_shards, &n_total);
+      if (segs.empty()) return;
+      std::vector<int32_t> ko(num_shards * K + 1), eo(num_shards * K + 1);
+      fused_offsets(t, fused_slot_size_host, num_shards, nullptr, ko.data(), eo.data());
+      std::vector<int64_t> gb(num_shards + 1);
+      for (int s = 0; s <= num_shards; ++s) gb[s] = ko[s * K];
+      run_upsert_groups(t, segs.data(), (int)segs.size(), gb.data(), num_shards, ids_dev, grads_dev,
+                        learning_rate_host, n_lr, req_time, (cudaStream_t)stream);
+      return;
+    }
     // shard by shard = the reference's single-thread order (multi_hash_table_update_op.cc:286-300)
     for (int s = 0; s < num_shards; ++s) {
       int64_t n_total = 0;
@@ -459,6 +473,9 @@ int mono_grouping_destroy(mono_grouping_t* g) {
   cudaDeviceSynchronize();
   g->ws.release();
   if (g->h_counts) cudaFreeHost(g->h_counts);
+  if (g->ev_claimed) cudaEventDestroy(g->ev_claimed);
+  if (g->ev_copied) cudaEventDestroy(g->ev_copied);
+  if (g->side) cudaStreamDestroy(g->side);
   delete g;
   return MONO_OK;
 }
@@ -480,6 +497,89 @@ int mono_grouping_reduce(mono_grouping_t* g, const float* pooled_grad_dev, int64
     require(g && pooled_grad_dev && out_rows_dev, "grouping_reduce: null argument");
     grouping_reduce(g, pooled_grad_dev, grad_stride, grad_col, row_offsets_dev, n_rows, pooling, out_rows_dev,
                     (cudaStream_t)stream);
+  });
+}
+
+int mono_peer_create(int32_t device, int32_t world, int32_t rank, int64_t bytes, mono_peer_t** out) {
+  return guarded([&] {
+    require(out != nullptr && bytes >= 0, "mono_peer_create: bad arguments");
+    *out = peer_create(device, world, rank, (size_t)bytes);
+  });
+}
+
+int mono_peer_destroy(mono_peer_t* p) {
+  return guarded([&] { peer_destroy(p); });
+}
+
+int mono_peer_detach(mono_peer_t* p) {
+  return guarded([&] {
+    require(p != nullptr, "mono_peer_detach: null argument");
+    peer_detach(p);
+  });
+}
+
+int mono_peer_handle(mono_peer_t* p, void* handle_out_64) {
+  return guarded([&] {
+    require(p && handle_out_64, "mono_peer_handle: null argument");
+    peer_handle(p, handle_out_64);
+  });
+}
+
+int mono_peer_attach(mono_peer_t* p, const void* handles, int32_t n_handles) {
+  return guarded([&] {
+    require(p && handles, "mono_peer_attach: null argument");
+    require(n_handles == p->world, "mono_peer_attach: one handle per rank");
+    peer_attach(p, handles);
+  });
+}
+
+int mono_peer_local(mono_peer_t* p, void** data_dev_out) {
+  return guarded([&] {
+    require(p && data_dev_out, "mono_peer_local: null argument");
+    *data_dev_out = p->local + kPeerFlagBytes;
+  });
+}
+
+int mono_peer_barrier(mono_peer_t* p, void* stream) {
+  return guarded([&] {
+    require(p != nullptr, "mono_peer_barrier: null argument");
+    peer_barrier(p, (cudaStream_t)stream);
+  });
+}
+
+int mono_peer_put(mono_peer_t* p, int64_t region_off, const int64_t* dst_off, const void* src_dev,
+                  const int64_t* src_off, const int64_t* nbytes, void* stream) {
+  return guarded([&] {
+    require(p && dst_off && src_dev && src_off && nbytes, "mono_peer_put: null argument");
+    peer_put(p, region_off, dst_off, src_dev, src_off, nbytes, (cudaStream_t)stream);
+  });
+}
+
+int mono_mtable_lookup_push(mono_mtable_t* t, int32_t k, const int64_t* ids_dev, const int64_t* counts,
+                            mono_peer_t* p, int64_t region_off, const int64_t* dst_row_off, void* stream) {
+  return guarded([&] {
+    require(t && counts && p && dst_row_off, "mono_mtable_lookup_push: null argument");
+    require(k >= 0 && k < (int)t->tables.size(), "mono_mtable_lookup_push: bad table index");
+    require(p->device == t->device, "mono_mtable_lookup_push: window and table on different devices");
+    use_device(t);
+    const int D = t->tables[k].dim;
+    PeerOut po = peer_out(p, region_off, dst_row_off, counts, (int64_t)D * 4);
+    const int64_t n = po.start[po.n];
+    require(n == 0 || ids_dev != nullptr, "mono_mtable_lookup_push: null ids");
+    launch_lookup_push(t, k, ids_dev, n, po, (cudaStream_t)stream);
+  });
+}
+
+int mono_grouping_reduce_push(mono_grouping_t* g, const float* pooled_grad_dev, int64_t grad_stride,
+                              int32_t grad_col, const int32_t* row_offsets_dev, int64_t n_rows,
+                              int32_t pooling, const int64_t* shard_counts, mono_peer_t* p,
+                              int64_t region_off, const int64_t* dst_row_off, void* stream) {
+  return guarded([&] {
+    require(g && pooled_grad_dev && shard_counts && p && dst_row_off, "grouping_reduce_push: null argument");
+    require(p->device == g->device, "grouping_reduce_push: window and grouping on different devices");
+    PeerOut po = peer_out(p, region_off, dst_row_off, shard_counts, (int64_t)g->dim * 4);
+    grouping_reduce_push(g, pooled_grad_dev, grad_stride, grad_col, row_offsets_dev, n_rows, pooling, po,
+                         (cudaStream_t)stream);
   });
 }
 

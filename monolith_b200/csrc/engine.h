@@ -161,14 +161,62 @@ struct mono_grouping {
   const uint32_t* perm = nullptr;
   uint32_t* run_start = nullptr;
   uint32_t* run_first_pos = nullptr;
-  uint32_t* ord_of_run = nullptr;
   uint32_t* ctr = nullptr;
   char* tail = nullptr;      // scratch for reduce()
   size_t tail_bytes = 0;
-  uint32_t* h_counts = nullptr;  // pinned
+  uint32_t* h_counts = nullptr;  // pinned: per-owner distinct counts [256] + overflow flag
+  cudaStream_t side = nullptr;   // carries the early counts copy while the sort runs on the caller's stream
+  cudaEvent_t ev_claimed = nullptr, ev_copied = nullptr;
+};
+
+// ---- NVLink peer window (peer.cu) ----------------------------------------------------------------
+namespace mono {
+constexpr int kMaxPeers = 16;
+constexpr size_t kPeerFlagBytes = 4096;  // head of every window: arrival flags written by the peers
+
+// By-value kernel argument of the push kernels: item i of a list partitioned into `n` consecutive
+// parts goes to base[r] + (i - start[r]) * item_bytes, r = the part holding i.  base[r] points into
+// rank r's window (a peer mapping of it), already offset to where this rank's items begin there.
+struct PeerOut {
+  char* base[kMaxPeers];
+  int64_t start[kMaxPeers + 1];
+  int n;
+};
+__device__ __forceinline__ int peer_part(const PeerOut& po, int64_t i) {
+  int r = 0;
+#pragma unroll
+  for (int q = 1; q < kMaxPeers; ++q)
+    if (q < po.n && i >= po.start[q]) r = q;
+  return r;
+}
+}  // namespace mono
+
+struct mono_peer {
+  int device = 0, world = 1, rank = 0;
+  size_t bytes = 0;                      // data bytes of every rank's window (after the flag page)
+  char* local = nullptr;                 // this rank's window (cudaMalloc: flag page + data)
+  char* base[mono::kMaxPeers] = {};      // base[r]: rank r's window as mapped into this process
+  bool attached = false;
+  uint64_t seq = 0;                      // barrier sequence number (same on every rank)
 };
 
 namespace mono {
+
+mono_peer* peer_create(int device, int world, int rank, size_t bytes);
+void peer_destroy(mono_peer* p);
+void peer_detach(mono_peer* p);
+void peer_handle(mono_peer* p, void* out64);
+void peer_attach(mono_peer* p, const void* handles);
+void peer_barrier(mono_peer* p, cudaStream_t s);
+void peer_put(mono_peer* p, int64_t region_off, const int64_t* dst_off, const void* src,
+              const int64_t* src_off, const int64_t* nbytes, cudaStream_t s);
+PeerOut peer_out(mono_peer* p, int64_t region_off, const int64_t* dst_item_off, const int64_t* counts,
+                 int64_t item_bytes);
+void launch_lookup_push(mono_mtable* mt, int k, const int64_t* ids_dev, int64_t n_total, const PeerOut& po,
+                        cudaStream_t s);
+void grouping_reduce_push(mono_grouping* g, const float* pooled_grad, int64_t grad_stride, int grad_col,
+                          const int32_t* row_offsets, int64_t n_rows, int pooling, const PeerOut& po,
+                          cudaStream_t s);
 
 void grouping_build(mono_grouping* g, const int64_t* fids_dev, int64_t M, int N, int dim,
                     int64_t* uniq_out, int32_t* occ_offset_out, int32_t* shard_counts_host,
@@ -204,6 +252,11 @@ void run_upsert(mono_mtable* mt, UpsertOp op, const CallSeg* h_segs, int nsegs,
                 const int64_t* ids_dev, int64_t n_total, const float* vals_dev,
                 const float* lr_host, int n_lr, int64_t update_time, bool unique, bool dedup_sum,
                 int32_t* status_dev, cudaStream_t s);
+
+// optimize over `ngroups` groups of segments; ids unique inside a group, groups applied in order
+void run_upsert_groups(mono_mtable* mt, const CallSeg* h_segs, int nsegs, const int64_t* group_begin,
+                       int ngroups, const int64_t* ids_dev, const float* vals_dev, const float* lr_host,
+                       int n_lr, int64_t update_time, cudaStream_t s);
 
 void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t n_fids,
                        const int32_t* row_offsets, int64_t n_rows, int pooling,

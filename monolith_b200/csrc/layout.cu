@@ -70,6 +70,45 @@ gather_pool_kernel(const float* __restrict__ fused, const int32_t* __restrict__ 
   }
 }
 
+// One occurrence per output row (row_offsets == NULL: FusedGatherKernel proper) with 16-byte aligned rows:
+// the same two-phase shape as the table lookup (ops.cu lookup_kernel): a lane fetches one offset
+// (32 coalesced, independent loads per warp), then G lanes move one row with 128-bit accesses, 4 rows in
+// flight per lane before the first store.  Pooling over a single row is the identity for SUM and MEAN.
+template <int G>
+__global__ void __launch_bounds__(kThreads, 4)
+gather_rows_kernel(const float* __restrict__ fused, const int32_t* __restrict__ emb_offset, int64_t n_rows,
+                   int dim, float* __restrict__ out, int64_t out_stride, int out_col) {
+  constexpr int RPI = 32 / G, ITERS = G, UNR = 4;
+  const int lane = threadIdx.x & 31, gl = Group<G>::gl(), grp = lane / G;
+  const int c = gl * 4;
+  const int64_t wstride = (int64_t)gridDim.x * (kThreads / 32) * 32;
+  for (int64_t wbase = ((int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * 32; wbase < n_rows;
+       wbase += wstride) {
+    const int64_t i = wbase + lane;
+    const int32_t off = i < n_rows ? __ldg(emb_offset + i) : 0;
+#pragma unroll
+    for (int it0 = 0; it0 < ITERS; it0 += UNR) {
+      float4 x[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int32_t o = __shfl_sync(0xffffffffu, off, (it0 + u) * RPI + grp);
+        x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (wbase + (it0 + u) * RPI + grp < n_rows && c < dim) {
+          const float* src = fused + o + c;
+          // rows of a multi-table fused buffer may start at any float offset
+          x[u] = (o & 3) == 0 ? __ldg(reinterpret_cast<const float4*>(src))
+                              : make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(src + 3));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int64_t ir = wbase + (it0 + u) * RPI + grp;
+        if (ir < n_rows && c < dim) __stcs(reinterpret_cast<float4*>(out + ir * out_stride + out_col + c), x[u]);
+      }
+    }
+  }
+}
+
 // grad_fused[offset[m] : +dim] += g_row   (float atomics: several occurrences may share a row,
 // exactly like the reference's FusedGatherGradKernel atomicAdd, map_id_to_embedding.cu.cc:75-118)
 template <int G>
@@ -105,6 +144,15 @@ void launch_gather_pool(const float* fused_emb, const int32_t* emb_offset, const
   if (n_rows <= 0) return;
   if (pooling != MONO_POOL_SUM && pooling != MONO_POOL_MEAN) throw ArgError("gather_pool: SUM or MEAN");
   const int G = pick_group(dim);
+  if (row_offsets == nullptr && (dim & 3) == 0 && dim <= 4 * G && (out_stride & 3) == 0 && (out_col & 3) == 0 &&
+      ((reinterpret_cast<uintptr_t>(fused_emb) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+#define GR(GG) gather_rows_kernel<GG><<<resident_grid(gather_rows_kernel<GG>, n_rows, kThreads), kThreads, 0, s>>>( \
+      fused_emb, emb_offset, n_rows, dim, out, out_stride, out_col)
+    switch (G) { case 4: GR(4); break; case 8: GR(8); break; case 16: GR(16); break; default: GR(32); }
+#undef GR
+    MONO_CHECK_LAUNCH();
+    return;
+  }
   const int grid = grid_for(n_rows, kThreads / G);
 #define GP(GG) gather_pool_kernel<GG><<<grid, kThreads, 0, s>>>(fused_emb, emb_offset, row_offsets, n_rows, dim, pooling, out, out_stride, out_col)
   switch (G) { case 4: GP(4); break; case 8: GP(8); break; case 16: GP(16); break; default: GP(32); }

@@ -410,6 +410,58 @@ lookup_kernel(const TableDev* __restrict__ tables, const CallSeg* __restrict__ s
   }
 }
 
+// Owner lookup fused with the row exchange of the sharded forward (replaces FusedLookup + the
+// embedding all-to-all, ref: distributed_ps_sync.py:100-118): ids[] is the concatenation of the FID
+// buckets the requesters stored into this rank's window; the row of id i is written straight into the
+// window of the requester that asked for it (one 128-bit NVLink store per lane, a whole row per group).
+// Same two phases as lookup_kernel<G, true>.
+template <int G>
+__global__ void __launch_bounds__(kThreads, 6)
+lookup_push_kernel(const TableDev* __restrict__ t0, const int64_t* __restrict__ ids, int64_t n_total,
+                   const PeerOut po) {
+  constexpr int RPI = 32 / G;
+  constexpr int ITERS = G;
+  constexpr int UNR = 4;
+  const int lane = threadIdx.x & 31, gl = Group<G>::gl(), grp = lane / G;
+  const int c = gl * 4;
+  const int D0 = t0->dim;
+  const float* __restrict__ emb0 = t0->emb;
+  const uint32_t stride0 = t0->emb_stride;
+  const int64_t wstride = (int64_t)gridDim.x * (kThreads / 32) * 32;
+  for (int64_t wbase = ((int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * 32;
+       wbase < n_total; wbase += wstride) {
+    const int64_t i = wbase + lane;
+    uint32_t row = kEmptyRow;
+    if (i < n_total) row = probe_lane(t0, __ldg(ids + i));
+#pragma unroll
+    for (int it0 = 0; it0 < ITERS; it0 += UNR) {
+      float4 x[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const uint32_t r = __shfl_sync(0xffffffffu, row, (it0 + u) * RPI + grp);
+        x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r != kEmptyRow && c < D0)
+          x[u] = __ldg(reinterpret_cast<const float4*>(emb0 + (size_t)r * stride0 + c));
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int src_lane = (it0 + u) * RPI + grp;
+        const int64_t ir = wbase + src_lane;
+        const uint32_t r_st = __shfl_sync(0xffffffffu, row, src_lane);
+        if (ir >= n_total) continue;
+        const int pr = peer_part(po, ir);
+        float* dst = reinterpret_cast<float*>(po.base[pr]) + (ir - po.start[pr]) * D0;
+        if (c < D0) *reinterpret_cast<float4*>(dst + c) = x[u];
+        for (int cc = c + 4 * G; cc < D0; cc += 4 * G) {  // wide rows (dim > 128)
+          float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r_st != kEmptyRow) y = __ldg(reinterpret_cast<const float4*>(emb0 + (size_t)r_st * stride0 + cc));
+          *reinterpret_cast<float4*>(dst + cc) = y;
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads)
 contains_kernel(const TableDev* __restrict__ t, const int64_t* __restrict__ ids, int64_t n,
                 uint8_t* __restrict__ out) {
@@ -578,6 +630,7 @@ struct UpsertArgs {
   uint32_t* miss_list;       // item indices j that missed
   uint32_t* rowidx;          // per item j: resolved row (bit 31 = freshly inserted)
   int32_t* status;           // reinitialize only
+  int64_t pos0 = 0;          // apply pass without idx_list: item j is position pos0 + j
 };
 constexpr uint32_t kFreshBit = 0x80000000u;
 
@@ -711,7 +764,7 @@ __global__ void __launch_bounds__(kThreads) upsert_apply_kernel(UpsertArgs a) {
   for (int64_t j = (int64_t)blockIdx.x * (kThreads / G) + threadIdx.x / G; j < n; j += gstride) {
     const uint32_t ri = a.rowidx[j];
     if (ri == kEmptyRow) continue;  // row slab overflow was flagged
-    const int64_t i = a.idx_list ? (int64_t)a.idx_list[j] : j;
+    const int64_t i = a.idx_list ? (int64_t)a.idx_list[j] : j + a.pos0;
     const CallSeg sg = a.segs[a.nsegs > 1 ? find_seg(a.segs, a.nsegs, i) : 0];
     const TableDev* t = a.tables + sg.table;
     const bool fresh = (ri & kFreshBit) != 0;
@@ -742,7 +795,8 @@ __device__ __forceinline__ bool cas_set(SetEntry* addr, const SetEntry& val) {
 __global__ void __launch_bounds__(kThreads)
 dup_claim_kernel(const CallSeg* __restrict__ segs, int nsegs, const int64_t* __restrict__ ids,
                  const uint32_t* __restrict__ pending, int64_t n, SetEntry* set, uint32_t mask,
-                 uint32_t* __restrict__ slot_of) {
+                 uint32_t* __restrict__ slot_of, const uint32_t* __restrict__ n_dev = nullptr) {
+  if (n_dev) n = (int64_t)*n_dev;
   for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n;
        j += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = pending ? (int64_t)pending[j] : j;
@@ -782,6 +836,38 @@ dup_split_kernel(const uint32_t* __restrict__ pending, int64_t n, const SetEntry
     if (leader_of) leader_of[i] = (uint32_t)fp;
     if ((uint32_t)fp == i) leaders[atomicAdd(ctr, 1u)] = i;
     else rest[atomicAdd(ctr + 1, 1u)] = i;
+  }
+}
+
+// Misses of a call whose segments are each duplicate-free but may share FIDs with one another (the
+// owner side of the sharded backward: one segment per requesting rank).  The lowest position of a
+// missing FID inserts it (leaders -> resolve_miss_kernel); the others take the leader's row, not fresh.
+__global__ void __launch_bounds__(kThreads)
+miss_split_kernel(const uint32_t* __restrict__ miss_list, const uint32_t* __restrict__ n_miss,
+                  const SetEntry* __restrict__ set, const uint32_t* __restrict__ slot_of,
+                  uint32_t* __restrict__ leaders, uint32_t* __restrict__ followers,
+                  uint32_t* __restrict__ fol_leader, uint32_t* ctr /*[1] = leaders, [2] = followers*/) {
+  const int64_t n = *n_miss;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t i = miss_list[q];
+    const uint32_t fp = (uint32_t)set[slot_of[q]].first_pos;
+    if (fp == i) {
+      leaders[atomicAdd(ctr + 1, 1u)] = i;
+    } else {
+      const uint32_t k = atomicAdd(ctr + 2, 1u);
+      followers[k] = i;
+      fol_leader[k] = fp;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+miss_follow_kernel(const uint32_t* __restrict__ followers, const uint32_t* __restrict__ fol_leader,
+                   const uint32_t* __restrict__ n_fol, uint32_t* __restrict__ rowidx) {
+  const int64_t n = *n_fol;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t r = rowidx[fol_leader[k]];
+    rowidx[followers[k]] = r == kEmptyRow ? r : (r & ~kFreshBit);
   }
 }
 
@@ -900,6 +986,27 @@ void launch_lookup(mono_mtable* mt, const CallSeg* h_segs, int nsegs, const int6
   CallBlob cb = stage_call(mt, h_segs, nsegs, nullptr, 0, s);
   launch_lookup_staged(mt, cb.segs, nsegs, pick_group(max_dim_of(mt, h_segs, nsegs)), ids_dev, n_total,
                        out_dev, 0, 0, s);
+}
+
+void launch_lookup_push(mono_mtable* mt, int k, const int64_t* ids_dev, int64_t n_total, const PeerOut& po,
+                        cudaStream_t s) {
+  if (n_total <= 0) return;
+  const int D = mt->tables[k].dim;
+  if (D & 3) throw ArgError("lookup_push needs dim % 4 == 0 (16-byte peer stores)");
+  if (po.start[po.n] != n_total) throw ArgError("lookup_push: counts do not add up to the id count");
+  upload_tables(mt, s);
+  const TableDev* t = mt->d_tables + k;
+#define LPUSH(GG)                                                                                           \
+  lookup_push_kernel<GG><<<resident_grid(lookup_push_kernel<GG>, n_total, kThreads), kThreads, 0, s>>>(t, ids_dev, \
+                                                                                                       n_total, po)
+  switch (pick_group(D)) {
+    case 4: LPUSH(4); break;
+    case 8: LPUSH(8); break;
+    case 16: LPUSH(16); break;
+    default: LPUSH(32); break;
+  }
+#undef LPUSH
+  MONO_CHECK_LAUNCH();
 }
 
 void launch_lookup_pool(mono_mtable* mt, int k, const int64_t* fids_dev, const int32_t* row_offsets,
@@ -1147,6 +1254,101 @@ void run_upsert(mono_mtable* mt, UpsertOp op, const CallSeg* h_segs, int nsegs,
   }
 }
 
+
+// Optimize over several groups of segments (the shards of a fused call) where the ids are unique inside
+// a group but a FID may appear once per group: group g is applied after group g-1 (the reference's
+// shard-by-shard order, multi_hash_table_update_op.cc:286-300).  One resolve pass serves all groups and
+// nothing returns to the host; only the apply pass runs once per group.
+void run_upsert_groups(mono_mtable* mt, const CallSeg* h_segs, int nsegs, const int64_t* group_begin,
+                       int ngroups, const int64_t* ids_dev, const float* vals_dev, const float* lr_host,
+                       int n_lr, int64_t update_time, cudaStream_t s) {
+  if (nsegs <= 0 || ngroups <= 0) return;
+  const int64_t n_total = h_segs[nsegs - 1].id_end;
+  if (n_total <= 0) return;
+  if (h_segs[0].id_begin != 0) throw ArgError("grouped optimize: segments must start at id 0");
+  for (int i = 1; i < nsegs; ++i)
+    if (h_segs[i].id_begin != h_segs[i - 1].id_end) throw ArgError("call segments must be contiguous");
+  if (n_total >= (int64_t)1 << 31) throw ArgError("more than 2^31 ids in one call");
+  std::vector<uint64_t> per_table(mt->tables.size(), 0);
+  for (int i = 0; i < nsegs; ++i)
+    per_table[h_segs[i].table] += (uint64_t)(h_segs[i].id_end - h_segs[i].id_begin);
+  for (size_t k = 0; k < per_table.size(); ++k)
+    if (per_table[k]) ensure_capacity(mt, (int)k, per_table[k], s);
+  upload_tables(mt, s);
+  CallBlob cb = stage_call(mt, h_segs, nsegs, lr_host, n_lr, s);
+  const int G = pick_group(max_dim_of(mt, h_segs, nsegs));
+
+  uint32_t cap = 1024;
+  while (cap < 2 * (uint64_t)n_total) cap <<= 1;
+  // scratch: [ctr 64 B | miss_list | rowidx | leaders | followers | fol_leader | slot_of] u32[n_total] each
+  char* ws = (char*)mt->ws_miss.get(64 + 6 * sizeof(uint32_t) * (size_t)n_total, s);
+  uint32_t* ctr = reinterpret_cast<uint32_t*>(ws);  // [0] misses [1] leaders [2] followers
+  uint32_t* miss_list = reinterpret_cast<uint32_t*>(ws + 64);
+  uint32_t* rowidx = miss_list + n_total;
+  uint32_t* leaders = rowidx + n_total;
+  uint32_t* followers = leaders + n_total;
+  uint32_t* fol_leader = followers + n_total;
+  uint32_t* slot_of = fol_leader + n_total;
+  SetEntry* set = (SetEntry*)mt->ws_a.get(sizeof(SetEntry) * (size_t)cap, s);
+  MONO_CUDA(cudaMemsetAsync(ctr, 0, 64, s));
+  MONO_CUDA(cudaMemsetAsync(set, 0xFF, sizeof(SetEntry) * (size_t)cap, s));
+
+  UpsertArgs a;
+  a.tables = mt->d_tables;
+  a.segs = cb.segs;
+  a.nsegs = nsegs;
+  a.ids = ids_dev;
+  a.idx_list = nullptr;
+  a.n = n_total;
+  a.n_dev = nullptr;
+  a.vals = vals_dev;
+  a.lr = cb.lr;
+  a.update_ts = (uint32_t)update_time;
+  a.miss_ctr = ctr;
+  a.miss_list = miss_list;
+  a.rowidx = rowidx;
+  a.status = nullptr;
+  resolve_hit_kernel<false><<<resident_grid(resolve_hit_kernel<false>, n_total, kThreads), kThreads, 0, s>>>(a);
+  MONO_CHECK_LAUNCH();
+  // misses are few in steady state: small grids, counts stay on the device
+  const int gm = (int)std::min<int64_t>(148 * 2, (n_total + kThreads - 1) / kThreads);
+  dup_claim_kernel<<<gm, kThreads, 0, s>>>(cb.segs, nsegs, ids_dev, miss_list, 0, set, cap - 1, slot_of, ctr);
+  MONO_CHECK_LAUNCH();
+  miss_split_kernel<<<gm, kThreads, 0, s>>>(miss_list, ctr, set, slot_of, leaders, followers, fol_leader, ctr);
+  MONO_CHECK_LAUNCH();
+  UpsertArgs am = a;
+  am.miss_list = leaders;
+  am.miss_ctr = ctr + 1;
+  resolve_miss_kernel<false><<<gm, kThreads, 0, s>>>(am);
+  MONO_CHECK_LAUNCH();
+  miss_follow_kernel<<<gm, kThreads, 0, s>>>(followers, fol_leader, ctr + 2, rowidx);
+  MONO_CHECK_LAUNCH();
+  upsert_finalize_kernel<<<(cb.ntab + 63) / 64, 64, 0, s>>>(mt->d_tables, cb.table_ids, cb.ntab, ctr,
+                                                           (uint32_t)update_time);
+  MONO_CHECK_LAUNCH();
+  for (int g = 0; g < ngroups; ++g) {
+    const int64_t b = group_begin[g], e = group_begin[g + 1];
+    if (e <= b) continue;
+    UpsertArgs ag = a;
+    ag.pos0 = b;
+    ag.n = e - b;
+    ag.rowidx = rowidx + b;
+    switch (G) {
+      case 4: upsert_apply_kernel<4, kOpOptimize><<<resident_grid(upsert_apply_kernel<4, kOpOptimize>, ag.n, kThreads / 4), kThreads, 0, s>>>(ag); break;
+      case 8: upsert_apply_kernel<8, kOpOptimize><<<resident_grid(upsert_apply_kernel<8, kOpOptimize>, ag.n, kThreads / 8), kThreads, 0, s>>>(ag); break;
+      case 16: upsert_apply_kernel<16, kOpOptimize><<<resident_grid(upsert_apply_kernel<16, kOpOptimize>, ag.n, kThreads / 16), kThreads, 0, s>>>(ag); break;
+      default: upsert_apply_kernel<32, kOpOptimize><<<resident_grid(upsert_apply_kernel<32, kOpOptimize>, ag.n, kThreads / 32), kThreads, 0, s>>>(ag); break;
+    }
+    MONO_CHECK_LAUNCH();
+  }
+  for (size_t k = 0; k < per_table.size(); ++k) {
+    if (!per_table[k]) continue;
+    HostTable& t = mt->tables[k];
+    t.issued_total += per_table[k];
+    t.max_update_ts = std::max<int64_t>(t.max_update_ts, update_time);
+    request_snapshot(mt, (int)k, s);
+  }
+}
 
 // ==========================================================================================
 // Fused backward: pooled-grad scatter + sparse optimizer + expiry bump, deterministic, no float
@@ -1566,8 +1768,16 @@ __device__ __forceinline__ float4 sum_grad_rows(const GradSrc& gs, uint32_t s, u
 // Reduce: group per run, short runs are summed (in position order) into ugrad[j]; long runs are
 // queued.  No table access here: few registers, 8 resident blocks per SM, every gradient-row read is
 // independent of the others in flight.  Runs are ordered, so ugrad is written sequentially.
+// destination of run j's summed row: ugrad[j], or (po.n != 0: the sharded backward's fused gradient
+// exchange) row j of an owner-bucketed list whose part r lives in rank r's peer window.
+__device__ __forceinline__ float* run_dst(float* ugrad, const PeerOut& po, int64_t j, int D) {
+  if (po.n == 0) return ugrad + (size_t)j * D;
+  const int r = peer_part(po, j);
+  return reinterpret_cast<float*>(po.base[r]) + (j - po.start[r]) * D;
+}
+
 template <int G>
-__global__ void __launch_bounds__(kThreads, 6) run_sum_kernel(BwdArgs a) {
+__global__ void __launch_bounds__(kThreads, 6) run_sum_kernel(BwdArgs a, const PeerOut po) {
   const int gl = Group<G>::gl();
   const int c = gl * 4;
   const int64_t nr = *a.n_runs;
@@ -1575,7 +1785,7 @@ __global__ void __launch_bounds__(kThreads, 6) run_sum_kernel(BwdArgs a) {
   const bool in = c < D;
   const GradSrc gs = make_grad_src(a, c);
   const uint32_t* __restrict__ run_start = a.run_start;
-  float* __restrict__ ugrad = a.ugrad + c;
+  float* __restrict__ ugrad = a.ugrad;
   const int64_t gstride = (int64_t)gridDim.x * (kThreads / G);
   for (int64_t j = (int64_t)blockIdx.x * (kThreads / G) + threadIdx.x / G; j < nr; j += gstride) {
     const uint32_t s = run_start[j];
@@ -1585,7 +1795,7 @@ __global__ void __launch_bounds__(kThreads, 6) run_sum_kernel(BwdArgs a) {
       continue;
     }
     const float4 acc = sum_grad_rows<G, 4>(gs, s, len, in);
-    if (in) *reinterpret_cast<float4*>(ugrad + (size_t)j * D) = acc;
+    if (in) *reinterpret_cast<float4*>(run_dst(ugrad, po, j, D) + c) = acc;
   }
 }
 
@@ -1688,7 +1898,7 @@ __global__ void __launch_bounds__(kThreads, 6) pool_bwd_long_partial_kernel(BwdA
 
 // group per long run: combine its pieces in order into ugrad[j]
 template <int G>
-__global__ void __launch_bounds__(kThreads) pool_bwd_long_final_kernel(BwdArgs a) {
+__global__ void __launch_bounds__(kThreads) pool_bwd_long_final_kernel(BwdArgs a, const PeerOut po) {
   const int gl = Group<G>::gl(), c = gl * 4;
   const uint32_t nl = *a.n_long;
   const int D = a.td.dim;
@@ -1710,7 +1920,7 @@ __global__ void __launch_bounds__(kThreads) pool_bwd_long_final_kernel(BwdArgs a
         if (w0 + u == b) acc = p[u]; else add4(acc, p[u]);
       }
     }
-    if (c < D) *reinterpret_cast<float4*>(a.ugrad + (size_t)j * D + c) = acc;
+    if (c < D) *reinterpret_cast<float4*>(run_dst(a.ugrad, po, j, D) + c) = acc;
   }
 }
 
@@ -1758,6 +1968,8 @@ static void sort_and_runs(const SortWs& w, int64_t M, int bits, int pre_shift, c
   *skeys_out = kin;
   *perm_out = vin;
 }
+
+static const PeerOut no_peer = {};  // n == 0: the reduce kernels write their local ugrad buffer
 
 void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t n_fids,
                        const int32_t* row_offsets, int64_t n_rows, int pooling,
@@ -1890,14 +2102,14 @@ void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t 
     a.occ_row = occ;
   }
 #define BWD2(GG, OO)                                                                                             \
-  run_sum_kernel<GG><<<resident_grid(run_sum_kernel<GG>, M, kThreads / GG), kThreads, 0, s>>>(a);                \
+  run_sum_kernel<GG><<<resident_grid(run_sum_kernel<GG>, M, kThreads / GG), kThreads, 0, s>>>(a, no_peer);       \
   MONO_CHECK_LAUNCH();                                                                                           \
   long_prep_kernel<<<1, 1024, 0, s>>>(a);                                                                        \
   MONO_CHECK_LAUNCH();                                                                                           \
   pool_bwd_long_partial_kernel<GG>                                                                               \
       <<<resident_grid(pool_bwd_long_partial_kernel<GG>, (int64_t)max_pieces, 1), kThreads, 0, s>>>(a);          \
   MONO_CHECK_LAUNCH();                                                                                           \
-  pool_bwd_long_final_kernel<GG><<<148 * 2, kThreads, 0, s>>>(a);                                                \
+  pool_bwd_long_final_kernel<GG><<<148 * 2, kThreads, 0, s>>>(a, no_peer);                                       \
   MONO_CHECK_LAUNCH();                                                                                           \
   runs_apply_kernel<GG, OO><<<resident_grid(runs_apply_kernel<GG, OO>, M, kThreads / GG), kThreads, 0, s>>>(a);  \
   MONO_CHECK_LAUNCH()
@@ -2028,14 +2240,14 @@ void run_scatter_rows(int device, const int32_t* offs_dev, int64_t M, int dim, c
   }
   const int G = pick_group(D);
 #define EMIT(GG)                                                                                              \
-  run_sum_kernel<GG><<<resident_grid(run_sum_kernel<GG>, M, kThreads / GG), kThreads, 0, s>>>(a);             \
+  run_sum_kernel<GG><<<resident_grid(run_sum_kernel<GG>, M, kThreads / GG), kThreads, 0, s>>>(a, no_peer);    \
   MONO_CHECK_LAUNCH();                                                                                        \
   long_prep_kernel<<<1, 1024, 0, s>>>(a);                                                                     \
   MONO_CHECK_LAUNCH();                                                                                        \
   pool_bwd_long_partial_kernel<GG>                                                                            \
       <<<resident_grid(pool_bwd_long_partial_kernel<GG>, (int64_t)max_pieces, 1), kThreads, 0, s>>>(a);       \
   MONO_CHECK_LAUNCH();                                                                                        \
-  pool_bwd_long_final_kernel<GG><<<148 * 2, kThreads, 0, s>>>(a);                                             \
+  pool_bwd_long_final_kernel<GG><<<148 * 2, kThreads, 0, s>>>(a, no_peer);                                    \
   MONO_CHECK_LAUNCH();                                                                                        \
   runs_emit_kernel<GG><<<resident_grid(runs_emit_kernel<GG>, M, kThreads / GG), kThreads, 0, s>>>(a, skeys, shift, out_rows); \
   MONO_CHECK_LAUNCH()
@@ -2052,76 +2264,73 @@ void run_scatter_rows(int device, const int32_t* offs_dev, int64_t M, int dim, c
 
 // ==========================================================================================
 // Owner grouping: ONE grouping of a batch's FID occurrences shared by the forward (dedup + bucket by
-// owner for the all-to-all) and the backward (deterministic per-FID gradient reduction) of the sharded
+// owner for the exchange) and the backward (deterministic per-FID gradient reduction) of the sharded
 // step.  Functionally FusedReorderByIndices (ref: fused_reorder_by_indices.cc:38-123) for a single id
 // list, except that the order of the distinct FIDs inside a shard is the engine's (scratch-set slot
 // order), not first-occurrence order; mono_reorder_by_indices is the bit-exact op.
+//
+// The scratch set is split into N regions of R slots and a FID lives in region owner(fid) = fid mod N
+// (linear probing wraps inside the region).  Sorting the occurrences by slot therefore yields the runs
+// (one per distinct FID) already bucketed by owner: no separate partition pass, and a run's index IS its
+// position in the bucketed unique list.  The per-owner distinct counts fall out of the claim kernel (one
+// count per successful insert), i.e. after the FIRST kernel: they are copied to the host on a side
+// stream while the sort still runs, so the host can size and enqueue the exchange without idling the GPU.
 // ==========================================================================================
 __global__ void __launch_bounds__(kThreads)
-fid_claim_kernel(const int64_t* __restrict__ fids, int64_t n, SetEntry* set, uint32_t mask,
-                 uint32_t* __restrict__ slot_of) {
+fid_claim_kernel(const int64_t* __restrict__ fids, int64_t n, SetEntry* set, uint32_t R, int N,
+                 uint32_t* __restrict__ slot_of, uint32_t* __restrict__ owner_cnt /* [N], [256] = overflow */) {
+  __shared__ uint32_t cnt[256];
+  for (int d = threadIdx.x; d < 256; d += blockDim.x) cnt[d] = 0;
+  __syncthreads();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t key = fids[i];
-    uint32_t s = (uint32_t)(mix64((uint64_t)key) >> 20) & mask;
-    while (true) {
-      Entry e = ld_entry_cg(reinterpret_cast<Entry*>(set + s));
+    const uint32_t owner = (uint32_t)((uint64_t)key % (uint64_t)N);
+    const uint32_t base = owner * R;
+    uint32_t idx = __umulhi((uint32_t)(mix64((uint64_t)key) >> 24), R);
+    uint32_t found = 0xFFFFFFFFu;
+    for (uint32_t probes = 0; probes < R; ++probes) {
+      SetEntry* p = set + base + idx;
+      Entry e = ld_entry_cg(reinterpret_cast<Entry*>(p));
       if (e.row == kEmptyRow && e.ts == 0xFFFFFFFFu && e.key == -1) {
         SetEntry ne;
         ne.key = key;
         ne.table = 0;
         ne.first_pos = (int32_t)i;
-        if (cas_set(set + s, ne)) break;
+        if (cas_set(p, ne)) {
+          atomicAdd(&cnt[owner], 1u);
+          found = base + idx;
+          break;
+        }
+        --probes;  // lost the race: look at the same slot again
         continue;
       }
-      if (e.key == key && e.row == 0u) break;
-      s = (s + 1) & mask;
+      if (e.key == key && e.row == 0u) {
+        found = base + idx;
+        break;
+      }
+      idx = idx + 1 == R ? 0 : idx + 1;
     }
-    slot_of[i] = s;
+    if (found == 0xFFFFFFFFu) {  // region full (owner skew): the host retries with larger regions
+      owner_cnt[256] = 1;
+      found = base;
+    }
+    slot_of[i] = found;
   }
+  __syncthreads();
+  for (int d = threadIdx.x; d < N; d += blockDim.x)
+    if (cnt[d]) atomicAdd(owner_cnt + d, cnt[d]);
 }
 
-// key of run j for the owner partition: (uint64)fid % N
+// bucketed unique list and the per-occurrence row offsets: run j (slot order == owner-bucketed order)
 __global__ void __launch_bounds__(kThreads)
-run_owner_kernel(const int64_t* __restrict__ fids, const uint32_t* __restrict__ run_first_pos,
-                 const uint32_t* __restrict__ n_runs, int num_shards, uint32_t* __restrict__ key_out) {
-  const int64_t n = *n_runs;
-  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
-    key_out[j] = (uint32_t)((uint64_t)fids[run_first_pos[j]] % (uint64_t)num_shards);
-}
-
-// after the owner partition: position p of the partitioned run list holds run j = runs_sorted[p]
-__global__ void __launch_bounds__(kThreads)
-run_ordinal_kernel(const int64_t* __restrict__ fids, const uint32_t* __restrict__ run_first_pos,
-                   const uint32_t* __restrict__ runs_sorted, const uint32_t* __restrict__ n_runs,
-                   uint32_t* __restrict__ ord_of_run, int64_t* __restrict__ uniq_out) {
-  const int64_t n = *n_runs;
-  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
-    const uint32_t j = runs_sorted[p];
-    ord_of_run[j] = (uint32_t)p;
-    uniq_out[p] = fids[run_first_pos[j]];
-  }
-}
-
-__global__ void __launch_bounds__(kThreads)
-occ_ordinal_kernel(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ run_of_sorted,
-                   const uint32_t* __restrict__ ord_of_run, int64_t n, int dim, int32_t* __restrict__ occ_offset) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    occ_offset[perm[i]] = (int32_t)(ord_of_run[run_of_sorted[i]] * (uint32_t)dim);
-}
-
-// ugrad[j] (run order) -> out_rows[ord_of_run[j]] (owner-bucketed order)
-template <int G>
-__global__ void __launch_bounds__(kThreads)
-runs_permute_kernel(const float* __restrict__ ugrad, const uint32_t* __restrict__ ord_of_run,
-                    const uint32_t* __restrict__ n_runs, int D, float* __restrict__ out_rows) {
-  const int c = Group<G>::gl() * 4;
+group_emit_kernel(const int64_t* __restrict__ fids, const uint32_t* __restrict__ perm,
+                  const uint32_t* __restrict__ run_of_sorted, const uint32_t* __restrict__ run_first_pos,
+                  const uint32_t* __restrict__ n_runs, int64_t n, int dim, int32_t* __restrict__ occ_offset,
+                  int64_t* __restrict__ uniq_out) {
+  const int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = t0; i < n; i += stride) occ_offset[perm[i]] = (int32_t)(run_of_sorted[i] * (uint32_t)dim);
   const int64_t nr = *n_runs;
-  const int64_t gstride = (int64_t)gridDim.x * (kThreads / G);
-  for (int64_t j = (int64_t)blockIdx.x * (kThreads / G) + threadIdx.x / G; j < nr; j += gstride) {
-    if (c >= D) continue;
-    const float4 g = __ldcs(reinterpret_cast<const float4*>(ugrad + (size_t)j * D + c));
-    *reinterpret_cast<float4*>(out_rows + (size_t)ord_of_run[j] * D + c) = g;
-  }
+  for (int64_t j = t0; j < nr; j += stride) uniq_out[j] = fids[run_first_pos[j]];
 }
 
 void grouping_build(mono_grouping* g, const int64_t* fids_dev, int64_t M, int N, int dim,
@@ -2129,101 +2338,102 @@ void grouping_build(mono_grouping* g, const int64_t* fids_dev, int64_t M, int N,
                     int64_t* n_unique_host, cudaStream_t s) {
   MONO_CUDA(cudaSetDevice(g->device));
   if (N <= 0 || N > 256) throw ArgError("grouping: num_shards must be in [1, 256]");
-  if (M < 0 || M >= ((int64_t)1 << 31)) throw ArgError("grouping: bad occurrence count");
+  if (M < 0 || M >= ((int64_t)1 << 29)) throw ArgError("grouping: bad occurrence count");
   if ((dim & 3) || dim <= 0 || dim > 128) throw ArgError("grouping needs dim % 4 == 0 and dim <= 128");
   g->M = M;
   g->dim = dim;
+  g->skeys = nullptr;
   if (M == 0) {
     for (int n = 0; n < N; ++n) shard_counts_host[n] = 0;
     if (n_unique_host) *n_unique_host = 0;
     return;
   }
-  uint32_t cap = 1024;
-  while (cap < 2 * (uint64_t)M) cap <<= 1;
-  int bits = 0;
-  while ((1u << bits) < cap) ++bits;
-  const int nblk = (int)((M + kSortTile - 1) / kSortTile);
-  const size_t n_long_max = (size_t)M / kShortRun + 2;
-  const size_t max_pieces = (size_t)M / kSubRun + n_long_max + 2;
-  size_t off = 0;
-  auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
-  const size_t o_set = take(sizeof(SetEntry) * cap);
-  const size_t o_k0 = take(4 * (size_t)M), o_v0 = take(4 * (size_t)M), o_k1 = take(4 * (size_t)M), o_v1 = take(4 * (size_t)M);
-  const size_t o_blk = take(4 * (size_t)256 * nblk);
-  const size_t o_ctr = take(4096 + 4 * 256 * 8);
-  const size_t o_brun = take(4 * (size_t)nblk);
-  const size_t o_rs = take(4 * ((size_t)M + 1)), o_rfp = take(4 * (size_t)M), o_ros = take(4 * (size_t)M);
-  const size_t o_rk = take(4 * (size_t)M), o_rk2 = take(4 * (size_t)M), o_rv2 = take(4 * (size_t)M);
-  const size_t o_ord = take(4 * (size_t)M);
-  const size_t o_tail = off;
-  // reduce() scratch
-  const size_t o_occ = take(4 * (size_t)M);
-  const size_t o_ll = take(4 * n_long_max), o_llen = take(4 * n_long_max), o_lsb = take(4 * (n_long_max + 1));
-  const size_t o_part = take(sizeof(float) * max_pieces * dim);
-  const size_t o_pd = take(sizeof(uint2) * max_pieces);
-  const size_t o_ug = take(sizeof(float) * (size_t)M * dim);
-  (void)o_occ; (void)o_ll; (void)o_llen; (void)o_lsb; (void)o_part; (void)o_pd; (void)o_ug;
-  char* ws = (char*)g->ws.get(off, s);
-  g->tail = ws + o_tail;
-  g->tail_bytes = off - o_tail;
-  SetEntry* set = (SetEntry*)(ws + o_set);
-  uint32_t* ctr = (uint32_t*)(ws + o_ctr);
-  int32_t* dtot = (int32_t*)(ws + o_ctr + 4096);
-  MONO_CUDA(cudaMemsetAsync(set, 0xFF, sizeof(SetEntry) * cap, s));
-  MONO_CUDA(cudaMemsetAsync(ctr, 0, 4096 + 4 * 256 * 8, s));
-  SortWs sw;
-  sw.k0 = (uint32_t*)(ws + o_k0); sw.v0 = (uint32_t*)(ws + o_v0);
-  sw.k1 = (uint32_t*)(ws + o_k1); sw.v1 = (uint32_t*)(ws + o_v1);
-  sw.blk_cnt = (int32_t*)(ws + o_blk);
-  sw.dtot = dtot;
-  sw.blk_runs = (uint32_t*)(ws + o_brun);
-  sw.run_start = (uint32_t*)(ws + o_rs);
-  sw.run_first_pos = (uint32_t*)(ws + o_rfp);
-  sw.n_runs = ctr;
-  sw.run_of_sorted = (uint32_t*)(ws + o_ros);
-  fid_claim_kernel<<<resident_grid(fid_claim_kernel, M, kThreads), kThreads, 0, s>>>(fids_dev, M, set, cap - 1, sw.k0);
-  MONO_CHECK_LAUNCH();
-  const uint32_t* skeys = nullptr;
-  const uint32_t* perm = nullptr;
-  sort_and_runs(sw, M, bits, 0, &skeys, &perm, s);
-  // owner partition of the run list: one stable radix pass on key = fid % N (digit totals = shard counts)
-  uint32_t* rk = (uint32_t*)(ws + o_rk);
-  uint32_t* rk2 = (uint32_t*)(ws + o_rk2);
-  uint32_t* rv2 = (uint32_t*)(ws + o_rv2);
-  uint32_t* ord_of_run = (uint32_t*)(ws + o_ord);
-  int32_t* dt_owner = dtot + 256 * 6;
-  run_owner_kernel<<<resident_grid(run_owner_kernel, M, kThreads), kThreads, 0, s>>>(fids_dev, sw.run_first_pos, ctr, N, rk);
-  MONO_CHECK_LAUNCH();
-  const int gh = resident_grid(radix_pass_kernel<0>, nblk, 1), gs = resident_grid(radix_pass_kernel<1>, nblk, 1);
-  radix_pass_kernel<0><<<gh, kThreads, 0, s>>>(rk, nullptr, M, 0, 0, sw.blk_cnt, dt_owner, nblk, nullptr, nullptr, ctr);
-  MONO_CHECK_LAUNCH();
-  radix_rowscan_kernel<<<256, 32, 0, s>>>(sw.blk_cnt, nblk);
-  MONO_CHECK_LAUNCH();
-  radix_pass_kernel<1><<<gs, kThreads, 0, s>>>(rk, nullptr, M, 0, 0, sw.blk_cnt, dt_owner, nblk, rk2, rv2, ctr);
-  MONO_CHECK_LAUNCH();
-  run_ordinal_kernel<<<resident_grid(run_ordinal_kernel, M, kThreads), kThreads, 0, s>>>(fids_dev, sw.run_first_pos, rv2, ctr,
-                                                                                        ord_of_run, uniq_out);
-  MONO_CHECK_LAUNCH();
-  occ_ordinal_kernel<<<resident_grid(occ_ordinal_kernel, M, kThreads), kThreads, 0, s>>>(perm, sw.run_of_sorted, ord_of_run, M,
-                                                                                        dim, occ_offset_out);
-  MONO_CHECK_LAUNCH();
-  // shard counts (= digit totals of the owner pass) and the number of distinct FIDs to the host
-  if (!g->h_counts) MONO_CUDA(cudaHostAlloc((void**)&g->h_counts, 4 * 260, cudaHostAllocDefault));
-  MONO_CUDA(cudaMemcpyAsync(g->h_counts, dt_owner, 4 * 256, cudaMemcpyDeviceToHost, s));
-  MONO_CUDA(cudaMemcpyAsync(g->h_counts + 256, ctr, 4, cudaMemcpyDeviceToHost, s));
-  MONO_CUDA(cudaStreamSynchronize(s));
-  for (int n = 0; n < N; ++n) shard_counts_host[n] = (int32_t)g->h_counts[n];
-  if (n_unique_host) *n_unique_host = g->h_counts[256];
-  g->skeys = skeys;
-  g->perm = perm;
-  g->run_start = sw.run_start;
-  g->run_first_pos = sw.run_first_pos;
-  g->ord_of_run = ord_of_run;
-  g->ctr = ctr;
+  if (!g->h_counts) {
+    MONO_CUDA(cudaHostAlloc((void**)&g->h_counts, 4 * 260, cudaHostAllocDefault));
+    MONO_CUDA(cudaStreamCreateWithFlags(&g->side, cudaStreamNonBlocking));
+    MONO_CUDA(cudaEventCreateWithFlags(&g->ev_claimed, cudaEventDisableTiming));
+    MONO_CUDA(cudaEventCreateWithFlags(&g->ev_copied, cudaEventDisableTiming));
+  }
+  uint64_t cap0 = 1024;
+  while (cap0 < 2 * (uint64_t)M) cap0 <<= 1;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    // attempt 0: the regions share 2M slots (load <= 0.5 for hash-balanced owners);
+    // attempt 1 (a region overflowed: heavily skewed owners): every region can hold all M FIDs.
+    const uint64_t cap = attempt == 0 ? cap0 : cap0 * (uint64_t)N;
+    if (cap > ((uint64_t)1 << 31)) throw ArgError("grouping: FID owners too skewed for this batch size");
+    const uint32_t R = (uint32_t)(cap / (uint64_t)N);
+    int bits = 0;
+    while (((uint64_t)1 << bits) < cap) ++bits;
+    const int nblk = (int)((M + kSortTile - 1) / kSortTile);
+    const size_t n_long_max = (size_t)M / kShortRun + 2;
+    const size_t max_pieces = (size_t)M / kSubRun + n_long_max + 2;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_set = take(sizeof(SetEntry) * cap);
+    const size_t o_k0 = take(4 * (size_t)M), o_v0 = take(4 * (size_t)M), o_k1 = take(4 * (size_t)M), o_v1 = take(4 * (size_t)M);
+    const size_t o_blk = take(4 * (size_t)256 * nblk);
+    const size_t o_ctr = take(4096 + 4 * 256 * 4 + 4 * 260);
+    const size_t o_brun = take(4 * (size_t)nblk);
+    const size_t o_rs = take(4 * ((size_t)M + 1)), o_rfp = take(4 * (size_t)M), o_ros = take(4 * (size_t)M);
+    const size_t o_tail = off;
+    // reduce() scratch
+    take(4 * (size_t)M);                                                             // occ_row
+    take(4 * n_long_max); take(4 * n_long_max); take(4 * (n_long_max + 1));          // long run lists
+    take(sizeof(float) * max_pieces * dim);                                          // partial sums
+    take(sizeof(uint2) * max_pieces);                                                // piece descriptors
+    char* ws = (char*)g->ws.get(off, s);
+    g->tail = ws + o_tail;
+    g->tail_bytes = off - o_tail;
+    SetEntry* set = (SetEntry*)(ws + o_set);
+    uint32_t* ctr = (uint32_t*)(ws + o_ctr);
+    int32_t* dtot = (int32_t*)(ws + o_ctr + 4096);
+    uint32_t* owner_cnt = (uint32_t*)(ws + o_ctr + 4096 + 4 * 256 * 4);
+    MONO_CUDA(cudaMemsetAsync(set, 0xFF, sizeof(SetEntry) * cap, s));
+    MONO_CUDA(cudaMemsetAsync(ctr, 0, 4096 + 4 * 256 * 4 + 4 * 260, s));
+    SortWs sw;
+    sw.k0 = (uint32_t*)(ws + o_k0); sw.v0 = (uint32_t*)(ws + o_v0);
+    sw.k1 = (uint32_t*)(ws + o_k1); sw.v1 = (uint32_t*)(ws + o_v1);
+    sw.blk_cnt = (int32_t*)(ws + o_blk);
+    sw.dtot = dtot;
+    sw.blk_runs = (uint32_t*)(ws + o_brun);
+    sw.run_start = (uint32_t*)(ws + o_rs);
+    sw.run_first_pos = (uint32_t*)(ws + o_rfp);
+    sw.n_runs = ctr;
+    sw.run_of_sorted = (uint32_t*)(ws + o_ros);
+    fid_claim_kernel<<<resident_grid(fid_claim_kernel, M, kThreads), kThreads, 0, s>>>(fids_dev, M, set, R, N, sw.k0, owner_cnt);
+    MONO_CHECK_LAUNCH();
+    // counts -> host on the side stream, while the sort below keeps the GPU busy
+    MONO_CUDA(cudaEventRecord(g->ev_claimed, s));
+    MONO_CUDA(cudaStreamWaitEvent(g->side, g->ev_claimed, 0));
+    MONO_CUDA(cudaMemcpyAsync(g->h_counts, owner_cnt, 4 * 257, cudaMemcpyDeviceToHost, g->side));
+    MONO_CUDA(cudaEventRecord(g->ev_copied, g->side));
+    const uint32_t* skeys = nullptr;
+    const uint32_t* perm = nullptr;
+    sort_and_runs(sw, M, bits, 0, &skeys, &perm, s);
+    group_emit_kernel<<<resident_grid(group_emit_kernel, M, kThreads), kThreads, 0, s>>>(
+        fids_dev, perm, sw.run_of_sorted, sw.run_first_pos, ctr, M, dim, occ_offset_out, uniq_out);
+    MONO_CHECK_LAUNCH();
+    MONO_CUDA(cudaEventSynchronize(g->ev_copied));
+    if (g->h_counts[256] != 0) continue;  // region overflow: redo with full-size regions
+    int64_t total = 0;
+    for (int n = 0; n < N; ++n) {
+      shard_counts_host[n] = (int32_t)g->h_counts[n];
+      total += g->h_counts[n];
+    }
+    if (n_unique_host) *n_unique_host = total;
+    g->skeys = skeys;
+    g->perm = perm;
+    g->run_start = sw.run_start;
+    g->run_first_pos = sw.run_first_pos;
+    g->ctr = ctr;
+    return;
+  }
+  throw ArgError("grouping: scratch set overflow (internal)");
 }
 
-void grouping_reduce(mono_grouping* g, const float* pooled_grad, int64_t grad_stride, int grad_col,
-                     const int32_t* row_offsets, int64_t n_rows, int pooling, float* out_rows, cudaStream_t s) {
+static void grouping_reduce_impl(mono_grouping* g, const float* pooled_grad, int64_t grad_stride, int grad_col,
+                                 const int32_t* row_offsets, int64_t n_rows, int pooling, float* out_rows,
+                                 const PeerOut& po, cudaStream_t s) {
   MONO_CUDA(cudaSetDevice(g->device));
   const int64_t M = g->M;
   const int D = g->dim;
@@ -2231,7 +2441,7 @@ void grouping_reduce(mono_grouping* g, const float* pooled_grad, int64_t grad_st
   if (!g->skeys) throw ArgError("grouping_reduce before grouping_build");
   if (pooling != MONO_POOL_SUM && pooling != MONO_POOL_MEAN) throw ArgError("grouping_reduce: SUM or MEAN");
   if ((grad_stride & 3) || (grad_col & 3) || (reinterpret_cast<uintptr_t>(pooled_grad) & 15) ||
-      (reinterpret_cast<uintptr_t>(out_rows) & 15))
+      (po.n == 0 && (reinterpret_cast<uintptr_t>(out_rows) & 15)))
     throw ArgError("grouping_reduce needs 16-byte aligned rows");
   const size_t n_long_max = (size_t)M / kShortRun + 2;
   const size_t max_pieces = (size_t)M / kSubRun + n_long_max + 2;
@@ -2241,7 +2451,6 @@ void grouping_reduce(mono_grouping* g, const float* pooled_grad, int64_t grad_st
   const size_t o_ll = take(4 * n_long_max), o_llen = take(4 * n_long_max), o_lsb = take(4 * (n_long_max + 1));
   const size_t o_part = take(sizeof(float) * max_pieces * D);
   const size_t o_pd = take(sizeof(uint2) * max_pieces);
-  const size_t o_ug = take(sizeof(float) * (size_t)M * D);
   if (off > g->tail_bytes) throw ArgError("grouping scratch too small (internal)");
   char* ws = g->tail;
   BwdArgs a;
@@ -2264,7 +2473,7 @@ void grouping_reduce(mono_grouping* g, const float* pooled_grad, int64_t grad_st
   a.long_sub_base = (uint32_t*)(ws + o_lsb);
   a.partial = (float*)(ws + o_part);
   a.piece_desc = (uint2*)(ws + o_pd);
-  a.ugrad = (float*)(ws + o_ug);
+  a.ugrad = out_rows;  // runs are already in the bucketed order: the sums are written in place
   MONO_CUDA(cudaMemsetAsync(g->ctr + 4, 0, 4, s));  // n_long
   if (row_offsets) {
     uint32_t* occ = (uint32_t*)(ws + o_occ);
@@ -2274,17 +2483,14 @@ void grouping_reduce(mono_grouping* g, const float* pooled_grad, int64_t grad_st
   }
   const int G = pick_group(D);
 #define RED(GG)                                                                                               \
-  run_sum_kernel<GG><<<resident_grid(run_sum_kernel<GG>, M, kThreads / GG), kThreads, 0, s>>>(a);             \
+  run_sum_kernel<GG><<<resident_grid(run_sum_kernel<GG>, M, kThreads / GG), kThreads, 0, s>>>(a, po);         \
   MONO_CHECK_LAUNCH();                                                                                        \
   long_prep_kernel<<<1, 1024, 0, s>>>(a);                                                                     \
   MONO_CHECK_LAUNCH();                                                                                        \
   pool_bwd_long_partial_kernel<GG>                                                                            \
       <<<resident_grid(pool_bwd_long_partial_kernel<GG>, (int64_t)max_pieces, 1), kThreads, 0, s>>>(a);       \
   MONO_CHECK_LAUNCH();                                                                                        \
-  pool_bwd_long_final_kernel<GG><<<148 * 2, kThreads, 0, s>>>(a);                                             \
-  MONO_CHECK_LAUNCH();                                                                                        \
-  runs_permute_kernel<GG><<<resident_grid(runs_permute_kernel<GG>, M, kThreads / GG), kThreads, 0, s>>>(      \
-      a.ugrad, g->ord_of_run, g->ctr, D, out_rows);                                                           \
+  pool_bwd_long_final_kernel<GG><<<148 * 2, kThreads, 0, s>>>(a, po);                                         \
   MONO_CHECK_LAUNCH()
   switch (G) {
     case 4: RED(4); break;
@@ -2293,6 +2499,22 @@ void grouping_reduce(mono_grouping* g, const float* pooled_grad, int64_t grad_st
     default: RED(32); break;
   }
 #undef RED
+}
+
+// out_rows[u] = summed gradient of the u-th distinct FID of the bucketed list (ref: ScatterGrad)
+void grouping_reduce(mono_grouping* g, const float* pooled_grad, int64_t grad_stride, int grad_col,
+                     const int32_t* row_offsets, int64_t n_rows, int pooling, float* out_rows, cudaStream_t s) {
+  grouping_reduce_impl(g, pooled_grad, grad_stride, grad_col, row_offsets, n_rows, pooling, out_rows, no_peer, s);
+}
+
+// same, fused with the gradient exchange of the sharded backward: the row of the u-th distinct FID is stored
+// into the window of the rank that owns it (replaces the gradient all-to-all, ref:
+// distributed_ps_sync.py:531-573); the NVLink stores overlap the reduction, run by run.
+void grouping_reduce_push(mono_grouping* g, const float* pooled_grad, int64_t grad_stride, int grad_col,
+                          const int32_t* row_offsets, int64_t n_rows, int pooling, const PeerOut& po,
+                          cudaStream_t s) {
+  if (po.n <= 0) throw ArgError("grouping_reduce_push without a peer window");
+  grouping_reduce_impl(g, pooled_grad, grad_stride, grad_col, row_offsets, n_rows, pooling, nullptr, po, s);
 }
 
 }  // namespace mono

@@ -226,6 +226,51 @@ class PartitionedHashTable:
     return next(iter(d.values())).device
 
 
+class HostCounts:
+  """Per-step exchange of small host-side integer rows between the ranks of ONE node through a shared
+  /dev/shm mapping (every rank ends up with the full world x width matrix).  It replaces the count
+  all-to-all + device-to-host read of the NCCL path: the counts are already on the host (the grouping
+  returns them), so they never need to touch a GPU.  Double-buffered by step parity; a rank can run at
+  most one exchange ahead of the slowest one, because exchange e+1 completes only after every rank has
+  published e+1, which each does after reading all of e."""
+
+  def __init__(self, world: int, rank: int, width: int, group=None):
+    import mmap
+    import os
+    import uuid
+    import numpy as np
+    self.world, self.rank, self.width, self.epoch = world, rank, width, 0
+    nbytes = 2 * world * (width + 1) * 8
+    name = [f"/dev/shm/mono_counts_{os.getpid()}_{uuid.uuid4().hex}" if rank == 0 else None]
+    if rank == 0:
+      with open(name[0], "wb") as f:
+        f.write(b"\0" * nbytes)
+    if world > 1:
+      dist.broadcast_object_list(name, src=0, group=group)
+    self._f = open(name[0], "r+b")
+    self._mm = mmap.mmap(self._f.fileno(), nbytes)
+    self.arr = np.frombuffer(self._mm, dtype=np.int64).reshape(2, world, width + 1)
+    if world > 1:
+      dist.barrier(group=group)
+    if rank == 0:
+      os.unlink(name[0])
+
+  def exchange(self, row, timeout_s: float = 120.0):
+    import time
+    import numpy as np
+    self.epoch += 1
+    e, buf = self.epoch, self.arr[self.epoch & 1]
+    buf[self.rank, 1:] = np.asarray(row, dtype=np.int64)
+    buf[self.rank, 0] = e            # published after the payload (x86 store order)
+    t0 = None
+    while not bool((buf[:, 0] == e).all()):
+      if t0 is None:
+        t0 = time.monotonic()
+      elif time.monotonic() - t0 > timeout_s:
+        raise RuntimeError(f"HostCounts: rank {self.rank} timed out at exchange {e}")
+    return buf[:, 1:].copy()
+
+
 class ShardedStep:
   """Sparse train step of ONE table on N GPUs, fast path: the batch is grouped once
   (distribution_ops.Grouping) and that grouping serves both the forward (dedup + bucket by owner + pooling
@@ -233,15 +278,84 @@ class ShardedStep:
   as PartitionedHashTable.  Differences from the reference-layout path: the order of the distinct FIDs
   inside a shard bucket is the engine's, and no float atomics are used."""
 
-  def __init__(self, table, name: str, dim: int, world: int, rank: int, device, group=None):
+  def __init__(self, table, name: str, dim: int, world: int, rank: int, device, group=None,
+               exchange: Optional[str] = None):
+    """exchange: "peer" = NVLink peer windows (fused lookup+send / reduce+send kernels, flag barriers,
+    counts through /dev/shm; one node), "nccl" = all_to_all_single.  Default: env MONO_EXCHANGE, else
+    "peer" on CUDA devices."""
     from . import distribution_ops
     import os
     self.table, self.name, self.dim, self.N, self.rank, self.group = table, name, dim, world, rank, group
+    self.device = torch.device(device)
     self.dops = distribution_ops
     self.grouping = distribution_ops.Grouping(device)
     self.k = table.table_names.index(name)
     self.K = len(table.table_names)
     self.phases = _Phases(os.environ.get("MONO_TIMING", "0") == "1")
+    self.exchange = exchange or os.environ.get("MONO_EXCHANGE", "peer")
+    if self.exchange not in ("peer", "nccl"):
+      raise ValueError("exchange must be 'peer' or 'nccl'")
+    self.window = None
+    self.hostx = HostCounts(world, rank, world + 1, group) if self.exchange == "peer" else None
+    self.cap_rows = self.cap_recv = self._base_m = 0
+    self.peer_steps = self.nccl_steps = 0
+
+  # ---- NVLink window sizing: rows_in holds this rank's distinct rows (<= M), ids_in / grads_in what the
+  # other ranks send it (about sum_r U_r / N).  A step that does not fit re-creates the window first; every
+  # rank takes that decision from the same shared count matrix, so the re-creation is collective.
+  def _make_window(self, max_m: int):
+    D = self.dim
+    if self.window is not None:
+      torch.cuda.synchronize(self.device)
+      self.window.close(self.group)
+    self._base_m = max_m
+    self.cap_rows = int(max_m * 1.25) + 1024
+    self.cap_recv = int(max_m * 1.5) + 4096
+    al = lambda x: (x + 255) & ~255
+    self.off_ids = [0, al(self.cap_recv * 8)]
+    self.off_rows = self.off_ids[1] + al(self.cap_recv * 8)
+    self.off_grads = self.off_rows + al(self.cap_rows * D * 4)
+    total = self.off_grads + al(self.cap_recv * D * 4)
+    self.window = self.dops.PeerWindow(self.device, self.N, self.rank, total, self.group)
+
+  def _step_peer(self, fids, pooled_grad, out, req_time, row_offsets, pooling):
+    import numpy as np
+    N, D, me, ph = self.N, self.dim, self.rank, self.phases
+    ph.mark("start")
+    uniq, offs, shard_sizes = self.grouping.build(fids, N, D)                         # 1
+    ph.mark("f1_group")
+    mat = self.hostx.exchange([fids.numel()] + list(shard_sizes))                     # 2 (host only)
+    max_m, cnt = int(mat[:, 0].max()), mat[:, 1:]                                     # cnt[r][o]
+    need_recv = int(cnt.sum(axis=0).max())
+    if self.window is None or max_m > self.cap_rows or need_recv > self.cap_recv:      # same decision on every rank
+      self._make_window(max(max_m, int(need_recv / 1.5) + 1, self._base_m))
+    par = self.hostx.epoch & 1
+    recv = cnt[:, me]
+    tot_recv = int(recv.sum())
+    col_pre = np.concatenate([np.zeros((1, N), np.int64), np.cumsum(cnt, axis=0)])    # col_pre[r][o] = sum_{r'<r} cnt[r'][o]
+    row_pre = np.concatenate([np.zeros((N, 1), np.int64), np.cumsum(cnt, axis=1)], axis=1)  # row_pre[r][o] = sum_{o'<o} cnt[r][o']
+    my_seg = col_pre[me]                              # where my items start inside owner o's received list
+    self.window.put(self.off_ids[par], my_seg * 8, uniq, row_pre[me, :N] * 8, cnt[me] * 8)   # 3
+    self.window.barrier()
+    ph.mark("f3_put_ids")
+    ids_in = self.window.view(self.off_ids[par], tot_recv, torch.int64)
+    self.table.lookup_push(self.name, ids_in, recv, self.window, self.off_rows, row_pre[:, me])  # 4+5
+    self.window.barrier()
+    ph.mark("f5_lookup_push")
+    rows_in = self.window.view(self.off_rows, uniq.numel() * D, torch.float32)
+    self.dops.gather_pool(rows_in, offs, D, row_offsets, pooling, out=out)            # 6
+    ph.mark("f6_gather_pool")
+    self.grouping.reduce_push(pooled_grad, cnt[me], self.window, self.off_grads, my_seg, row_offsets, pooling)  # 7+8
+    self.window.barrier()
+    ph.mark("b8_reduce_push")
+    grads_in = self.window.view(self.off_grads, tot_recv * D, torch.float32)
+    slot = self._slot(recv)                                                           # 9
+    _, _, id_off, emb_off = self.table.fused_offsets(slot, N)
+    self.table.fused_apply_gradient(ids_in, ids_in, slot, grads_in, id_off, emb_off, 0, req_time, N)
+    ph.mark("b9_owner_apply")
+    ph.flush()
+    self.peer_steps += 1
+    return uniq.numel()
 
   def _slot(self, per_shard):
     """per-(shard, table) sizes with only this table populated."""
@@ -252,7 +366,10 @@ class ShardedStep:
 
   def step(self, fids: torch.Tensor, pooled_grad: torch.Tensor, out: torch.Tensor, req_time: int,
            row_offsets: Optional[torch.Tensor] = None, pooling: str = "sum"):
+    if self.exchange == "peer":
+      return self._step_peer(fids, pooled_grad, out, req_time, row_offsets, pooling)
     N, D, dev, ph = self.N, self.dim, fids.device, self.phases
+    self.nccl_steps += 1
     ph.mark("start")
     uniq, offs, shard_sizes = self.grouping.build(fids, N, D)                       # 1
     ph.mark("f1_group")

@@ -169,6 +169,81 @@ class Grouping:
                                               _ptr(row_offsets), n_rows, pool, _ptr(out_rows), _stream(self.device)))
     return out_rows
 
+  def reduce_push(self, pooled_grad: torch.Tensor, shard_sizes: Sequence[int], window: "PeerWindow", region_off: int,
+                  dst_row_off: Sequence[int], row_offsets: Optional[torch.Tensor] = None, pooling: str = "sum",
+                  grad_col: int = 0):
+    """reduce() whose output rows are stored into the owners' windows (fused gradient exchange)."""
+    n_rows = self._keep.numel() if row_offsets is None else row_offsets.numel() - 1
+    if row_offsets is not None:
+      row_offsets = row_offsets.to(torch.int32).contiguous()
+    pool = {"sum": _lib.POOL_SUM, "mean": _lib.POOL_MEAN}[pooling]
+    n = window.world
+    _lib.check(self._lib.mono_grouping_reduce_push(
+        self._h, _ptr(pooled_grad), pooled_grad.stride(0), grad_col, _ptr(row_offsets), n_rows, pool,
+        (C.c_int64 * n)(*[int(x) for x in shard_sizes]), window._h, int(region_off),
+        (C.c_int64 * n)(*[int(x) for x in dst_row_off]), _stream(self.device)))
+
+
+class _RawCuda:
+  """__cuda_array_interface__ carrier for a raw device pointer (torch.as_tensor makes a view of it)."""
+
+  def __init__(self, ptr: int, nbytes: int, owner):
+    self.owner = owner
+    self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class PeerWindow:
+  """One rank's NVLink window (mono_peer_*): device memory mapped into every peer process of the node.
+  Construction is collective over `group` (the 64-byte IPC handles are all-gathered)."""
+
+  def __init__(self, device, world: int, rank: int, nbytes: int, group=None):
+    import torch.distributed as dist
+    self._lib = _lib.load()
+    self.device = torch.device(device)
+    self.world, self.rank, self.nbytes = world, rank, int(nbytes)
+    h = C.c_void_p()
+    _lib.check(self._lib.mono_peer_create(self.device.index, world, rank, self.nbytes, C.byref(h)))
+    self._h = h
+    if world > 1:
+      buf = (C.c_uint8 * 64)()
+      _lib.check(self._lib.mono_peer_handle(self._h, buf))
+      mine = torch.tensor(list(buf), dtype=torch.uint8, device=self.device)
+      allh = torch.empty(64 * world, dtype=torch.uint8, device=self.device)
+      dist.all_gather_into_tensor(allh, mine, group=group)
+      raw = bytes(allh.cpu().tolist())
+      _lib.check(self._lib.mono_peer_attach(self._h, raw, world))
+      dist.barrier(group=group)   # every rank has mapped every window before anyone stores
+    p = C.c_void_p()
+    _lib.check(self._lib.mono_peer_local(self._h, C.byref(p)))
+    self._local = torch.as_tensor(_RawCuda(p.value, self.nbytes, self), device=self.device)
+
+  def close(self, group=None):
+    """Collective teardown: unmap the peers, rank barrier, free."""
+    if getattr(self, "_h", None):
+      import torch.distributed as dist
+      self._local = None
+      _lib.check(self._lib.mono_peer_detach(self._h))
+      if self.world > 1:
+        dist.barrier(group=group)
+      self._lib.mono_peer_destroy(self._h)
+      self._h = None
+
+  def view(self, offset: int, count: int, dtype: torch.dtype) -> torch.Tensor:
+    """`count` items of `dtype` of THIS rank's window starting at byte `offset`."""
+    nb = count * torch.empty(0, dtype=dtype).element_size()
+    return self._local[offset:offset + nb].view(dtype)
+
+  def barrier(self):
+    _lib.check(self._lib.mono_peer_barrier(self._h, _stream(self.device)))
+
+  def put(self, region_off: int, dst_off: Sequence[int], src: torch.Tensor, src_off: Sequence[int],
+          nbytes: Sequence[int]):
+    """nbytes[r] bytes of src (+ src_off[r]) -> rank r's window at region_off + dst_off[r]."""
+    n = self.world
+    arr = lambda xs: (C.c_int64 * n)(*[int(x) for x in xs])
+    _lib.check(self._lib.mono_peer_put(self._h, int(region_off), arr(dst_off), _ptr(src), arr(src_off), arr(nbytes),
+                                       _stream(self.device)))
+
 
 # ---- generic fused layout op ------------------------------------------------------------------
 @dataclasses.dataclass

@@ -285,6 +285,16 @@ class MultiHashTable:
     return self
 
   # ---- engine extensions -------------------------------------------------------------------
+  def lookup_push(self, slot: str, ids: torch.Tensor, counts: Sequence[int], window, region_off: int,
+                  dst_row_off: Sequence[int]):
+    """Owner-side lookup fused with the row exchange: ids = counts[0] ids of rank 0, counts[1] of rank 1, ...;
+    rank r's rows are stored into r's peer window at region_off + dst_row_off[r] rows (mono_mtable_lookup_push)."""
+    k = self._table_names.index(slot)
+    n = window.world
+    _lib.check(self._lib.mono_mtable_lookup_push(
+        self._h, k, _ptr(ids), (C.c_int64 * n)(*[int(x) for x in counts]), window._h, int(region_off),
+        (C.c_int64 * n)(*[int(x) for x in dst_row_off]), _stream(self._device)))
+
   def lookup_pool(self, slot: str, fids: torch.Tensor, row_offsets: Optional[torch.Tensor] = None,
                   pooling: str = "sum", out: Optional[torch.Tensor] = None, out_col: int = 0) -> torch.Tensor:
     """Fused probe + gather + SUM/MEAN pool (one kernel): the hot forward.  Equivalent to

@@ -119,7 +119,7 @@ def _fast_cfg():
   return {"t": table([(16, "adagrad", {})], [0.1])}
 
 
-def _fast_worker(rank, world, port, q):
+def _fast_worker(rank, world, port, q, exchange="peer"):
   try:
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
@@ -131,7 +131,7 @@ def _fast_worker(rank, world, port, q):
     from monolith_b200 import MultiHashTable
     from monolith_b200.distributed_ps import ShardedStep
     table = MultiHashTable(_fast_cfg(), device=dev)
-    st = ShardedStep(table, "t", 16, world, rank, dev)
+    st = ShardedStep(table, "t", 16, world, rank, dev, exchange=exchange)
     pooled_all = []
     for step in range(3):
       fids, g = _fast_batch(rank, step)
@@ -152,7 +152,10 @@ def _fast_worker(rank, world, port, q):
     raise
 
 
-def test_sharded_fast_step_two_gpus():
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+def test_sharded_fast_step_two_gpus(exchange):
+  """ShardedStep on 2 GPUs == one global oracle table; exchange over NVLink peer windows (fused
+  lookup+send / reduce+send kernels, flag barriers) and over NCCL all-to-all."""
   if torch.cuda.device_count() < 2:
     pytest.skip("needs 2 GPUs")
   import torch.multiprocessing as mp
@@ -160,8 +163,8 @@ def test_sharded_fast_step_two_gpus():
   world = 2
   ctx = mp.get_context("spawn")
   q = ctx.Queue()
-  port = 29900 + (os.getpid() % 90)
-  procs = [ctx.Process(target=_fast_worker, args=(r, world, port, q)) for r in range(world)]
+  port = 29900 + (os.getpid() % 90) + (7 if exchange == "nccl" else 0)
+  procs = [ctx.Process(target=_fast_worker, args=(r, world, port, q, exchange)) for r in range(world)]
   for p in procs:
     p.start()
   got = [q.get(timeout=240) for _ in range(world)]

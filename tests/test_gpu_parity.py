@@ -271,6 +271,11 @@ def test_fused_lookup_optimize_random(dev):
     cpu.fused_apply_gradient(ids, slot, g, N, req_time=77 + step)
   e_g = gpu.fused_lookup(T(ids, dev), slot.tolist(), N)[0].cpu().numpy()
   np.testing.assert_array_equal(e_g, cpu.fused_lookup(ids, slot, N)[0])
+  for name in cpu.names:  # rows, optimizer state and timestamps of everything ever inserted
+    keys = cpu.keys(name)
+    got = gpu.lookup_entry(name, T(keys, dev))["raw"].cpu().numpy()
+    np.testing.assert_array_equal(got.view(np.uint32), cpu.lookup_entry(name, keys).view(np.uint32))
+    assert gpu.size(name) == keys.size
 
 
 @pytest.mark.parametrize("dim", [1, 8, 16, 17, 32, 64, 128, 256])
@@ -411,6 +416,89 @@ def test_owner_grouping_build_reduce(N, dev):
   np.testing.assert_allclose(out[~cold], want[~cold], rtol=2e-3, atol=2e-3)
   out2 = g.reduce(T(pg, dev), torch.empty(u.size * D, device=dev)).cpu().numpy().reshape(-1, D)
   np.testing.assert_array_equal(out, out2)
+
+
+def test_owner_grouping_skewed_owners(dev):
+  """Every FID has the same owner: the owner's region of the scratch set overflows and the grouping is
+  rebuilt with full-size regions; results are unchanged."""
+  from monolith_b200 import distribution_ops as dops
+  rng = np.random.default_rng(3)
+  D, M, N = 8, 150000, 8
+  fids = (rng.integers(0, 100000, M).astype(np.int64) * N) + 5          # owner 5 for all
+  g = dops.Grouping(dev)
+  uniq, offs, sizes = g.build(T(fids, dev), N, D)
+  u, o = uniq.cpu().numpy(), offs.cpu().numpy()
+  assert np.array_equal(np.sort(u), np.unique(fids))
+  assert sizes == [0, 0, 0, 0, 0, u.size, 0, 0]
+  assert np.array_equal(u[o // D], fids)
+  pg = rng.standard_normal((M, D)).astype(np.float32)
+  out = g.reduce(T(pg, dev), torch.empty(u.size * D, device=dev)).cpu().numpy()
+  np.testing.assert_array_equal(out, orc.gather_pool_grad(pg, o, D, u.size * D))
+
+
+def test_peer_window_single_rank_ops(dev):
+  """mono_peer_* with world == 1 (the rank is its own peer): put, barrier, fused lookup+push and
+  reduce+push land where the NCCL path's buffers would."""
+  from monolith_b200 import MultiHashTable, distribution_ops as dops
+  rng = np.random.default_rng(5)
+  D, n = 16, 5000
+  t = MultiHashTable({"t": table([(D, "adagrad", {})], [0.1])}, device=dev)
+  keys = rng.choice(1 << 40, n, replace=False).astype(np.int64)
+  vals = rng.standard_normal((n, D)).astype(np.float32)
+  t.assign({"t": (T(keys, dev), T(vals, dev))}, req_time=1)
+  w = dops.PeerWindow(dev, 1, 0, 1 << 22)
+  # put: 8-byte items at an odd item offset (falls back to 8-byte vectors)
+  w.put(256, [24], T(keys, dev), [8], [8 * (n - 1)])
+  w.barrier()
+  np.testing.assert_array_equal(w.view(256 + 24, n - 1, torch.int64).cpu().numpy(), keys[1:])
+  # lookup_push: rows of present and absent ids at a row offset inside the region
+  q = np.concatenate([keys[:300], np.array([-5, 77], np.int64)])
+  t.lookup_push("t", T(q, dev), [q.size], w, 1 << 20, [3])
+  w.barrier()
+  got = w.view((1 << 20) + 3 * D * 4, q.size * D, torch.float32).cpu().numpy().reshape(-1, D)
+  np.testing.assert_array_equal(got[:300], vals[:300])
+  assert not got[300:].any()
+  # reduce_push == reduce
+  fids = keys[rng.integers(0, 200, 3000)]
+  g = dops.Grouping(dev)
+  uniq, offs, sizes = g.build(T(fids, dev), 1, D)
+  pg = T(rng.standard_normal((3000, D)).astype(np.float32), dev)
+  want = g.reduce(pg, torch.empty(uniq.numel() * D, device=dev)).cpu().numpy()
+  g.reduce_push(pg, sizes, w, 2 << 20, [1])
+  w.barrier()
+  np.testing.assert_array_equal(w.view((2 << 20) + D * 4, uniq.numel() * D, torch.float32).cpu().numpy(), want)
+  with pytest.raises(Exception):
+    w.put(0, [(1 << 22) - 8], T(keys, dev), [0], [16])    # outside the window
+  w.close()
+
+
+@pytest.mark.parametrize("pooling", ["sum", "mean"])
+def test_sharded_step_peer_single_rank(pooling, dev):
+  """ShardedStep over the peer window with world == 1 against the oracle table (same protocol as the 2-GPU test)."""
+  from monolith_b200 import MultiHashTable
+  from monolith_b200.distributed_ps import ShardedStep
+  rng = np.random.default_rng(11)
+  D = 16
+  cfg = {"t": table([(D, "adagrad", {})], [0.1])}
+  t = MultiHashTable(cfg, device=dev)
+  o = orc.OracleMultiHashTable(cfg)
+  st = ShardedStep(t, "t", D, 1, 0, dev, exchange="peer")
+  for step in range(4):
+    n_rows = 3000 + 500 * step                       # growing batches: the window is re-created once
+    lens = rng.integers(0, 4, n_rows)
+    ro = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    fids = (np.int64(9) << 48) | rng.integers(0, 1500, int(ro[-1])).astype(np.int64)
+    pg = rng.standard_normal((n_rows, D)).astype(np.float32)
+    out = torch.empty(n_rows, D, device=dev)
+    st.step(T(fids, dev), T(pg, dev), out, 30 + step, row_offsets=T(ro, dev), pooling=pooling)
+    np.testing.assert_array_equal(out.cpu().numpy(), o.lookup_pool("t", fids, ro, pooling))
+    u, inv = orc.dedup(fids)
+    ug = orc.gather_pool_grad(pg, inv * D, D, u.size * D, ro, pooling).reshape(-1, D)
+    o.apply_gradients({"t": (u, ug)}, req_time=30 + step)
+  keys = o.keys("t")
+  got = t.lookup_entry("t", T(keys, dev))["raw"].cpu().numpy()
+  np.testing.assert_array_equal(got.view(np.uint32), o.lookup_entry("t", keys).view(np.uint32))
+  assert st.peer_steps == 4
 
 
 def _layout_case(rng, B, n_emb_lists, with_shared):
