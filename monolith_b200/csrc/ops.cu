@@ -1368,6 +1368,7 @@ void run_upsert_groups(mono_mtable* mt, const CallSeg* h_segs, int nsegs, const 
 //               in piece order (fixed association => run-to-run bit-stable).
 // ==========================================================================================
 constexpr int kSortTile = kThreads * 8;
+constexpr int kFastRun = 4;
 constexpr int kShortRun = 64;
 constexpr int kSubRun = 1024;
 
@@ -1612,7 +1613,8 @@ struct BwdArgs {
   int grad_col;
   const float* lr;              // device, slice learning rates of the table
   // long runs
-  uint32_t* n_long;
+  uint32_t* n_long;             // counters: n_long, n_med = n_long + 1, work_ctr = n_long + 2 (zeroed per call)
+  uint32_t* med_list;           // runs of kFastRun < len <= kShortRun (run index j)
   uint32_t* long_list;          // run index j
   uint32_t* long_len;
   uint32_t* long_sub_base;      // exclusive prefix of sub-piece counts (+ total at [n_long])
@@ -1776,9 +1778,18 @@ __device__ __forceinline__ float* run_dst(float* ugrad, const PeerOut& po, int64
   return reinterpret_cast<float*>(po.base[r]) + (j - po.start[r]) * D;
 }
 
+// Warp tile of 32 runs: a lane fetches one run's bounds (coalesced), then every group takes RU runs per
+// iteration.  Runs of <= FL occurrences (the bulk of a Zipf batch) go through the fast path: the RU*FL
+// permutation entries are fetched by RU*FL lanes at once and all RU*FL gradient rows are requested before
+// the first add, so a group keeps up to 8 independent 128-byte reads in flight instead of ~1.5.
 template <int G>
-__global__ void __launch_bounds__(kThreads, 6) run_sum_kernel(BwdArgs a, const PeerOut po) {
-  const int gl = Group<G>::gl();
+__global__ void __launch_bounds__(kThreads, 4) run_sum_kernel(BwdArgs a, const PeerOut po) {
+  constexpr int RPI = 32 / G;          // groups per warp
+  constexpr int RU = G >= 8 ? 2 : 1;   // runs per group per iteration
+  constexpr int FL = kFastRun;         // fast-path run length
+  static_assert(RU * FL <= G, "perm prefetch needs one lane per (run, occurrence)");
+  const int lane = threadIdx.x & 31, gl = Group<G>::gl(), grp = lane / G, gb = Group<G>::base();
+  const uint32_t gmask = Group<G>::mask();
   const int c = gl * 4;
   const int64_t nr = *a.n_runs;
   const int D = a.td.dim;
@@ -1786,17 +1797,72 @@ __global__ void __launch_bounds__(kThreads, 6) run_sum_kernel(BwdArgs a, const P
   const GradSrc gs = make_grad_src(a, c);
   const uint32_t* __restrict__ run_start = a.run_start;
   float* __restrict__ ugrad = a.ugrad;
-  const int64_t gstride = (int64_t)gridDim.x * (kThreads / G);
-  for (int64_t j = (int64_t)blockIdx.x * (kThreads / G) + threadIdx.x / G; j < nr; j += gstride) {
-    const uint32_t s = run_start[j];
-    const uint32_t len = run_start[j + 1] - s;
-    if (len > kShortRun) {
-      if (gl == 0) a.long_list[atomicAdd(a.n_long, 1u)] = (uint32_t)j;
-      continue;
+  const int pu = gl / FL, pk = gl % FL;  // this lane's (run, occurrence) in the perm prefetch
+  const int64_t wstride = (int64_t)gridDim.x * (kThreads / 32) * 32;
+  for (int64_t wbase = ((int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * 32; wbase < nr;
+       wbase += wstride) {
+    uint32_t s_l = 0, e_l = 0;
+    if (wbase + lane < nr) {
+      s_l = run_start[wbase + lane];
+      e_l = run_start[wbase + lane + 1];
     }
-    const float4 acc = sum_grad_rows<G, 4>(gs, s, len, in);
-    if (in) *reinterpret_cast<float4*>(run_dst(ugrad, po, j, D) + c) = acc;
+#pragma unroll 1
+    for (int it = 0; it < G / RU; ++it) {
+      const int t0 = (it * RPI + grp) * RU;  // tile-local index of this group's first run
+      const uint32_t s_p = __shfl_sync(0xffffffffu, s_l, min(t0 + pu, 31));
+      const uint32_t n_p = __shfl_sync(0xffffffffu, e_l, min(t0 + pu, 31)) - s_p;
+      uint32_t m_l = 0;
+      if (pu < RU && (uint32_t)pk < n_p && n_p <= (uint32_t)FL) m_l = gs.perm[s_p + pk];
+      uint32_t s[RU], len[RU];
+      float4 x[RU][FL];
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        s[u] = __shfl_sync(0xffffffffu, s_l, t0 + u);
+        len[u] = __shfl_sync(0xffffffffu, e_l, t0 + u) - s[u];
+#pragma unroll
+        for (int k = 0; k < FL; ++k) {
+          const uint32_t m = __shfl_sync(gmask, m_l, gb + u * FL + k);
+          x[u][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if ((uint32_t)k < len[u] && len[u] <= (uint32_t)FL && in) x[u][k] = occ_grad4(gs, m);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        const int64_t j = wbase + t0 + u;
+        if (j >= nr) continue;
+        if (len[u] > kShortRun) {
+          if (gl == 0) a.long_list[atomicAdd(a.n_long, 1u)] = (uint32_t)j;
+          continue;
+        }
+        if (len[u] > (uint32_t)FL) {  // medium run: its own kernel (uniform work per group here)
+          if (gl == 0) a.med_list[atomicAdd(a.n_long + 1, 1u)] = (uint32_t)j;
+          continue;
+        }
+        float4 acc = x[u][0];
+#pragma unroll
+        for (int k = 1; k < FL; ++k)
+          if ((uint32_t)k < len[u]) add4(acc, x[u][k]);
+        if (in) *reinterpret_cast<float4*>(run_dst(ugrad, po, j, D) + c) = acc;
+      }
+    }
   }
+}
+
+// Medium runs (kFastRun < len <= kShortRun), one group per run, summed in position order.  Launched
+// with one group per POSSIBLE medium run (the count lives on the device): the hardware block scheduler
+// balances the uneven run lengths, blocks past the count exit at once.
+template <int G>
+__global__ void __launch_bounds__(kThreads) run_sum_med_kernel(BwdArgs a, const PeerOut po) {
+  const int gl = Group<G>::gl(), c = gl * 4;
+  const int64_t q = (int64_t)blockIdx.x * (kThreads / G) + threadIdx.x / G;
+  if (q >= (int64_t)a.n_long[1]) return;
+  const int D = a.td.dim;
+  const bool in = c < D;
+  const GradSrc gs = make_grad_src(a, c);
+  const uint32_t j = a.med_list[q];
+  const uint32_t s = a.run_start[j];
+  const float4 acc = sum_grad_rows<G, 4>(gs, s, a.run_start[j + 1] - s, in);
+  if (in) *reinterpret_cast<float4*>(run_dst(a.ugrad, po, j, D) + c) = acc;
 }
 
 // Apply: group per run; rowidx[j], ugrad[j] and the row's w / state are all independent loads.
@@ -1869,7 +1935,7 @@ __global__ void __launch_bounds__(1024) long_prep_kernel(BwdArgs a) {
 // block per piece of a long run: kThreads/G groups reduce contiguous slices in order, then the
 // slices are combined in order (fixed association: deterministic)
 template <int G>
-__global__ void __launch_bounds__(kThreads, 6) pool_bwd_long_partial_kernel(BwdArgs a) {
+__global__ void __launch_bounds__(kThreads, 4) pool_bwd_long_partial_kernel(BwdArgs a) {
   constexpr int NG = kThreads / G;
   __shared__ float4 sm[NG][G];
   const int gl = Group<G>::gl(), g = threadIdx.x / G, c = gl * 4;
@@ -1879,12 +1945,17 @@ __global__ void __launch_bounds__(kThreads, 6) pool_bwd_long_partial_kernel(BwdA
   const GradSrc gs = make_grad_src(a, c);
   const uint2* __restrict__ desc = a.piece_desc;
   float* __restrict__ partial = a.partial + c;
-  for (uint32_t wi = blockIdx.x; wi < total; wi += gridDim.x) {
+  __shared__ uint32_t next_piece;
+  while (true) {  // pieces differ 16x in size: blocks pull the next one from a device counter
+    if (threadIdx.x == 0) next_piece = atomicAdd(a.n_long + 2, 1u);
+    __syncthreads();
+    const uint32_t wi = next_piece;
+    if (wi >= total) break;
     const uint2 d = desc[wi];
     const uint32_t len = d.y;
     const uint32_t per = (len + NG - 1) / NG;
     const uint32_t b = min(len, g * per), e = min(len, b + per);
-    sm[g][gl] = sum_grad_rows<G, 4>(gs, d.x + b, e - b, in);
+    sm[g][gl] = sum_grad_rows<G, (G >= 8 ? 8 : 4)>(gs, d.x + b, e - b, in);
     __syncthreads();
     if (g == 0) {
       float4 t = sm[0][gl];
@@ -1969,6 +2040,31 @@ static void sort_and_runs(const SortWs& w, int64_t M, int bits, int pre_shift, c
   *perm_out = vin;
 }
 
+// run reduction: fast runs inline, medium runs, then the long runs' pieces; ugrad[j] (or the peer
+// window row of run j) holds the sum of run j afterwards.  The three counters at a.n_long must be zero.
+static void launch_reduce(const BwdArgs& a, const PeerOut& po, int G, int64_t M, size_t max_pieces, cudaStream_t s) {
+  const int64_t med_max = M / (kFastRun + 1) + 1;
+#define RED(GG)                                                                                               \
+  run_sum_kernel<GG><<<resident_grid(run_sum_kernel<GG>, M, kThreads), kThreads, 0, s>>>(a, po);              \
+  MONO_CHECK_LAUNCH();                                                                                        \
+  run_sum_med_kernel<GG><<<(unsigned)((med_max + kThreads / GG - 1) / (kThreads / GG)), kThreads, 0, s>>>(a, po); \
+  MONO_CHECK_LAUNCH();                                                                                        \
+  long_prep_kernel<<<1, 1024, 0, s>>>(a);                                                                     \
+  MONO_CHECK_LAUNCH();                                                                                        \
+  pool_bwd_long_partial_kernel<GG>                                                                            \
+      <<<resident_grid(pool_bwd_long_partial_kernel<GG>, (int64_t)max_pieces, 1), kThreads, 0, s>>>(a);       \
+  MONO_CHECK_LAUNCH();                                                                                        \
+  pool_bwd_long_final_kernel<GG><<<148 * 2, kThreads, 0, s>>>(a, po);                                         \
+  MONO_CHECK_LAUNCH()
+  switch (G) {
+    case 4: RED(4); break;
+    case 8: RED(8); break;
+    case 16: RED(16); break;
+    default: RED(32); break;
+  }
+#undef RED
+}
+
 static const PeerOut no_peer = {};  // n == 0: the reduce kernels write their local ugrad buffer
 
 void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t n_fids,
@@ -2019,6 +2115,7 @@ void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t 
   const size_t o_part = take(sizeof(float) * max_pieces * D);
   const size_t o_pd = take(sizeof(uint2) * max_pieces);
   const size_t o_ug = take(sizeof(float) * (size_t)M * D);
+  const size_t o_med = take(4 * ((size_t)M / (kFastRun + 1) + 2));
   char* ws = (char*)mt->ws_a.get(off, s);
   SetEntry* set = (SetEntry*)(ws + o_set);
   uint32_t *k0 = (uint32_t*)(ws + o_k0), *v0 = (uint32_t*)(ws + o_v0);
@@ -2094,6 +2191,7 @@ void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t 
   a.partial = (float*)(ws + o_part);
   a.piece_desc = (uint2*)(ws + o_pd);
   a.ugrad = (float*)(ws + o_ug);
+  a.med_list = (uint32_t*)(ws + o_med);
   a.scratch = a.ugrad;
   if (row_offsets) {
     uint32_t* occ = (uint32_t*)(ws + o_occ);
@@ -2101,16 +2199,8 @@ void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t 
     MONO_CHECK_LAUNCH();
     a.occ_row = occ;
   }
+  launch_reduce(a, no_peer, G, M, max_pieces, s);
 #define BWD2(GG, OO)                                                                                             \
-  run_sum_kernel<GG><<<resident_grid(run_sum_kernel<GG>, M, kThreads / GG), kThreads, 0, s>>>(a, no_peer);       \
-  MONO_CHECK_LAUNCH();                                                                                           \
-  long_prep_kernel<<<1, 1024, 0, s>>>(a);                                                                        \
-  MONO_CHECK_LAUNCH();                                                                                           \
-  pool_bwd_long_partial_kernel<GG>                                                                               \
-      <<<resident_grid(pool_bwd_long_partial_kernel<GG>, (int64_t)max_pieces, 1), kThreads, 0, s>>>(a);          \
-  MONO_CHECK_LAUNCH();                                                                                           \
-  pool_bwd_long_final_kernel<GG><<<148 * 2, kThreads, 0, s>>>(a, no_peer);                                       \
-  MONO_CHECK_LAUNCH();                                                                                           \
   runs_apply_kernel<GG, OO><<<resident_grid(runs_apply_kernel<GG, OO>, M, kThreads / GG), kThreads, 0, s>>>(a);  \
   MONO_CHECK_LAUNCH()
 #define BWD(GG)                                                         \
@@ -2190,6 +2280,7 @@ void run_scatter_rows(int device, const int32_t* offs_dev, int64_t M, int dim, c
   const size_t o_part = take(sizeof(float) * max_pieces * D);
   const size_t o_pd = take(sizeof(uint2) * max_pieces);
   const size_t o_ug = take(sizeof(float) * (size_t)M * D);
+  const size_t o_med = take(4 * ((size_t)M / (kFastRun + 1) + 2));
   char* ws = nullptr;
   MONO_CUDA(cudaMallocAsync((void**)&ws, off, s));
   uint32_t* ctr = (uint32_t*)(ws + o_ctr);
@@ -2232,6 +2323,7 @@ void run_scatter_rows(int device, const int32_t* offs_dev, int64_t M, int dim, c
   a.partial = (float*)(ws + o_part);
   a.piece_desc = (uint2*)(ws + o_pd);
   a.ugrad = (float*)(ws + o_ug);
+  a.med_list = (uint32_t*)(ws + o_med);
   if (row_offsets) {
     uint32_t* occ = (uint32_t*)(ws + o_occ);
     occ_row_kernel<<<resident_grid(occ_row_kernel, n_rows, kThreads), kThreads, 0, s>>>(row_offsets, n_rows, occ);
@@ -2239,16 +2331,8 @@ void run_scatter_rows(int device, const int32_t* offs_dev, int64_t M, int dim, c
     a.occ_row = occ;
   }
   const int G = pick_group(D);
+  launch_reduce(a, no_peer, G, M, max_pieces, s);
 #define EMIT(GG)                                                                                              \
-  run_sum_kernel<GG><<<resident_grid(run_sum_kernel<GG>, M, kThreads / GG), kThreads, 0, s>>>(a, no_peer);    \
-  MONO_CHECK_LAUNCH();                                                                                        \
-  long_prep_kernel<<<1, 1024, 0, s>>>(a);                                                                     \
-  MONO_CHECK_LAUNCH();                                                                                        \
-  pool_bwd_long_partial_kernel<GG>                                                                            \
-      <<<resident_grid(pool_bwd_long_partial_kernel<GG>, (int64_t)max_pieces, 1), kThreads, 0, s>>>(a);       \
-  MONO_CHECK_LAUNCH();                                                                                        \
-  pool_bwd_long_final_kernel<GG><<<148 * 2, kThreads, 0, s>>>(a, no_peer);                                    \
-  MONO_CHECK_LAUNCH();                                                                                        \
   runs_emit_kernel<GG><<<resident_grid(runs_emit_kernel<GG>, M, kThreads / GG), kThreads, 0, s>>>(a, skeys, shift, out_rows); \
   MONO_CHECK_LAUNCH()
   switch (G) {
@@ -2381,6 +2465,7 @@ void grouping_build(mono_grouping* g, const int64_t* fids_dev, int64_t M, int N,
     take(4 * n_long_max); take(4 * n_long_max); take(4 * (n_long_max + 1));          // long run lists
     take(sizeof(float) * max_pieces * dim);                                          // partial sums
     take(sizeof(uint2) * max_pieces);                                                // piece descriptors
+    take(4 * ((size_t)M / (kFastRun + 1) + 2));                                      // medium run list
     char* ws = (char*)g->ws.get(off, s);
     g->tail = ws + o_tail;
     g->tail_bytes = off - o_tail;
@@ -2451,6 +2536,7 @@ static void grouping_reduce_impl(mono_grouping* g, const float* pooled_grad, int
   const size_t o_ll = take(4 * n_long_max), o_llen = take(4 * n_long_max), o_lsb = take(4 * (n_long_max + 1));
   const size_t o_part = take(sizeof(float) * max_pieces * D);
   const size_t o_pd = take(sizeof(uint2) * max_pieces);
+  const size_t o_med = take(4 * ((size_t)M / (kFastRun + 1) + 2));
   if (off > g->tail_bytes) throw ArgError("grouping scratch too small (internal)");
   char* ws = g->tail;
   BwdArgs a;
@@ -2474,31 +2560,15 @@ static void grouping_reduce_impl(mono_grouping* g, const float* pooled_grad, int
   a.partial = (float*)(ws + o_part);
   a.piece_desc = (uint2*)(ws + o_pd);
   a.ugrad = out_rows;  // runs are already in the bucketed order: the sums are written in place
-  MONO_CUDA(cudaMemsetAsync(g->ctr + 4, 0, 4, s));  // n_long
+  a.med_list = (uint32_t*)(ws + o_med);
+  MONO_CUDA(cudaMemsetAsync(g->ctr + 4, 0, 12, s));  // n_long, n_med, work counter
   if (row_offsets) {
     uint32_t* occ = (uint32_t*)(ws + o_occ);
     occ_row_kernel<<<resident_grid(occ_row_kernel, n_rows, kThreads), kThreads, 0, s>>>(row_offsets, n_rows, occ);
     MONO_CHECK_LAUNCH();
     a.occ_row = occ;
   }
-  const int G = pick_group(D);
-#define RED(GG)                                                                                               \
-  run_sum_kernel<GG><<<resident_grid(run_sum_kernel<GG>, M, kThreads / GG), kThreads, 0, s>>>(a, po);         \
-  MONO_CHECK_LAUNCH();                                                                                        \
-  long_prep_kernel<<<1, 1024, 0, s>>>(a);                                                                     \
-  MONO_CHECK_LAUNCH();                                                                                        \
-  pool_bwd_long_partial_kernel<GG>                                                                            \
-      <<<resident_grid(pool_bwd_long_partial_kernel<GG>, (int64_t)max_pieces, 1), kThreads, 0, s>>>(a);       \
-  MONO_CHECK_LAUNCH();                                                                                        \
-  pool_bwd_long_final_kernel<GG><<<148 * 2, kThreads, 0, s>>>(a, po);                                         \
-  MONO_CHECK_LAUNCH()
-  switch (G) {
-    case 4: RED(4); break;
-    case 8: RED(8); break;
-    case 16: RED(16); break;
-    default: RED(32); break;
-  }
-#undef RED
+  launch_reduce(a, po, pick_group(D), M, max_pieces, s);
 }
 
 // out_rows[u] = summed gradient of the u-th distinct FID of the bucketed list (ref: ScatterGrad)
