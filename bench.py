@@ -49,6 +49,8 @@ def parse():
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-e2e", action="store_true")
   ap.add_argument("--sharded", action="store_true", help="run the sharded step (ShardedStep) even at N=1 (profiling)")
+  ap.add_argument("--remote-frac", type=float, default=None,
+                  help="experiment: fraction of a rank's FID occurrences owned by other ranks (default: natural 1 - 1/N)")
   ap.add_argument("--exchange", default=None, choices=["peer", "nccl"],
                   help="exchange of the sharded step: NVLink peer windows (default) or NCCL all-to-all")
   return ap.parse_args()
@@ -69,7 +71,9 @@ class Zipf:
     return np.searchsorted(self.cdf, rng.random(size), side="left").astype(np.int64)
 
 
-def make_batches(n_batches, batch, keys_per_slot, seed, zipf_s=ZIPF_S):
+def make_batches(n_batches, batch, keys_per_slot, seed, zipf_s=ZIPF_S, remote=None):
+  """remote = (frac, world, rank): experiment knob (--remote-frac) that re-draws the owner of every FID so
+  that `frac` of a rank's occurrences belong to OTHER ranks (emulates the N=8 traffic volume on 2 GPUs)."""
   rng = np.random.default_rng(seed)
   z = Zipf(keys_per_slot, zipf_s)
   # rank -> id via a fixed permutation-free affine map so that hot ids are spread over the table
@@ -79,6 +83,11 @@ def make_batches(n_batches, batch, keys_per_slot, seed, zipf_s=ZIPF_S):
     for s in range(1, SLOTS + 1):
       rank = z.sample(rng, batch)
       ident = (rank * 2654435761) % keys_per_slot  # bijection on [0, keys_per_slot) only if coprime; fine: stays in range
+      if remote is not None:
+        frac, world, me = remote
+        other = (me + 1 + rng.integers(0, max(world - 1, 1), batch)) % world
+        owner = np.where(rng.random(batch) < frac, other, me)
+        ident = np.minimum((ident // world) * world + owner, keys_per_slot - 1)
       cols.append((np.int64(s) << np.int64(48)) | ident)
     out.append(np.stack(cols, 1).reshape(-1))  # sample-major: fid index = b * SLOTS + slot
   return out
@@ -220,6 +229,7 @@ def workload_config(args, batch):
                   "reduce, Adagrad upsert with expiry bump)" + (
                       "; sharded: group by owner, FID/row/grad exchange over NVLink peer windows (fused lookup+send, reduce+send)"
                       if (args.gpus > 1 or getattr(args, "sharded", False)) else ""),
+      **({"remote_frac_experiment": args.remote_frac} if getattr(args, "remote_frac", None) is not None else {}),
       "zipf_s": args.zipf, "keys": args.keys, "dim": DIM, "slots": SLOTS, "batch_per_gpu": batch, "fids_per_step_per_gpu": batch * SLOTS,
       "l2_hygiene": "inputs larger than L2: 2.6 GB table + 4 rotating batches, 268 MB pooled output per step",
       "parallelism": (f"fid-hash sharding x{args.gpus}, exchange={getattr(args, 'exchange', None) or os.environ.get('MONO_EXCHANGE', 'peer')}"
@@ -269,7 +279,8 @@ def run_ours(args):
 
   NB = 4
   M = args.batch * SLOTS
-  batches_np = make_batches(NB, args.batch, gkeys_per_slot, seed=2 + rank, zipf_s=args.zipf)
+  batches_np = make_batches(NB, args.batch, gkeys_per_slot, seed=2 + rank, zipf_s=args.zipf,
+                            remote=None if args.remote_frac is None else (args.remote_frac, world, rank))
   fids_dev = [torch.from_numpy(b).to(dev) for b in batches_np]
   gen = torch.Generator(device=dev)
   gen.manual_seed(5 + rank)

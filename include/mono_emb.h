@@ -363,6 +363,8 @@ int mono_embedding_to_layout_grad(int32_t device, float* const* emb_grad_ptrs_de
  *   barrier : stream-ordered; returns immediately.  Every rank must call it the same number of times.
  *   put     : nbytes[r] bytes from src_dev + src_off[r] into rank r's window at region_off + dst_off[r]
  *             (multiples of 8 bytes).
+ *   get     : the mirror of put: nbytes[r] bytes of rank r's window at region_off + src_off[r] are read
+ *             into dst_dev + dst_off[r] (multiples of 16 bytes).
  *   lookup_push       : fused lookup + row exchange.  ids_dev = counts[0] ids of rank 0, then counts[1]
  *             of rank 1, ...; the row of rank r's i-th id is stored into rank r's window at
  *             region_off + (dst_row_off[r] + i) * dim * 4.  Absent ids give zero rows.  dim % 4 == 0.
@@ -379,6 +381,8 @@ int mono_peer_local(mono_peer_t* p, void** data_dev_out);
 int mono_peer_barrier(mono_peer_t* p, void* stream);
 int mono_peer_put(mono_peer_t* p, int64_t region_off, const int64_t* dst_off, const void* src_dev,
                   const int64_t* src_off, const int64_t* nbytes, void* stream);
+int mono_peer_get(mono_peer_t* p, int64_t region_off, const int64_t* src_off, void* dst_dev,
+                  const int64_t* dst_off, const int64_t* nbytes, void* stream);
 int mono_mtable_lookup_push(mono_mtable_t* t, int32_t k, const int64_t* ids_dev, const int64_t* counts,
                             mono_peer_t* p, int64_t region_off, const int64_t* dst_row_off, void* stream);
 int mono_grouping_reduce_push(mono_grouping_t* g, const float* pooled_grad_dev, int64_t grad_stride,

@@ -81,6 +81,7 @@ SIGNATURES = {
     "mono_peer_local": (C.c_int, [_p, C.POINTER(_p)]),
     "mono_peer_barrier": (C.c_int, [_p, _p]),
     "mono_peer_put": (C.c_int, [_p, _i64, _p, _p, _p, _p, _p]),
+    "mono_peer_get": (C.c_int, [_p, _i64, _p, _p, _p, _p, _p]),
     "mono_mtable_lookup_push": (C.c_int, [_p, _i32, _p, _p, _p, _i64, _p, _p]),
     "mono_grouping_reduce_push": (C.c_int, [_p, _p, _i64, _i32, _p, _i64, _i32, _p, _p, _i64, _p, _p]),
     "mono_gather_pool": (C.c_int, [_i32, _p, _p, _p, _i64, _i32, _i32, _p, _i64, _i32, _p]),

@@ -555,6 +555,14 @@ int mono_peer_put(mono_peer_t* p, int64_t region_off, const int64_t* dst_off, co
   });
 }
 
+int mono_peer_get(mono_peer_t* p, int64_t region_off, const int64_t* src_off, void* dst_dev,
+                  const int64_t* dst_off, const int64_t* nbytes, void* stream) {
+  return guarded([&] {
+    require(p && src_off && dst_dev && dst_off && nbytes, "mono_peer_get: null argument");
+    peer_get(p, region_off, src_off, dst_dev, dst_off, nbytes, (cudaStream_t)stream);
+  });
+}
+
 int mono_mtable_lookup_push(mono_mtable_t* t, int32_t k, const int64_t* ids_dev, const int64_t* counts,
                             mono_peer_t* p, int64_t region_off, const int64_t* dst_row_off, void* stream) {
   return guarded([&] {

@@ -210,6 +210,8 @@ void peer_attach(mono_peer* p, const void* handles);
 void peer_barrier(mono_peer* p, cudaStream_t s);
 void peer_put(mono_peer* p, int64_t region_off, const int64_t* dst_off, const void* src,
               const int64_t* src_off, const int64_t* nbytes, cudaStream_t s);
+void peer_get(mono_peer* p, int64_t region_off, const int64_t* src_off, void* dst, const int64_t* dst_off,
+              const int64_t* nbytes, cudaStream_t s);
 PeerOut peer_out(mono_peer* p, int64_t region_off, const int64_t* dst_item_off, const int64_t* counts,
                  int64_t item_bytes);
 void launch_lookup_push(mono_mtable* mt, int k, const int64_t* ids_dev, int64_t n_total, const PeerOut& po,

@@ -1746,14 +1746,17 @@ __device__ __forceinline__ float4 sum_grad_rows(const GradSrc& gs, uint32_t s, u
   const int gl = Group<G>::gl(), gb = Group<G>::base();
   const uint32_t gmask = Group<G>::mask();
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  // the next G permutation entries are requested before the current G rows, so the row reads of
+  // chunk q never wait for an index load (only the very first chunk pays the two-level chain)
+  uint32_t m_cur = (uint32_t)gl < len ? gs.perm[s + gl] : 0u;
   for (uint32_t q0 = 0; q0 < len; q0 += G) {
-    const uint32_t m_l = (q0 + gl < len) ? gs.perm[s + q0 + gl] : 0u;
+    const uint32_t m_next = (q0 + G + gl < len) ? gs.perm[s + q0 + G + gl] : 0u;
     const int cnt = (int)min((uint32_t)G, len - q0);
     for (int u0 = 0; u0 < cnt; u0 += UNR) {
       float4 g[UNR];
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
-        const uint32_t m = __shfl_sync(gmask, m_l, gb + min(u0 + u, G - 1));
+        const uint32_t m = __shfl_sync(gmask, m_cur, gb + min(u0 + u, G - 1));
         g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (u0 + u < cnt && in) g[u] = occ_grad4(gs, m);
       }
@@ -1763,13 +1766,11 @@ __device__ __forceinline__ float4 sum_grad_rows(const GradSrc& gs, uint32_t s, u
         if (q0 + u0 + u == 0) acc = g[u]; else add4(acc, g[u]);
       }
     }
+    m_cur = m_next;
   }
   return acc;
 }
 
-// Reduce: group per run, short runs are summed (in position order) into ugrad[j]; long runs are
-// queued.  No table access here: few registers, 8 resident blocks per SM, every gradient-row read is
-// independent of the others in flight.  Runs are ordered, so ugrad is written sequentially.
 // destination of run j's summed row: ugrad[j], or (po.n != 0: the sharded backward's fused gradient
 // exchange) row j of an owner-bucketed list whose part r lives in rank r's peer window.
 __device__ __forceinline__ float* run_dst(float* ugrad, const PeerOut& po, int64_t j, int D) {
@@ -1778,18 +1779,18 @@ __device__ __forceinline__ float* run_dst(float* ugrad, const PeerOut& po, int64
   return reinterpret_cast<float*>(po.base[r]) + (j - po.start[r]) * D;
 }
 
-// Warp tile of 32 runs: a lane fetches one run's bounds (coalesced), then every group takes RU runs per
-// iteration.  Runs of <= FL occurrences (the bulk of a Zipf batch) go through the fast path: the RU*FL
-// permutation entries are fetched by RU*FL lanes at once and all RU*FL gradient rows are requested before
-// the first add, so a group keeps up to 8 independent 128-byte reads in flight instead of ~1.5.
+// Fast runs (<= kFastRun occurrences: the bulk of a Zipf batch).  Warp tile of 32 runs, everything that
+// can be fetched lane-parallel is: (A) lane l reads run l's bounds and its <= 4 permutation entries
+// (coalesced, independent), medium / long runs are appended to their lists with one atomic per warp;
+// (B) CH runs per group are reduced together: for occurrence k = 0..3 all CH gradient rows are requested
+// before the first add, so a warp keeps up to 16 independent 128-byte row reads in flight (the op is
+// bound by random row reads).  Adds stay in occurrence order (bit-exact with the reference).
 template <int G>
 __global__ void __launch_bounds__(kThreads, 4) run_sum_kernel(BwdArgs a, const PeerOut po) {
-  constexpr int RPI = 32 / G;          // groups per warp
-  constexpr int RU = G >= 8 ? 2 : 1;   // runs per group per iteration
-  constexpr int FL = kFastRun;         // fast-path run length
-  static_assert(RU * FL <= G, "perm prefetch needs one lane per (run, occurrence)");
-  const int lane = threadIdx.x & 31, gl = Group<G>::gl(), grp = lane / G, gb = Group<G>::base();
-  const uint32_t gmask = Group<G>::mask();
+  constexpr int RPI = 32 / G;            // groups per warp
+  constexpr int FL = kFastRun;
+  constexpr int CH = 4;                  // runs reduced together by one group (G >= 4 runs per group and tile)
+  const int lane = threadIdx.x & 31, gl = Group<G>::gl(), grp = lane / G;
   const int c = gl * 4;
   const int64_t nr = *a.n_runs;
   const int D = a.td.dim;
@@ -1797,52 +1798,63 @@ __global__ void __launch_bounds__(kThreads, 4) run_sum_kernel(BwdArgs a, const P
   const GradSrc gs = make_grad_src(a, c);
   const uint32_t* __restrict__ run_start = a.run_start;
   float* __restrict__ ugrad = a.ugrad;
-  const int pu = gl / FL, pk = gl % FL;  // this lane's (run, occurrence) in the perm prefetch
   const int64_t wstride = (int64_t)gridDim.x * (kThreads / 32) * 32;
   for (int64_t wbase = ((int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * 32; wbase < nr;
        wbase += wstride) {
-    uint32_t s_l = 0, e_l = 0;
-    if (wbase + lane < nr) {
-      s_l = run_start[wbase + lane];
-      e_l = run_start[wbase + lane + 1];
+    // ---- phase A: lane per run ----
+    const int64_t j_l = wbase + lane;
+    uint32_t s_l = 0, len_l = 0;
+    if (j_l < nr) {
+      s_l = run_start[j_l];
+      len_l = run_start[j_l + 1] - s_l;
     }
+    const uint32_t fast_len = len_l <= (uint32_t)FL ? len_l : 0u;  // 0: not handled here
+    uint32_t m_l[FL];
+#pragma unroll
+    for (int k = 0; k < FL; ++k) m_l[k] = (uint32_t)k < fast_len ? gs.perm[s_l + k] : 0u;
+    {
+      const bool med = len_l > (uint32_t)FL && len_l <= (uint32_t)kShortRun;
+      const bool lng = len_l > (uint32_t)kShortRun;
+      const uint32_t bm = __ballot_sync(0xffffffffu, med), bl = __ballot_sync(0xffffffffu, lng);
+      if (bm) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(a.n_long + 1, (uint32_t)__popc(bm));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (med) a.med_list[base + __popc(bm & ((1u << lane) - 1u))] = (uint32_t)j_l;
+      }
+      if (bl) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(a.n_long, (uint32_t)__popc(bl));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lng) a.long_list[base + __popc(bl & ((1u << lane) - 1u))] = (uint32_t)j_l;
+      }
+    }
+    // ---- phase B: group per run, CH runs at a time ----
 #pragma unroll 1
-    for (int it = 0; it < G / RU; ++it) {
-      const int t0 = (it * RPI + grp) * RU;  // tile-local index of this group's first run
-      const uint32_t s_p = __shfl_sync(0xffffffffu, s_l, min(t0 + pu, 31));
-      const uint32_t n_p = __shfl_sync(0xffffffffu, e_l, min(t0 + pu, 31)) - s_p;
-      uint32_t m_l = 0;
-      if (pu < RU && (uint32_t)pk < n_p && n_p <= (uint32_t)FL) m_l = gs.perm[s_p + pk];
-      uint32_t s[RU], len[RU];
-      float4 x[RU][FL];
+    for (int it0 = 0; it0 < G; it0 += CH) {
+      float4 acc[CH];
+      uint32_t len[CH];
 #pragma unroll
-      for (int u = 0; u < RU; ++u) {
-        s[u] = __shfl_sync(0xffffffffu, s_l, t0 + u);
-        len[u] = __shfl_sync(0xffffffffu, e_l, t0 + u) - s[u];
+      for (int t = 0; t < CH; ++t) len[t] = __shfl_sync(0xffffffffu, fast_len, (it0 + t) * RPI + grp);
 #pragma unroll
-        for (int k = 0; k < FL; ++k) {
-          const uint32_t m = __shfl_sync(gmask, m_l, gb + u * FL + k);
-          x[u][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if ((uint32_t)k < len[u] && len[u] <= (uint32_t)FL && in) x[u][k] = occ_grad4(gs, m);
+      for (int k = 0; k < FL; ++k) {
+        float4 x[CH];
+#pragma unroll
+        for (int t = 0; t < CH; ++t) {
+          const uint32_t m = __shfl_sync(0xffffffffu, m_l[k], (it0 + t) * RPI + grp);
+          x[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if ((uint32_t)k < len[t] && in) x[t] = occ_grad4(gs, m);
+        }
+#pragma unroll
+        for (int t = 0; t < CH; ++t) {
+          if (k == 0) acc[t] = x[t];
+          else if ((uint32_t)k < len[t]) add4(acc[t], x[t]);
         }
       }
 #pragma unroll
-      for (int u = 0; u < RU; ++u) {
-        const int64_t j = wbase + t0 + u;
-        if (j >= nr) continue;
-        if (len[u] > kShortRun) {
-          if (gl == 0) a.long_list[atomicAdd(a.n_long, 1u)] = (uint32_t)j;
-          continue;
-        }
-        if (len[u] > (uint32_t)FL) {  // medium run: its own kernel (uniform work per group here)
-          if (gl == 0) a.med_list[atomicAdd(a.n_long + 1, 1u)] = (uint32_t)j;
-          continue;
-        }
-        float4 acc = x[u][0];
-#pragma unroll
-        for (int k = 1; k < FL; ++k)
-          if ((uint32_t)k < len[u]) add4(acc, x[u][k]);
-        if (in) *reinterpret_cast<float4*>(run_dst(ugrad, po, j, D) + c) = acc;
+      for (int t = 0; t < CH; ++t) {
+        const int64_t j = wbase + (it0 + t) * RPI + grp;
+        if (len[t] != 0 && in) *reinterpret_cast<float4*>(run_dst(ugrad, po, j, D) + c) = acc[t];
       }
     }
   }
@@ -1861,7 +1873,7 @@ __global__ void __launch_bounds__(kThreads) run_sum_med_kernel(BwdArgs a, const 
   const GradSrc gs = make_grad_src(a, c);
   const uint32_t j = a.med_list[q];
   const uint32_t s = a.run_start[j];
-  const float4 acc = sum_grad_rows<G, 4>(gs, s, a.run_start[j + 1] - s, in);
+  const float4 acc = sum_grad_rows<G, (G >= 8 ? 8 : 4)>(gs, s, a.run_start[j + 1] - s, in);
   if (in) *reinterpret_cast<float4*>(run_dst(a.ugrad, po, j, D) + c) = acc;
 }
 

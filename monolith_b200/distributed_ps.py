@@ -91,9 +91,15 @@ class _Phases:
   def __init__(self, enabled):
     import os
     self.enabled = enabled
+    self.level = int(os.environ.get("MONO_TIMING", "0") or 0)
     self.marks = []
     self.acc = {}
     self.skip = int(os.environ.get("MONO_TIMING_SKIP", "5"))  # warm-up steps left out of the averages
+
+  def fine(self, name):
+    """extra marks inside a phase (MONO_TIMING=2): kernel time vs the barrier wait that follows"""
+    if self.enabled and self.level >= 2:
+      self.mark(name)
 
   def mark(self, name):
     if self.enabled:
@@ -291,10 +297,17 @@ class ShardedStep:
     self.grouping = distribution_ops.Grouping(device)
     self.k = table.table_names.index(name)
     self.K = len(table.table_names)
-    self.phases = _Phases(os.environ.get("MONO_TIMING", "0") == "1")
+    self.phases = _Phases(os.environ.get("MONO_TIMING", "0") in ("1", "2"))
     self.exchange = exchange or os.environ.get("MONO_EXCHANGE", "peer")
     if self.exchange not in ("peer", "nccl"):
       raise ValueError("exchange must be 'peer' or 'nccl'")
+    # bulk rows / gradients: "push" = the producing kernel stores them into the consumer's window (fused
+    # lookup+send / reduce+send; default), "pull" = the producer writes its own window and the consumer
+    # copies it over with remote loads (one more pass; measured slower on 2 GPUs at both 1/2 and 7/8 remote
+    # share: 0.93 vs 0.86 ms and 1.18 vs 1.07 ms per step, profiles/r1_exchange_ab.md)
+    self.bulk = os.environ.get("MONO_PEER_BULK", "push")
+    if self.bulk not in ("pull", "push"):
+      raise ValueError("MONO_PEER_BULK must be 'pull' or 'push'")
     self.window = None
     self.hostx = HostCounts(world, rank, world + 1, group) if self.exchange == "peer" else None
     self.cap_rows = self.cap_recv = self._base_m = 0
@@ -316,6 +329,10 @@ class ShardedStep:
     self.off_rows = self.off_ids[1] + al(self.cap_recv * 8)
     self.off_grads = self.off_rows + al(self.cap_rows * D * 4)
     total = self.off_grads + al(self.cap_recv * D * 4)
+    # pull mode: rows_out (owner side, what the requesters read) and grads_out (requester side)
+    self.off_rows_out = total
+    self.off_grads_out = self.off_rows_out + al(self.cap_recv * D * 4)
+    total = self.off_grads_out + al(self.cap_rows * D * 4)
     self.window = self.dops.PeerWindow(self.device, self.N, self.rank, total, self.group)
 
   def _step_peer(self, fids, pooled_grad, out, req_time, row_offsets, pooling):
@@ -336,20 +353,41 @@ class ShardedStep:
     row_pre = np.concatenate([np.zeros((N, 1), np.int64), np.cumsum(cnt, axis=1)], axis=1)  # row_pre[r][o] = sum_{o'<o} cnt[r][o']
     my_seg = col_pre[me]                              # where my items start inside owner o's received list
     self.window.put(self.off_ids[par], my_seg * 8, uniq, row_pre[me, :N] * 8, cnt[me] * 8)   # 3
+    ph.fine("f3a_put_kernel")
     self.window.barrier()
     ph.mark("f3_put_ids")
     ids_in = self.window.view(self.off_ids[par], tot_recv, torch.int64)
-    self.table.lookup_push(self.name, ids_in, recv, self.window, self.off_rows, row_pre[:, me])  # 4+5
-    self.window.barrier()
-    ph.mark("f5_lookup_push")
     rows_in = self.window.view(self.off_rows, uniq.numel() * D, torch.float32)
+    grads_in = self.window.view(self.off_grads, tot_recv * D, torch.float32)
+    slot = self._slot(recv)
+    if self.bulk == "push":
+      self.table.lookup_push(self.name, ids_in, recv, self.window, self.off_rows, row_pre[:, me])  # 4+5
+      ph.fine("f5a_lookup_push_kernel")
+      self.window.barrier()
+      ph.mark("f5_lookup_push")
+    else:
+      rows_out = self.window.view(self.off_rows_out, tot_recv * D, torch.float32)     # 4 owner: rows of requester r at col_pre[r][me]
+      self.table.fused_lookup(ids_in, slot, N, out=rows_out)
+      ph.fine("f5a_owner_lookup")
+      self.window.barrier()
+      ph.fine("f5b_barrier")
+      self.window.get(self.off_rows_out, col_pre[me, :] * D * 4, rows_in, row_pre[me, :N] * D * 4, cnt[me] * D * 4)  # 5 pull
+      ph.mark("f5_lookup_pull")
     self.dops.gather_pool(rows_in, offs, D, row_offsets, pooling, out=out)            # 6
     ph.mark("f6_gather_pool")
-    self.grouping.reduce_push(pooled_grad, cnt[me], self.window, self.off_grads, my_seg, row_offsets, pooling)  # 7+8
-    self.window.barrier()
-    ph.mark("b8_reduce_push")
-    grads_in = self.window.view(self.off_grads, tot_recv * D, torch.float32)
-    slot = self._slot(recv)                                                           # 9
+    if self.bulk == "push":
+      self.grouping.reduce_push(pooled_grad, cnt[me], self.window, self.off_grads, my_seg, row_offsets, pooling)  # 7+8
+      ph.fine("b8a_reduce_push_kernels")
+      self.window.barrier()
+      ph.mark("b8_reduce_push")
+    else:
+      grads_out = self.window.view(self.off_grads_out, uniq.numel() * D, torch.float32)
+      self.grouping.reduce(pooled_grad, grads_out, row_offsets, pooling)              # 7 requester: bucketed by owner
+      ph.fine("b8a_reduce")
+      self.window.barrier()
+      ph.fine("b8b_barrier")
+      self.window.get(self.off_grads_out, row_pre[:, me] * D * 4, grads_in, col_pre[:N, me] * D * 4, recv * D * 4)  # 8 pull
+      ph.mark("b8_reduce_pull")                                                        # 9
     _, _, id_off, emb_off = self.table.fused_offsets(slot, N)
     self.table.fused_apply_gradient(ids_in, ids_in, slot, grads_in, id_off, emb_off, 0, req_time, N)
     ph.mark("b9_owner_apply")

@@ -245,6 +245,15 @@ class PeerWindow:
                                        _stream(self.device)))
 
 
+  def get(self, region_off: int, src_off: Sequence[int], dst: torch.Tensor, dst_off: Sequence[int],
+          nbytes: Sequence[int]):
+    """nbytes[r] bytes of rank r's window at region_off + src_off[r] -> dst (+ dst_off[r], bytes)."""
+    n = self.world
+    arr = lambda xs: (C.c_int64 * n)(*[int(x) for x in xs])
+    _lib.check(self._lib.mono_peer_get(self._h, int(region_off), arr(src_off), _ptr(dst), arr(dst_off), arr(nbytes),
+                                       _stream(self.device)))
+
+
 # ---- generic fused layout op ------------------------------------------------------------------
 @dataclasses.dataclass
 class SliceTask:

@@ -252,14 +252,18 @@ class MultiHashTable:
     _lib.check(self._lib.mono_mtable_fused_offsets(self._h, ss, num_of_shards, emb_splits, id_off, emb_off))
     return ss, list(emb_splits), list(id_off), list(emb_off)
 
-  def fused_lookup(self, ids: torch.Tensor, fused_slot_size: Sequence[int], num_of_shards: int, req_time: int = 0):
+  def fused_lookup(self, ids: torch.Tensor, fused_slot_size: Sequence[int], num_of_shards: int, req_time: int = 0,
+                   out: Optional[torch.Tensor] = None):
     """ref: multi_hash_table_ops.py:442-454 -> MonolithMultiHashTableFusedLookup.
     Returns (embeddings, embedding_splits, id_offsets, embedding_offsets, indices)."""
     ids = _ids(ids, self._device)
     ss, emb_splits, id_off, emb_off = self.fused_offsets(fused_slot_size, num_of_shards)
     if id_off[-1] != ids.numel():
       raise ValueError("fused_slot_size does not cover ids")
-    out = torch.empty(emb_off[-1], dtype=torch.float32, device=self._device)
+    if out is None:
+      out = torch.empty(emb_off[-1], dtype=torch.float32, device=self._device)
+    elif out.numel() < emb_off[-1] or out.dtype != torch.float32 or not out.is_contiguous():
+      raise ValueError("fused_lookup: out must be a contiguous float32 buffer of at least emb_offsets[-1] floats")
     _lib.check(self._lib.mono_mtable_fused_lookup(self._h, _ptr(ids), ss, num_of_shards, int(req_time), _ptr(out),
                                                   _stream(self._device)))
     return out, emb_splits, id_off, emb_off, ids

@@ -131,6 +131,9 @@ def _fast_worker(rank, world, port, q, exchange="peer"):
     from monolith_b200 import MultiHashTable
     from monolith_b200.distributed_ps import ShardedStep
     table = MultiHashTable(_fast_cfg(), device=dev)
+    if exchange.startswith("peer-"):
+      os.environ["MONO_PEER_BULK"] = exchange.split("-")[1]
+      exchange = "peer"
     st = ShardedStep(table, "t", 16, world, rank, dev, exchange=exchange)
     pooled_all = []
     for step in range(3):
@@ -152,10 +155,10 @@ def _fast_worker(rank, world, port, q, exchange="peer"):
     raise
 
 
-@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+@pytest.mark.parametrize("exchange", ["peer-pull", "peer-push", "nccl"])
 def test_sharded_fast_step_two_gpus(exchange):
-  """ShardedStep on 2 GPUs == one global oracle table; exchange over NVLink peer windows (fused
-  lookup+send / reduce+send kernels, flag barriers) and over NCCL all-to-all."""
+  """ShardedStep on 2 GPUs == one global oracle table; exchange over NVLink peer windows (bulk data pulled
+  by the consumer, or pushed by the fused lookup+send / reduce+send kernels; flag barriers) and over NCCL."""
   if torch.cuda.device_count() < 2:
     pytest.skip("needs 2 GPUs")
   import torch.multiprocessing as mp
@@ -163,7 +166,7 @@ def test_sharded_fast_step_two_gpus(exchange):
   world = 2
   ctx = mp.get_context("spawn")
   q = ctx.Queue()
-  port = 29900 + (os.getpid() % 90) + (7 if exchange == "nccl" else 0)
+  port = 29900 + (os.getpid() % 90) + {"peer-pull": 0, "peer-push": 3, "nccl": 7}[exchange]
   procs = [ctx.Process(target=_fast_worker, args=(r, world, port, q, exchange)) for r in range(world)]
   for p in procs:
     p.start()

@@ -467,16 +467,24 @@ def test_peer_window_single_rank_ops(dev):
   g.reduce_push(pg, sizes, w, 2 << 20, [1])
   w.barrier()
   np.testing.assert_array_equal(w.view((2 << 20) + D * 4, uniq.numel() * D, torch.float32).cpu().numpy(), want)
+  # get: the mirror of put (here from the rank's own window)
+  dst = torch.zeros(q.size * D, device=dev)
+  w.get(1 << 20, [3 * D * 4], dst, [0], [q.size * D * 4])
+  np.testing.assert_array_equal(dst.cpu().numpy().reshape(-1, D), got)
   with pytest.raises(Exception):
     w.put(0, [(1 << 22) - 8], T(keys, dev), [0], [16])    # outside the window
+  with pytest.raises(Exception):
+    w.get(0, [(1 << 22) - 16], dst, [0], [32])
   w.close()
 
 
+@pytest.mark.parametrize("bulk", ["pull", "push"])
 @pytest.mark.parametrize("pooling", ["sum", "mean"])
-def test_sharded_step_peer_single_rank(pooling, dev):
+def test_sharded_step_peer_single_rank(pooling, bulk, dev, monkeypatch):
   """ShardedStep over the peer window with world == 1 against the oracle table (same protocol as the 2-GPU test)."""
   from monolith_b200 import MultiHashTable
   from monolith_b200.distributed_ps import ShardedStep
+  monkeypatch.setenv("MONO_PEER_BULK", bulk)
   rng = np.random.default_rng(11)
   D = 16
   cfg = {"t": table([(D, "adagrad", {})], [0.1])}
