@@ -1456,37 +1456,60 @@ radix_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restri
   }
 }
 
-// exclusive scan of every digit row blk_cnt[d][0..nblk): one warp per digit; 1024 elements per
-// step are loaded coalesced into registers up front (32 independent loads), scanned with shuffles,
-// and stored coalesced.
-__global__ void __launch_bounds__(32) radix_rowscan_kernel(int32_t* __restrict__ blk_cnt, int nblk) {
-  const int lane = threadIdx.x;
+// per-tile digit histogram (the counting half of a pass): shared-memory atomics, one tile per block
+// iteration, same tiling as the scatter kernel (radix_pass_kernel<1>)
+__global__ void __launch_bounds__(kThreads)
+radix_hist_kernel(const uint32_t* __restrict__ keys_in, int64_t n, int shift, int pre_shift,
+                  int32_t* __restrict__ blk_cnt, int32_t* __restrict__ dtot, int nblk) {
+  static_assert(kThreads == 256, "one digit per thread");
+  __shared__ int32_t cnt[256];
+  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blk * kSortTile;
+#pragma unroll
+    for (int c = 0; c < kSortTile; c += kThreads) {
+      const int64_t i = base + c + threadIdx.x;
+      if (i < n) atomicAdd(&cnt[((keys_in[i] >> pre_shift) >> shift) & 255u], 1);
+    }
+    __syncthreads();
+    const int v = cnt[threadIdx.x];
+    blk_cnt[(size_t)threadIdx.x * nblk + blk] = v;
+    if (v) atomicAdd(dtot + threadIdx.x, v);
+    __syncthreads();
+  }
+}
+
+// exclusive scan of every digit row blk_cnt[d][0..nblk): one 1024-thread block per digit
+__global__ void __launch_bounds__(1024) radix_rowscan_kernel(int32_t* __restrict__ blk_cnt, int nblk) {
+  __shared__ int32_t wsum[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int32_t* row = blk_cnt + (size_t)blockIdx.x * nblk;
   int carry = 0;
   for (int base = 0; base < nblk; base += 1024) {
-    int v[32];
+    const int idx = base + threadIdx.x;
+    const int v = idx < nblk ? row[idx] : 0;
+    int x = v;
 #pragma unroll
-    for (int t = 0; t < 32; ++t) {
-      const int idx = base + t * 32 + lane;
-      v[t] = idx < nblk ? row[idx] : 0;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
     }
-#pragma unroll
-    for (int t = 0; t < 32; ++t) {
-      int x = v[t];
+    if (lane == 31) wsum[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      int t = wsum[lane];
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, x, o);
-        if (lane >= o) x += y;
+        const int y = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += y;
       }
-      const int excl = carry + x - v[t];
-      carry += __shfl_sync(0xffffffffu, x, 31);
-      v[t] = excl;
+      wsum[lane] = t;
     }
-#pragma unroll
-    for (int t = 0; t < 32; ++t) {
-      const int idx = base + t * 32 + lane;
-      if (idx < nblk) row[idx] = v[t];
-    }
+    __syncthreads();
+    if (idx < nblk) row[idx] = carry + (w ? wsum[w - 1] : 0) + x - v;
+    carry += wsum[31];
+    __syncthreads();
   }
 }
 
@@ -2026,14 +2049,14 @@ static void sort_and_runs(const SortWs& w, int64_t M, int bits, int pre_shift, c
   const int nblk = (int)((M + kSortTile - 1) / kSortTile);
   const uint32_t* vin = nullptr;  // first pass: value = position
   uint32_t *kin = w.k0, *kout = w.k1, *vout = w.v1;
-  const int gh = resident_grid(radix_pass_kernel<0>, nblk, 1);
+  const int gh = resident_grid(radix_hist_kernel, nblk, 1);
   const int gs = resident_grid(radix_pass_kernel<1>, nblk, 1);
   for (int p = 0; p < passes; ++p) {
     int32_t* dt = w.dtot + 256 * p;
     const int ps = p == 0 ? pre_shift : 0;
-    radix_pass_kernel<0><<<gh, kThreads, 0, s>>>(kin, vin, M, 8 * p, ps, w.blk_cnt, dt, nblk, nullptr, nullptr, nullptr);
+    radix_hist_kernel<<<gh, kThreads, 0, s>>>(kin, M, 8 * p, ps, w.blk_cnt, dt, nblk);
     MONO_CHECK_LAUNCH();
-    radix_rowscan_kernel<<<256, 32, 0, s>>>(w.blk_cnt, nblk);
+    radix_rowscan_kernel<<<256, 1024, 0, s>>>(w.blk_cnt, nblk);
     MONO_CHECK_LAUNCH();
     radix_pass_kernel<1><<<gs, kThreads, 0, s>>>(kin, vin, M, 8 * p, ps, w.blk_cnt, dt, nblk, kout, vout, nullptr);
     MONO_CHECK_LAUNCH();
@@ -2076,6 +2099,9 @@ static void launch_reduce(const BwdArgs& a, const PeerOut& po, int G, int64_t M,
   }
 #undef RED
 }
+
+__global__ void fid_claim_kernel(const int64_t* __restrict__ fids, int64_t n, SetEntry* set, uint32_t R, int N,
+                                 uint32_t* __restrict__ slot_of, uint32_t* __restrict__ owner_cnt);
 
 static const PeerOut no_peer = {};  // n == 0: the reduce kernels write their local ugrad buffer
 
@@ -2139,8 +2165,8 @@ void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t 
   MONO_CUDA(cudaMemsetAsync(ctr, 0, 4096 + 4 * 256 * 4, s));
 
   // 1 claim: k0[i] = set slot of occurrence i
-  dup_claim_kernel<<<resident_grid(dup_claim_kernel, M, kThreads), kThreads, 0, s>>>(cb.segs, 1, fids_dev, nullptr, M,
-                                                                                    set, cap - 1, k0);
+  // (one table, no first-occurrence bookkeeping needed: the lighter single-list claim; ctr + 512.. is unused scratch)
+  fid_claim_kernel<<<resident_grid(fid_claim_kernel, M, kThreads), kThreads, 0, s>>>(fids_dev, M, set, cap, 1, k0, ctr + 512);
   MONO_CHECK_LAUNCH();
   // 2 stable LSD radix sort of (slot, position)  +  3 ordered run list
   SortWs sw;
