@@ -7,8 +7,11 @@ FID = (slot << 48) | rank, rank ~ truncated Zipf(1.05) over 5 M ids per slot.
 
 One "step" = the whole sparse part of one training step for one batch:
     forward : fused probe + row gather + per-slot pool of the M = 2B FID occurrences -> pooled [B, 2*32]
-    backward: FID dedup (first-occurrence order) + scatter of the pooled grads to the U unique rows
-              + fused Adagrad update + expiry-timestamp bump (upsert)
+    backward: group the occurrences by FID (scratch set + stable radix sort), deterministic per-FID sum of
+              the pooled grads (no float atomics), fused Adagrad update + expiry-timestamp bump (upsert)
+  N > 1 (torchrun, one rank per GPU, weak scaling): the same step sharded by fid mod N (ShardedStep): group by
+  owner, FIDs / rows / row gradients exchanged through NVLink peer windows (fused lookup+send and
+  reduce+send kernels, flag barriers), owners apply the requesters' gradients in rank order.
 `value`  = FID occurrences (lookups) per second over all ranks, inputs resident in HBM.
 `e2e`    = same step through the public Python API with pinned HOST inputs (FIDs, pooled grads) copied
            H2D and the pooled embeddings copied D2H inside the timed region.
