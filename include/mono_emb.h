@@ -234,6 +234,10 @@ int mono_mtable_export(mono_mtable_t* t, int32_t k, int64_t* cursor, int64_t max
 /* Upsert full rows (emb + optimizer state + ts), ref: Restore, cuckoo_embedding_hash_table.cc:299-320 */
 int mono_mtable_restore_rows(mono_mtable_t* t, int32_t k, const int64_t* ids_dev, int64_t n,
                              const float* entry_in_dev, void* stream);
+/* Restore side of max_update_ts: the reference's Restore returns the largest last_update_ts_sec it read and
+ * the table keeps it (cuckoo_embedding_hash_table.cc:299-321; embedding_hash_table_tf_bridge.cc Restore);
+ * the caller reports it here after mono_mtable_restore_rows (max with the current value). */
+int mono_mtable_note_update_ts(mono_mtable_t* t, int32_t k, int64_t ts);
 
 /* ---- dedup + shard (requester side) ------------------------------------------------------- */
 
@@ -403,6 +407,47 @@ int mono_mtable_optimize_host(mono_mtable_t* t, const int64_t* ids_host,
                               const int64_t* id_split_host, const float* grads_host,
                               const float* learning_rate_host, int64_t update_time,
                               int64_t global_step, uint32_t flags);
+
+/* ---- checkpoint files in the reference's on-disk format (host-only) -------
+ * ref: MonolithMultiHashTableSave / Restore, RT/ops/multi_hash_table_save_restore_ops.cc:105-388.
+ *   <basename>-%05d-of-%05d      TFRecord stream, Snappy block compression: per table, one serialized
+ *                                EntryDump (embedding_hash_table.proto:45-50) per live entry
+ *   <basename>.meta-%05d-of-%05d TFRecord stream: one MultiHashTableMetadata {table_name, num_entries}
+ *                                per table, in the order the tables were written
+ * Rows cross this boundary in mono_mtable_export / mono_mtable_restore_rows layout:
+ * n x (dim + state_floats + 2) floats = [num | optimizer state | found | last_update_ts (u32 bits)].
+ * writer: open -> (begin_table -> add* -> end_table)* -> close(commit = 1 renames the temporary files).
+ *   add drops expired entries like the reference's save (max_update_ts - ts >= expire_days(slot) * 86400);
+ *   expire_days_by_slot has 32768 entries (slot = (id >> 48) & 0x7fff) or is NULL (keep everything).
+ * reader: open -> (next_table -> read*)* -> close; read decodes against the caller's segment list.
+ * snappy = 1: the reference's data-file container; 0: plain TFRecord (the metadata file is always plain).
+ * encode_entry / decode_entry / crc32c / snappy_* expose the building blocks to the tests. */
+typedef struct mono_ckpt_writer mono_ckpt_writer_t;
+typedef struct mono_ckpt_reader mono_ckpt_reader_t;
+const char* mono_ckpt_last_error(void);
+int mono_ckpt_writer_open(const char* data_path, const char* meta_path, int32_t snappy,
+                          mono_ckpt_writer_t** out);
+int mono_ckpt_writer_begin_table(mono_ckpt_writer_t* w, const char* name, const mono_segment_cfg* segs,
+                                 int32_t nsegs);
+int mono_ckpt_writer_add(mono_ckpt_writer_t* w, const int64_t* ids_host, const float* rows_host, int64_t n,
+                         int64_t max_update_ts, const int64_t* expire_days_by_slot, int64_t* n_written);
+int mono_ckpt_writer_end_table(mono_ckpt_writer_t* w);
+int mono_ckpt_writer_close(mono_ckpt_writer_t* w, int32_t commit);
+int mono_ckpt_reader_open(const char* data_path, const char* meta_path, int32_t snappy,
+                          mono_ckpt_reader_t** out);
+int mono_ckpt_reader_next_table(mono_ckpt_reader_t* r, char* name_out, int32_t cap, int64_t* num_entries,
+                                int32_t* has);
+int mono_ckpt_reader_read(mono_ckpt_reader_t* r, const mono_segment_cfg* segs, int32_t nsegs,
+                          int64_t* ids_out_host, float* rows_out_host, int64_t max_n, int64_t* n_read);
+int mono_ckpt_reader_close(mono_ckpt_reader_t* r);
+int64_t mono_ckpt_encode_entry(const mono_segment_cfg* segs, int32_t nsegs, int64_t id, const float* row,
+                               void* out, int64_t out_cap);
+int mono_ckpt_decode_entry(const mono_segment_cfg* segs, int32_t nsegs, const void* rec, int64_t n,
+                           int64_t* id_out, float* row_out);
+uint32_t mono_ckpt_crc32c(const void* data, int64_t n);
+uint32_t mono_ckpt_masked_crc32c(const void* data, int64_t n);
+int64_t mono_ckpt_snappy_compress(const void* in, int64_t n, void* out, int64_t out_cap);
+int64_t mono_ckpt_snappy_uncompress(const void* in, int64_t n, void* out, int64_t out_cap);
 
 /* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */
 int64_t mono_kernel_launch_count(void);

@@ -91,6 +91,23 @@ SIGNATURES = {
                                            C.POINTER(SliceTask), _i32, _p, _p]),
     "mono_embedding_to_layout_grad": (C.c_int, [_i32, _p, _p, _i32, _p, _i64, _p, _i32, _p, _i32, _i32,
                                                 C.POINTER(SliceTask), _i32, _p, _p]),
+    "mono_mtable_note_update_ts": (C.c_int, [_p, _i32, _i64]),
+    "mono_ckpt_last_error": (C.c_char_p, []),
+    "mono_ckpt_writer_open": (C.c_int, [C.c_char_p, C.c_char_p, _i32, C.POINTER(_p)]),
+    "mono_ckpt_writer_begin_table": (C.c_int, [_p, C.c_char_p, C.POINTER(SegmentCfg), _i32]),
+    "mono_ckpt_writer_add": (C.c_int, [_p, _p, _p, _i64, _i64, _p, C.POINTER(_i64)]),
+    "mono_ckpt_writer_end_table": (C.c_int, [_p]),
+    "mono_ckpt_writer_close": (C.c_int, [_p, _i32]),
+    "mono_ckpt_reader_open": (C.c_int, [C.c_char_p, C.c_char_p, _i32, C.POINTER(_p)]),
+    "mono_ckpt_reader_next_table": (C.c_int, [_p, C.c_char_p, _i32, C.POINTER(_i64), C.POINTER(_i32)]),
+    "mono_ckpt_reader_read": (C.c_int, [_p, C.POINTER(SegmentCfg), _i32, _p, _p, _i64, C.POINTER(_i64)]),
+    "mono_ckpt_reader_close": (C.c_int, [_p]),
+    "mono_ckpt_encode_entry": (_i64, [C.POINTER(SegmentCfg), _i32, _i64, _p, _p, _i64]),
+    "mono_ckpt_decode_entry": (C.c_int, [C.POINTER(SegmentCfg), _i32, _p, _i64, C.POINTER(_i64), _p]),
+    "mono_ckpt_crc32c": (C.c_uint32, [_p, _i64]),
+    "mono_ckpt_masked_crc32c": (C.c_uint32, [_p, _i64]),
+    "mono_ckpt_snappy_compress": (_i64, [_p, _i64, _p, _i64]),
+    "mono_ckpt_snappy_uncompress": (_i64, [_p, _i64, _p, _i64]),
     "mono_mtable_lookup_host": (C.c_int, [_p, _p, _p, _p]),
     "mono_mtable_lookup_pool_host": (C.c_int, [_p, _i32, _p, _p, _i64, _i64, _i32, _p]),
     "mono_mtable_optimize_host": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _u32]),

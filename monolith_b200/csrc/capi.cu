@@ -433,6 +433,13 @@ int mono_mtable_restore_rows(mono_mtable_t* t, int32_t k, const int64_t* ids_dev
   });
 }
 
+int mono_mtable_note_update_ts(mono_mtable_t* t, int32_t k, int64_t ts) {
+  return guarded([&] {
+    require(t && k >= 0 && k < (int)t->tables.size(), "bad table index");
+    t->tables[k].max_update_ts = std::max<int64_t>(t->tables[k].max_update_ts, ts);
+  });
+}
+
 int mono_reorder_by_indices(int32_t device, const int64_t* ids_dev, const int64_t* id_split_host,
                             int32_t num_lists, int32_t num_shards, const int32_t* dims_host,
                             int32_t rank0_empty, int64_t* output_dev, int32_t* sizes_dev,

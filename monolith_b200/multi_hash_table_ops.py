@@ -380,6 +380,37 @@ class MultiHashTable:
       if n.value:
         yield ids[:n.value], rows[:n.value]
 
+  # ---- checkpoints in the reference's on-disk format (checkpoint.py, csrc/ckpt.cu) -------------
+  @property
+  def configs(self):
+    return self._configs
+
+  def entry_width(self, slot: str) -> int:
+    """floats per exported row: dim + optimizer state + found + last_update_ts."""
+    k = self._table_names.index(slot)
+    return self._dims[k] + self._lib.mono_mtable_state_floats(self._h, k) + 2
+
+  def max_update_ts(self, slot: str) -> int:
+    """ref: EmbeddingHashTableTfBridge::max_update_ts_sec."""
+    return int(self._lib.mono_mtable_max_update_ts(self._h, self._table_names.index(slot)))
+
+  def note_update_ts(self, slot: str, ts: int):
+    _lib.check(self._lib.mono_mtable_note_update_ts(self._h, self._table_names.index(slot), int(ts)))
+    return self
+
+  def save(self, basename: str, nshards: int = -1) -> "MultiHashTable":
+    """ref: multi_hash_table_ops.py:409-415 -> MonolithMultiHashTableSave: `<basename>-%05d-of-%05d` (Snappy
+    TFRecords of EntryDump) + `<basename>.meta-%05d-of-%05d`; expired entries are not written."""
+    from . import checkpoint
+    checkpoint.save(self, basename, nshards)
+    return self
+
+  def restore(self, basename: str) -> "MultiHashTable":
+    """ref: multi_hash_table_ops.py:417-420 -> MonolithMultiHashTableRestore."""
+    from . import checkpoint
+    checkpoint.restore(self, basename)
+    return self
+
   def restore_rows(self, slot: str, ids: torch.Tensor, raw_rows: torch.Tensor):
     k = self._table_names.index(slot)
     ids, raw_rows = _ids(ids, self._device), _f32(raw_rows, self._device)

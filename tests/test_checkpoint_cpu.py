@@ -1,0 +1,336 @@
+"""Checkpoint files in the reference's format (csrc/ckpt.cu, monolith_b200/checkpoint.py) — CPU tests.
+
+What pins what:
+  * crc32c: RFC 3720 B.4 known answers; TFRecord framing: an independent bit-wise crc32c + struct packing here
+  * Snappy codec: pyarrow's Snappy (both directions, literal / 1-, 2-, 4-byte-offset copies)
+  * EntryDump / OptimizerDump / MultiHashTableMetadata wire bytes: the protobuf runtime, with message descriptors
+    transcribed from embedding_hash_table.proto:45-50,139-142 and optimizer.proto:28-30,56-57,69-72,130-135,232-252
+    (byte-for-byte equal to what the protobuf runtime serializes, and decoding packed and unpacked floats)
+  * file layout: multi_hash_table_save_restore_ops.cc (names, metadata counts, TTL filter, unknown tables skipped)
+The Snappy block container is restated from TF's snappy_outputbuffer.cc and has no TF-written fixture.
+"""
+import ctypes as C
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from monolith_b200 import _lib, checkpoint as ck
+
+OPT_SGD, OPT_ADAGRAD, OPT_FTRL, OPT_ADAM = _lib.OPT_SGD, _lib.OPT_ADAGRAD, _lib.OPT_FTRL, _lib.OPT_ADAM
+
+
+def lib():
+  return _lib.load()
+
+
+def segs_of(spec):
+  arr = (_lib.SegmentCfg * len(spec))()
+  for i, (dim, opt) in enumerate(spec):
+    arr[i].dim, arr[i].opt_type = dim, opt
+  return arr
+
+
+def state_floats(spec):
+  return sum({OPT_SGD: 0, OPT_ADAGRAD: d, OPT_FTRL: 2 * d, OPT_ADAM: 2 * d + 2}[o] for d, o in spec)
+
+
+def crc32c_ref(data: bytes) -> int:
+  c = 0xFFFFFFFF
+  for b in data:
+    c ^= b
+    for _ in range(8):
+      c = (c >> 1) ^ (0x82F63B78 & -(c & 1))
+  return c ^ 0xFFFFFFFF
+
+
+def masked_ref(data: bytes) -> int:
+  c = crc32c_ref(data)
+  return (((c >> 15) | (c << 17)) + 0xa282ead8) & 0xFFFFFFFF
+
+
+def test_crc32c_known_answers():
+  L = lib()
+  crc = lambda b: L.mono_ckpt_crc32c(b, len(b))
+  assert crc(b"123456789") == 0xE3069283
+  assert crc(bytes(32)) == 0x8A9136AA              # RFC 3720 B.4
+  assert crc(b"\xff" * 32) == 0x62A8AB43
+  assert crc(bytes(range(32))) == 0x46DD794E
+  assert crc(bytes(range(31, -1, -1))) == 0x113FDB5C
+  rng = np.random.default_rng(0)
+  for n in (0, 1, 7, 8, 9, 63, 1000):
+    b = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+    assert crc(b) == crc32c_ref(b)
+    assert L.mono_ckpt_masked_crc32c(b, len(b)) == masked_ref(b)
+
+
+@pytest.mark.parametrize("kind", ["empty", "one", "text", "zeros", "random", "periodic_far", "mixed"])
+def test_snappy_against_pyarrow(kind):
+  pa = pytest.importorskip("pyarrow")
+  codec = pa.Codec("snappy")
+  rng = np.random.default_rng(7)
+  data = {
+      "empty": b"", "one": b"x", "text": b"the quick brown fox jumps over the lazy dog. " * 400,
+      "zeros": bytes(300000), "random": rng.integers(0, 256, 200000, dtype=np.uint8).tobytes(),
+      # period 70000 > 65535: only 4-byte-offset copies can express it (pyarrow side), ours falls back to literals
+      "periodic_far": (rng.integers(0, 256, 70000, dtype=np.uint8).tobytes()) * 3,
+      "mixed": b"".join(rng.integers(0, 4, 50, dtype=np.uint8).tobytes() + rng.integers(0, 256, 13, dtype=np.uint8).tobytes()
+                        for _ in range(3000)),
+  }[kind]
+  L = lib()
+  out = C.create_string_buffer(len(data) + len(data) // 6 + 64)
+  n = L.mono_ckpt_snappy_compress(data, len(data), out, len(out))
+  assert n > 0
+  ours = out.raw[:n]
+  assert codec.decompress(ours, len(data), asbytes=True) == data if data else True       # ours -> pyarrow
+  if kind in ("text", "zeros"):
+    assert n < len(data) // 3                                                          # it does compress
+  theirs = codec.compress(data, asbytes=True)                                           # pyarrow -> ours
+  back = C.create_string_buffer(max(len(data), 1))
+  m = L.mono_ckpt_snappy_uncompress(theirs, len(theirs), back, len(back))
+  assert m == len(data) and back.raw[:m] == data
+  m = L.mono_ckpt_snappy_uncompress(ours, n, back, len(back))
+  assert m == len(data) and back.raw[:m] == data
+  if len(theirs) > 8:                                                                   # corruption is reported
+    assert L.mono_ckpt_snappy_uncompress(theirs[:-3], len(theirs) - 3, back, len(back)) < 0
+
+
+# ---- protobuf messages transcribed from the reference .proto files ---------------------------------
+def _proto_classes():
+  pytest.importorskip("google.protobuf")
+  from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+  F = descriptor_pb2.FieldDescriptorProto
+  fd = descriptor_pb2.FileDescriptorProto(name="mono_ckpt_test.proto", package="t", syntax="proto2")
+
+  def msg(name, fields):
+    m = fd.message_type.add(name=name)
+    for fname, num, typ, label, tname, packed in fields:
+      f = m.field.add(name=fname, number=num, type=typ, label=label)
+      if tname:
+        f.type_name = ".t." + tname
+      if packed:
+        f.options.packed = True
+    return m
+
+  OPT, REP = F.LABEL_OPTIONAL, F.LABEL_REPEATED
+  msg("AdagradOptimizerDump", [("norm", 1, F.TYPE_FLOAT, REP, None, False)])
+  msg("SgdOptimizerDump", [])
+  msg("FtrlOptimizerDump", [("zero", 1, F.TYPE_FLOAT, REP, None, False), ("norm", 2, F.TYPE_FLOAT, REP, None, False)])
+  msg("AdamOptimizerDump", [("m", 1, F.TYPE_FLOAT, REP, None, False), ("v", 2, F.TYPE_FLOAT, REP, None, False),
+                            ("beta1_power", 3, F.TYPE_FLOAT, OPT, None, False), ("beta2_power", 4, F.TYPE_FLOAT, OPT, None, False)])
+  msg("SingleOptimizerDump", [("adagrad", 1, F.TYPE_MESSAGE, OPT, "AdagradOptimizerDump", False),
+                              ("sgd", 2, F.TYPE_MESSAGE, OPT, "SgdOptimizerDump", False),
+                              ("ftrl", 3, F.TYPE_MESSAGE, OPT, "FtrlOptimizerDump", False),
+                              ("adam", 7, F.TYPE_MESSAGE, OPT, "AdamOptimizerDump", False)])
+  msg("OptimizerDump", [("dump", 1, F.TYPE_MESSAGE, REP, "SingleOptimizerDump", False)])
+  for name, packed in (("EntryDump", False), ("EntryDumpPacked", True)):
+    msg(name, [("id", 1, F.TYPE_SFIXED64, OPT, None, False), ("num", 2, F.TYPE_FLOAT, REP, None, packed),
+               ("opt", 3, F.TYPE_MESSAGE, OPT, "OptimizerDump", False),
+               ("last_update_ts_sec", 4, F.TYPE_INT64, OPT, None, False)])
+  msg("MultiHashTableMetadata", [("table_name", 1, F.TYPE_STRING, OPT, None, False),
+                                 ("num_entries", 2, F.TYPE_UINT64, OPT, None, False)])
+  pool = descriptor_pool.DescriptorPool()
+  pool.Add(fd)
+  get = lambda n: message_factory.GetMessageClass(pool.FindMessageTypeByName("t." + n))
+  return {n: get(n) for n in ("EntryDump", "EntryDumpPacked", "MultiHashTableMetadata")}
+
+
+SPEC = [(3, OPT_ADAGRAD), (2, OPT_SGD), (4, OPT_FTRL), (2, OPT_ADAM)]
+
+
+def _row(rng, spec, ts):
+  dim, st = sum(d for d, _ in spec), state_floats(spec)
+  row = rng.standard_normal(dim + st + 2).astype(np.float32)
+  row[dim + st:] = np.array([1, ts], np.uint32).view(np.float32)
+  return row
+
+
+def _fill_proto(m, fid, row, spec, ts):
+  dim = sum(d for d, _ in spec)
+  m.id = fid
+  m.num.extend(row[:dim].tolist())
+  st = row[dim:]
+  for d, o in spec:
+    s = m.opt.dump.add()
+    if o == OPT_ADAGRAD:
+      s.adagrad.norm.extend(st[:d].tolist()); st = st[d:]
+    elif o == OPT_SGD:
+      s.sgd.SetInParent()
+    elif o == OPT_FTRL:
+      s.ftrl.norm.extend(st[:d].tolist()); s.ftrl.zero.extend(st[d:2 * d].tolist()); st = st[2 * d:]
+    else:
+      s.adam.m.extend(st[:d].tolist()); s.adam.v.extend(st[d:2 * d].tolist())
+      s.adam.beta1_power, s.adam.beta2_power = float(st[2 * d]), float(st[2 * d + 1]); st = st[2 * d + 2:]
+  m.last_update_ts_sec = ts
+
+
+def test_entry_dump_wire_bytes_match_protobuf():
+  cls = _proto_classes()
+  L, rng = lib(), np.random.default_rng(3)
+  segs = segs_of(SPEC)
+  for fid, ts in ((5 << 48 | 77, 1700000000), (-3, 0), (2**63 - 1, 2**32 - 1)):
+    row = _row(rng, SPEC, ts)
+    buf = C.create_string_buffer(4096)
+    n = L.mono_ckpt_encode_entry(segs, len(SPEC), fid, row.ctypes.data_as(C.c_void_p), buf, len(buf))
+    assert n > 0
+    m = cls["EntryDump"]()
+    _fill_proto(m, fid, row, SPEC, ts)
+    assert buf.raw[:n] == m.SerializeToString()                      # byte for byte what protobuf writes
+    for variant in ("EntryDump", "EntryDumpPacked"):                 # and we read both float encodings
+      p = cls[variant]()
+      _fill_proto(p, fid, row, SPEC, ts)
+      wire = p.SerializeToString()
+      out = np.zeros_like(row)
+      fid_out = C.c_int64(0)
+      assert L.mono_ckpt_decode_entry(segs, len(SPEC), wire, len(wire), C.byref(fid_out), out.ctypes.data_as(C.c_void_p)) == 0
+      assert fid_out.value == fid
+      np.testing.assert_array_equal(out.view(np.uint32), row.view(np.uint32))
+  # missing optional fields: zeros / ts 0 (ref: restore sets last_update_ts_sec = 0 when absent, :377-379)
+  m = cls["EntryDump"]()
+  m.id = 9
+  wire = m.SerializeToString()
+  out = np.ones(sum(d for d, _ in SPEC) + state_floats(SPEC) + 2, np.float32)
+  fid_out = C.c_int64(0)
+  assert L.mono_ckpt_decode_entry(segs, len(SPEC), wire, len(wire), C.byref(fid_out), out.ctypes.data_as(C.c_void_p)) == 0
+  assert fid_out.value == 9 and not out[:-2].any() and out[-2:].view(np.uint32).tolist() == [1, 0]
+  assert L.mono_ckpt_decode_entry(segs, len(SPEC), b"\x0a\xff", 2, C.byref(fid_out), out.ctypes.data_as(C.c_void_p)) != 0
+
+
+def _parse_tfrecords(stream: bytes):
+  recs, p = [], 0
+  while p < len(stream):
+    (n,) = struct.unpack_from("<Q", stream, p)
+    assert struct.unpack_from("<I", stream, p + 8)[0] == masked_ref(stream[p:p + 8])
+    data = stream[p + 12:p + 12 + n]
+    assert struct.unpack_from("<I", stream, p + 12 + n)[0] == masked_ref(data)
+    recs.append(data)
+    p += 16 + n
+  return recs
+
+
+@pytest.mark.parametrize("snappy", [True, False])
+def test_file_layout_and_roundtrip(tmp_path, snappy):
+  pa = pytest.importorskip("pyarrow")
+  cls = _proto_classes()
+  rng = np.random.default_rng(11)
+  base = str(tmp_path / "ckpt" / "model.ckpt-100-emb")
+  os.makedirs(os.path.dirname(base))
+  tables = {"item": [(8, OPT_ADAGRAD)], "user": SPEC}
+  n_rows = {"item": 9000, "user": 700}     # item: > 256 KiB of records -> several Snappy blocks
+  data, nshards = {}, 2
+  writers = [ck.ShardWriter(base, i, nshards, snappy) for i in range(nshards)]
+  for name in sorted(tables):
+    spec = tables[name]
+    ids = rng.choice(1 << 40, n_rows[name], replace=False).astype(np.int64) | (np.int64(3) << 48)
+    rows = np.stack([_row(rng, spec, 1000 + int(i % 50)) for i in range(ids.size)])
+    data[name] = (ids, rows)
+    for i, w in enumerate(writers):
+      w.begin_table(name, segs_of(spec))
+      m = (ids.view(np.uint64) % np.uint64(nshards)) == i
+      assert w.add(ids[m], rows[m]) == int(m.sum())
+      w.end_table()
+  for w in writers:
+    w.close(True)
+  assert sorted(os.listdir(os.path.dirname(base))) == [
+      "model.ckpt-100-emb-00000-of-00002", "model.ckpt-100-emb-00001-of-00002",
+      "model.ckpt-100-emb.meta-00000-of-00002", "model.ckpt-100-emb.meta-00001-of-00002"]   # no temporaries left
+  assert ck.validate_sharded_files(base, [os.path.join(os.path.dirname(base), f) for f in os.listdir(os.path.dirname(base))]) == 2
+  # independent decode of shard 0: container -> TFRecords -> protobuf
+  raw = open(ck.sharded_file_name(base, 0, nshards), "rb").read()
+  if snappy:
+    codec, stream, p, nblocks = pa.Codec("snappy"), b"", 0, 0
+    while p < len(raw):
+      ulen, clen = struct.unpack_from(">II", raw, p)
+      stream += codec.decompress(raw[p + 8:p + 8 + clen], ulen, asbytes=True)
+      p += 8 + clen
+      nblocks += 1
+    assert nblocks > 1 and len(raw) < len(stream)
+  else:
+    stream = raw
+  recs = _parse_tfrecords(stream)
+  metas = [cls["MultiHashTableMetadata"].FromString(r) for r in _parse_tfrecords(open(ck.sharded_meta_file_name(base, 0, nshards), "rb").read())]
+  assert [m.table_name for m in metas] == ["item", "user"] and sum(m.num_entries for m in metas) == len(recs)
+  off = 0
+  for m in metas:
+    ids, rows = data[m.table_name]
+    sel = (ids.view(np.uint64) % np.uint64(nshards)) == 0
+    assert m.num_entries == int(sel.sum())
+    dim = sum(d for d, _ in tables[m.table_name])
+    for fid, row, rec in zip(ids[sel], rows[sel], recs[off:off + m.num_entries]):
+      e = cls["EntryDump"].FromString(rec)
+      assert e.id == fid and e.last_update_ts_sec == int(row[-1:].view(np.uint32)[0])
+      np.testing.assert_array_equal(np.array(e.num, np.float32), row[:dim])
+      assert len(e.opt.dump) == len(tables[m.table_name])
+    off += m.num_entries
+  # our reader: every table back, bit for bit; a table the reader does not ask for is skipped
+  got = {}
+  for i in range(nshards):
+    r = ck.ShardReader(base, i, nshards, snappy)
+    while True:
+      nt = r.next_table()
+      if nt is None:
+        break
+      name, cnt = nt
+      if name == "item" and i == 1:
+        continue                                   # skip: next_table must step over its records
+      spec = tables[name]
+      width = sum(d for d, _ in spec) + state_floats(spec) + 2
+      parts = []
+      while True:
+        ids, rows = r.read(segs_of(spec), width, 256)
+        if ids.size == 0:
+          break
+        parts.append((ids.copy(), rows.copy()))
+      assert sum(p[0].size for p in parts) == cnt
+      got.setdefault(name, []).extend(parts)
+    r.close()
+  for name in tables:
+    ids = np.concatenate([p[0] for p in got[name]])
+    rows = np.concatenate([p[1] for p in got[name]])
+    want_ids, want_rows = data[name]
+    if name == "item":
+      keep = (want_ids.view(np.uint64) % np.uint64(nshards)) == 0
+      want_ids, want_rows = want_ids[keep], want_rows[keep]
+    o, wo = np.argsort(ids), np.argsort(want_ids)
+    np.testing.assert_array_equal(ids[o], want_ids[wo])
+    np.testing.assert_array_equal(rows[o].view(np.uint32), want_rows[wo].view(np.uint32))
+
+
+def test_ttl_filter_at_save_and_errors(tmp_path):
+  base = str(tmp_path / "t")
+  spec = [(2, OPT_SGD)]
+  w = ck.ShardWriter(base, 0, 1)
+  w.begin_table("t", segs_of(spec))
+  ids = np.array([(1 << 48) | 1, (1 << 48) | 2, (2 << 48) | 3, (2 << 48) | 4], np.int64)
+  rows = np.zeros((4, 4), np.float32)
+  day = 24 * 3600
+  rows[:, -1] = np.array([100, 100 + 5 * day, 100, 100 + 5 * day], np.uint32).view(np.float32)
+  days = np.full(1 << 15, 36500, np.int64)
+  days[1], days[2] = 5, 6
+  # ref :214-221: dropped when max_update_ts - ts >= expire_days(slot) * 86400
+  assert w.add(ids, rows, max_update_ts=100 + 5 * day, expire_days=days) == 3      # slot 1, ts 100: exactly 5 days -> dropped
+  assert w.add(ids, rows, max_update_ts=100 + 6 * day, expire_days=days) == 2      # slot 2, ts 100: 6 days -> dropped too
+  with pytest.raises(RuntimeError):
+    w.close(True)                                                                   # table not ended
+  assert not any(f.startswith("t") for f in os.listdir(tmp_path))                   # nothing committed, temporaries removed
+  with pytest.raises(RuntimeError):
+    ck.ShardReader(base, 0, 1)
+  with pytest.raises(ValueError):
+    ck.validate_sharded_files(base, [base + "-00000-of-00002"])                     # shard 1 missing
+  with pytest.raises(ValueError):
+    ck.validate_sharded_files(base, [base + "-00000-of-00002", base + "-00001-of-00003"])
+  assert ck.validate_sharded_files(base, [base + "-00000-of-00001", base + "-junk", base + ".meta-00000-of-00001"]) == 1
+  assert ck.pick_nshards(-1, 10) == 1 and ck.pick_nshards(-1, 2_500_000) == 2 and ck.pick_nshards(-1, 10**9) == 4
+  assert ck.pick_nshards(3, 0) == 3
+  # a corrupted data file is reported, not silently accepted
+  w = ck.ShardWriter(base, 0, 1, snappy=False)
+  w.begin_table("t", segs_of(spec)); w.add(ids, rows); w.end_table(); w.close(True)
+  path = ck.sharded_file_name(base, 0, 1)
+  blob = bytearray(open(path, "rb").read())
+  blob[20] ^= 0x40
+  open(path, "wb").write(bytes(blob))
+  r = ck.ShardReader(base, 0, 1, snappy=False)
+  assert r.next_table() == ("t", 4)
+  with pytest.raises(RuntimeError):
+    r.read(segs_of(spec), 4, 16)

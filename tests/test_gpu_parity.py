@@ -418,6 +418,58 @@ def test_owner_grouping_build_reduce(N, dev):
   np.testing.assert_array_equal(out, out2)
 
 
+def test_checkpoint_save_restore_reference_format(dev, tmp_path):
+  """MultiHashTable.save -> files in the reference's layout -> restore into a fresh table: rows, optimizer
+  state and timestamps bit-identical, expired rows not written (save op :214-221), max_update_ts carried over,
+  unknown tables skipped.  (The byte format itself is pinned on CPU in tests/test_checkpoint_cpu.py.)"""
+  from monolith_b200 import MultiHashTable, checkpoint as ck
+  rng = np.random.default_rng(17)
+  day = 24 * 3600
+  cfg = {
+      "mixed": table([(3, "adagrad", {"initial_accumulator_value": 0.1}), (2, "sgd", {}),
+                      (4, "ftrl", {"initial_accumulator_value": 0.1, "beta": 1.0, "l1": 0.001, "l2": 0.01}), (5, "adam", {})],
+                     [0.1, 0.2, 0.05, 0.01], slot_expire_times={7: 2}),
+      "vec": table([(8, "adagrad", {"initial_accumulator_value": 0.1})], [0.05]),
+  }
+  src = MultiHashTable(cfg, device=dev)
+  keys = {"mixed": (np.int64(7) << 48) | rng.choice(1 << 30, 5000, replace=False).astype(np.int64),
+          "vec": (np.int64(2) << 48) | rng.choice(1 << 30, 300000, replace=False).astype(np.int64)}   # > 1 export chunk
+  t0 = 1_700_000_000
+  for step, ts in enumerate((t0, t0 + 2 * day, t0 + 3 * day)):   # a third of the keys is written at each time
+    batch = {}
+    for name, k in keys.items():
+      sel = k[step::3]
+      D = sum(s.dim_size for s in cfg[name].table_config.segments)
+      batch[name] = (T(sel, dev), T(rng.standard_normal((sel.size, D)).astype(np.float32), dev))
+    src.apply_gradients(batch, req_time=ts)
+  base = str(tmp_path / "ckpt" / "model.ckpt-7")
+  src.save(base, nshards=3)
+  files = sorted(os.listdir(tmp_path / "ckpt"))
+  assert files == [f"model.ckpt-7-{i:05d}-of-00003" for i in range(3)] + [f"model.ckpt-7.meta-{i:05d}-of-00003" for i in range(3)]
+  # slot 7 expires after 2 days: rows last written at t0 (3 days before max_update_ts) are dropped, t0 + 2 days kept
+  live = {"mixed": np.concatenate([keys["mixed"][1::3], keys["mixed"][2::3]]), "vec": keys["vec"]}
+  dst_cfg = dict(cfg)
+  dst_cfg["extra"] = sgd_table(2)                              # a table the checkpoint does not know
+  dst = MultiHashTable(dst_cfg, device=dev)
+  read = ck.restore(dst, base)
+  assert read == {"mixed": live["mixed"].size, "vec": live["vec"].size}
+  for name in cfg:
+    assert dst.size(name) == live[name].size
+    want = src.lookup_entry(name, T(live[name], dev))["raw"].cpu().numpy()
+    got = dst.lookup_entry(name, T(live[name], dev))["raw"].cpu().numpy()
+    np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert dst.max_update_ts(name) == t0 + 3 * day == src.max_update_ts(name)
+  dead = keys["mixed"][0::3]
+  assert not dst.lookup_entry("mixed", T(dead, dev))["found"].any()
+  assert dst.size("extra") == 0
+  # training continues identically from the restored state
+  g = rng.standard_normal((1000, 8)).astype(np.float32)
+  for t_ in (src, dst):
+    t_.apply_gradients({"vec": (T(keys["vec"][:1000], dev), T(g, dev))}, req_time=t0 + 4 * day)
+  np.testing.assert_array_equal(src.lookup_entry("vec", T(keys["vec"][:1000], dev))["raw"].cpu().numpy().view(np.uint32),
+                                dst.lookup_entry("vec", T(keys["vec"][:1000], dev))["raw"].cpu().numpy().view(np.uint32))
+
+
 def test_owner_grouping_skewed_owners(dev):
   """Every FID has the same owner: the owner's region of the scratch set overflows and the grouping is
   rebuilt with full-size regions; results are unchanged."""
