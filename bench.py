@@ -14,9 +14,9 @@ One "step" = the whole sparse part of one training step for one batch:
   reduce+send kernels, flag barriers), owners apply the requesters' gradients in rank order.
 `value`  = FID occurrences (lookups) per second over all ranks, inputs resident in HBM.
 `e2e`    = same step through the public Python API with pinned HOST inputs (FIDs, pooled grads) copied
-           H2D and the pooled embeddings copied D2H inside the timed region.  At N=1 the forward is issued
-           in --e2e-chunks slices so that the D2H of pooled rows and the H2D of gradients overlap (PCIe full
-           duplex); a gradient slice is sent only after its pooled slice has reached the host.
+           H2D and the pooled embeddings copied D2H inside the timed region: forward, pooled rows to the
+           host and gradients back in --e2e-chunks slices (PCIe full duplex; a gradient slice is sent only
+           after its pooled slice has reached the host), then the backward.
 `--impl reference` times the CPU restatement of the reference's parameter-server path (oracle port;
 the reference itself needs bazel + TensorFlow and cannot be built here) on the host cores.
 """
@@ -54,7 +54,7 @@ def parse():
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-e2e", action="store_true")
   ap.add_argument("--e2e-chunks", type=int, default=8,
-                  help="e2e leg at N=1: forward slices pipelined over PCIe in both directions (1 = sequential copies)")
+                  help="e2e leg: slices of the pooled-rows D2H / gradient H2D round trip (1 = sequential copies)")
   ap.add_argument("--sharded", action="store_true", help="run the sharded step (ShardedStep) even at N=1 (profiling)")
   ap.add_argument("--remote-frac", type=float, default=None,
                   help="experiment: fraction of a rank's FID occurrences owned by other ranks (default: natural 1 - 1/N)")
@@ -347,33 +347,22 @@ def run_ours(args):
     pooled_pin = torch.empty(M, DIM).pin_memory()
     d_f, d_g = torch.empty(M, dtype=torch.int64, device=dev), torch.empty(M, DIM, device=dev)
 
-    KCH = max(1, args.e2e_chunks) if not use_sharded else 1
-    if KCH > 1:
-      s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-      ev_f = [torch.cuda.Event() for _ in range(KCH)]
-      ev_o = [torch.cuda.Event() for _ in range(KCH)]
-      ev_in = torch.cuda.Event()
-      cs = (M + KCH - 1) // KCH
+    KCH = max(1, args.e2e_chunks)
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    ev_fwd, ev_in = torch.cuda.Event(), torch.cuda.Event()
+    ev_o = [torch.cuda.Event() for _ in range(KCH)]
+    cs = (M + KCH - 1) // KCH
 
-    def e2e_step(i):
+    def host_round_trip():
+      """pooled rows D2H, gradients H2D, in KCH slices so that PCIe runs full duplex: gradient slice c leaves
+      the host only AFTER pooled slice c has arrived (the dependency a host-side dense tower imposes) and
+      overlaps the D2H of slice c+1.  Returns the device gradient buffer, ready on the current stream."""
       main = torch.cuda.current_stream()
-      d_f.copy_(fids_pin[i % NB], non_blocking=True)
-      if KCH == 1:
-        d_g.copy_(pgrad_pin, non_blocking=True)
-        step(i, d_f, d_g, pooled)
-        pooled_pin.copy_(pooled, non_blocking=True)
-        main.synchronize()  # the caller consumes the pooled rows on the host
-        return
-      # Same step, forward issued in KCH slices so that PCIe runs full duplex: the pooled rows of slice c go
-      # D2H while slice c+1 is looked up, and the gradient of slice c is sent H2D only AFTER its pooled rows
-      # have reached the host (the dependency a host-side dense tower imposes), overlapping the D2H of slice
-      # c+1.  One backward over the whole batch once every gradient slice has arrived: step semantics unchanged.
+      ev_fwd.record(main)
+      s_out.wait_event(ev_fwd)
       for c in range(KCH):
         sl = slice(c * cs, min(M, (c + 1) * cs))
-        table.lookup_pool("item", d_f[sl], None, "sum", out=pooled[sl])
-        ev_f[c].record(main)
         with torch.cuda.stream(s_out):
-          s_out.wait_event(ev_f[c])
           pooled_pin[sl].copy_(pooled[sl], non_blocking=True)
           ev_o[c].record(s_out)
         with torch.cuda.stream(s_in):
@@ -381,16 +370,25 @@ def run_ours(args):
           d_g[sl].copy_(pgrad_pin[sl], non_blocking=True)
       ev_in.record(s_in)
       main.wait_event(ev_in)
-      table.pool_backward("item", d_f, d_g, None, "sum", req_time=1000 + i)
-      main.synchronize()
+      return d_g
+
+    def e2e_step(i):
+      main = torch.cuda.current_stream()
+      d_f.copy_(fids_pin[i % NB], non_blocking=True)
+      if use_sharded:
+        sharded.step(d_f, host_round_trip, pooled, 1000 + i)
+      else:
+        table.lookup_pool("item", d_f, None, "sum", out=pooled)
+        table.pool_backward("item", d_f, host_round_trip(), None, "sum", req_time=1000 + i)
+      main.synchronize()  # pooled rows are on the host, the update is applied
 
     es, ew = max(3, args.steps // 4), 2
     ems, _ = timed(e2e_step, es, ew)
     e2e = {"value": M * world * es / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * M + 4 * M * DIM,
            "d2h_bytes_per_step": 4 * M * DIM, "ms_per_step": ems / es,
-           "pipeline": (f"forward in {KCH} slices: D2H of pooled slice c overlaps the lookup of slice c+1 and the H2D of "
-                        f"gradient slice c-1 (sent only after pooled slice c-1 reached the host); one backward per step"
-                        if KCH > 1 else "sequential: H2D inputs, step, D2H pooled rows")}
+           "pipeline": (f"H2D FIDs, forward, then pooled rows D2H and gradients H2D in {KCH} slices, full duplex: gradient "
+                        f"slice c is sent only after pooled slice c reached the host; then the backward"
+                        if KCH > 1 else "sequential: H2D FIDs, forward, D2H pooled rows, H2D gradients, backward")}
 
   # ---- per-kernel timing for the roofline (dominant kernel: fused lookup+pool forward) --------
   roof = None

@@ -375,6 +375,8 @@ class ShardedStep:
       ph.mark("f5_lookup_pull")
     self.dops.gather_pool(rows_in, offs, D, row_offsets, pooling, out=out)            # 6
     ph.mark("f6_gather_pool")
+    if callable(pooled_grad):   # forward enqueued: the caller's dense tower / host round trip goes here
+      pooled_grad = pooled_grad()
     if self.bulk == "push":
       self.grouping.reduce_push(pooled_grad, cnt[me], self.window, self.off_grads, my_seg, row_offsets, pooling)  # 7+8
       ph.fine("b8a_reduce_push_kernels")
@@ -402,8 +404,11 @@ class ShardedStep:
       out[n * self.K + self.k] = int(per_shard[n])
     return out
 
-  def step(self, fids: torch.Tensor, pooled_grad: torch.Tensor, out: torch.Tensor, req_time: int,
+  def step(self, fids: torch.Tensor, pooled_grad, out: torch.Tensor, req_time: int,
            row_offsets: Optional[torch.Tensor] = None, pooling: str = "sum"):
+    """One sparse train step.  `pooled_grad` is the gradient w.r.t. the pooled rows written to `out`, or a
+    callable returning it: the callable runs once the forward has been enqueued (what produces the gradient —
+    the dense tower, or a round trip of `out` to the host — belongs there)."""
     if self.exchange == "peer":
       return self._step_peer(fids, pooled_grad, out, req_time, row_offsets, pooling)
     N, D, dev, ph = self.N, self.dim, fids.device, self.phases
@@ -426,6 +431,8 @@ class ShardedStep:
     ph.mark("f5_a2a_rows")
     self.dops.gather_pool(recv_rows, offs, D, row_offsets, pooling, out=out)          # 6
     ph.mark("f6_gather_pool")
+    if callable(pooled_grad):
+      pooled_grad = pooled_grad()
     grad_rows = torch.empty(uniq.numel() * D, dtype=torch.float32, device=dev)        # 7
     self.grouping.reduce(pooled_grad, grad_rows, row_offsets, pooling)
     ph.mark("b7_reduce_grads")
