@@ -277,6 +277,24 @@ class HostCounts:
     return buf[:, 1:].copy()
 
 
+def exchange_plan(cnt, me: int):
+  """Offsets of the peer-window exchange for rank `me`, from the N x N count matrix cnt[r][o] = number of
+  distinct FIDs requester r sends to owner o (identical on every rank).  All in items (FIDs / rows):
+    recv[r]        what this rank, as an owner, receives from requester r
+    bucket_at[o]   where this rank's bucket for owner o starts in its own bucketed unique list (= rows_in)
+    seg_at[o]      where this rank's items start inside owner o's received list (ids_in / grads_in of o)
+    rows_dst[r]    as an owner: where requester r's bucket for this rank starts in r's rows_in
+    recv_at[r]     as an owner: where requester r's items start in this rank's received list
+  so that the received lists are compact, requester-major — exactly an all-to-all-v result."""
+  import numpy as np
+  cnt = np.asarray(cnt, dtype=np.int64)
+  N = cnt.shape[0]
+  col_pre = np.concatenate([np.zeros((1, N), np.int64), np.cumsum(cnt, axis=0)])          # [r][o] = sum_{r' < r} cnt[r'][o]
+  row_pre = np.concatenate([np.zeros((N, 1), np.int64), np.cumsum(cnt, axis=1)], axis=1)  # [r][o] = sum_{o' < o} cnt[r][o']
+  return {"recv": cnt[:, me].copy(), "bucket_at": row_pre[me, :N].copy(), "seg_at": col_pre[me, :].copy(),
+          "rows_dst": row_pre[:N, me].copy(), "recv_at": col_pre[:N, me].copy()}
+
+
 class ShardedStep:
   """Sparse train step of ONE table on N GPUs, fast path: the batch is grouped once
   (distribution_ops.Grouping) and that grouping serves both the forward (dedup + bucket by owner + pooling
@@ -347,12 +365,10 @@ class ShardedStep:
     if self.window is None or max_m > self.cap_rows or need_recv > self.cap_recv:      # same decision on every rank
       self._make_window(max(max_m, int(need_recv / 1.5) + 1, self._base_m))
     par = self.hostx.epoch & 1
-    recv = cnt[:, me]
+    plan = exchange_plan(cnt, me)
+    recv, my_seg, bucket_at = plan["recv"], plan["seg_at"], plan["bucket_at"]
     tot_recv = int(recv.sum())
-    col_pre = np.concatenate([np.zeros((1, N), np.int64), np.cumsum(cnt, axis=0)])    # col_pre[r][o] = sum_{r'<r} cnt[r'][o]
-    row_pre = np.concatenate([np.zeros((N, 1), np.int64), np.cumsum(cnt, axis=1)], axis=1)  # row_pre[r][o] = sum_{o'<o} cnt[r][o']
-    my_seg = col_pre[me]                              # where my items start inside owner o's received list
-    self.window.put(self.off_ids[par], my_seg * 8, uniq, row_pre[me, :N] * 8, cnt[me] * 8)   # 3
+    self.window.put(self.off_ids[par], my_seg * 8, uniq, bucket_at * 8, cnt[me] * 8)        # 3
     ph.fine("f3a_put_kernel")
     self.window.barrier()
     ph.mark("f3_put_ids")
@@ -361,7 +377,7 @@ class ShardedStep:
     grads_in = self.window.view(self.off_grads, tot_recv * D, torch.float32)
     slot = self._slot(recv)
     if self.bulk == "push":
-      self.table.lookup_push(self.name, ids_in, recv, self.window, self.off_rows, row_pre[:, me])  # 4+5
+      self.table.lookup_push(self.name, ids_in, recv, self.window, self.off_rows, plan["rows_dst"])  # 4+5
       ph.fine("f5a_lookup_push_kernel")
       self.window.barrier()
       ph.mark("f5_lookup_push")
@@ -371,7 +387,7 @@ class ShardedStep:
       ph.fine("f5a_owner_lookup")
       self.window.barrier()
       ph.fine("f5b_barrier")
-      self.window.get(self.off_rows_out, col_pre[me, :] * D * 4, rows_in, row_pre[me, :N] * D * 4, cnt[me] * D * 4)  # 5 pull
+      self.window.get(self.off_rows_out, my_seg * D * 4, rows_in, bucket_at * D * 4, cnt[me] * D * 4)  # 5 pull
       ph.mark("f5_lookup_pull")
     self.dops.gather_pool(rows_in, offs, D, row_offsets, pooling, out=out)            # 6
     ph.mark("f6_gather_pool")
@@ -388,7 +404,7 @@ class ShardedStep:
       ph.fine("b8a_reduce")
       self.window.barrier()
       ph.fine("b8b_barrier")
-      self.window.get(self.off_grads_out, row_pre[:, me] * D * 4, grads_in, col_pre[:N, me] * D * 4, recv * D * 4)  # 8 pull
+      self.window.get(self.off_grads_out, plan["rows_dst"] * D * 4, grads_in, plan["recv_at"] * D * 4, recv * D * 4)  # 8 pull
       ph.mark("b8_reduce_pull")                                                        # 9
     _, _, id_off, emb_off = self.table.fused_offsets(slot, N)
     self.table.fused_apply_gradient(ids_in, ids_in, slot, grads_in, id_off, emb_off, 0, req_time, N)

@@ -121,3 +121,93 @@ def test_sharded_exchange_matches_single_table():
       k_r, e_r = got[r][2][name]
       np.testing.assert_array_equal(k_r, mine)  # shard membership = fid mod N
       np.testing.assert_array_equal(e_r.view(np.uint32), glob.lookup_entry(name, mine).view(np.uint32))
+
+
+# ---- host-side logic of the NVLink peer-window exchange (ShardedStep) ---------------------------------
+@pytest.mark.parametrize("N", [1, 2, 3, 8])
+def test_exchange_plan_layouts_are_all_to_all_v(N):
+  """exchange_plan(): simulate the three transfers of the peer-window step with numpy arrays as windows and
+  check that every received list is the compact, requester-major concatenation an all-to-all-v would give,
+  and that rows / gradients line up with the FIDs they belong to."""
+  from monolith_b200.distributed_ps import exchange_plan
+  rng = np.random.default_rng(N)
+  cnt = rng.integers(0, 7, (N, N)).astype(np.int64)
+  cnt[rng.integers(0, N), rng.integers(0, N)] = 0
+  plans = [exchange_plan(cnt, r) for r in range(N)]
+  # requester r's bucketed unique list: items tagged (r, owner, i)
+  uniq = [[(r, o, i) for o in range(N) for i in range(cnt[r, o])] for r in range(N)]
+  for r in range(N):
+    for o in range(N):
+      assert uniq[r][plans[r]["bucket_at"][o]:plans[r]["bucket_at"][o] + cnt[r, o]] == [(r, o, i) for i in range(cnt[r, o])]
+  # 1. FIDs: requester r puts bucket o at seg_at[o] of owner o's ids_in
+  ids_in = [[None] * int(cnt[:, o].sum()) for o in range(N)]
+  for r in range(N):
+    for o in range(N):
+      for i in range(cnt[r, o]):
+        dst = plans[r]["seg_at"][o] + i
+        assert ids_in[o][dst] is None                         # no two requesters collide
+        ids_in[o][dst] = uniq[r][plans[r]["bucket_at"][o] + i]
+  for o in range(N):
+    assert ids_in[o] == [(r, o, i) for r in range(N) for i in range(cnt[r, o])]     # compact, requester-major
+    assert plans[o]["recv"].tolist() == cnt[:, o].tolist()
+    assert plans[o]["recv_at"].tolist() == np.concatenate([[0], np.cumsum(cnt[:, o])])[:N].tolist()
+  # 2. rows: owner o stores the row of its k-th received id into requester r's rows_in at rows_dst[r] + i
+  rows_in = [[None] * len(uniq[r]) for r in range(N)]
+  for o in range(N):
+    k = 0
+    for r in range(N):
+      for i in range(cnt[r, o]):
+        rows_in[r][plans[o]["rows_dst"][r] + i] = ("row of", ids_in[o][k])
+        k += 1
+  for r in range(N):
+    assert rows_in[r] == [("row of", u) for u in uniq[r]]     # row j of rows_in belongs to unique FID j
+  # 3. gradients: requester r stores the gradient of its j-th unique FID at seg_at[o] + i of owner o's grads_in
+  grads_in = [[None] * len(ids_in[o]) for o in range(N)]
+  for r in range(N):
+    for o in range(N):
+      for i in range(cnt[r, o]):
+        grads_in[o][plans[r]["seg_at"][o] + i] = ("grad of", uniq[r][plans[r]["bucket_at"][o] + i])
+  for o in range(N):
+    assert grads_in[o] == [("grad of", u) for u in ids_in[o]]  # aligned with ids_in: fused_apply sees (id, grad) pairs
+
+
+def _hostcounts_worker(rank, world, port, q):
+  try:
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from monolith_b200.distributed_ps import HostCounts
+    hx = HostCounts(world, rank, 3)
+    seen = []
+    for e in range(200):
+      row = [e * 10 + rank, rank, e]
+      if rank == 1 and e % 17 == 0:
+        import time
+        time.sleep(0.002)            # a slow rank: the fast one must wait, never read a stale row
+      seen.append(hx.exchange(row).tolist())
+    q.put((rank, seen))
+    dist.barrier()
+    dist.destroy_process_group()
+  except Exception:
+    import traceback
+    q.put((rank, "ERROR: " + traceback.format_exc()))
+    raise
+
+
+def test_host_counts_exchange_two_ranks():
+  """HostCounts (the /dev/shm count matrix that replaces the count all-to-all): 200 back-to-back exchanges on 2
+  ranks, one of them randomly slow; every rank sees every rank's row of the same epoch."""
+  world = 2
+  ctx = mp.get_context("spawn")
+  q = ctx.Queue()
+  port = 29600 + (os.getpid() % 300)
+  procs = [ctx.Process(target=_hostcounts_worker, args=(r, world, port, q)) for r in range(world)]
+  for p in procs:
+    p.start()
+  got = dict(q.get(timeout=120) for _ in range(world))
+  for p in procs:
+    p.join(timeout=60)
+  for r in range(world):
+    assert not isinstance(got[r], str), got[r]
+    assert got[r] == [[[e * 10 + rr, rr, e] for rr in range(world)] for e in range(200)]
