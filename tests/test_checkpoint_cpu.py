@@ -334,3 +334,54 @@ def test_ttl_filter_at_save_and_errors(tmp_path):
   assert r.next_table() == ("t", 4)
   with pytest.raises(RuntimeError):
     r.read(segs_of(spec), 4, 16)
+
+
+@pytest.mark.parametrize("case", [
+    # (default_expire_days, {slot: days}, ids, values, write_ts, expected lookup after save -> restore)
+    dict(name="ttl_zero", default=0, slots={}, ids=[-1, 1], values=[1.0, 2.0], ts=0, expect=[0.0, 0.0]),          # hash_table_ops_test.py:381-395
+    dict(name="ttl_not_zero", default=3600, slots={}, ids=[-1, 1], values=[1.0, 2.0], ts=0, expect=[1.0, 2.0]),   # :397-411
+    dict(name="ttl_by_slots", default=3600, slots={1: 0, 2: 1}, ids=[1 << 48, 2 << 48], values=[1.0, 2.0], ts=100,
+         expect=[0.0, 2.0]),                                                                                       # :413-466
+], ids=lambda c: c["name"])
+def test_reference_ttl_goldens_through_the_files(tmp_path, case):
+  """The reference's save-time TTL tests, replayed at the file level: entries written at `ts` into a table whose
+  max_update_ts is `ts`; what a restore would find = what the reader returns (absent -> lookup gives 0).
+  FID -1 is a legal key and falls in slot 0x7fff (reader_util.h:36-38)."""
+  spec = [(1, OPT_SGD)]
+  days = np.full(1 << 15, case["default"], np.int64)
+  for s_, d in case["slots"].items():
+    days[s_] = d
+  ids = np.array(case["ids"], np.int64)
+  rows = np.zeros((ids.size, 3), np.float32)
+  rows[:, 0] = case["values"]
+  rows[:, 1:] = np.array([[1, case["ts"]]] * ids.size, np.uint32).view(np.float32)
+  base = str(tmp_path / "table")
+  w = ck.ShardWriter(base, 0, 1)
+  w.begin_table("t", segs_of(spec))
+  w.add(ids, rows, max_update_ts=case["ts"], expire_days=days)
+  w.end_table()
+  w.close(True)
+  r = ck.ShardReader(base, 0, 1)
+  name, cnt = r.next_table()
+  got_ids, got_rows = r.read(segs_of(spec), 3, 16)
+  assert name == "t" and cnt == got_ids.size
+  table = {int(i): float(v) for i, v in zip(got_ids, got_rows[:, 0])}
+  assert [table.get(int(i), 0.0) for i in ids] == case["expect"]
+  assert r.next_table() is None
+  # saving what was restored and restoring again changes nothing (the second half of :440-466)
+  w = ck.ShardWriter(base + "_new", 0, 1)
+  w.begin_table("t", segs_of(spec))
+  w.add(got_ids, got_rows, max_update_ts=case["ts"], expire_days=days)
+  w.end_table()
+  w.close(True)
+  r2 = ck.ShardReader(base + "_new", 0, 1)
+  r2.next_table()
+  ids2, rows2 = r2.read(segs_of(spec), 3, 16)
+  np.testing.assert_array_equal(ids2, got_ids)
+  np.testing.assert_array_equal(rows2.view(np.uint32), got_rows.view(np.uint32))
+
+
+def test_restore_not_found(tmp_path):
+  """ref: test_restore_not_found, hash_table_ops_test.py:468-476: restoring a basename without files is an error."""
+  with pytest.raises(ValueError):
+    ck.validate_sharded_files(str(tmp_path / "nothing_here"), [])
