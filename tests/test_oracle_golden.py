@@ -189,3 +189,31 @@ def test_live_ref_library_if_present():
       ref.ref_adagrad(orc.p(a), orc.p(an), orc.p(g), C.c_int64(dim), C.c_float(0.01), C.c_float(0.0))
       orc.lib().orc_adagrad(orc.p(b), orc.p(bn), orc.p(g), C.c_int64(dim), C.c_float(0.01), C.c_float(0.0))
     assert np.array_equal(a, b) and np.array_equal(an, bn)
+
+
+def test_layout_pooling_vs_reference_numpy_oracle_fixture():
+  """orc_embedding_to_layout (GatherEmb + pooling, fused_embedding_to_layout.cc:26-59,468-540) against the
+  reference's own numpy pooling oracle (fused_embedding_to_layout_test.py:91-116), run by
+  tests/golden/make_layout_golden.py.  SUM and FIRSTN are exact; MEAN is sum/n in the numpy oracle but
+  sum of x_i/n in the op: 1e-6 relative."""
+  from monolith_b200._lib import POOL_FIRSTN, POOL_MEAN, POOL_SUM
+  from monolith_b200.distribution_ops import SliceTask
+  z = np.load(os.path.join(G, "ref_layout_pooling.npz"))
+  code = {0: POOL_SUM, 1: POOL_MEAN, 2: POOL_FIRSTN}
+  for ci in range(int(z["n_cases"])):
+    pt, max_len = int(z[f"c{ci}_pooling"]), int(z[f"c{ci}_max_len"])
+    tab, idx, offs, want = z[f"c{ci}_table"], z[f"c{ci}_idx"], z[f"c{ci}_offs"], z[f"c{ci}_expect"]
+    B, dim = offs.size - 1, tab.shape[1]
+    # v3 encoding of ONE feature over one embedding list (parse_sparse_feature.cc:259-330)
+    fid_offset = (idx * dim).astype(np.uint64)                      # list 0 << 32 | float offset of the row
+    feature_offset = np.concatenate([offs[:-1], [idx.size]]).astype(np.int32)
+    nfl_offset = np.array([0, feature_offset.size], np.uint32)
+    if code[pt] == POOL_FIRSTN:
+      task, shape = SliceTask(0, 0, dim, POOL_FIRSTN, max_len, 0, max_len * dim, 0, 0), (B, max_len, dim)
+    else:
+      task, shape = SliceTask(0, 0, dim, code[pt], 0, 0, dim, 0, 0), (B, dim)
+    got = orc.embedding_to_layout([tab], [1], fid_offset, feature_offset, nfl_offset, B, [task], [shape])[0]
+    if code[pt] == POOL_MEAN:
+      np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-7)
+    else:
+      np.testing.assert_array_equal(got, want)
