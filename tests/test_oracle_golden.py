@@ -217,3 +217,26 @@ def test_layout_pooling_vs_reference_numpy_oracle_fixture():
       np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-7)
     else:
       np.testing.assert_array_equal(got, want)
+
+
+def test_distributed_ps_closed_form_ftrl_bias_adagrad_vec():
+  """Closed-form expectation of the reference's sharded fwd+bwd test (NT/distributed_ps_test.py:787-882): rows
+  [bias: FTRL dim 1 | vec: Adagrad], every value assigned 3.0, gradient 2.0 on every element, lr 1.0,
+  initial_accumulator_value 0.1, beta 0 -> bias = -lr*z/(sqrt(n)+beta), vec = 3 - lr/sqrt(g^2+0.1)*g (1e-6)."""
+  import math
+  init_val, g, lr, acc, beta = 3.0, 2.0, 1.0, 0.1, 0.0
+  ada_grad = lr / math.sqrt(g * g + acc) * g
+  n = acc + g * g
+  sigma = (math.sqrt(n) - math.sqrt(acc)) / lr
+  z = g - sigma * init_val
+  ftrl_val = -lr * z / (math.sqrt(n) + beta)
+  cfg = {"uid": table([(1, "ftrl", {"initial_accumulator_value": acc, "beta": beta, "l1": 0.0, "l2": 0.0}),
+                       (4, "adagrad", {"initial_accumulator_value": acc})], [lr, lr])}
+  t = orc.OracleMultiHashTable(cfg)
+  fids = np.arange(18, dtype=np.int64)                      # the test's FIDs 0..17, owners = fid mod 2
+  t.assign({"uid": (fids, np.full((18, 5), init_val, np.float32))})
+  t.apply_gradients({"uid": (fids, np.full((18, 5), g, np.float32))})
+  got = t.lookup({"uid": fids})["uid"]
+  np.testing.assert_allclose(got[:, 0], ftrl_val, atol=1e-6, rtol=0)
+  np.testing.assert_allclose(got[:, 1:], init_val - ada_grad, atol=1e-6, rtol=0)
+  assert sorted(fids[fids % 2 == 0].tolist()) == [0, 2, 4, 6, 8, 10, 12, 14, 16]   # uid:0/cid:0/gid:0 shards of the test
