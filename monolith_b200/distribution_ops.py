@@ -70,6 +70,83 @@ def unique_with_inverse(ids: torch.Tensor, sync: bool = True):
   return uniq, inv[:n], n_dev
 
 
+def sharding_sparse_fids(features: Dict[str, Tuple[torch.Tensor, torch.Tensor]], feature_table: Dict[str, str],
+                         feature_dims_sum: Dict[str, int], num_of_shards: int, shared_features: Sequence[str] = (),
+                         reorder_fn=None):
+  """Outputs of the reference's ShardingSparseFids (version 3+, unique = true) from per-feature FID lists —
+  ref: ShardingSparseFidsOp::FillFidList / CreateOffsetTensor, NT/data/kernels/parse_sparse_feature.cc:187-330;
+  Python model: NT/data/parse_sparse_feature_test.py:87-240.
+
+  features[name] = (fids int64[n], row_splits int64[rows + 1]) — CSR over the samples of the batch (a shared
+  feature has ONE row).  Returns a dict:
+    fid_list       list of K*N int64 tensors, index = table_index * N + shard (tables in sorted-name order): the
+                   (table, shard) list is the concatenation, over the table's features in sorted-name order, of
+                   each feature's distinct FIDs of that shard in first-occurrence order
+    fid_offset     int64[M] holding the reference's uint64: (table_index * N + shard) << 32 | float offset of the
+                   FID's row inside that (table, shard) list, rows of feature f being dims_sum[f] floats wide
+    feature_offset int32[#(feature, row) + 1]; nfl_offset int64[#features + 1] (bit 31 = shared), features in
+                   sorted-name order — exactly what mono_embedding_to_layout consumes
+  The dedup / shard / offset work is ONE FusedReorderByIndices launch over the features as lists (per-list
+  dims = dims_sum, shard-major / list-minor output, bit-exact kernel); the rest is index arithmetic on device.
+  (The reference dedups per (feature, shard); FIDs carry their slot, so features never share a FID.)"""
+  N = int(num_of_shards)
+  if reorder_fn is None:
+    reorder_fn = lambda lists, n, dims: fused_reorder_by_indices(lists, n, dims, rank0_empty_shard=False)
+  names = sorted(features)
+  tables = sorted({feature_table[n] for n in names})
+  t_idx = {t: i for i, t in enumerate(tables)}
+  order = sorted(names, key=lambda n: (t_idx[feature_table[n]], n))      # table-major, feature-minor
+  F, K = len(order), len(tables)
+  lists = [features[n][0].reshape(-1).to(torch.int64) for n in order]
+  dims = [int(feature_dims_sum[n]) for n in order]
+  device = lists[0].device if lists else torch.device("cpu")
+  out, _, slot_sizes, _, offs = reorder_fn(lists, N, dims)
+  slot = torch.as_tensor([int(x) for x in slot_sizes], dtype=torch.int64).reshape(N, F)
+  width = slot * torch.as_tensor(dims, dtype=torch.int64).reshape(1, F)
+  flat_id = torch.cumsum(slot.reshape(-1), 0) - slot.reshape(-1)           # exclusive, shard-major / list-minor
+  flat_emb = torch.cumsum(width.reshape(-1), 0) - width.reshape(-1)
+  id_base, emb_base = flat_id.reshape(N, F), flat_emb.reshape(N, F)
+  first = {}                                                               # first / last list index of every table
+  for j, n in enumerate(order):
+    k = t_idx[feature_table[n]]
+    first.setdefault(k, [j, j])[1] = j
+  fid_list = []
+  for k in range(K):
+    j0, j1 = first[k]
+    for n in range(N):
+      b = int(id_base[n, j0])
+      e = int(id_base[n, j1] + slot[n, j1])
+      fid_list.append(out[b:e])
+  # fid_offset blocks, computed in list order, emitted in sorted-feature-name order
+  occ_start = [0]
+  for l in lists:
+    occ_start.append(occ_start[-1] + l.numel())
+  wrap = (1 << 64) % N
+  blocks = {}
+  for j, n in enumerate(order):
+    v = lists[j]
+    k = t_idx[feature_table[n]]
+    shard = torch.remainder(torch.remainder(v, N) + wrap * (v < 0).to(torch.int64), N)   # (uint64)fid % N
+    base = emb_base[:, first[k][0]].to(device)
+    local = offs[occ_start[j]:occ_start[j + 1]].to(torch.int64) - base[shard]
+    blocks[n] = ((k * N + shard) << 32) | local
+  feature_offset, nfl_offset, pieces, total = [], [], [], 0
+  shared = set(shared_features)
+  for n in names:
+    nfl_offset.append(len(feature_offset) | ((1 << 31) if n in shared else 0))
+    rs = [int(x) for x in features[n][1].reshape(-1).tolist()]
+    feature_offset.extend(total + r for r in rs[:-1])
+    total += rs[-1]
+    pieces.append(blocks[n])
+  feature_offset.append(total)
+  nfl_offset.append(len(feature_offset))
+  fid_offset = torch.cat(pieces) if pieces else torch.empty(0, dtype=torch.int64, device=device)
+  return {"fid_list": fid_list, "fid_offset": fid_offset,
+          "feature_offset": torch.as_tensor(feature_offset, dtype=torch.int32, device=device),
+          "nfl_offset": torch.as_tensor(nfl_offset, dtype=torch.int64, device=device),
+          "table_names": tables, "feature_names": names}
+
+
 def gather_pool(fused_embeddings: torch.Tensor, fused_embedding_offsets: torch.Tensor, dim: int,
                 row_offsets: Optional[torch.Tensor] = None, pooling: str = "sum",
                 out: Optional[torch.Tensor] = None, out_col: int = 0) -> torch.Tensor:

@@ -240,3 +240,59 @@ def test_distributed_ps_closed_form_ftrl_bias_adagrad_vec():
   np.testing.assert_allclose(got[:, 0], ftrl_val, atol=1e-6, rtol=0)
   np.testing.assert_allclose(got[:, 1:], init_val - ada_grad, atol=1e-6, rtol=0)
   assert sorted(fids[fids % 2 == 0].tolist()) == [0, 2, 4, 6, 8, 10, 12, 14, 16]   # uid:0/cid:0/gid:0 shards of the test
+
+
+def test_sharding_sparse_fids_vs_reference_python_model_fixture():
+  """distribution_ops.sharding_sparse_fids (row a2: ShardingSparseFids outputs) against the reference's own Python
+  model of the op (parse_sparse_feature_test.py:87-240, run by tests/golden/make_sharding_golden.py): per-(table,
+  shard) FID lists, fid_offset (index << 32 | float offset, per-feature dims_sum), feature_offset, nfl_offset with the
+  shared flag — all exact.  The dedup / shard step is served by the oracle's FusedReorderByIndices here (CPU); on
+  the GPU the same adapter runs on mono_reorder_by_indices, which is bit-exact with it (tests/test_gpu_parity.py)."""
+  import torch
+  from monolith_b200 import distribution_ops as dops
+
+  def reorder_fn(lists, n, dims):
+    out, ss, sl, _, offs = orc.reorder_by_indices([l.numpy() for l in lists], n, dims)
+    return torch.from_numpy(out), ss.tolist(), sl.tolist(), None, torch.from_numpy(offs)
+
+  z = np.load(os.path.join(G, "ref_sharding_sparse_fids.npz"))
+  for ci in range(int(z["n_cases"])):
+    names = [str(n) for n in z[f"c{ci}_names"]]
+    N = int(z[f"c{ci}_N"])
+    feats = {n: (torch.from_numpy(z[f"c{ci}_fids_{n}"]), torch.from_numpy(z[f"c{ci}_splits_{n}"])) for n in names}
+    table_of = {n: str(t) for n, t in zip(names, z[f"c{ci}_tables"])}
+    dims_sum = {n: int(d) for n, d in zip(names, z[f"c{ci}_dims_sum"])}
+    shared = [n for n, s in zip(names, z[f"c{ci}_shared"]) if s]
+    r = dops.sharding_sparse_fids(feats, table_of, dims_sum, N, shared, reorder_fn=reorder_fn)
+    assert r["nfl_offset"].numpy().astype(np.uint32).tolist() == z[f"c{ci}_nfl_offset"].tolist()
+    assert r["feature_offset"].numpy().tolist() == z[f"c{ci}_feature_offset"].tolist()
+    assert r["fid_offset"].numpy().view(np.uint64).tolist() == z[f"c{ci}_fid_offset_unique"].tolist()
+    K = int(z[f"c{ci}_n_tables"])
+    assert len(r["fid_list"]) == K * N
+    for k in range(K):
+      for n in range(N):
+        assert r["fid_list"][k * N + n].numpy().tolist() == z[f"c{ci}_list_{k}_{n}"].tolist(), (ci, k, n)
+
+
+def test_sharding_sparse_fids_negative_fids_use_unsigned_shard():
+  """shard = (uint64)fid % N also for FIDs with the top bit set (parse_sparse_feature.cc:205 `value % ps_num_` on
+  uint64): the adapter's signed-remainder arithmetic must agree with numpy's uint64 arithmetic."""
+  import torch
+  from monolith_b200 import distribution_ops as dops
+
+  def reorder_fn(lists, n, dims):
+    out, ss, sl, _, offs = orc.reorder_by_indices([l.numpy() for l in lists], n, dims)
+    return torch.from_numpy(out), ss.tolist(), sl.tolist(), None, torch.from_numpy(offs)
+
+  rng = np.random.default_rng(5)
+  fids = rng.integers(-2**63, 2**63 - 1, 500).astype(np.int64)
+  fids[:4] = [-1, np.iinfo(np.int64).min, np.iinfo(np.int64).max, 0]
+  for N in (1, 2, 3, 5, 8, 64):
+    r = dops.sharding_sparse_fids({"f": (torch.from_numpy(fids), torch.tensor([0, fids.size]))}, {"f": "t"}, {"f": 4}, N,
+                                  reorder_fn=reorder_fn)
+    shard = (fids.view(np.uint64) % np.uint64(N)).astype(np.int64)
+    assert ((r["fid_offset"].numpy() >> 32) == shard).all()                    # table index 0: index1 == shard
+    for n in range(N):
+      want = fids[shard == n]
+      _, first = np.unique(want, return_index=True)
+      assert r["fid_list"][n].numpy().tolist() == want[np.sort(first)].tolist()  # first-occurrence order
