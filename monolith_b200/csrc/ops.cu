@@ -11,7 +11,6 @@
 // 64 B + 128 B HBM accesses in flight, so occupancy (memory-level parallelism), not staging, is the
 // lever.
 #include <algorithm>
-#include <cstdlib>
 #include <cstring>
 
 #include "engine.h"
@@ -1457,98 +1456,6 @@ radix_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restri
   }
 }
 
-// EXPERIMENTAL (opt-in: MONO_RADIX_STAGED=1; not the default, not yet measured): the scatter half of a pass
-// with the tile reordered in shared memory first.  The direct scatter above writes every (key, value) as a
-// lone 4-byte store (a 2 048-item tile spreads over 256 bins: ~8 items per bin, one 32-byte sector touched
-// per item); here the tile is laid out digit by digit in shared memory and written back in order, so the 8
-// items of a bin leave as one contiguous 32-byte piece.  Same ranks, same output, bit for bit.
-__global__ void __launch_bounds__(kThreads)
-radix_scatter_staged_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, int64_t n,
-                            int shift, int pre_shift, const int32_t* __restrict__ blk_cnt,
-                            const int32_t* __restrict__ dtot, int nblk, uint32_t* __restrict__ keys_out,
-                            uint32_t* __restrict__ vals_out) {
-  static_assert(kThreads == 256, "one digit per thread");
-  __shared__ int32_t wcnt[kThreads / 32][256];
-  __shared__ int32_t bbase[256];
-  __shared__ int32_t dbase[256];
-  __shared__ int32_t tstart[256];
-  __shared__ int32_t wtot[kThreads / 32];
-  __shared__ uint32_t skey[kSortTile];
-  __shared__ uint32_t sval[kSortTile];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  constexpr int NW = kThreads / 32;
-  constexpr int kPerWarp = kSortTile / NW;
-  auto block_excl_scan = [&](int v) {  // exclusive scan of one value per thread over the block
-    int x = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
-    }
-    if (lane == 31) wtot[w] = x;
-    __syncthreads();
-    int off = 0;
-    for (int ww = 0; ww < w; ++ww) off += wtot[ww];
-    __syncthreads();
-    return off + x - v;
-  };
-  dbase[threadIdx.x] = block_excl_scan(dtot[threadIdx.x]);
-  __syncthreads();
-  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-    const int64_t tbeg = (int64_t)blk * kSortTile;
-    const int64_t wbeg = tbeg + (int64_t)w * kPerWarp;
-    for (int d = lane; d < 256; d += 32) wcnt[w][d] = 0;
-    __syncwarp();
-    for (int c = 0; c < kPerWarp; c += 32) {
-      const int64_t i = wbeg + c + lane;
-      const int dg = i < n ? (int)(((keys_in[i] >> pre_shift) >> shift) & 255u) : -1;
-      const uint32_t same = __match_any_sync(0xffffffffu, dg);
-      if (dg >= 0 && lane == (__ffs(same) - 1)) wcnt[w][dg] += __popc(same);
-      __syncwarp();
-    }
-    __syncthreads();
-    int run = 0;  // digit threadIdx.x: per-warp counts -> exclusive prefix over the warps, total in `run`
-    for (int ww = 0; ww < NW; ++ww) {
-      const int v = wcnt[ww][threadIdx.x];
-      wcnt[ww][threadIdx.x] = run;
-      run += v;
-    }
-    bbase[threadIdx.x] = blk_cnt[(size_t)threadIdx.x * nblk + blk] + dbase[threadIdx.x];
-    const int ts = block_excl_scan(run);  // where digit threadIdx.x starts inside the reordered tile
-    tstart[threadIdx.x] = ts;
-    __syncthreads();
-    for (int c = 0; c < kPerWarp; c += 32) {
-      const int64_t i = wbeg + c + lane;
-      uint32_t key = 0, val = 0;
-      int dg = -1;
-      if (i < n) {
-        key = keys_in[i] >> pre_shift;
-        val = vals_in ? vals_in[i] : (uint32_t)i;
-        dg = (int)((key >> shift) & 255u);
-      }
-      const uint32_t same = __match_any_sync(0xffffffffu, dg);
-      if (dg >= 0) {
-        const int p = tstart[dg] + wcnt[w][dg] + __popc(same & ((1u << lane) - 1u));
-        skey[p] = key;
-        sval[p] = val;
-      }
-      __syncwarp();
-      if (dg >= 0 && lane == (__ffs(same) - 1)) wcnt[w][dg] += __popc(same);
-      __syncwarp();
-    }
-    __syncthreads();
-    const int tile_n = (int)min((int64_t)kSortTile, n - tbeg);
-    for (int p = threadIdx.x; p < tile_n; p += kThreads) {
-      const uint32_t key = skey[p];
-      const int dg = (int)((key >> shift) & 255u);
-      const int g = bbase[dg] + (p - tstart[dg]);
-      keys_out[g] = key;
-      vals_out[g] = sval[p];
-    }
-    __syncthreads();
-  }
-}
-
 // per-tile digit histogram (the counting half of a pass): shared-memory atomics, one tile per block
 // iteration, same tiling as the scatter kernel (radix_pass_kernel<1>)
 __global__ void __launch_bounds__(kThreads)
@@ -2144,8 +2051,6 @@ static void sort_and_runs(const SortWs& w, int64_t M, int bits, int pre_shift, c
   uint32_t *kin = w.k0, *kout = w.k1, *vout = w.v1;
   const int gh = resident_grid(radix_hist_kernel, nblk, 1);
   const int gs = resident_grid(radix_pass_kernel<1>, nblk, 1);
-  static const bool staged = [] { const char* e = std::getenv("MONO_RADIX_STAGED"); return e && e[0] == '1'; }();
-  const int gst = staged ? resident_grid(radix_scatter_staged_kernel, nblk, 1) : 0;
   for (int p = 0; p < passes; ++p) {
     int32_t* dt = w.dtot + 256 * p;
     const int ps = p == 0 ? pre_shift : 0;
@@ -2153,10 +2058,7 @@ static void sort_and_runs(const SortWs& w, int64_t M, int bits, int pre_shift, c
     MONO_CHECK_LAUNCH();
     radix_rowscan_kernel<<<256, 1024, 0, s>>>(w.blk_cnt, nblk);
     MONO_CHECK_LAUNCH();
-    if (staged)
-      radix_scatter_staged_kernel<<<gst, kThreads, 0, s>>>(kin, vin, M, 8 * p, ps, w.blk_cnt, dt, nblk, kout, vout);
-    else
-      radix_pass_kernel<1><<<gs, kThreads, 0, s>>>(kin, vin, M, 8 * p, ps, w.blk_cnt, dt, nblk, kout, vout, nullptr);
+    radix_pass_kernel<1><<<gs, kThreads, 0, s>>>(kin, vin, M, 8 * p, ps, w.blk_cnt, dt, nblk, kout, vout, nullptr);
     MONO_CHECK_LAUNCH();
     vin = vout;
     std::swap(kin, kout);
