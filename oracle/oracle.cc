@@ -141,6 +141,46 @@ struct Row {
   uint32_t ts = 0;          // ref: RT/hash_table/entry_defs.h:31-39
 };
 
+// Counting admission filter — restatement of monolith::hash_filter::HashFilter<uint16_t>
+// (RT/hash_filter/hash_filter.h:34-165, filter.h:60-61): open addressing over capacity * 1.5 (+64) 16-bit cells,
+// cell = 12-bit signature << 4 | 4-bit saturating count, at most 64 probes; add() returns the count BEFORE the
+// increment (0 for a new FID, 15 when the probe window is exhausted).  The cell a FID lands in depends on
+// absl::Hash (salted per process) and is therefore unpinned; counts are pinned as long as signatures do not collide.
+struct HashFilter {
+  static constexpr int kCountBit = 4, kMaxStep = 64;
+  static constexpr uint32_t kMaxCount = (1u << kCountBit) - 1;
+  std::vector<uint16_t> map;
+  uint64_t total_size = 0, capacity = 0, num_elements = 0, failure_count = 0;
+  explicit HashFilter(uint64_t cap) : capacity(cap) {
+    total_size = (uint64_t)(cap * 1.5);
+    if (total_size == 0) total_size = 1;
+    map.assign(total_size + kMaxStep, 0);
+  }
+  static uint16_t Signature(uint64_t fid) { return (uint16_t)(((fid >> 17) | (fid << 15)) & 0x0FFF); }  // :128
+  uint32_t Add(int64_t fid_, uint32_t count) {  // :69-76 + iterator add :40-62
+    const uint64_t fid = (uint64_t)fid_;
+    const uint16_t sign = Signature(fid);
+    size_t pos = (size_t)(Mix64(fid) % total_size);
+    for (int step = 0; step < kMaxStep; ++step) {
+      uint16_t& v = map[pos];
+      if (v == 0 || (v >> kCountBit) == sign) {
+        if (count > kMaxCount) count = kMaxCount;
+        if (v == 0) {
+          num_elements = std::min(num_elements + 1, capacity);
+          v = (uint16_t)((sign << kCountBit) + count);
+          return 0;
+        }
+        const uint32_t c = v & kMaxCount;
+        if (c + count >= kMaxCount) v |= (uint16_t)kMaxCount; else v = (uint16_t)(v + count);
+        return c;
+      }
+      if (++pos == map.size()) pos = 0;
+    }
+    ++failure_count;
+    return kMaxCount;
+  }
+};
+
 struct Table {
   std::string name;
   std::vector<mono_segment_cfg> segs;
@@ -150,6 +190,20 @@ struct Table {
   uint64_t seed = 0;
   int64_t max_update_ts = 0;
   std::unordered_map<int64_t, Row> m;
+  // admission filter (absent = the dummy filter, which never filters: dummy_hash_filter.h:31-52)
+  std::shared_ptr<HashFilter> filter;
+  uint32_t default_threshold = 0;
+  std::unordered_map<uint32_t, uint32_t> slot_threshold;
+  // ref: HashFilterTfBridge::ShouldBeFiltered (hash_filter_tf_bridge.h:36-47) -> HashFilter::ShouldBeFiltered
+  // (hash_filter.h:137-144): threshold <= 0 never filters; otherwise add(fid, count) < threshold
+  bool ShouldBeFiltered(int64_t fid, uint32_t count) {
+    if (!filter) return false;
+    const uint32_t slot = (uint32_t)(((uint64_t)fid >> 48) & 0x7FFF);
+    auto it = slot_threshold.find(slot);
+    const uint32_t thr = it == slot_threshold.end() ? default_threshold : it->second;
+    if (thr == 0) return false;
+    return filter->Add(fid, count) < thr;
+  }
 
   // ref: EntryAccessor::Init (entry_accessor.cc:165-169): initializer then optimizer Init.
   void Init(int64_t fid, Row* r) const {
@@ -270,6 +324,7 @@ void TableBatchOptimize(Table* t, const int64_t* ids, int64_t n, const float* gr
     // tf_bridge.cc:270-310: first occurrence copies, later occurrences ReduceSum into it.
     std::vector<float> cache((size_t)n * D);
     std::unordered_map<int64_t, float*> ids_to_grads;
+    std::unordered_map<int64_t, uint32_t> ids_to_counts;
     std::vector<int64_t> order;
     for (int64_t i = 0; i < n; ++i) {
       auto it = ids_to_grads.find(ids[i]);
@@ -277,19 +332,30 @@ void TableBatchOptimize(Table* t, const int64_t* ids, int64_t n, const float* gr
         float* dst = cache.data() + ids_to_grads.size() * D;
         std::memcpy(dst, grads + i * D, sizeof(float) * D);
         ids_to_grads[ids[i]] = dst;
+        ids_to_counts[ids[i]] = 1;
         order.push_back(ids[i]);
       } else {
         float* dst = it->second;
         const float* src = grads + i * D;
         for (int j = 0; j < D; ++j) dst[j] = dst[j] + src[j];  // avx_utils.h:247-254 ReduceSum(a,b)
+        ++ids_to_counts[ids[i]];
       }
     }
-    for (int64_t id : order) {
+    // second step (tf_bridge.cc:296-310): ids absent from the table pass the filter with their occurrence count
+    std::vector<int64_t> kept;
+    for (int64_t id : order)
+      if (t->m.count(id) || !t->ShouldBeFiltered(id, ids_to_counts[id])) kept.push_back(id);
+    for (int64_t id : kept) {
       const float* g = ids_to_grads[id];
       t->Upsert(id, [&](Row* r) { r->ts = (uint32_t)update_time; t->Optimize(r, g, lr); });
     }
   } else {
-    for (int64_t i = 0; i < n; ++i) {
+    // tf_bridge.cc:312-326: the whole id list is filtered FIRST (Contains sees the table as it was before this
+    // call, each absent occurrence adds 1 to its counter), then the survivors are optimized in order
+    std::vector<int64_t> kept;
+    for (int64_t i = 0; i < n; ++i)
+      if (t->m.count(ids[i]) || !t->ShouldBeFiltered(ids[i], 1)) kept.push_back(i);
+    for (int64_t i : kept) {
       const float* g = grads + i * D;
       t->Upsert(ids[i], [&](Row* r) { r->ts = (uint32_t)update_time; t->Optimize(r, g, lr); });
     }
@@ -430,6 +496,19 @@ int orc_mtable_fused_optimize(orc_mtable* t, const int64_t* ids, const int32_t* 
   return 0;
 }
 
+// Attach a counting hash filter to table k (ref: hash_filter_ops.create_hash_filters + SlotOccurrenceThresholdConfig,
+// embedding_hash_table.proto:100-110).  n_slots per-slot thresholds override the default; threshold 0 = never filter.
+int orc_mtable_set_hash_filter(orc_mtable* t, int32_t k, int64_t capacity, uint32_t default_threshold,
+                               const uint32_t* slots, const uint32_t* thresholds, int32_t n_slots) {
+  if (k < 0 || k >= (int)t->tables.size()) return 1;
+  Table& tb = t->tables[k];
+  tb.filter = std::make_shared<HashFilter>((uint64_t)capacity);
+  tb.default_threshold = default_threshold;
+  tb.slot_threshold.clear();
+  for (int i = 0; i < n_slots; ++i) tb.slot_threshold[slots[i]] = thresholds[i];
+  return 0;
+}
+
 // ref: MultiHashTableAssignOp (multi_hash_table_update_op.cc:106-145) -> TfBridge::Assign
 // (tf_bridge.cc:179-206) -> CuckooEmbeddingHashTable::Assign (cuckoo_..cc:185-203).
 int orc_mtable_assign(orc_mtable* t, const int64_t* ids, const int64_t* id_split,
@@ -440,11 +519,12 @@ int orc_mtable_assign(orc_mtable* t, const int64_t* ids, const int64_t* id_split
     tb.BumpMaxTs(update_time);
     for (int64_t i = id_split[k]; i < id_split[k + 1]; ++i) {
       const float* v = values + voff;
+      voff += tb.dim;
+      if (!tb.m.count(ids[i]) && tb.ShouldBeFiltered(ids[i], 1)) continue;  // tf_bridge.cc:181-185
       tb.Upsert(ids[i], [&](Row* r) {
         r->ts = (uint32_t)update_time;
         std::memcpy(r->data.data(), v, sizeof(float) * tb.dim);  // entry_accessor.cc:175-179
       });
-      voff += tb.dim;
     }
   }
   return 0;
@@ -460,11 +540,12 @@ int orc_mtable_assign_add(orc_mtable* t, const int64_t* ids, const int64_t* id_s
     for (int64_t i = id_split[k]; i < id_split[k + 1]; ++i) {
       tb.BumpMaxTs(update_time);
       const float* v = values + voff;
+      voff += tb.dim;
+      if (tb.ShouldBeFiltered(ids[i], 1)) continue;  // AssignAdd2 has no Contains check (tf_bridge.cc:224-232)
       tb.Upsert(ids[i], [&](Row* r) {
         r->ts = (uint32_t)update_time;
         for (int j = 0; j < tb.dim; ++j) r->data[j] += v[j];  // entry_accessor.cc:181-187
       });
-      voff += tb.dim;
     }
   }
   return 0;

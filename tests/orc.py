@@ -72,6 +72,14 @@ class OracleMultiHashTable:
     except Exception:
       pass
 
+  def set_hash_filter(self, slot, capacity, default_threshold, slot_thresholds=None):
+    """Counting admission filter on table `slot` (oracle only so far: SURVEY §8(f) row 2)."""
+    st = slot_thresholds or {}
+    ks = np.ascontiguousarray(np.array(list(st.keys()), np.uint32))
+    vs = np.ascontiguousarray(np.array(list(st.values()), np.uint32))
+    assert lib().orc_mtable_set_hash_filter(self.h, self.names.index(slot), C.c_int64(capacity),
+                                            C.c_uint32(default_threshold), p(ks), p(vs), len(st)) == 0
+
   def lrs(self):
     out = []
     for n in self.names:

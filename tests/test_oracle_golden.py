@@ -296,3 +296,31 @@ def test_sharding_sparse_fids_negative_fids_use_unsigned_shard():
       want = fids[shard == n]
       _, first = np.unique(want, return_index=True)
       assert r["fid_list"][n].numpy().tolist() == want[np.sort(first)].tolist()  # first-occurrence order
+
+
+def test_hash_filter_threshold_schedule_golden():
+  """Counting hash filter, oracle side (next-row prep): the reference's
+  test_gradients_with_hash_filter (NT/hash_table_ops_test.py:223-260): dim 1, SGD lr 0.1, occurrence_threshold 3,
+  ids [0, 0, 1] with gradient -1 applied four times -> lookups of [0, 1] after each step."""
+  t = orc.OracleMultiHashTable({"t": sgd_table(1, 0.1)})
+  t.set_hash_filter("t", capacity=1000, default_threshold=3)
+  ids = np.array([0, 0, 1], np.int64)
+  expected = [[[0.0], [0.0]], [[0.1], [0.0]], [[0.3], [0.0]], [[0.5], [0.1]]]
+  for want in expected:
+    t.apply_gradients({"t": (ids, -np.ones((3, 1), np.float32))})
+    np.testing.assert_allclose(t.lookup({"t": np.array([0, 1], np.int64)})["t"], want, rtol=1e-6, atol=1e-7)
+  # threshold 0 (and tables without a filter) never filter; per-slot thresholds override the default
+  t2 = orc.OracleMultiHashTable({"t": sgd_table(1, 0.1)})
+  t2.set_hash_filter("t", capacity=1000, default_threshold=0, slot_thresholds={2: 2})
+  a, b = np.int64(5), (np.int64(2) << 48) | np.int64(5)
+  t2.apply_gradients({"t": (np.array([a, b], np.int64), -np.ones((2, 1), np.float32))})
+  np.testing.assert_allclose(t2.lookup({"t": np.array([a, b], np.int64)})["t"], [[0.1], [0.0]], rtol=1e-6)
+  t2.apply_gradients({"t": (np.array([a, b], np.int64), -np.ones((2, 1), np.float32))})
+  t2.apply_gradients({"t": (np.array([a, b], np.int64), -np.ones((2, 1), np.float32))})
+  np.testing.assert_allclose(t2.lookup({"t": np.array([a, b], np.int64)})["t"], [[0.3], [0.1]], rtol=1e-6)
+  # the dedup path passes the occurrence count to the filter (tf_bridge.cc:296-310): [7,7,7] counts 3 at once
+  t3 = orc.OracleMultiHashTable({"t": sgd_table(1, 0.1)})
+  t3.set_hash_filter("t", capacity=1000, default_threshold=3)
+  for want in ([[0.0]], [[0.3]]):   # first call: previous count 0 < 3 -> filtered (counter becomes 3); second: 3 !< 3
+    t3.apply_gradients({"t": (np.array([7, 7, 7], np.int64), -np.ones((3, 1), np.float32))}, enable_dedup=True)
+    np.testing.assert_allclose(t3.lookup({"t": np.array([7], np.int64)})["t"], want, rtol=1e-6, atol=1e-7)
