@@ -261,6 +261,12 @@ def run_ours(args):
   dev = torch.device("cuda", local)
   if world > 1:
     dist.init_process_group("nccl", device_id=dev)
+  if not os.path.exists(_lib.LIB_PATH):  # a checkout without the (git-ignored) .so: build it, loudly, once
+    if rank == 0:
+      import subprocess
+      subprocess.check_call(["bash", os.path.join(ROOT, "monolith_b200", "csrc", "build.sh")], stdout=sys.stderr)
+    if world > 1:
+      dist.barrier()
   lib = _lib.load()
 
   use_sharded = world > 1 or args.sharded

@@ -13,6 +13,20 @@ def pytest_configure(config):
 
 
 @pytest.fixture(scope="session", autouse=True)
+def _build_cuda_library():
+  """Build libmono_emb.so when a checkout arrives without it (the .so is git-ignored; nvcc cross-compiles in ~2 min).
+  This is the same recipe as __graft_entry__.build(); a failed build fails the session loudly — there is no fallback."""
+  import glob
+  import subprocess
+  so = os.path.join(ROOT, "monolith_b200", "lib", "libmono_emb.so")
+  srcs = glob.glob(os.path.join(ROOT, "monolith_b200", "csrc", "*.cu*")) + \
+      glob.glob(os.path.join(ROOT, "monolith_b200", "csrc", "*.h")) + [os.path.join(ROOT, "include", "mono_emb.h")]
+  if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in srcs):
+    subprocess.check_call(["bash", os.path.join(ROOT, "monolith_b200", "csrc", "build.sh")])
+  yield
+
+
+@pytest.fixture(scope="session", autouse=True)
 def _build_oracle():
   """The oracle is test infrastructure: build it on demand (g++ only, a few seconds)."""
   import subprocess
