@@ -70,3 +70,28 @@ def test_product_never_imports_oracle():
         txt = open(os.path.join(dirpath, f)).read()
         for needle in ("liboracle", "import orc", "from tests", "orc_", "oracle/_ref", '#include "../../oracle'):
           assert needle not in txt, (f, needle)
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+  """The boundary is a C ABI: include/mono_emb.h compiles as C99 (-pedantic) and a plain C program links against
+  libmono_emb.so and calls it (no GPU needed for these entry points)."""
+  import shutil
+  import subprocess
+  if shutil.which("gcc") is None:
+    pytest.skip("no gcc")
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  src = tmp_path / "abi.c"
+  src.write_text('#include <string.h>\n#include "mono_emb.h"\n'
+                 'int main(void) {\n'
+                 '  mono_segment_cfg seg; mono_table_cfg cfg; mono_slice_task task;\n'
+                 '  memset(&seg, 0, sizeof seg); memset(&cfg, 0, sizeof cfg); memset(&task, 0, sizeof task);\n'
+                 '  if (mono_abi_version() != MONO_EMB_ABI_VERSION) return 1;\n'
+                 '  if (mono_ckpt_crc32c("123456789", 9) != 0xE3069283u) return 2;\n'
+                 '  if (mono_kernel_launch_count() != 0) return 3;\n'
+                 '  return (int)(sizeof seg + sizeof cfg + sizeof task) == 44 + 64 + 36 ? 0 : 4;\n'
+                 '}\n')
+  libdir = os.path.join(root, "monolith_b200", "lib")
+  exe = tmp_path / "abi"
+  subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                         str(src), "-o", str(exe), "-L", libdir, "-lmono_emb", "-Wl,-rpath," + libdir])
+  assert subprocess.run([str(exe)]).returncode == 0
