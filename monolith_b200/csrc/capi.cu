@@ -37,7 +37,13 @@ void require(bool c, const char* msg) {
   if (!c) throw ArgError(msg);
 }
 
-void use_device(const mono_mtable_t* t) { MONO_CUDA(cudaSetDevice(t->device)); }
+// Every entry point that touches a table's device state or scratch takes the handle's lock for the duration of
+// the (asynchronous) enqueue and selects its device: host threads may share one handle, as the reference's
+// interface allows (embedding_hash_table_interface.h:32-33); recursive because the *_host variants nest.
+struct HandleGuard {
+  std::unique_lock<std::recursive_mutex> lk;
+  explicit HandleGuard(const mono_mtable_t* t) : lk(t->mu) { MONO_CUDA(cudaSetDevice(t->device)); }
+};
 
 // segments of a per-table call (id_split over K tables; values laid out table after table)
 std::vector<CallSeg> table_segs(const mono_mtable_t* t, const int64_t* id_split, int width_extra,
@@ -183,7 +189,7 @@ int64_t mono_mtable_max_update_ts(const mono_mtable_t* t, int32_t k) { return t-
 int mono_mtable_size(mono_mtable_t* t, int32_t k, int64_t* out_size, void* stream) {
   return guarded([&] {
     require(k >= 0 && k < (int)t->tables.size(), "bad table index");
-    use_device(t);
+    HandleGuard hg_(t);
     uint32_t c[kNumCtrs];
     read_counters_sync(t, k, (cudaStream_t)stream, c);
     *out_size = c[kCtrSize];
@@ -193,7 +199,7 @@ int mono_mtable_size(mono_mtable_t* t, int32_t k, int64_t* out_size, void* strea
 int mono_mtable_lookup(mono_mtable_t* t, const int64_t* ids_dev, const int64_t* id_split_host,
                        float* emb_out_dev, void* stream) {
   return guarded([&] {
-    use_device(t);
+    HandleGuard hg_(t);
     int64_t n_total = 0;
     auto segs = table_segs(t, id_split_host, 0, &n_total, nullptr);
     if (segs.empty()) return;
@@ -241,7 +247,7 @@ int mono_mtable_fused_lookup(mono_mtable_t* t, const int64_t* ids_dev,
                              const int32_t* fused_slot_size_host, int32_t num_shards,
                              int64_t /*req_time*/, float* emb_out_dev, void* stream) {
   return guarded([&] {
-    use_device(t);
+    HandleGuard hg_(t);
     require(num_shards > 0 && fused_slot_size_host, "fused_lookup: bad arguments");
     int64_t n_total = 0;
     auto segs = fused_segs(t, fused_slot_size_host, num_shards, 0, num_shards, &n_total);
@@ -254,7 +260,7 @@ int mono_mtable_contains(mono_mtable_t* t, int32_t k, const int64_t* ids_dev, in
                          uint8_t* out_dev, void* stream) {
   return guarded([&] {
     require(k >= 0 && k < (int)t->tables.size(), "bad table index");
-    use_device(t);
+    HandleGuard hg_(t);
     launch_contains(t, k, ids_dev, n, out_dev, (cudaStream_t)stream);
   });
 }
@@ -264,7 +270,7 @@ int mono_mtable_lookup_pool(mono_mtable_t* t, int32_t k, const int64_t* fids_dev
                             float* out_dev, int64_t out_stride, int32_t out_col, void* stream) {
   return guarded([&] {
     require(k >= 0 && k < (int)t->tables.size(), "bad table index");
-    use_device(t);
+    HandleGuard hg_(t);
     launch_lookup_pool(t, k, fids_dev, row_offsets_dev, n_rows, pooling, out_dev, out_stride, out_col,
                        (cudaStream_t)stream);
   });
@@ -279,7 +285,7 @@ int mono_mtable_pool_backward(mono_mtable_t* t, int32_t k, const int64_t* fids_d
     require(k >= 0 && k < (int)t->tables.size(), "bad table index");
     require(fids_dev && pooled_grad_dev && learning_rate_host, "pool_backward: null argument");
     require(row_offsets_dev != nullptr || n_rows == n_fids, "pool_backward: n_rows must equal n_fids without offsets");
-    use_device(t);
+    HandleGuard hg_(t);
     run_pool_backward(t, k, fids_dev, n_fids, row_offsets_dev, n_rows, pooling, pooled_grad_dev, grad_stride,
                       grad_col, learning_rate_host, update_time, (cudaStream_t)stream);
   });
@@ -289,7 +295,7 @@ int mono_mtable_optimize(mono_mtable_t* t, const int64_t* ids_dev, const int64_t
                          const float* grads_dev, const float* learning_rate_host,
                          int64_t update_time, int64_t /*global_step*/, uint32_t flags, void* stream) {
   return guarded([&] {
-    use_device(t);
+    HandleGuard hg_(t);
     require(learning_rate_host != nullptr, "learning_rate is null");
     int64_t n_total = 0;
     int n_lr = 0;
@@ -308,7 +314,7 @@ int mono_mtable_fused_optimize(mono_mtable_t* t, const int64_t* ids_dev,
                                int64_t /*global_step*/, int32_t num_shards, uint32_t flags,
                                void* stream) {
   return guarded([&] {
-    use_device(t);
+    HandleGuard hg_(t);
     require(num_shards > 0 && fused_slot_size_host && learning_rate_host, "fused_optimize: bad arguments");
     const int K = (int)t->tables.size();
     if (id_offsets_host && grad_offsets_host) {  // must agree with ComputeFusedOffsets
@@ -350,7 +356,7 @@ static int assign_like(mono_mtable_t* t, UpsertOp op, const int64_t* ids_dev,
                        const int64_t* id_split_host, const float* values_dev, int64_t update_time,
                        uint32_t flags, void* stream) {
   return guarded([&] {
-    use_device(t);
+    HandleGuard hg_(t);
     int64_t n_total = 0;
     auto segs = table_segs(t, id_split_host, 0, &n_total, nullptr);
     if (segs.empty()) return;
@@ -372,7 +378,7 @@ int mono_mtable_assign_add(mono_mtable_t* t, const int64_t* ids_dev, const int64
 int mono_mtable_reinitialize(mono_mtable_t* t, int32_t k, const int64_t* ids_dev, int64_t n,
                              int32_t* status_dev, int64_t update_time, void* stream) {
   return guarded([&] {
-    use_device(t);
+    HandleGuard hg_(t);
     require(status_dev != nullptr, "status is null");
     if (n <= 0) return;
     if (k < 0 || k >= (int)t->tables.size()) {  // unknown table: all -1 (update_op.cc:207-214)
@@ -393,7 +399,7 @@ int mono_mtable_reinitialize(mono_mtable_t* t, int32_t k, const int64_t* ids_dev
 int mono_mtable_evict(mono_mtable_t* t, int32_t k, int64_t max_update_time, void* stream) {
   return guarded([&] {
     require(k >= 0 && k < (int)t->tables.size(), "bad table index");
-    use_device(t);
+    HandleGuard hg_(t);
     evict_table(t, k, max_update_time, (cudaStream_t)stream);
   });
 }
@@ -402,7 +408,7 @@ int mono_mtable_lookup_entry(mono_mtable_t* t, int32_t k, const int64_t* ids_dev
                              float* entry_out_dev, void* stream) {
   return guarded([&] {
     require(k >= 0 && k < (int)t->tables.size(), "bad table index");
-    use_device(t);
+    HandleGuard hg_(t);
     launch_lookup_entry(t, k, ids_dev, n, entry_out_dev, (cudaStream_t)stream);
   });
 }
@@ -411,7 +417,7 @@ int mono_mtable_export(mono_mtable_t* t, int32_t k, int64_t* cursor, int64_t max
                        int64_t* ids_out_dev, float* entry_out_dev, int64_t* n_out, void* stream) {
   return guarded([&] {
     require(k >= 0 && k < (int)t->tables.size() && cursor && n_out && max_n > 0, "export: bad arguments");
-    use_device(t);
+    HandleGuard hg_(t);
     *n_out = export_rows(t, k, cursor, max_n, ids_out_dev, entry_out_dev, (cudaStream_t)stream);
   });
 }
@@ -420,7 +426,7 @@ int mono_mtable_restore_rows(mono_mtable_t* t, int32_t k, const int64_t* ids_dev
                              const float* entry_in_dev, void* stream) {
   return guarded([&] {
     require(k >= 0 && k < (int)t->tables.size(), "bad table index");
-    use_device(t);
+    HandleGuard hg_(t);
     if (n <= 0) return;
     CallSeg s;
     s.id_begin = 0;
@@ -576,7 +582,7 @@ int mono_mtable_lookup_push(mono_mtable_t* t, int32_t k, const int64_t* ids_dev,
     require(t && counts && p && dst_row_off, "mono_mtable_lookup_push: null argument");
     require(k >= 0 && k < (int)t->tables.size(), "mono_mtable_lookup_push: bad table index");
     require(p->device == t->device, "mono_mtable_lookup_push: window and table on different devices");
-    use_device(t);
+    HandleGuard hg_(t);
     const int D = t->tables[k].dim;
     PeerOut po = peer_out(p, region_off, dst_row_off, counts, (int64_t)D * 4);
     const int64_t n = po.start[po.n];
@@ -669,7 +675,7 @@ int mono_embedding_to_layout_grad(int32_t device, float* const* emb_grad_ptrs_de
 int mono_mtable_lookup_host(mono_mtable_t* t, const int64_t* ids_host, const int64_t* id_split_host,
                             float* emb_out_host) {
   return guarded([&] {
-    use_device(t);
+    HandleGuard hg_(t);
     cudaStream_t s = t->own_stream;
     int64_t n_total = 0;
     auto segs = table_segs(t, id_split_host, 0, &n_total, nullptr);
@@ -695,7 +701,7 @@ int mono_mtable_lookup_pool_host(mono_mtable_t* t, int32_t k, const int64_t* fid
                                  int32_t pooling, float* out_host) {
   return guarded([&] {
     require(k >= 0 && k < (int)t->tables.size(), "bad table index");
-    use_device(t);
+    HandleGuard hg_(t);
     cudaStream_t s = t->own_stream;
     if (n_rows <= 0) return;
     const int D = t->tables[k].dim;
@@ -722,7 +728,7 @@ int mono_mtable_optimize_host(mono_mtable_t* t, const int64_t* ids_host,
                               const float* learning_rate_host, int64_t update_time,
                               int64_t /*global_step*/, uint32_t flags) {
   return guarded([&] {
-    use_device(t);
+    HandleGuard hg_(t);
     cudaStream_t s = t->own_stream;
     int64_t n_total = 0;
     int n_lr = 0;

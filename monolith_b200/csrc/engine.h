@@ -136,6 +136,7 @@ struct HostTable {
 }  // namespace mono
 
 struct mono_mtable {
+  mutable std::recursive_mutex mu;  // serialises host threads on this handle (capi.cu HandleGuard)
   int device = 0;
   std::vector<mono::HostTable> tables;
   mono::TableDev* d_tables = nullptr;  // device array [K]
