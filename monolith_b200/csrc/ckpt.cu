@@ -160,6 +160,9 @@ bool snappy_uncompress(const uint8_t* in, size_t n, std::string* out) {
     if (!(b & 0x80)) break;
     shift += 7;
   }
+  // a copy element expands at most 3 bytes -> 64: a declared length beyond that is corrupt (and must not be
+  // allowed to drive the allocation below)
+  if (ulen > (uint64_t)n * 32 + 64) return false;
   const size_t base = out->size();
   out->reserve(base + ulen);
   while (p < n) {
@@ -519,18 +522,26 @@ uint32_t mono_ckpt_crc32c(const void* data, int64_t n) { return crc32c(data, (si
 uint32_t mono_ckpt_masked_crc32c(const void* data, int64_t n) { return masked_crc(data, (size_t)n); }
 
 int64_t mono_ckpt_snappy_compress(const void* in, int64_t n, void* out, int64_t out_cap) {
-  std::string s;
-  snappy_compress(static_cast<const uint8_t*>(in), (size_t)n, &s);
-  if ((int64_t)s.size() > out_cap) return -(int64_t)s.size();
-  std::memcpy(out, s.data(), s.size());
-  return (int64_t)s.size();
+  try {
+    std::string s;
+    snappy_compress(static_cast<const uint8_t*>(in), (size_t)n, &s);
+    if ((int64_t)s.size() > out_cap) return -(int64_t)s.size();
+    std::memcpy(out, s.data(), s.size());
+    return (int64_t)s.size();
+  } catch (const std::exception&) {
+    return INT64_MIN;
+  }
 }
 int64_t mono_ckpt_snappy_uncompress(const void* in, int64_t n, void* out, int64_t out_cap) {
-  std::string s;
-  if (!snappy_uncompress(static_cast<const uint8_t*>(in), (size_t)n, &s)) return -1;
-  if ((int64_t)s.size() > out_cap) return -2;
-  std::memcpy(out, s.data(), s.size());
-  return (int64_t)s.size();
+  try {
+    std::string s;
+    if (!snappy_uncompress(static_cast<const uint8_t*>(in), (size_t)n, &s)) return -1;
+    if ((int64_t)s.size() > out_cap) return -2;
+    std::memcpy(out, s.data(), s.size());
+    return (int64_t)s.size();
+  } catch (const std::exception&) {
+    return -3;
+  }
 }
 
 // serialized EntryDump of one entry; row = [num(dim) | state | found | ts] (mono_mtable_export layout)

@@ -385,3 +385,57 @@ def test_restore_not_found(tmp_path):
   """ref: test_restore_not_found, hash_table_ops_test.py:468-476: restoring a basename without files is an error."""
   with pytest.raises(ValueError):
     ck.validate_sharded_files(str(tmp_path / "nothing_here"), [])
+
+
+def test_snappy_and_entry_codec_fuzz():
+  """Property checks (hypothesis): any byte string survives our Snappy codec in both directions against pyarrow's,
+  and any float / id bit pattern survives the EntryDump codec (NaN payloads, infinities, denormals, -0.0 included)."""
+  hyp = pytest.importorskip("hypothesis")
+  st = pytest.importorskip("hypothesis.strategies")
+  pa = pytest.importorskip("pyarrow")
+  codec, L = pa.Codec("snappy"), lib()
+
+  @hyp.settings(max_examples=150, deadline=None)
+  @hyp.given(st.one_of(st.binary(max_size=3000),
+                       st.builds(lambda a, n, b: a * n + b, st.binary(min_size=1, max_size=40), st.integers(1, 200), st.binary(max_size=20))))
+  def snappy_roundtrip(data):
+    out = C.create_string_buffer(len(data) + len(data) // 6 + 64)
+    n = L.mono_ckpt_snappy_compress(data, len(data), out, len(out))
+    assert n > 0
+    if data:
+      assert codec.decompress(out.raw[:n], len(data), asbytes=True) == data
+    theirs = codec.compress(data, asbytes=True)
+    back = C.create_string_buffer(max(len(data), 1))
+    assert L.mono_ckpt_snappy_uncompress(theirs, len(theirs), back, len(back)) == len(data)
+    assert back.raw[:len(data)] == data
+
+  snappy_roundtrip()
+
+  segs = segs_of(SPEC)
+  width = sum(d for d, _ in SPEC) + state_floats(SPEC) + 2
+
+  @hyp.settings(max_examples=150, deadline=None)
+  @hyp.given(st.integers(-2**63, 2**63 - 1), st.lists(st.integers(0, 2**32 - 1), min_size=width - 2, max_size=width - 2),
+             st.integers(0, 2**32 - 1))
+  def entry_roundtrip(fid, bits, ts):
+    row = np.array(bits + [1, ts], np.uint32).view(np.float32)
+    buf = C.create_string_buffer(8192)
+    n = L.mono_ckpt_encode_entry(segs, len(SPEC), fid, row.ctypes.data_as(C.c_void_p), buf, len(buf))
+    assert n > 0
+    out = np.zeros(width, np.float32)
+    fid_out = C.c_int64(0)
+    assert L.mono_ckpt_decode_entry(segs, len(SPEC), buf.raw[:n], n, C.byref(fid_out), out.ctypes.data_as(C.c_void_p)) == 0
+    assert fid_out.value == fid and out.view(np.uint32).tolist() == row.view(np.uint32).tolist()
+
+  entry_roundtrip()
+
+  @hyp.settings(max_examples=100, deadline=None)
+  @hyp.given(st.binary(max_size=200))
+  def decoder_never_crashes_on_garbage(blob):
+    out = np.zeros(width, np.float32)
+    fid_out = C.c_int64(0)
+    L.mono_ckpt_decode_entry(segs, len(SPEC), blob, len(blob), C.byref(fid_out), out.ctypes.data_as(C.c_void_p))   # any status
+    back = C.create_string_buffer(4096)
+    L.mono_ckpt_snappy_uncompress(blob, len(blob), back, len(back))                                                 # any status
+
+  decoder_never_crashes_on_garbage()
