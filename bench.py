@@ -49,7 +49,13 @@ def parse():
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
   ap.add_argument("--batch", type=int, default=1 << 20, help="samples per GPU per step")
   ap.add_argument("--keys", type=int, default=10_000_000, help="resident keys per GPU-shard set (total at N=1)")
-  ap.add_argument("--cpu-batch", type=int, default=1 << 16, help="samples per step of the CPU arm / cpu_baseline")
+  ap.add_argument("--cpu-batch", type=int, default=None,
+                  help="samples per step of the CPU arm / cpu_baseline (default: --batch, so that both arms run the same config)")
+  ap.add_argument("--cpu-threads", type=int, default=0,
+                  help="threads (= PS shards) of the CPU arm; 0 = sweep {1, 8, 16, 32, 64, 128} <= host cores and keep the best")
+  ap.add_argument("--repeats", type=int, default=5, help="the timed region of --steps steps is repeated this often; the median is reported")
+  ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity check that precedes the timed region")
+  ap.add_argument("--no-extras", action="store_true", help="skip the extra roofline lines (uniform FIDs, CSR pooling, small batch)")
   ap.add_argument("--zipf", type=float, default=ZIPF_S, help="Zipf exponent of the FID ranks (0 = uniform)")
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-e2e", action="store_true")
@@ -170,59 +176,94 @@ class Clocks:
 # ---------------------------------------------------------------------------------------------
 # CPU arm (reference PS path, oracle port)
 # ---------------------------------------------------------------------------------------------
-def cpu_arm(keys, batch, steps, warmup, cores):
-  """Times orc_ps_train_step (see oracle/oracle.cc) with `cores` PS shards / threads."""
+def _fastps(lib, keys, threads):
   import ctypes as C
   from monolith_b200 import entry
-  from tests import orc
-  lib = orc.lib()
-  lib.orc_ps_train_step.restype = C.c_int64
   seg = entry.CombineAsSegment(DIM, entry.RandomUniformInitializer(-0.05, 0.05),
                                entry.AdagradOptimizer(LR, INIT_ACC))
   cfg = {"item": entry.HashTableConfigInstance(entry.TableConfig([seg], initial_capacity=keys, init_seed=1), [LR])}
   arr, keep = entry.to_c_table_cfgs(cfg)
   ps = C.c_void_p()
-  lib.orc_ps_create(arr, cores, C.byref(ps))
-  keys_per_slot = keys // SLOTS
+  lib.orc_fastps_create(arr, threads, C.byref(ps))
   t0 = time.time()
-  lib.orc_ps_fill_slots(ps, SLOTS, C.c_int64(keys_per_slot))
-  fill_s = time.time() - t0
-  batches = make_batches(4, batch, keys_per_slot, seed=2)
+  lib.orc_fastps_fill_slots(ps, SLOTS, C.c_int64(keys // SLOTS))
+  return ps, time.time() - t0, keep
+
+
+def cpu_arm(keys, batch, steps, warmup, threads, zipf_s=ZIPF_S, candidates=(1, 8, 16, 32, 64, 128)):
+  """Times the tuned CPU restatement of the reference PS path (oracle/oracle.cc orc_fastps_train_step: persistent
+  worker pool, flat per-shard tables, dedup / scatter partitioned by shard, reference AVX Adagrad, built
+  -O3 -mavx -mavx2 -mfma) on the SAME workload as the GPU arm.  threads = PS shards = worker threads; 0 = sweep
+  `candidates` (one timed step each after one warm-up step) and keep the fastest."""
+  import ctypes as C
+  from tests import orc
+  lib = orc.lib()
+  lib.orc_fastps_train_step.restype = C.c_int64
+  cores = os.cpu_count() or 1
+  keys_per_slot = keys // SLOTS
+  batches = make_batches(4, batch, keys_per_slot, seed=2, zipf_s=zipf_s)
   M = batch * SLOTS
   rng = np.random.default_rng(5)
   pg = rng.standard_normal((M, DIM)).astype(np.float32)
   out = np.zeros((M, DIM), np.float32)
   lr = np.array([LR], np.float32)
-  times, uniq = [], []
-  for i in range(warmup + steps):
+
+  def one(ps, i):
     f = batches[i % len(batches)]
     t0 = time.perf_counter()
-    u = lib.orc_ps_train_step(ps, orc.p(f), C.c_int64(M), None, C.c_int64(M), 0, orc.p(pg), orc.p(out), orc.p(lr),
-                              C.c_int64(1000 + i))
-    dt = time.perf_counter() - t0
+    u = lib.orc_fastps_train_step(ps, orc.p(f), C.c_int64(M), None, C.c_int64(M), 0, orc.p(pg), orc.p(out), orc.p(lr),
+                                  C.c_int64(1000 + i))
+    return time.perf_counter() - t0, u
+
+  sweep = {}
+  if threads <= 0:
+    cand = sorted({min(c, cores) for c in candidates} | {cores})
+    best = None
+    for c in cand:
+      ps, _, keep = _fastps(lib, keys, c)
+      one(ps, 0)
+      dt = min(one(ps, 1)[0], one(ps, 2)[0])
+      lib.orc_fastps_destroy(ps)
+      sweep[c] = M / dt
+      if best is None or dt < best[0]:
+        best = (dt, c)
+    threads = best[1]
+  ps, fill_s, keep = _fastps(lib, keys, threads)
+  times, uniq = [], []
+  for i in range(warmup + steps):
+    dt, u = one(ps, i)
     if i >= warmup:
       times.append(dt)
       uniq.append(u)
-  lib.orc_ps_destroy(ps)
+  lib.orc_fastps_destroy(ps)
   total = float(np.sum(times))
   return {"value": M * steps / total, "ms_per_step": 1e3 * total / steps, "fill_s": fill_s, "batch": batch,
-          "M": M, "U_mean": float(np.mean(uniq))}
+          "M": M, "U_mean": float(np.mean(uniq)), "threads": threads, "host_cores": cores,
+          "thread_sweep_lookups_per_s": {str(k): v for k, v in sweep.items()},
+          "ms_per_step_min": 1e3 * float(np.min(times)), "ms_per_step_max": 1e3 * float(np.max(times))}
+
+
+CPU_KIND_NOTE = ("tuned CPU restatement of the reference PS path (persistent pool, flat per-shard tables, shard-partitioned "
+                 "dedup/scatter, reference AVX Adagrad, -O3 -mavx2 -mfma); the reference itself needs bazel + TensorFlow and "
+                 "cannot be built here")
 
 
 def run_reference(args):
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return
-  cores = os.cpu_count() or 1
-  r = cpu_arm(args.keys, args.cpu_batch, args.steps, args.warmup, cores)
+  batch = args.cpu_batch or args.batch
+  r = cpu_arm(args.keys, batch, args.steps, args.warmup, args.cpu_threads, args.zipf)
   line = {
       "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
       "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-      "config": workload_config(args, args.cpu_batch),
-      "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": cores, "kind": "port",
-                       "sample": f"{args.steps} steps x {r['M']} FIDs (batch {args.cpu_batch} samples) on a {args.keys}-key "
-                                 f"table; CPU restatement of the reference PS path (reference build unavailable: no bazel/TF)"},
+      "config": workload_config(args, batch),
+      "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["threads"], "host_cores": r["host_cores"], "kind": "port",
+                       "thread_sweep_lookups_per_s": r["thread_sweep_lookups_per_s"],
+                       "ms_per_step_min": r["ms_per_step_min"], "ms_per_step_max": r["ms_per_step_max"],
+                       "sample": f"{args.steps} steps x {r['M']} FIDs (batch {batch} samples) on a {args.keys}-key "
+                                 f"table; {CPU_KIND_NOTE}"},
       "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
       "gpu_launches": 0,
   }
@@ -245,18 +286,171 @@ def workload_config(args, batch):
 
 
 # ---------------------------------------------------------------------------------------------
+# parity check (oracle as the checker; runs before the timed region, on every rank)
+# ---------------------------------------------------------------------------------------------
+def _parity_batch(rank, step, n=6000):
+  rng = np.random.default_rng(1000 * step + rank)
+  ids = rng.integers(0, 900, n)
+  ids[rng.random(n) < 0.25] = 3                    # hot FID shared by every rank (a > 64-occurrence run)
+  new = rng.random(n) < 0.02                       # FIDs first seen in this step (upserts), a few occurrences each
+  ids[new] = 2000 + 50 * step + rng.integers(0, 50, int(new.sum()))
+  fids = (np.int64(5) << 48) | ids.astype(np.int64)
+  g = rng.standard_normal((n, 16)).astype(np.float32)
+  return fids, g
+
+
+def parity_check(world, rank, dev, steps=3):
+  """One small sparse train job (3 steps x 6000 FIDs per rank, one hot FID shared by all ranks, new FIDs every step)
+  run through the SAME path the timed region uses (N = 1: lookup_pool + pool_backward; N > 1: ShardedStep over the
+  NVLink peer windows), then compared on rank 0 with ONE global oracle table that applies the requesters' gradients
+  in rank order (ref protocol: NT/distributed_ps_test.py:892-975): pooled rows and final entries [emb | Adagrad state |
+  ts] bit for bit for FIDs whose gradient sums have <= 64 terms (reference summation order); the hot FID (1500-term
+  sums: piecewise fp32 on the GPU, sequential fp32 on the CPU; tests/test_gpu_parity.py checks both against fp64)
+  within `hot_tolerance`, with the measured error reported."""
+  import torch
+  import torch.distributed as dist
+  from monolith_b200 import MultiHashTable, entry
+  D = 16
+  hot = (np.int64(5) << 48) | np.int64(3)
+
+  def cfg():
+    seg = entry.CombineAsSegment(D, entry.RandomUniformInitializer(-0.05, 0.05), entry.AdagradOptimizer(0.1, 0.1))
+    return {"t": entry.HashTableConfigInstance(entry.TableConfig([seg], initial_capacity=64, init_seed=9), [0.1])}
+
+  table = MultiHashTable(cfg(), device=dev)
+  st = None
+  if world > 1:
+    from monolith_b200.distributed_ps import ShardedStep
+    st = ShardedStep(table, "t", D, world, rank, dev)
+  pooled_all = []
+  for step in range(steps):
+    fids, g = _parity_batch(rank, step)
+    f_d, g_d = torch.from_numpy(fids).to(dev), torch.from_numpy(g).to(dev)
+    out = torch.empty(fids.size, D, device=dev)
+    if st is None:
+      table.lookup_pool("t", f_d, None, "sum", out=out)
+      table.pool_backward("t", f_d, g_d, None, "sum", req_time=20 + step)
+    else:
+      st.step(f_d, g_d, out, 20 + step)
+    pooled_all.append(out.cpu().numpy())
+  ks, rows = [], []
+  for ids, raw in table.export("t", chunk=1 << 14):
+    ks.append(ids.cpu().numpy())
+    rows.append(raw.cpu().numpy())
+  ks, rows = np.concatenate(ks), np.concatenate(rows)
+  o = np.argsort(ks)
+  mine = (pooled_all, ks[o], rows[o])
+  if st is not None and st.window is not None:
+    torch.cuda.synchronize(dev)
+    st.window.close(None)
+  table.close()
+  if world > 1:
+    got = [None] * world
+    dist.all_gather_object(got, mine)
+  else:
+    got = [mine]
+  if rank != 0:
+    return None
+  from tests import orc
+  glob = orc.OracleMultiHashTable(cfg())
+  res = {"ranks": world, "steps": steps, "fids_per_rank_per_step": 6000, "ok": True, "pooled_rows_bit_exact": 0,
+         "pooled_rows_hot": 0, "entries_bit_exact": 0, "hot_max_rel_err": 0.0, "errors": []}
+
+  def rel(a, b):
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-3))) if a.size else 0.0
+
+  try:
+    for step in range(steps):
+      batches = [_parity_batch(r, step) for r in range(world)]
+      for r, (fids, g) in enumerate(batches):
+        want = glob.lookup_pool("t", fids, None, "sum")
+        cold = fids != hot
+        np.testing.assert_array_equal(got[r][0][step][cold].view(np.uint32), want[cold].view(np.uint32))
+        res["pooled_rows_bit_exact"] += int(cold.sum())
+        res["pooled_rows_hot"] += int((~cold).sum())
+        res["hot_max_rel_err"] = max(res["hot_max_rel_err"], rel(got[r][0][step][~cold], want[~cold]))
+      for r, (fids, g) in enumerate(batches):      # owners apply requester 0's rows, then requester 1's, ...
+        u, inv = orc.dedup(fids)
+        ug = orc.gather_pool_grad(g, inv * D, D, u.size * D).reshape(-1, D)
+        glob.apply_gradients({"t": (u, ug)}, req_time=20 + step)
+    keys = glob.keys("t")
+    for r in range(world):
+      own = keys[(keys.view(np.uint64) % np.uint64(world)) == r]
+      k_r, e_r = got[r][1], got[r][2]
+      np.testing.assert_array_equal(k_r, own)
+      want = glob.lookup_entry("t", own)
+      cold = own != hot
+      np.testing.assert_array_equal(e_r[cold].view(np.uint32), want[cold].view(np.uint32))
+      res["entries_bit_exact"] += int(cold.sum())
+      np.testing.assert_array_equal(e_r[~cold][:, -2:].view(np.uint32), want[~cold][:, -2:].view(np.uint32))
+      res["hot_max_rel_err"] = max(res["hot_max_rel_err"], rel(e_r[~cold][:, :-2], want[~cold][:, :-2]))
+    if res["hot_max_rel_err"] > 2e-3:
+      raise AssertionError(f"hot FID differs by {res['hot_max_rel_err']:.3g} relative")
+  except AssertionError as e:
+    res["ok"] = False
+    res["errors"].append(str(e)[:400])
+  res["hot_tolerance"] = 2e-3
+  return res
+
+
+# ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
+def bind_numa(local):
+  """Pin this process (and the pinned buffers it allocates afterwards) to the CPUs next to its GPU: 8 ranks driving
+  PCIe from the wrong socket cost the e2e leg 2.9x per GPU in round 1."""
+  try:
+    import pynvml
+    pynvml.nvmlInit()
+    h = pynvml.nvmlDeviceGetHandleByIndex(local)
+    words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+    cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+    cpus &= set(os.sched_getaffinity(0))
+    if cpus:
+      os.sched_setaffinity(0, cpus)
+      return len(cpus)
+  except Exception:
+    pass
+  return None
+
+
+class Tower:
+  """Stand-in dense tower of the DSSM (ref model: markdown/demo/demo_model.py:47-84): pooled [B, 2*32] -> bf16 MLP
+  64 -> 256 -> 1 -> logistic loss against labels; forward + backward produce the gradient w.r.t. the pooled rows.
+  Dense layers are out of scope: plain torch / cuBLAS on tensor cores, used only to close the e2e loop on
+  the device and as the thing the exchange overlaps with."""
+
+  def __init__(self, dev, batch, seed=0):
+    import torch
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    self.w1 = (torch.randn(SLOTS * DIM, 256, device=dev, generator=g) * 0.05).to(torch.bfloat16).requires_grad_(True)
+    self.w2 = (torch.randn(256, 1, device=dev, generator=g) * 0.05).to(torch.bfloat16).requires_grad_(True)
+    self.batch = batch
+
+  def grad(self, pooled, labels, grad_out):
+    """loss (device scalar) and d loss / d pooled written into grad_out [M, DIM]."""
+    import torch
+    x = pooled.view(self.batch, SLOTS * DIM).detach().requires_grad_(True)
+    h = torch.relu(x.to(torch.bfloat16) @ self.w1)
+    logit = (h @ self.w2).float().squeeze(1)
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(logit, labels)
+    gx, = torch.autograd.grad(loss, [x])
+    grad_out.view(self.batch, SLOTS * DIM).copy_(gx)
+    return loss.detach()
+
+
 def run_ours(args):
   import torch
   import torch.distributed as dist
-  from monolith_b200 import MultiHashTable, _lib, distribution_ops as dops, entry
+  from monolith_b200 import MultiHashTable, _lib, entry
 
   world = int(os.environ.get("WORLD_SIZE", "1"))
   rank = int(os.environ.get("RANK", "0"))
   local = int(os.environ.get("LOCAL_RANK", "0"))
   if world != args.gpus:
     raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+  numa_cpus = bind_numa(local)
   torch.cuda.set_device(local)
   dev = torch.device("cuda", local)
   if world > 1:
@@ -268,6 +462,23 @@ def run_ours(args):
     if world > 1:
       dist.barrier()
   lib = _lib.load()
+
+  # ---- parity first: the same path as the timed region, against ONE global oracle table ----
+  parity = None
+  if not args.no_parity:
+    parity = parity_check(world, rank, dev)
+    if rank == 0 and not parity["ok"]:
+      print(json.dumps({"metric": METRIC, "parity_check": parity, "error": "parity check failed"}), flush=True)
+    if world > 1:
+      flag = torch.tensor([1 if (rank != 0 or parity["ok"]) else 0], device=dev)
+      dist.broadcast(flag, 0)
+      bad = flag.item() == 0
+    else:
+      bad = not parity["ok"]
+    if bad:
+      if world > 1:
+        dist.destroy_process_group()
+      raise SystemExit(3)
 
   use_sharded = world > 1 or args.sharded
   if use_sharded:
@@ -299,7 +510,6 @@ def run_ours(args):
   gen.manual_seed(5 + rank)
   pgrad_dev = torch.randn(M, DIM, device=dev, generator=gen)
   pooled = torch.empty(M, DIM, device=dev)
-  uniq_counts = []
 
   if use_sharded:
     sharded = ShardedStep(table, "item", DIM, world, rank, dev, exchange=args.exchange)
@@ -307,94 +517,132 @@ def run_ours(args):
   def step(i, fids, pgrad, out):
     if not use_sharded:
       table.lookup_pool("item", fids, None, "sum", out=out)
-      table.pool_backward("item", fids, pgrad, None, "sum", req_time=1000 + i)
+      table.pool_backward("item", fids, pgrad() if callable(pgrad) else pgrad, None, "sum", req_time=1000 + i)
       return 0
     return sharded.step(fids, pgrad, out, 1000 + i)
 
-  def timed(fn, steps, warmup):
-    for i in range(warmup):
-      fn(i)
-    torch.cuda.synchronize()
-    if world > 1:
-      dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l0 = lib.mono_kernel_launch_count()
-    e0.record()
-    for i in range(steps):
-      fn(warmup + i)
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-      dist.barrier()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    launches = lib.mono_kernel_launch_count() - l0
-    if world > 1:
-      t = torch.tensor([ms], device=dev)
-      dist.all_reduce(t, op=dist.ReduceOp.MAX)
-      ms = float(t.item())
-    return ms, launches
+  counter = [0]
+
+  def timed(fn, steps, warmup, repeats=1):
+    """`repeats` timed regions of exactly `steps` steps each (barrier + synchronize on both sides, CUDA events, max
+    over ranks); returns (median ms of a region, launches of the last region, all region times)."""
+    for _ in range(warmup):
+      fn(counter[0])
+      counter[0] += 1
+    regions, launches = [], 0
+    for _ in range(max(1, repeats)):
+      torch.cuda.synchronize()
+      if world > 1:
+        dist.barrier()
+      torch.cuda.synchronize()
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      l0 = lib.mono_kernel_launch_count()
+      e0.record()
+      for _ in range(steps):
+        fn(counter[0])
+        counter[0] += 1
+      e1.record()
+      torch.cuda.synchronize()
+      if world > 1:
+        dist.barrier()
+      torch.cuda.synchronize()
+      ms = e0.elapsed_time(e1)
+      launches = lib.mono_kernel_launch_count() - l0
+      if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+      regions.append(ms)
+    return float(np.median(regions)), launches, regions
 
   def dev_step(i):
-    uniq_counts.append(step(i, fids_dev[i % NB], pgrad_dev, pooled))
+    step(i, fids_dev[i % NB], pgrad_dev, pooled)
 
   with Clocks(local) as clk:
-    ms, launches = timed(dev_step, args.steps, args.warmup)
+    ms, launches, regions = timed(dev_step, args.steps, args.warmup, args.repeats)
   # unique FIDs per batch (counted once, outside the timed region; the fused step never needs it on the host)
   U_mean = float(np.mean([np.unique(b).size for b in batches_np]))
   value = M * world * args.steps / (ms * 1e-3)
 
-  # ---- e2e: pinned host inputs, H2D + D2H inside the timed region, public API --------------
+  # ---- e2e: host FIDs + labels in (pinned, H2D inside the timed region), loss out (D2H), public API ----------
   e2e = None
   if not args.no_e2e:
     fids_pin = [torch.from_numpy(b).pin_memory() for b in batches_np]
-    pgrad_pin = pgrad_dev.cpu().pin_memory()
-    pooled_pin = torch.empty(M, DIM).pin_memory()
-    d_f, d_g = torch.empty(M, dtype=torch.int64, device=dev), torch.empty(M, DIM, device=dev)
-
-    KCH = max(1, args.e2e_chunks)
-    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-    ev_fwd, ev_in = torch.cuda.Event(), torch.cuda.Event()
-    ev_o = [torch.cuda.Event() for _ in range(KCH)]
-    cs = (M + KCH - 1) // KCH
-
-    def host_round_trip():
-      """pooled rows D2H, gradients H2D, in KCH slices so that PCIe runs full duplex: gradient slice c leaves
-      the host only AFTER pooled slice c has arrived (the dependency a host-side dense tower imposes) and
-      overlaps the D2H of slice c+1.  Returns the device gradient buffer, ready on the current stream."""
-      main = torch.cuda.current_stream()
-      ev_fwd.record(main)
-      s_out.wait_event(ev_fwd)
-      for c in range(KCH):
-        sl = slice(c * cs, min(M, (c + 1) * cs))
-        with torch.cuda.stream(s_out):
-          pooled_pin[sl].copy_(pooled[sl], non_blocking=True)
-          ev_o[c].record(s_out)
-        with torch.cuda.stream(s_in):
-          s_in.wait_event(ev_o[c])
-          d_g[sl].copy_(pgrad_pin[sl], non_blocking=True)
-      ev_in.record(s_in)
-      main.wait_event(ev_in)
-      return d_g
+    labels_pin = (torch.rand(args.batch) < 0.3).float().pin_memory()
+    loss_pin = torch.empty(1).pin_memory()
+    d_f = [torch.empty(M, dtype=torch.int64, device=dev) for _ in range(2)]
+    d_lab = torch.empty(args.batch, device=dev)
+    d_g = torch.empty(M, DIM, device=dev)
+    tower = Tower(dev, args.batch)
 
     def e2e_step(i):
+      """What a training job does per step: the input pipeline hands over HOST FIDs + labels; forward, dense tower
+      forward/backward on the device, sparse backward; the loss comes back to the host."""
       main = torch.cuda.current_stream()
-      d_f.copy_(fids_pin[i % NB], non_blocking=True)
-      if use_sharded:
-        sharded.step(d_f, host_round_trip, pooled, 1000 + i)
-      else:
-        table.lookup_pool("item", d_f, None, "sum", out=pooled)
-        table.pool_backward("item", d_f, host_round_trip(), None, "sum", req_time=1000 + i)
-      main.synchronize()  # pooled rows are on the host, the update is applied
+      f = d_f[i & 1]
+      f.copy_(fids_pin[i % NB], non_blocking=True)
+      d_lab.copy_(labels_pin, non_blocking=True)
+      loss = []
 
-    es, ew = max(3, args.steps // 4), 2
-    ems, _ = timed(e2e_step, es, ew)
-    e2e = {"value": M * world * es / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * M + 4 * M * DIM,
-           "d2h_bytes_per_step": 4 * M * DIM, "ms_per_step": ems / es,
-           "pipeline": (f"H2D FIDs, forward, then pooled rows D2H and gradients H2D in {KCH} slices, full duplex: gradient "
-                        f"slice c is sent only after pooled slice c reached the host; then the backward"
-                        if KCH > 1 else "sequential: H2D FIDs, forward, D2H pooled rows, H2D gradients, backward")}
+      def grads():
+        loss.append(tower.grad(pooled, d_lab, d_g))
+        return d_g
+
+      step(i, f, grads, pooled)
+      loss_pin.copy_(loss[0].reshape(1), non_blocking=True)
+      main.synchronize()  # the loss is on the host, the update is applied
+
+    es, ew = max(3, args.steps // 2), 3
+    ems, _, eregions = timed(e2e_step, es, ew, max(1, min(3, args.repeats)))
+
+    def tower_only(i):  # context: how much of the e2e step is not the sparse path
+      tower.grad(pooled, d_lab, d_g)
+
+    tms, _, _ = timed(tower_only, 10, 3)
+    e2e = {"value": M * world * es / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * M + 4 * args.batch,
+           "d2h_bytes_per_step": 4, "ms_per_step": ems / es, "ms_per_step_regions": [r / es for r in eregions],
+           "dense_tower_ms": tms / 10,
+           "pipeline": "per step: H2D of the step's FIDs (pinned int64[M]) and labels, fused lookup+pool forward, stand-in "
+                       "DSSM tower (bf16 MLP 64-256-1 + logistic loss, torch/cuBLAS) forward+backward on the device, fused sparse "
+                       "backward, D2H of the loss; the host synchronises every step"}
+
+    # round-1 variant for continuity: a HOST-resident tower (pooled rows D2H, gradients H2D: 553 MB over PCIe per step)
+    if world == 1 and not args.no_extras:
+      pgrad_pin = pgrad_dev.cpu().pin_memory()
+      pooled_pin = torch.empty(M, DIM).pin_memory()
+      KCH = max(1, args.e2e_chunks)
+      s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+      ev_fwd, ev_in = torch.cuda.Event(), torch.cuda.Event()
+      ev_o = [torch.cuda.Event() for _ in range(KCH)]
+      cs = (M + KCH - 1) // KCH
+
+      def host_round_trip():
+        main = torch.cuda.current_stream()
+        ev_fwd.record(main)
+        s_out.wait_event(ev_fwd)
+        for c in range(KCH):
+          sl = slice(c * cs, min(M, (c + 1) * cs))
+          with torch.cuda.stream(s_out):
+            pooled_pin[sl].copy_(pooled[sl], non_blocking=True)
+            ev_o[c].record(s_out)
+          with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_o[c])
+            d_g[sl].copy_(pgrad_pin[sl], non_blocking=True)
+        ev_in.record(s_in)
+        main.wait_event(ev_in)
+        return d_g
+
+      def e2e_host_step(i):
+        f = d_f[i & 1]
+        f.copy_(fids_pin[i % NB], non_blocking=True)
+        step(i, f, host_round_trip, pooled)
+        torch.cuda.current_stream().synchronize()
+
+      hms, _, _ = timed(e2e_host_step, 3, 2)
+      e2e["host_tower_variant"] = {
+          "value": M * 3 / (hms * 1e-3), "ms_per_step": hms / 3, "h2d_bytes_per_step": 8 * M + 4 * M * DIM,
+          "d2h_bytes_per_step": 4 * M * DIM,
+          "note": f"round-1 definition: pooled rows D2H and gradients H2D in {KCH} full-duplex slices (a host-resident tower)"}
 
   # ---- per-kernel timing for the roofline (dominant kernel: fused lookup+pool forward) --------
   roof = None
@@ -409,7 +657,7 @@ def run_ours(args):
     def only_fwd(i):
       table.lookup_pool("item", fids_dev[i % NB], None, "sum", out=pooled)
 
-    fms, _ = timed(only_fwd, 20, 5)
+    fms, _, _ = timed(only_fwd, 20, 5, 3)
     fwd_s = fms * 1e-3 / 20
     A = fwd_bytes(M, U_mean) / fwd_s / 1e9
     traffic = None
@@ -417,49 +665,68 @@ def run_ours(args):
       traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("lookup_pool_dram_bytes_per_launch")
     except Exception:
       pass
-    # backward pieces (reported for context)
-    uniq, _, _, _, offs = dops.fused_reorder_by_indices([fids_dev[0]], 1, [DIM], rank0_empty_shard=False)
-    ugrad = dops.gather_pool_grad(pgrad_dev, offs, DIM, uniq.numel() * DIM)
-
-    def only_opt(i):
-      table.apply_gradients({"item": (uniq, ugrad)}, req_time=5000 + i, ids_unique=True)
-
-    oms, _ = timed(only_opt, 20, 5)
-
-    def only_dedup(i):
-      dops.fused_reorder_by_indices([fids_dev[i % NB]], 1, [DIM], rank0_empty_shard=False)
-
-    dms, _ = timed(only_dedup, 20, 5)
-
-    def only_scatter(i):
-      dops.gather_pool_grad(pgrad_dev, offs, DIM, uniq.numel() * DIM)
-
-    sms, _ = timed(only_scatter, 20, 5)
 
     def only_bwd(i):
       table.pool_backward("item", fids_dev[i % NB], pgrad_dev, None, "sum", req_time=6000 + i)
 
-    bms, _ = timed(only_bwd, 20, 5)
-    Uo = uniq.numel()
+    bms, _, _ = timed(only_bwd, 20, 5, 3)
+    bwd_s = bms * 1e-3 / 20
     roof = {
         "bound": "hbm", "kernel": "lookup_kernel<8,true> (fused probe + row gather + per-slot pool forward, 1 FID per pooled row)", "achieved": A,
         "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": A / peak, "frac_of_nominal_8000": A / 8000.0,
         "traffic": traffic, "algorithmic_bytes_per_launch": fwd_bytes(M, U_mean), "launch_ms": fwd_s * 1e3,
         "lookups_per_s_fwd_only": M / fwd_s,
-        "others": {
-            "optimize_ms": oms / 20, "optimize_GBps": (Uo * (32 + 16 * DIM + 8) + 4 * DIM * Uo) / (oms * 1e-3 / 20) / 1e9,
-            "dedup_ms": dms / 20, "scatter_ms": sms / 20, "U": Uo,
-            "fused_backward_ms": bms / 20, "fused_backward_GBps": bwd_bytes(M, U_mean) / (bms * 1e-3 / 20) / 1e9
-        },
+        "backward": {"what": "fused backward, whole launch chain (group FIDs, per-FID grad reduce, Adagrad upsert)",
+                     "ms": bwd_s * 1e3, "algorithmic_bytes": bwd_bytes(M, U_mean),
+                     "achieved": bwd_bytes(M, U_mean) / bwd_s / 1e9, "frac": bwd_bytes(M, U_mean) / bwd_s / 1e9 / peak},
+        "others": {"fused_backward_ms": bwd_s * 1e3, "fused_backward_GBps": bwd_bytes(M, U_mean) / bwd_s / 1e9},
     }
+    if not args.no_extras:
+      ex = {}
+      # (1) uniform FIDs (no hot rows in L2): forward only
+      ub = make_batches(2, args.batch, gkeys_per_slot, seed=77, zipf_s=0.0)
+      uf = [torch.from_numpy(b).to(dev) for b in ub]
+      Uu = float(np.mean([np.unique(b).size for b in ub]))
+
+      def fwd_uniform(i):
+        table.lookup_pool("item", uf[i % 2], None, "sum", out=pooled)
+
+      ums, _, _ = timed(fwd_uniform, 20, 5, 3)
+      ex["forward_uniform_fids"] = {"ms": ums / 20, "U": Uu, "achieved": fwd_bytes(M, Uu) / (ums * 1e-3 / 20) / 1e9,
+                                    "frac": fwd_bytes(M, Uu) / (ums * 1e-3 / 20) / 1e9 / peak}
+      # (2) the CSR pooling kernel (lookup_pool_kernel): 4 FIDs per pooled row, SUM and MEAN
+      ro4 = torch.arange(0, M + 1, 4, device=dev, dtype=torch.int32)
+      R4 = M // 4
+      for pool in ("sum", "mean"):
+
+        def fwd_csr(i, pool=pool):
+          table.lookup_pool("item", fids_dev[i % NB], ro4, pool, out=pooled[:R4])
+
+        cms, _, _ = timed(fwd_csr, 20, 5, 3)
+        by = 8 * M + 4 * (R4 + 1) + U_mean * (32 + 4 * DIM) + 4 * DIM * R4
+        ex[f"forward_csr_pool_4_{pool}"] = {"kernel": "lookup_pool_kernel<8,1,4>", "ms": cms / 20, "algorithmic_bytes": by,
+                                            "achieved": by / (cms * 1e-3 / 20) / 1e9, "frac": by / (cms * 1e-3 / 20) / 1e9 / peak}
+      # (3) the batch SURVEY 8(d) quotes (B = 65 536, M = 131 072): launch-bound regime of the same step
+      sb = 1 << 16
+      sf = [t[:sb * SLOTS].contiguous() for t in fids_dev]
+
+      def small_step(i):
+        table.lookup_pool("item", sf[i % NB], None, "sum", out=pooled[:sb * SLOTS])
+        table.pool_backward("item", sf[i % NB], pgrad_dev[:sb * SLOTS], None, "sum", req_time=8000 + i)
+
+      sms, _, _ = timed(small_step, 20, 5, 3)
+      ex["step_batch_65536"] = {"ms": sms / 20, "lookups_per_s": sb * SLOTS / (sms * 1e-3 / 20)}
+      roof["extras"] = ex
 
   cpu = None
   if world == 1 and rank == 0 and not args.no_cpu_baseline:
     cores = os.cpu_count() or 1
-    r = cpu_arm(args.keys, args.cpu_batch, 6, 2, cores)
-    cpu = {"value": r["value"], "unit": UNIT, "cores": cores, "kind": "port",
-           "sample": f"6 steps x {r['M']} FIDs (batch {args.cpu_batch} samples) on the full {args.keys}-key table, "
-                     f"{cores} PS shards/threads; CPU restatement of the reference PS path (reference build unavailable)",
+    r = cpu_arm(args.keys, args.cpu_batch or args.batch, 4, 1, args.cpu_threads, args.zipf,
+                candidates=(max(1, cores // 4), max(1, cores // 2), cores))
+    cpu = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "host_cores": r["host_cores"], "kind": "port",
+           "thread_sweep_lookups_per_s": r["thread_sweep_lookups_per_s"],
+           "sample": f"4 steps x {r['M']} FIDs (batch {r['batch']} samples, the GPU arm's batch) on the full {args.keys}-key table; "
+                     f"{CPU_KIND_NOTE}",
            "ms_per_step": r["ms_per_step"]}
 
   if rank == 0:
@@ -467,8 +734,11 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, args.batch),
+        "repeats": {"n": len(regions), "statistic": "median", "ms_per_step_min": min(regions) / args.steps,
+                    "ms_per_step_max": max(regions) / args.steps},
         "samples_per_sec": args.batch * world * args.steps / (ms * 1e-3), "unique_fids_per_step": U_mean,
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+        "parity_check": parity, "numa_bound_cpus": numa_cpus,
     }
     print(json.dumps(line), flush=True)
   if use_sharded and rank == 0 and sharded.phases.enabled:

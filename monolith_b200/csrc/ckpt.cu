@@ -15,9 +15,11 @@
 // TFRecord framing (tensorflow/core/lib/io/record_writer.cc): u64 length | u32 masked crc32c(length) | data |
 // u32 masked crc32c(data), little endian, mask = rotr(crc, 15) + 0xa282ead8.
 // Snappy block container (tensorflow/core/lib/io/snappy/snappy_outputbuffer.cc, TF 2.4 as pinned by the
-// reference's WORKSPACE): per flushed input buffer u32 BE uncompressed length | u32 BE compressed length |
-// raw Snappy bytes.  TensorFlow is not available in this image, so the container layout is restated from the
-// TF source and NOT pinned by a TF-written fixture ("parity unpinned" for the container; record framing,
+// reference's WORKSPACE): per flushed 256 KiB input buffer ONE u32 big-endian COMPRESSED length, then the raw
+// Snappy block (SnappyOutputBuffer::Deflate writes only that length; SnappyInputBuffer reads it and takes the
+// uncompressed size from the Snappy preamble).  TensorFlow is not available in this image, so the container
+// layout is restated from the TF source and NOT pinned by a TF-written fixture ("parity unpinned" for the
+// container — round 1 wrote an extra uncompressed-length word, corrected in round 2; record framing,
 // crc32c, Snappy codec and the protobuf wire bytes are pinned in tests/test_checkpoint_cpu.py against
 // known-answer vectors, pyarrow's Snappy and the protobuf runtime).
 #include <cstdio>
@@ -403,10 +405,9 @@ static void flush_block(mono_ckpt_writer* w, bool all) {
     if (w->snappy) {
       std::string comp;
       snappy_compress(reinterpret_cast<const uint8_t*>(w->block.data()), n, &comp);
-      char h[8];
-      be32(h, (uint32_t)n);
-      be32(h + 4, (uint32_t)comp.size());
-      write_all(w->data.f, h, 8);
+      char h[4];  // TF's SnappyOutputBuffer::Deflate: 4-byte big-endian COMPRESSED length, then the raw block
+      be32(h, (uint32_t)comp.size());
+      write_all(w->data.f, h, 4);
       write_all(w->data.f, comp.data(), comp.size());
     } else {
       write_all(w->data.f, w->block.data(), n);
@@ -432,18 +433,18 @@ static bool fill(mono_ckpt_reader* r, size_t need) {  // make buf[pos, pos+need)
       r->pos = 0;
     }
     if (r->snappy) {
-      unsigned char h[8];
-      const size_t got = std::fread(h, 1, 8, r->data.f);
+      unsigned char h[4];
+      const size_t got = std::fread(h, 1, 4, r->data.f);
       if (got == 0) return false;
-      if (got != 8) throw std::runtime_error("checkpoint: truncated Snappy block header");
-      const uint32_t ulen = (h[0] << 24) | (h[1] << 16) | (h[2] << 8) | h[3];
-      const uint32_t clen = (h[4] << 24) | (h[5] << 16) | (h[6] << 8) | h[7];
+      if (got != 4) throw std::runtime_error("checkpoint: truncated Snappy block header");
+      // TF's SnappyInputBuffer::ReadCompressedBlockLength: one big-endian length; the uncompressed size comes
+      // from the Snappy preamble (Snappy_GetUncompressedLength), which snappy_uncompress validates
+      const uint32_t clen = ((uint32_t)h[0] << 24) | (h[1] << 16) | (h[2] << 8) | h[3];
+      if (clen > (64u << 20)) throw std::runtime_error("checkpoint: implausible Snappy block length");
       std::string comp(clen, '\0');
       if (clen && std::fread(&comp[0], 1, clen, r->data.f) != clen)
         throw std::runtime_error("checkpoint: truncated Snappy block");
-      const size_t before = r->buf.size();
-      if (!snappy_uncompress(reinterpret_cast<const uint8_t*>(comp.data()), clen, &r->buf) ||
-          r->buf.size() - before != ulen)
+      if (!snappy_uncompress(reinterpret_cast<const uint8_t*>(comp.data()), clen, &r->buf))
         throw std::runtime_error("checkpoint: corrupt Snappy block");
     } else {
       char tmp[1 << 16];

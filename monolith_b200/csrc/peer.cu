@@ -12,6 +12,7 @@
 // peer's flag page (fence.sys + st.release.sys) and waits for all peers' numbers (ld.acquire.sys).
 // Everything is stream-ordered; the host never waits for a peer.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "engine.h"
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(PeerFlags pf, uint64_t
   const uint64_t* mine = pf.flags[pf.rank] + r;
   const uint64_t t0 = global_ns();
   while (ld_acquire_sys(mine) < seq) {
-    if (global_ns() - t0 > timeout_ns) {
+    if (timeout_ns != 0 && global_ns() - t0 > timeout_ns) {
       printf("mono_peer: rank %d timed out waiting for rank %d at barrier %llu\n", pf.rank, r,
              (unsigned long long)seq);
       __trap();
@@ -64,7 +65,14 @@ void peer_barrier(mono_peer* p, cudaStream_t s) {
   pf.world = p->world;
   pf.rank = p->rank;
   ++p->seq;
-  peer_barrier_kernel<<<1, 32, 0, s>>>(pf, p->seq, 30ull * 1000 * 1000 * 1000);
+  // MONO_PEER_TIMEOUT_S: seconds a rank waits for a peer before the kernel traps (default 600; 0 = wait for ever).
+  // The wait covers everything a peer does between two barriers (its dense tower, a checkpoint, a data stall).
+  static const uint64_t timeout_ns = [] {
+    const char* e = std::getenv("MONO_PEER_TIMEOUT_S");
+    const double sec = e ? std::atof(e) : 600.0;
+    return sec <= 0 ? 0ull : (uint64_t)(sec * 1e9);
+  }();
+  peer_barrier_kernel<<<1, 32, 0, s>>>(pf, p->seq, timeout_ns);
   MONO_CHECK_LAUNCH();
 }
 

@@ -243,8 +243,13 @@ class HostCounts:
   def __init__(self, world: int, rank: int, width: int, group=None):
     import mmap
     import os
+    import platform
     import uuid
     import numpy as np
+    if platform.machine() not in ("x86_64", "AMD64"):
+      # payload-then-epoch publication below relies on x86 total store order; a weakly ordered host (aarch64)
+      # needs release/acquire atomics here -- use exchange="nccl" there
+      raise RuntimeError("HostCounts needs an x86-64 host (store ordering); use the NCCL exchange on this platform")
     self.world, self.rank, self.width, self.epoch = world, rank, width, 0
     nbytes = 2 * world * (width + 1) * 8
     name = [f"/dev/shm/mono_counts_{os.getpid()}_{uuid.uuid4().hex}" if rank == 0 else None]

@@ -7,7 +7,8 @@ What pins what:
     transcribed from embedding_hash_table.proto:45-50,139-142 and optimizer.proto:28-30,56-57,69-72,130-135,232-252
     (byte-for-byte equal to what the protobuf runtime serializes, and decoding packed and unpacked floats)
   * file layout: multi_hash_table_save_restore_ops.cc (names, metadata counts, TTL filter, unknown tables skipped)
-The Snappy block container is restated from TF's snappy_outputbuffer.cc and has no TF-written fixture.
+The Snappy block container (u32 BE compressed length | raw block, per 256 KiB input buffer) is restated from TF's
+snappy_outputbuffer.cc / snappy_inputbuffer.cc and has no TF-written fixture: unpinned.
 """
 import ctypes as C
 import os
@@ -241,9 +242,19 @@ def test_file_layout_and_roundtrip(tmp_path, snappy):
   if snappy:
     codec, stream, p, nblocks = pa.Codec("snappy"), b"", 0, 0
     while p < len(raw):
-      ulen, clen = struct.unpack_from(">II", raw, p)
-      stream += codec.decompress(raw[p + 8:p + 8 + clen], ulen, asbytes=True)
-      p += 8 + clen
+      # TF SnappyOutputBuffer layout: u32 BE compressed length | raw Snappy block (uncompressed size = Snappy varint preamble)
+      clen, = struct.unpack_from(">I", raw, p)
+      blk = raw[p + 4:p + 4 + clen]
+      ulen, shift, q = 0, 0, 0
+      while True:
+        ulen |= (blk[q] & 0x7F) << shift
+        shift += 7
+        q += 1
+        if not blk[q - 1] & 0x80:
+          break
+      assert ulen <= 256 * 1024                          # RecordWriter's Snappy input buffer
+      stream += codec.decompress(blk, ulen, asbytes=True)
+      p += 4 + clen
       nblocks += 1
     assert nblocks > 1 and len(raw) < len(stream)
   else:

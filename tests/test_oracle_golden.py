@@ -324,3 +324,63 @@ def test_hash_filter_threshold_schedule_golden():
   for want in ([[0.0]], [[0.3]]):   # first call: previous count 0 < 3 -> filtered (counter becomes 3); second: 3 !< 3
     t3.apply_gradients({"t": (np.array([7, 7, 7], np.int64), -np.ones((3, 1), np.float32))}, enable_dedup=True)
     np.testing.assert_allclose(t3.lookup({"t": np.array([7], np.int64)})["t"], want, rtol=1e-6, atol=1e-7)
+
+
+def test_fastps_baseline_equals_oracle_ps_step():
+  """The tuned CPU baseline timed by bench.py (orc_fastps_*: persistent pool, flat tables, partitioned dedup and
+  scatter) computes exactly what the plain oracle PS step (orc_ps_train_step over the oracle tables) computes:
+  pooled rows bit for bit, and every touched entry [emb | Adagrad state] bit for bit, over several steps with
+  hot FIDs, unseen FIDs (upserts) and CSR mean pooling."""
+  import ctypes as C
+  from monolith_b200 import entry
+  lib = orc.lib()
+  lib.orc_ps_train_step.restype = C.c_int64
+  lib.orc_fastps_train_step.restype = C.c_int64
+  D = 16
+  seg = entry.CombineAsSegment(D, entry.RandomUniformInitializer(-0.05, 0.05), entry.AdagradOptimizer(0.05, 0.1))
+  cfg = {"t": entry.HashTableConfigInstance(entry.TableConfig([seg], initial_capacity=1000, init_seed=3), [0.05])}
+  arr, keep = entry.to_c_table_cfgs(cfg)
+  T = 5
+  a, b = C.c_void_p(), C.c_void_p()
+  lib.orc_ps_create(arr, T, C.byref(a))
+  lib.orc_fastps_create(arr, T, C.byref(b))
+  lib.orc_ps_fill_slots(a, 2, C.c_int64(300))
+  lib.orc_fastps_fill_slots(b, 2, C.c_int64(300))
+  rng = np.random.default_rng(11)
+  lr = np.array([0.05], np.float32)
+  seen = set()
+  for step in range(4):
+    for csr in (False, True):
+      M = 4000
+      ids = rng.integers(0, 500, M)            # 300..499 are not pre-filled: upserted by the optimizer
+      ids[rng.random(M) < 0.2] = 7             # hot FID
+      fids = ((rng.integers(1, 3, M).astype(np.int64)) << 48) | ids.astype(np.int64)
+      seen.update(fids.tolist())
+      if csr:
+        cuts = np.sort(rng.choice(np.arange(1, M), 900, replace=False))
+        ro = np.concatenate([[0], cuts, [M]]).astype(np.int32)
+        pooling = 1
+      else:
+        ro, pooling = None, 0
+      R = M if ro is None else ro.size - 1
+      pg = rng.standard_normal((R, D)).astype(np.float32)
+      o1, o2 = np.zeros((R, D), np.float32), np.zeros((R, D), np.float32)
+      u1 = lib.orc_ps_train_step(a, orc.p(fids), C.c_int64(M), orc.p(ro), C.c_int64(R), pooling, orc.p(pg), orc.p(o1),
+                                 orc.p(lr), C.c_int64(100 + step))
+      u2 = lib.orc_fastps_train_step(b, orc.p(fids), C.c_int64(M), orc.p(ro), C.c_int64(R), pooling, orc.p(pg),
+                                     orc.p(o2), orc.p(lr), C.c_int64(100 + step))
+      assert u1 == u2 == np.unique(fids).size
+      np.testing.assert_array_equal(o1.view(np.uint32), o2.view(np.uint32))
+  lib.orc_fastps_size.restype = C.c_int64
+  assert lib.orc_ps_size(a) == lib.orc_fastps_size(b)
+  # entries: one more forward over every FID ever seen reads the rows both implementations hold
+  allf = np.array(sorted(seen), np.int64)
+  o1, o2 = np.zeros((allf.size, D), np.float32), np.zeros((allf.size, D), np.float32)
+  lib.orc_ps_lookup_pool(a, orc.p(allf), None, C.c_int64(allf.size), C.c_int64(allf.size), 0, orc.p(o1))
+  ent = np.zeros(2 * D, np.float32)
+  for i, f in enumerate(allf):
+    assert lib.orc_fastps_entry(b, C.c_int64(int(f)), orc.p(ent)) == 1
+    o2[i] = ent[:D]
+  np.testing.assert_array_equal(o1.view(np.uint32), o2.view(np.uint32))
+  lib.orc_ps_destroy(a)
+  lib.orc_fastps_destroy(b)
