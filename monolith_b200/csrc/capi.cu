@@ -161,7 +161,7 @@ int mono_mtable_destroy(mono_mtable_t* t) {
   for (auto& tb : t->tables) table_free(tb);
   if (t->d_tables) cudaFree(t->d_tables);
   t->ring.destroy();
-  t->ws_miss.release(); t->ws_a.release(); t->ws_b.release(); t->ws_c.release();
+  t->ws_miss.release(); t->ws_a.release(); t->ws_b.release(); t->ws_c.release(); t->claim_set.release();
   t->ws_d.release(); t->ws_e.release(); t->ws_host_in.release(); t->ws_host_out.release();
   if (t->pinned_in) cudaFreeHost(t->pinned_in);
   if (t->pinned_out) cudaFreeHost(t->pinned_out);
@@ -485,6 +485,7 @@ int mono_grouping_destroy(mono_grouping_t* g) {
   cudaSetDevice(g->device);
   cudaDeviceSynchronize();
   g->ws.release();
+  g->claim_set.release();
   if (g->h_counts) cudaFreeHost(g->h_counts);
   if (g->ev_claimed) cudaEventDestroy(g->ev_claimed);
   if (g->ev_copied) cudaEventDestroy(g->ev_copied);

@@ -175,6 +175,26 @@ __device__ __forceinline__ bool cas_entry(Entry* addr, const Entry& cmp, const E
   return o0 == c0 && o1 == c1;
 }
 
+// compare-and-swap that returns the value found (== cmp on success)
+__device__ __forceinline__ Entry cas_entry_old(Entry* addr, const Entry& cmp, const Entry& val) {
+  unsigned long long c0 = (unsigned long long)cmp.key, c1 = ((unsigned long long)cmp.ts << 32) | cmp.row;
+  unsigned long long v0 = (unsigned long long)val.key, v1 = ((unsigned long long)val.ts << 32) | val.row;
+  unsigned long long o0, o1;
+  asm volatile(
+      "{\n\t.reg .b128 c, v, o;\n\t"
+      "mov.b128 c, {%2, %3};\n\tmov.b128 v, {%4, %5};\n\t"
+      "atom.global.cas.b128 o, [%6], c, v;\n\t"
+      "mov.b128 {%0, %1}, o;\n\t}"
+      : "=l"(o0), "=l"(o1)
+      : "l"(c0), "l"(c1), "l"(v0), "l"(v1), "l"(addr)
+      : "memory");
+  Entry e;
+  e.key = (long long)o0;
+  e.row = (uint32_t)o1;
+  e.ts = (uint32_t)(o1 >> 32);
+  return e;
+}
+
 __device__ __forceinline__ Entry exch_entry(Entry* addr, const Entry& val) {
   unsigned long long v0 = (unsigned long long)val.key, v1 = ((unsigned long long)val.ts << 32) | val.row;
   unsigned long long o0, o1;

@@ -97,6 +97,34 @@ struct DevBuf {
   }
 };
 
+// Scratch open-addressing set of the claim kernels, versioned by an epoch in every entry: an entry whose
+// epoch differs from the current call's is EMPTY, so the set is never cleared between calls (clearing 16 B
+// x 2 x occurrences cost ~15 us per step); it is zero-filled once per (re)allocation and when the epoch wraps.
+struct ClaimSet {
+  DevBuf buf;
+  void* init_ptr = nullptr;
+  size_t init_bytes = 0;
+  uint32_t epoch = 0;
+  // returns the set (>= bytes) and the epoch to claim with
+  void* get(size_t bytes, cudaStream_t s, uint32_t* epoch_out) {
+    void* p = buf.get(bytes, s);
+    if (p != init_ptr || buf.cap > init_bytes || epoch >= 0xFFFFFFF0u) {
+      MONO_CUDA(cudaMemsetAsync(p, 0, buf.cap, s));
+      init_ptr = p;
+      init_bytes = buf.cap;
+      epoch = 0;
+    }
+    *epoch_out = ++epoch;
+    return p;
+  }
+  void release() {
+    buf.release();
+    init_ptr = nullptr;
+    init_bytes = 0;
+    epoch = 0;
+  }
+};
+
 // Ring of pinned host blocks mirrored by device blocks: small per-call descriptors (segments,
 // learning rates) are written to a pinned block and copied H2D on the call's stream.
 struct StageRing {
@@ -143,6 +171,7 @@ struct mono_mtable {
   bool tables_dirty = true;
   mono::StageRing ring;
   mono::DevBuf ws_miss, ws_a, ws_b, ws_c, ws_d, ws_e, ws_host_in, ws_host_out;
+  mono::ClaimSet claim_set;  // pool_backward's FID grouping set
   void* pinned_in = nullptr;
   size_t pinned_in_cap = 0;
   void* pinned_out = nullptr;
@@ -155,6 +184,7 @@ struct mono_mtable {
 struct mono_grouping {
   int device = 0;
   mono::DevBuf ws;
+  mono::ClaimSet claim_set;
   int64_t M = 0;
   int dim = 0;
   // views into ws valid after build()

@@ -1582,7 +1582,9 @@ runs_scan_kernel(uint32_t* __restrict__ blk_runs, int nblk, uint32_t* __restrict
 __global__ void __launch_bounds__(kThreads)
 runs_write_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ perm, int64_t n, int nblk,
                   const uint32_t* __restrict__ blk_runs, uint32_t* __restrict__ run_start,
-                  uint32_t* __restrict__ run_first_pos, uint32_t* __restrict__ run_of_sorted /* optional */) {
+                  uint32_t* __restrict__ run_first_pos, uint32_t* __restrict__ run_of_sorted /* optional */,
+                  const Entry* __restrict__ claim_set /* optional: rowidx[j] = row parked in run j's set entry */,
+                  uint32_t* __restrict__ rowidx) {
   __shared__ uint32_t wc[kThreads / 32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   constexpr int NW = kThreads / 32;
@@ -1604,6 +1606,7 @@ runs_write_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict
         const uint32_t j = base + __popc(bal & ((1u << lane) - 1u));
         run_start[j] = (uint32_t)i;
         run_first_pos[j] = perm[i];
+        if (claim_set) rowidx[j] = claim_set[skeys[i]].row;
       }
       if (run_of_sorted && i < n) run_of_sorted[i] = base + __popc(bal & (0xffffffffu >> (31 - lane))) - 1;
       base += __popc(bal);
@@ -2041,6 +2044,8 @@ struct SortWs {
   uint32_t* run_first_pos;      // [M]
   uint32_t* n_runs;             // device counter, zeroed
   uint32_t* run_of_sorted = nullptr;  // optional [M]: run index of every sorted element
+  const Entry* claim_set = nullptr;   // optional: the claim set (keys are its slots) holding resolved rows ...
+  uint32_t* rowidx = nullptr;         // ... gathered per run into rowidx[j]
 };
 
 // stable LSD radix sort of (key >> pre_shift, position) over `bits` key bits, then the ordered run
@@ -2071,7 +2076,7 @@ static void sort_and_runs(const SortWs& w, int64_t M, int bits, int pre_shift, c
   runs_scan_kernel<<<1, 1024, 0, s>>>(w.blk_runs, nblk, w.n_runs, w.run_start, M);
   MONO_CHECK_LAUNCH();
   runs_write_kernel<<<resident_grid(runs_write_kernel, nblk, 1), kThreads, 0, s>>>(
-      kin, vin, M, nblk, w.blk_runs, w.run_start, w.run_first_pos, w.run_of_sorted);
+      kin, vin, M, nblk, w.blk_runs, w.run_start, w.run_first_pos, w.run_of_sorted, w.claim_set, w.rowidx);
   MONO_CHECK_LAUNCH();
   *skeys_out = kin;
   *perm_out = vin;
@@ -2102,8 +2107,108 @@ static void launch_reduce(const BwdArgs& a, const PeerOut& po, int G, int64_t M,
 #undef RED
 }
 
-__global__ void fid_claim_kernel(const int64_t* __restrict__ fids, int64_t n, SetEntry* set, uint32_t R, int N,
-                                 uint32_t* __restrict__ slot_of, uint32_t* __restrict__ owner_cnt);
+// Claim set entry (16 B, viewed as Entry): key = FID, ts = epoch of the call that claimed it (any other value =
+// empty: the set is never cleared, engine.h ClaimSet), row = the FID's resolved table row (RESOLVE) or 0.
+// Claimed entries never change during the kernel, so every read may be served by L1 (plain ld.global): the hot
+// FIDs of a Zipf batch (8 % of the occurrences hit ONE slot) are answered per SM instead of serialising on one
+// L2 slice.  A stale L1 line can only show "empty" for a slot that has been claimed meanwhile; the CAS then
+// fails and returns the true entry.
+// RESOLVE (single-GPU fused backward): the thread that wins a slot is the only one for its FID, so it also
+// resolves the FID in the table right away — lane-level probe, expiry-timestamp bump
+// (ref: entry.SetTimestamp(update_time), cuckoo_embedding_hash_table.cc:243), row index parked in the set
+// entry; absent FIDs are queued (set slot) for claim_miss_kernel.  No separate resolve pass over the uniques.
+struct ClaimResolve {
+  const TableDev* t;
+  uint32_t update_ts;
+  uint32_t* miss_ctr;
+  uint32_t* miss_slots;
+};
+
+template <bool RESOLVE>
+__global__ void __launch_bounds__(kThreads)
+fid_claim_kernel(const int64_t* __restrict__ fids, int64_t n, Entry* set, uint32_t R, int N, uint32_t epoch,
+                 uint32_t* __restrict__ slot_of, uint32_t* __restrict__ owner_cnt /* [N], [256] = overflow */,
+                 ClaimResolve cr) {
+  __shared__ uint32_t cnt[256];
+  for (int d = threadIdx.x; d < 256; d += blockDim.x) cnt[d] = 0;
+  __syncthreads();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t key = __ldg(fids + i);
+    const uint32_t owner = N == 1 ? 0u : (uint32_t)((uint64_t)key % (uint64_t)N);
+    const uint32_t base = owner * R;
+    uint32_t idx = __umulhi((uint32_t)(mix64((uint64_t)key) >> 24), R);
+    uint32_t found = 0xFFFFFFFFu;
+    bool won = false;
+    for (uint32_t probes = 0; probes < R; ++probes) {
+      Entry* p = set + base + idx;
+      Entry e = ld_entry(p);  // L1-cacheable
+      while (e.ts != epoch) {  // empty as far as we can see: claim it (CAS against what we saw)
+        Entry ne;
+        ne.key = key;
+        ne.row = kEmptyRow;
+        ne.ts = epoch;
+        const Entry old = cas_entry_old(p, e, ne);
+        if (old.key == e.key && old.row == e.row && old.ts == e.ts) {
+          won = true;
+          e = ne;
+        } else {
+          e = old;  // somebody else changed it: the true entry (claimed this epoch, or a different stale one)
+        }
+      }
+      if (e.key == key) {
+        found = base + idx;
+        break;
+      }
+      idx = idx + 1 == R ? 0 : idx + 1;
+    }
+    if (found == 0xFFFFFFFFu) {  // region full (owner skew): the host retries with larger regions
+      owner_cnt[256] = 1;
+      found = base;
+      won = false;
+    }
+    slot_of[i] = found;
+    if (won) {
+      atomicAdd(&cnt[owner], 1u);
+      if (RESOLVE) {
+        Entry* slot = nullptr;
+        const uint32_t row = probe_lane_slot(cr.t, key, &slot);
+        if (row != kEmptyRow) {
+          slot->ts = cr.update_ts;
+          set[found].row = row;
+        } else {
+          cr.miss_slots[atomicAdd(cr.miss_ctr, 1u)] = found;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < N; d += blockDim.x)
+    if (cnt[d]) atomicAdd(owner_cnt + d, cnt[d]);
+}
+
+// FIDs the claim found absent from the table (each exactly once): take a row (free list first, then the bump
+// allocator), publish {fid, row, ts} with the lock-free cuckoo insert and park row | fresh in the set entry.
+__global__ void __launch_bounds__(kThreads)
+claim_miss_kernel(const TableDev* __restrict__ t, Entry* set, const uint32_t* __restrict__ miss_ctr,
+                  const uint32_t* __restrict__ miss_slots, uint32_t update_ts) {
+  const int64_t n = (int64_t)*miss_ctr;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t sl = miss_slots[q];
+    const uint32_t ticket = atomicAdd(t->ctrs + kCtrMiss, 1u);
+    const uint32_t fc = t->ctrs[kCtrFree];  // stable during this kernel (finalize updates it)
+    const uint32_t row = ticket < fc ? t->free_list[fc - 1 - ticket] : t->ctrs[kCtrBump] + (ticket - fc);
+    if (row >= t->row_cap) {
+      atomicOr(t->ctrs + kCtrError, 2u);
+      continue;  // the set entry keeps kEmptyRow: the run is skipped by the apply pass
+    }
+    Entry e;
+    e.key = ld_entry_cg(set + sl).key;
+    e.row = row;
+    e.ts = update_ts;
+    cuckoo_insert(t, e);
+    set[sl].row = row | kFreshBit;
+  }
+}
 
 static const PeerOut no_peer = {};  // n == 0: the reduce kernels write their local ugrad buffer
 
@@ -2136,13 +2241,11 @@ void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t 
   while (cap < 2 * (uint64_t)M) cap <<= 1;
   int bits = 0;
   while ((1u << bits) < cap) ++bits;
-  const int passes = (bits + 7) / 8;
   const int nblk = (int)((M + kSortTile - 1) / kSortTile);
   const size_t n_long_max = (size_t)M / kShortRun + 2;
   const size_t max_pieces = (size_t)M / kSubRun + n_long_max + 2;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
-  const size_t o_set = take(sizeof(SetEntry) * cap);
   const size_t o_k0 = take(4 * (size_t)M), o_v0 = take(4 * (size_t)M);
   const size_t o_k1 = take(4 * (size_t)M), o_v1 = take(4 * (size_t)M);
   const size_t o_blk = take(4 * (size_t)256 * nblk);
@@ -2157,20 +2260,32 @@ void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t 
   const size_t o_ug = take(sizeof(float) * (size_t)M * D);
   const size_t o_med = take(4 * ((size_t)M / (kFastRun + 1) + 2));
   char* ws = (char*)mt->ws_a.get(off, s);
-  SetEntry* set = (SetEntry*)(ws + o_set);
+  uint32_t epoch = 0;
+  Entry* set = (Entry*)mt->claim_set.get(sizeof(Entry) * (size_t)cap, s, &epoch);
   uint32_t *k0 = (uint32_t*)(ws + o_k0), *v0 = (uint32_t*)(ws + o_v0);
   uint32_t *k1 = (uint32_t*)(ws + o_k1), *v1 = (uint32_t*)(ws + o_v1);
   int32_t* blk_cnt = (int32_t*)(ws + o_blk);
   uint32_t* ctr = (uint32_t*)(ws + o_ctr);  // [0] n_runs [4] n_long [8] miss_ctr
   int32_t* dtot = (int32_t*)(ws + o_ctr + 4096);
-  MONO_CUDA(cudaMemsetAsync(set, 0xFF, sizeof(SetEntry) * cap, s));
   MONO_CUDA(cudaMemsetAsync(ctr, 0, 4096 + 4 * 256 * 4, s));
 
-  // 1 claim: k0[i] = set slot of occurrence i
-  // (one table, no first-occurrence bookkeeping needed: the lighter single-list claim; ctr + 512.. is unused scratch)
-  fid_claim_kernel<<<resident_grid(fid_claim_kernel, M, kThreads), kThreads, 0, s>>>(fids_dev, M, set, cap, 1, k0, ctr + 512);
+  // 1 claim: k0[i] = set slot of occurrence i; the winner of a slot resolves its FID in the table (row parked in
+  //   the set entry, expiry timestamp bumped) or queues it as absent
+  ClaimResolve cr;
+  cr.t = mt->d_tables + k;
+  cr.update_ts = (uint32_t)update_time;
+  cr.miss_ctr = ctr + 8;
+  cr.miss_slots = (uint32_t*)(ws + o_miss);
+  fid_claim_kernel<true><<<resident_grid(fid_claim_kernel<true>, M, kThreads), kThreads, 0, s>>>(
+      fids_dev, M, set, cap, 1, epoch, k0, ctr + 512, cr);
   MONO_CHECK_LAUNCH();
-  // 2 stable LSD radix sort of (slot, position)  +  3 ordered run list
+  // 2 absent FIDs: allocate a row + lock-free insert (few in steady state: a small grid; count stays on the device)
+  claim_miss_kernel<<<resident_grid(claim_miss_kernel, std::min<int64_t>(M, 148 * 2 * kThreads), kThreads), kThreads, 0, s>>>(
+      mt->d_tables + k, set, ctr + 8, cr.miss_slots, (uint32_t)update_time);
+  MONO_CHECK_LAUNCH();
+  upsert_finalize_kernel<<<1, 64, 0, s>>>(mt->d_tables, cb.table_ids, cb.ntab, ctr + 8, (uint32_t)update_time);
+  MONO_CHECK_LAUNCH();
+  // 3 stable LSD radix sort of (slot, position)  +  4 ordered run list (with each run's resolved row)
   SortWs sw;
   sw.k0 = k0; sw.v0 = v0; sw.k1 = k1; sw.v1 = v1;
   sw.blk_cnt = blk_cnt; sw.dtot = dtot;
@@ -2178,33 +2293,13 @@ void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t 
   sw.run_start = (uint32_t*)(ws + o_rs);
   sw.run_first_pos = (uint32_t*)(ws + o_rfp);
   sw.n_runs = ctr;
+  sw.claim_set = set;
+  sw.rowidx = (uint32_t*)(ws + o_ridx);
   const uint32_t* skeys = nullptr;
   const uint32_t* perm = nullptr;
   sort_and_runs(sw, M, bits, 0, &skeys, &perm, s);
   uint32_t* run_start = sw.run_start;
   uint32_t* run_first_pos = sw.run_first_pos;
-  // 4 resolve (+ insert) the run keys
-  UpsertArgs ua;
-  ua.tables = mt->d_tables;
-  ua.segs = cb.segs;
-  ua.nsegs = 1;
-  ua.ids = fids_dev;
-  ua.idx_list = run_first_pos;
-  ua.n = M;
-  ua.n_dev = ctr;
-  ua.vals = nullptr;
-  ua.lr = cb.lr;
-  ua.update_ts = (uint32_t)update_time;
-  ua.miss_ctr = ctr + 8;
-  ua.miss_list = (uint32_t*)(ws + o_miss);
-  ua.rowidx = (uint32_t*)(ws + o_ridx);
-  ua.status = nullptr;
-  resolve_hit_kernel<false><<<resident_grid(resolve_hit_kernel<false>, M, kThreads), kThreads, 0, s>>>(ua);
-  MONO_CHECK_LAUNCH();
-  resolve_miss_kernel<false><<<resident_grid(resolve_miss_kernel<false>, M, kThreads), kThreads, 0, s>>>(ua);
-  MONO_CHECK_LAUNCH();
-  upsert_finalize_kernel<<<1, 64, 0, s>>>(mt->d_tables, cb.table_ids, cb.ntab, ctr + 8, (uint32_t)update_time);
-  MONO_CHECK_LAUNCH();
   // 5 reduce + update
   BwdArgs a;
   a.td = ht.dev;  // descriptor is current: ensure_capacity / upload_tables ran above
@@ -2216,7 +2311,7 @@ void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t 
   a.n_runs = ctr;
   a.run_start = run_start;
   a.run_first_pos = run_first_pos;
-  a.rowidx = ua.rowidx;
+  a.rowidx = sw.rowidx;
   a.occ_row = nullptr;
   a.row_offsets = row_offsets;
   a.pooling = pooling;
@@ -2400,51 +2495,6 @@ void run_scatter_rows(int device, const int32_t* offs_dev, int64_t M, int dim, c
 // count per successful insert), i.e. after the FIRST kernel: they are copied to the host on a side
 // stream while the sort still runs, so the host can size and enqueue the exchange without idling the GPU.
 // ==========================================================================================
-__global__ void __launch_bounds__(kThreads)
-fid_claim_kernel(const int64_t* __restrict__ fids, int64_t n, SetEntry* set, uint32_t R, int N,
-                 uint32_t* __restrict__ slot_of, uint32_t* __restrict__ owner_cnt /* [N], [256] = overflow */) {
-  __shared__ uint32_t cnt[256];
-  for (int d = threadIdx.x; d < 256; d += blockDim.x) cnt[d] = 0;
-  __syncthreads();
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t key = fids[i];
-    const uint32_t owner = (uint32_t)((uint64_t)key % (uint64_t)N);
-    const uint32_t base = owner * R;
-    uint32_t idx = __umulhi((uint32_t)(mix64((uint64_t)key) >> 24), R);
-    uint32_t found = 0xFFFFFFFFu;
-    for (uint32_t probes = 0; probes < R; ++probes) {
-      SetEntry* p = set + base + idx;
-      Entry e = ld_entry_cg(reinterpret_cast<Entry*>(p));
-      if (e.row == kEmptyRow && e.ts == 0xFFFFFFFFu && e.key == -1) {
-        SetEntry ne;
-        ne.key = key;
-        ne.table = 0;
-        ne.first_pos = (int32_t)i;
-        if (cas_set(p, ne)) {
-          atomicAdd(&cnt[owner], 1u);
-          found = base + idx;
-          break;
-        }
-        --probes;  // lost the race: look at the same slot again
-        continue;
-      }
-      if (e.key == key && e.row == 0u) {
-        found = base + idx;
-        break;
-      }
-      idx = idx + 1 == R ? 0 : idx + 1;
-    }
-    if (found == 0xFFFFFFFFu) {  // region full (owner skew): the host retries with larger regions
-      owner_cnt[256] = 1;
-      found = base;
-    }
-    slot_of[i] = found;
-  }
-  __syncthreads();
-  for (int d = threadIdx.x; d < N; d += blockDim.x)
-    if (cnt[d]) atomicAdd(owner_cnt + d, cnt[d]);
-}
-
 // bucketed unique list and the per-occurrence row offsets: run j (slot order == owner-bucketed order)
 __global__ void __launch_bounds__(kThreads)
 group_emit_kernel(const int64_t* __restrict__ fids, const uint32_t* __restrict__ perm,
@@ -2493,7 +2543,6 @@ void grouping_build(mono_grouping* g, const int64_t* fids_dev, int64_t M, int N,
     const size_t max_pieces = (size_t)M / kSubRun + n_long_max + 2;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
-    const size_t o_set = take(sizeof(SetEntry) * cap);
     const size_t o_k0 = take(4 * (size_t)M), o_v0 = take(4 * (size_t)M), o_k1 = take(4 * (size_t)M), o_v1 = take(4 * (size_t)M);
     const size_t o_blk = take(4 * (size_t)256 * nblk);
     const size_t o_ctr = take(4096 + 4 * 256 * 4 + 4 * 260);
@@ -2509,11 +2558,11 @@ void grouping_build(mono_grouping* g, const int64_t* fids_dev, int64_t M, int N,
     char* ws = (char*)g->ws.get(off, s);
     g->tail = ws + o_tail;
     g->tail_bytes = off - o_tail;
-    SetEntry* set = (SetEntry*)(ws + o_set);
+    uint32_t epoch = 0;
+    Entry* set = (Entry*)g->claim_set.get(sizeof(Entry) * (size_t)cap, s, &epoch);
     uint32_t* ctr = (uint32_t*)(ws + o_ctr);
     int32_t* dtot = (int32_t*)(ws + o_ctr + 4096);
     uint32_t* owner_cnt = (uint32_t*)(ws + o_ctr + 4096 + 4 * 256 * 4);
-    MONO_CUDA(cudaMemsetAsync(set, 0xFF, sizeof(SetEntry) * cap, s));
     MONO_CUDA(cudaMemsetAsync(ctr, 0, 4096 + 4 * 256 * 4 + 4 * 260, s));
     SortWs sw;
     sw.k0 = (uint32_t*)(ws + o_k0); sw.v0 = (uint32_t*)(ws + o_v0);
@@ -2525,7 +2574,8 @@ void grouping_build(mono_grouping* g, const int64_t* fids_dev, int64_t M, int N,
     sw.run_first_pos = (uint32_t*)(ws + o_rfp);
     sw.n_runs = ctr;
     sw.run_of_sorted = (uint32_t*)(ws + o_ros);
-    fid_claim_kernel<<<resident_grid(fid_claim_kernel, M, kThreads), kThreads, 0, s>>>(fids_dev, M, set, R, N, sw.k0, owner_cnt);
+    fid_claim_kernel<false><<<resident_grid(fid_claim_kernel<false>, M, kThreads), kThreads, 0, s>>>(
+        fids_dev, M, set, R, N, epoch, sw.k0, owner_cnt, ClaimResolve{});
     MONO_CHECK_LAUNCH();
     // counts -> host on the side stream, while the sort below keeps the GPU busy
     MONO_CUDA(cudaEventRecord(g->ev_claimed, s));

@@ -1,0 +1,331 @@
+// rowops.cuh — device code shared by ops.cu (lookup / upsert family) and bwd.cu (fused backward): the sparse
+// optimizer steps restated op by op, apply_row, and the lane-per-key probes.
+#pragma once
+
+#include "engine.h"
+
+namespace mono {
+
+// ------------------------------------------------------------------------------------------
+// optimizer math (bit-exact with oracle/oracle.cc; every step is an explicit IEEE op so that
+// nvcc never contracts a*b+c on its own)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int state_floats_dev(const SegDev& s) {
+  switch (s.opt_type) {
+    case MONO_OPT_ADAGRAD: return s.dim;
+    case MONO_OPT_FTRL: return 2 * s.dim;
+    case MONO_OPT_ADAM: return 2 * s.dim + 2;
+    default: return 0;
+  }
+}
+
+__device__ __forceinline__ float init_emb_value(const TableDev* t, const SegDev& s, int64_t key,
+                                                int col) {
+  switch (s.init_type) {
+    case MONO_INIT_ONES: return 1.0f;
+    case MONO_INIT_CONSTANT: return s.init_a;
+    case MONO_INIT_UNIFORM: return uniform_init(t->seed, key, col, s.init_a, s.init_b);
+    default: return 0.0f;
+  }
+}
+
+// initial value of state float `lj` (local index inside the segment's state block)
+// ref: adagrad_optimizer.cc:47-52, ftrl_optimizer.cc:45-52, adam_optimizer.cc:44-55
+__device__ __forceinline__ float init_state_value(const SegDev& s, int lj) {
+  switch (s.opt_type) {
+    case MONO_OPT_ADAGRAD: return s.p[0];
+    case MONO_OPT_FTRL: return lj < s.dim ? s.p[0] : 0.0f;
+    case MONO_OPT_ADAM: return lj < 2 * s.dim ? 0.0f : (lj == 2 * s.dim ? s.p[0] : s.p[1]);
+    default: return 0.0f;
+  }
+}
+
+// One element of one optimizer step.  a/b are the element's state values
+// (Adagrad: a = norm; FTRL: a = norm, b = zero; Adam: a = m, b = v).  `lr` is the slice learning rate
+// (for Adam: the bias-corrected lr_t of the row).  `avx_form` selects the reference's AVX-path
+// arithmetic for Adagrad (first floor(dim/8)*8 lanes, ref: avx_utils.h:96-119) vs the baseline form.
+template <int OPT>
+__device__ __forceinline__ void opt_elem_t(const float* __restrict__ p, bool avx_form, float lr, float g,
+                                           float& w, float& a, float& b) {
+  if (OPT == MONO_OPT_SGD) {  // sgd_optimizer.cc:46-48
+    w = __fsub_rn(w, __fmul_rn(lr, g));
+  } else if (OPT == MONO_OPT_ADAGRAD) {
+    const float wd = p[1];
+    if (avx_form) {  // avx_utils.h:106-113
+      float ug = __fmaf_rn(wd, w, g);
+      float nn = __fmaf_rn(ug, ug, a);
+      a = nn;
+      float eff = __fdiv_rn(lr, __fsqrt_rn(nn));
+      w = __fmaf_rn(-eff, g, w);
+    } else {  // avx_utils.h:31-37
+      float gg = __fadd_rn(g, __fmul_rn(wd, w));
+      a = __fadd_rn(a, __fmul_rn(gg, gg));
+      float eff = __fdiv_rn(lr, __fsqrt_rn(a));
+      w = __fsub_rn(w, __fmul_rn(eff, gg));
+    }
+  } else if (OPT == MONO_OPT_FTRL) {  // ftrl_optimizer.cc:62-75
+    const float beta = p[1], l1 = p[2], l2 = p[3];
+    float norm_new = __fadd_rn(a, __fmul_rn(g, g));
+    float sigma = __fdiv_rn(__fsub_rn(__fsqrt_rn(norm_new), __fsqrt_rn(a)), lr);
+    b = __fadd_rn(b, __fsub_rn(g, __fmul_rn(sigma, w)));
+    a = norm_new;
+    if (fabsf(b) > l1) {
+      float sb = signbit(b) ? 1.0f : 0.0f;
+      float num = __fmul_rn(lr, __fsub_rn(__fmul_rn(sb, l1), b));
+      float den = __fadd_rn(__fadd_rn(__fsqrt_rn(a), beta), __fmul_rn(l2, lr));
+      w = __fdiv_rn(num, den);
+    } else {
+      w = 0.0f;
+    }
+  } else if (OPT == MONO_OPT_ADAM) {  // adam_optimizer.cc:65-80
+    const float beta1 = p[0], beta2 = p[1], eps = p[2], wd = p[3];
+    const bool nesterov = p[4] != 0.0f;
+    float cur = __fadd_rn(g, __fmul_rn(wd, w));
+    float new_m = __fadd_rn(a, __fmul_rn(__fsub_rn(cur, a), __fsub_rn(1.0f, beta1)));
+    float new_v = __fadd_rn(b, __fmul_rn(__fsub_rn(__fmul_rn(cur, cur), b), __fsub_rn(1.0f, beta2)));
+    float den = __fadd_rn(__fsqrt_rn(new_v), eps);
+    if (nesterov) {
+      float t1 = __fadd_rn(__fmul_rn(cur, __fsub_rn(1.0f, beta1)), __fmul_rn(beta1, new_m));
+      w = __fsub_rn(w, __fdiv_rn(__fmul_rn(t1, lr), den));
+    } else {
+      w = __fsub_rn(w, __fdiv_rn(__fmul_rn(new_m, lr), den));
+    }
+    a = new_m;
+    b = new_v;
+  }
+}
+
+__device__ __forceinline__ void opt_elem(const SegDev& s, bool avx_form, float lr, float g, float& w,
+                                         float& a, float& b) {
+  switch (s.opt_type) {
+    case MONO_OPT_SGD: opt_elem_t<MONO_OPT_SGD>(s.p, avx_form, lr, g, w, a, b); break;
+    case MONO_OPT_ADAGRAD: opt_elem_t<MONO_OPT_ADAGRAD>(s.p, avx_form, lr, g, w, a, b); break;
+    case MONO_OPT_FTRL: opt_elem_t<MONO_OPT_FTRL>(s.p, avx_form, lr, g, w, a, b); break;
+    case MONO_OPT_ADAM: opt_elem_t<MONO_OPT_ADAM>(s.p, avx_form, lr, g, w, a, b); break;
+  }
+}
+
+__device__ __forceinline__ float adam_lr(float lr0, float b1p, float b2p) {  // adam_optimizer.cc:63
+  return __fdiv_rn(__fmul_rn(lr0, __fsqrt_rn(__fsub_rn(1.0f, b2p))), __fsub_rn(1.0f, b1p));
+}
+
+__device__ __forceinline__ int seg_of_col(const TableDev* t, int c) {
+  int s = 0;
+  for (int i = 1; i < t->num_segs; ++i)
+    if (c >= t->segs[i].col_begin) s = i;
+  return s;
+}
+__device__ __forceinline__ int seg_of_state(const TableDev* t, int j) {
+  int s = 0;
+  for (int i = 1; i < t->num_segs; ++i)
+    if (j >= t->segs[i].state_off) s = i;
+  return s;
+}
+
+// Apply operation OP to row `row` of table t with G lanes.  `fresh` == row was just allocated for a
+// key that was absent (ref: UpsertEntry init_fn: Init then fn, cuckoo_embedding_hash_table.cc:346-353).
+// vals points at this id's dim floats (grad / value); for kOpRestore at dim+state+2 floats.
+template <int G, int OP>
+__device__ __forceinline__ void apply_row(const TableDev* __restrict__ t, uint32_t row, int64_t key,
+                                          const float* __restrict__ vals,
+                                          const float* __restrict__ lr, bool fresh) {
+  const int gl = Group<G>::gl();
+  const int D = t->dim;
+  float* __restrict__ w_row = t->emb + (size_t)row * t->emb_stride;
+  float* __restrict__ s_row = t->state + (size_t)row * t->state_stride;
+  const bool init_all = fresh || OP == kOpReinit;
+
+  if (OP == kOpOptimize) {
+    // ---- fast path: one segment, dim % 4 == 0: 128-bit accesses on w, state and grad ----
+    const SegDev& s0 = t->segs[0];
+    if (t->num_segs == 1 && (D & 3) == 0 && ((reinterpret_cast<uintptr_t>(vals) & 15) == 0)) {
+      const float lr0 = lr[0];
+      float lrt = lr0;
+      float b1p = 0.f, b2p = 0.f;
+      if (s0.opt_type == MONO_OPT_ADAM) {
+        b1p = init_all ? s0.p[0] : s_row[2 * D];
+        b2p = init_all ? s0.p[1] : s_row[2 * D + 1];
+        lrt = adam_lr(lr0, b1p, b2p);
+      }
+      const int d8 = D & ~7;
+      for (int c = gl * 4; c < D; c += G * 4) {
+        float4 g4 = __ldg(reinterpret_cast<const float4*>(vals + c));
+        float4 w4, a4 = make_float4(0, 0, 0, 0), b4 = make_float4(0, 0, 0, 0);
+        if (init_all) {
+          w4.x = init_emb_value(t, s0, key, c);
+          w4.y = init_emb_value(t, s0, key, c + 1);
+          w4.z = init_emb_value(t, s0, key, c + 2);
+          w4.w = init_emb_value(t, s0, key, c + 3);
+          a4.x = a4.y = a4.z = a4.w = init_state_value(s0, 0);
+          b4.x = b4.y = b4.z = b4.w = init_state_value(s0, D);
+        } else {
+          w4 = *reinterpret_cast<const float4*>(w_row + c);
+          if (s0.opt_type != MONO_OPT_SGD) a4 = *reinterpret_cast<const float4*>(s_row + c);
+          if (s0.opt_type == MONO_OPT_FTRL || s0.opt_type == MONO_OPT_ADAM)
+            b4 = *reinterpret_cast<const float4*>(s_row + D + c);
+        }
+        const bool avx = c < d8;  // c is a multiple of 4 and d8 of 8: the 4 lanes agree
+        opt_elem(s0, avx, lrt, g4.x, w4.x, a4.x, b4.x);
+        opt_elem(s0, avx, lrt, g4.y, w4.y, a4.y, b4.y);
+        opt_elem(s0, avx, lrt, g4.z, w4.z, a4.z, b4.z);
+        opt_elem(s0, avx, lrt, g4.w, w4.w, a4.w, b4.w);
+        *reinterpret_cast<float4*>(w_row + c) = w4;
+        if (s0.opt_type != MONO_OPT_SGD) *reinterpret_cast<float4*>(s_row + c) = a4;
+        if (s0.opt_type == MONO_OPT_FTRL || s0.opt_type == MONO_OPT_ADAM)
+          *reinterpret_cast<float4*>(s_row + D + c) = b4;
+      }
+      if (s0.opt_type == MONO_OPT_ADAM) {  // adam_optimizer.cc:82-83
+        __syncwarp(Group<G>::mask());  // every lane has read the old powers
+        if (gl == 0) {
+          s_row[2 * D] = __fmul_rn(b1p, s0.p[0]);
+          s_row[2 * D + 1] = __fmul_rn(b2p, s0.p[1]);
+        }
+      }
+      return;
+    }
+  }
+
+  // ---- generic path: any segment mix, any dim; one float per lane per step ----
+  if (OP == kOpRestore) {
+    for (int c = gl; c < D; c += G) w_row[c] = vals[c];
+    for (int j = gl; j < t->state_dim; j += G) s_row[j] = vals[D + j];
+    return;
+  }
+  for (int c = gl; c < D; c += G) {
+    const int si = seg_of_col(t, c);
+    const SegDev& s = t->segs[si];
+    const int lc = c - s.col_begin;
+    float w = init_all ? init_emb_value(t, s, key, c) : w_row[c];
+    if (OP == kOpAssign) {
+      w = vals[c];
+    } else if (OP == kOpAssignAdd) {
+      w = __fadd_rn(w, vals[c]);
+    } else if (OP == kOpOptimize) {
+      float a = 0.f, b = 0.f, lrt = lr[si];
+      float* sp = s_row + s.state_off;
+      if (s.opt_type == MONO_OPT_ADAGRAD) {
+        a = init_all ? s.p[0] : sp[lc];
+      } else if (s.opt_type == MONO_OPT_FTRL) {
+        a = init_all ? s.p[0] : sp[lc];
+        b = init_all ? 0.0f : sp[s.dim + lc];
+      } else if (s.opt_type == MONO_OPT_ADAM) {
+        a = init_all ? 0.0f : sp[lc];
+        b = init_all ? 0.0f : sp[s.dim + lc];
+        float b1p = init_all ? s.p[0] : sp[2 * s.dim];
+        float b2p = init_all ? s.p[1] : sp[2 * s.dim + 1];
+        lrt = adam_lr(lrt, b1p, b2p);
+      }
+      opt_elem(s, lc < (s.dim & ~7), lrt, vals[c], w, a, b);
+      if (s.opt_type == MONO_OPT_ADAGRAD) {
+        sp[lc] = a;
+      } else if (s.opt_type == MONO_OPT_FTRL || s.opt_type == MONO_OPT_ADAM) {
+        sp[lc] = a;
+        sp[s.dim + lc] = b;
+      }
+    }
+    w_row[c] = w;
+  }
+  if (OP == kOpOptimize) {
+    // per-row beta powers advance once per step (after every lane has read the old values)
+    __syncwarp(Group<G>::mask());
+    if (gl == 0) {
+      for (int si = 0; si < t->num_segs; ++si) {
+        const SegDev& s = t->segs[si];
+        if (s.opt_type != MONO_OPT_ADAM) continue;
+        float* sp = s_row + s.state_off;
+        float b1p = init_all ? s.p[0] : sp[2 * s.dim];
+        float b2p = init_all ? s.p[1] : sp[2 * s.dim + 1];
+        sp[2 * s.dim] = __fmul_rn(b1p, s.p[0]);
+        sp[2 * s.dim + 1] = __fmul_rn(b2p, s.p[1]);
+      }
+    }
+  } else if (init_all) {
+    // assign / assign_add / reinitialize on a fresh (or re-initialised) row: optimizer Init
+    for (int j = gl; j < t->state_dim; j += G) {
+      const SegDev& s = t->segs[seg_of_state(t, j)];
+      s_row[j] = init_state_value(s, j - s.state_off);
+    }
+  }
+}
+
+// lane-per-key probe of the bucketised table: the whole 64-byte bucket with 4 x LDG.128 per lane
+__device__ __forceinline__ uint32_t probe_lane(const TableDev* __restrict__ t, int64_t key) {
+  const Entry* __restrict__ buckets = t->buckets;
+  uint32_t b1, b2;
+  bucket_pair(key, t->num_buckets, b1, b2);
+  uint32_t row = kEmptyRow;
+  {
+    const Entry* p = buckets + (size_t)b1 * kBucketSlots;
+    Entry e0 = ld_entry_nc(p), e1 = ld_entry_nc(p + 1), e2 = ld_entry_nc(p + 2), e3 = ld_entry_nc(p + 3);
+    if (e0.key == key && e0.row < kTombRow) row = e0.row;
+    if (e1.key == key && e1.row < kTombRow) row = e1.row;
+    if (e2.key == key && e2.row < kTombRow) row = e2.row;
+    if (e3.key == key && e3.row < kTombRow) row = e3.row;
+  }
+  if (row == kEmptyRow) {
+    const Entry* p = buckets + (size_t)b2 * kBucketSlots;
+    Entry e0 = ld_entry_nc(p), e1 = ld_entry_nc(p + 1), e2 = ld_entry_nc(p + 2), e3 = ld_entry_nc(p + 3);
+    if (e0.key == key && e0.row < kTombRow) row = e0.row;
+    if (e1.key == key && e1.row < kTombRow) row = e1.row;
+    if (e2.key == key && e2.row < kTombRow) row = e2.row;
+    if (e3.key == key && e3.row < kTombRow) row = e3.row;
+    if (row == kEmptyRow && t->ctrs[kCtrStash] != 0) {
+      const uint32_t mask = t->stash_cap - 1;
+      const uint32_t s = (uint32_t)(mix64((uint64_t)key) >> 17) & mask;
+      for (uint32_t i = 0; i <= mask; ++i) {
+        Entry e = ld_entry_cg(t->stash + ((s + i) & mask));
+        if (e.row == kEmptyRow) break;
+        if (e.key == key && e.row < kTombRow) { row = e.row; break; }
+      }
+    }
+  }
+  return row;
+}
+
+
+constexpr uint32_t kFreshBit = 0x80000000u;
+
+// probe that also returns the matching entry's address (for the timestamp bump)
+__device__ __forceinline__ uint32_t probe_lane_slot(const TableDev* __restrict__ t, int64_t key,
+                                                    Entry** slot) {
+  Entry* buckets = t->buckets;
+  uint32_t b1, b2;
+  bucket_pair(key, t->num_buckets, b1, b2);
+  uint32_t row = kEmptyRow;
+#pragma unroll
+  for (int round = 0; round < 2; ++round) {
+    Entry* p = buckets + (size_t)(round == 0 ? b1 : b2) * kBucketSlots;
+    Entry e0 = ld_entry(p), e1 = ld_entry(p + 1), e2 = ld_entry(p + 2), e3 = ld_entry(p + 3);
+    if (e0.key == key && e0.row < kTombRow) { row = e0.row; *slot = p; }
+    if (e1.key == key && e1.row < kTombRow) { row = e1.row; *slot = p + 1; }
+    if (e2.key == key && e2.row < kTombRow) { row = e2.row; *slot = p + 2; }
+    if (e3.key == key && e3.row < kTombRow) { row = e3.row; *slot = p + 3; }
+    if (row != kEmptyRow) return row;
+  }
+  if (t->ctrs[kCtrStash] != 0) {
+    const uint32_t mask = t->stash_cap - 1;
+    const uint32_t s = (uint32_t)(mix64((uint64_t)key) >> 17) & mask;
+    for (uint32_t i = 0; i <= mask; ++i) {
+      Entry* p = t->stash + ((s + i) & mask);
+      Entry e = ld_entry_cg(p);
+      if (e.row == kEmptyRow) break;
+      if (e.key == key && e.row < kTombRow) { *slot = p; return e.row; }
+    }
+  }
+  return kEmptyRow;
+}
+
+
+// ---- host helpers implemented in ops.cu ----
+struct CallBlob {  // device pointers into the staged per-call descriptor block
+  const CallSeg* segs;
+  const float* lr;
+  const int32_t* table_ids;
+  int ntab;
+};
+CallBlob stage_call(mono_mtable* mt, const CallSeg* h_segs, int nsegs, const float* lr_host, int n_lr, cudaStream_t s);
+int pick_group(int max_dim);
+// folds the call's per-table miss tickets into the allocator counters (upsert_finalize_kernel)
+void launch_upsert_finalize(mono_mtable* mt, const CallBlob& cb, uint32_t* miss_ctr, uint32_t update_ts, cudaStream_t s);
+
+}  // namespace mono
