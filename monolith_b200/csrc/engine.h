@@ -188,13 +188,14 @@ struct mono_grouping {
   int64_t M = 0;
   int dim = 0;
   // views into ws valid after build()
-  const uint32_t* skeys = nullptr;
-  const uint32_t* perm = nullptr;
+  const uint2* sorted = nullptr;        // {set slot, position} sorted by slot, stable
   uint32_t* run_start = nullptr;
   uint32_t* run_first_pos = nullptr;
+  uint32_t* piece_run_base = nullptr;
   uint32_t* ctr = nullptr;
-  char* tail = nullptr;      // scratch for reduce()
-  size_t tail_bytes = 0;
+  uint32_t* occ = nullptr;              // scratch of reduce(): occurrence -> pooled row
+  float* part = nullptr;                // long-run block sums
+  void* meta = nullptr;                 // SegMeta[2 * pieces]
   uint32_t* h_counts = nullptr;  // pinned: per-owner distinct counts [256] + overflow flag
   cudaStream_t side = nullptr;   // carries the early counts copy while the sort runs on the caller's stream
   cudaEvent_t ev_claimed = nullptr, ev_copied = nullptr;
