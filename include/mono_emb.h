@@ -452,6 +452,13 @@ int64_t mono_ckpt_snappy_uncompress(const void* in, int64_t n, void* out, int64_
 /* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */
 int64_t mono_kernel_launch_count(void);
 
+/* Engine tuning knobs (process-wide; no reference counterpart).  Known names:
+ *   "lookup_tma"  0 / 1: single-table lookups with packed output rows use the TMA-staged kernel (bulk row copies
+ *                 global -> shared -> global) instead of the register-path kernel.  Results are identical.
+ * Returns MONO_ERR_INVALID_ARGUMENT for an unknown name.  mono_get_option returns the current value (or -1). */
+int mono_set_option(const char* name, int64_t value);
+int64_t mono_get_option(const char* name);
+
 #ifdef __cplusplus
 }
 #endif

@@ -112,6 +112,18 @@ const char* mono_last_error(void) { return g_last_error.c_str(); }
 int32_t mono_abi_version(void) { return MONO_EMB_ABI_VERSION; }
 int64_t mono_kernel_launch_count(void) { return g_launches.load(); }
 
+int mono_set_option(const char* name, int64_t value) {
+  return guarded([&] {
+    require(name != nullptr, "set_option: null name");
+    if (std::strcmp(name, "lookup_tma") == 0) g_opt_lookup_tma.store(value != 0 ? 1 : 0);
+    else throw ArgError(std::string("unknown option: ") + name);
+  });
+}
+int64_t mono_get_option(const char* name) {
+  if (name && std::strcmp(name, "lookup_tma") == 0) return g_opt_lookup_tma.load();
+  return -1;
+}
+
 int mono_mtable_create(const mono_table_cfg* cfgs, int32_t n_tables, int32_t device,
                        mono_mtable_t** out) {
   return guarded([&] {

@@ -17,6 +17,7 @@
 namespace mono {
 
 extern std::atomic<int64_t> g_launches;  // kernels launched by this library
+extern std::atomic<int> g_opt_lookup_tma; // mono_set_option("lookup_tma")
 #define MONO_COUNT_LAUNCH() (::mono::g_launches.fetch_add(1, std::memory_order_relaxed))
 
 struct CudaError : std::runtime_error {

@@ -11,6 +11,7 @@
 // 64 B + 128 B HBM accesses in flight, so occupancy (memory-level parallelism), not staging, is the
 // lever.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "rowops.cuh"
@@ -185,6 +186,107 @@ lookup_push_kernel(const TableDev* __restrict__ t0, const int64_t* __restrict__ 
       }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA-staged lookup (single table, packed output rows): the north-star's "TMA to stage rows through shared memory".
+// Per warp tile of 32 FIDs:
+//   A. lane-per-key probe (as above) -> 32 row indices;
+//   B. every lane that found its FID issues ONE bulk copy global -> shared of its whole row
+//      (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes, 64..512 B, SASS UBLKCP): 32 row
+//      fetches in flight per warp at zero register cost; absent FIDs get zeros written by their lane;
+//   C. while the copies fly the warp probes its NEXT tile (software pipeline: the FID -> bucket -> row chain of
+//      tile t+1 hides behind the row traffic of tile t);
+//   D. mbarrier wait, then ONE bulk store shared -> global of the tile's 32 contiguous output rows
+//      (cp.async.bulk.global.shared::cta, 2..16 KB).
+// The rows never touch registers.  Two tile buffers per warp, so the store of tile t drains while tile t+1 loads.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+template <int ROWB>  // bytes per row: dim * 4, a multiple of 16
+__global__ void __launch_bounds__(kThreads)
+lookup_tma_kernel(const TableDev* __restrict__ t0, const int64_t* __restrict__ ids, int64_t n_total,
+                  float* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int NW = kThreads / 32;
+  constexpr int TILEB = 32 * ROWB;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned char* buf0 = smem_raw + (size_t)(w * 2) * TILEB;
+  const uint32_t buf_s0 = smem_u32(buf0);
+  uint64_t* mb = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NW * 2 * TILEB) + w * 2;
+  const uint32_t mbar0 = smem_u32(mb);
+  if (lane == 0) {
+    mbar_init(mbar0, 1);
+    mbar_init(mbar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const float* __restrict__ emb0 = t0->emb;
+  const uint32_t stride0 = t0->emb_stride;
+  const int64_t ntiles = (n_total + 31) / 32;
+  const int64_t tstride = (int64_t)gridDim.x * NW;
+  int64_t tile = (int64_t)blockIdx.x * NW + w;
+  uint32_t row = kEmptyRow;
+  if (tile < ntiles && tile * 32 + lane < n_total) row = probe_lane(t0, __ldg(ids + tile * 32 + lane));
+  for (uint32_t it = 0; tile < ntiles; ++it) {
+    const int b = it & 1;
+    const uint32_t parity = (it >> 1) & 1u;
+    const uint32_t buf_s = buf_s0 + (uint32_t)b * TILEB, mbar = mbar0 + (uint32_t)b * 8;
+    if (it >= 2) {  // buffer b was read by the bulk store of iteration it - 2
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      __syncwarp();
+    }
+    const int nvalid = (int)min((int64_t)32, n_total - tile * 32);
+    const uint32_t found = __ballot_sync(0xffffffffu, row != kEmptyRow);
+    if (lane == 0) mbar_expect_tx(mbar, (uint32_t)__popc(found) * ROWB);
+    __syncwarp();
+    if (row != kEmptyRow) {
+      bulk_g2s(buf_s + lane * ROWB, emb0 + (size_t)row * stride0, ROWB, mbar);
+    } else if (lane < nvalid) {
+      uint4* z = reinterpret_cast<uint4*>(buf0 + (size_t)b * TILEB + (size_t)lane * ROWB);
+#pragma unroll
+      for (int q = 0; q < ROWB / 16; ++q) z[q] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    // ---- the next tile's probe chain runs while this tile's rows are in flight ----
+    const int64_t next = tile + tstride;
+    uint32_t row_next = kEmptyRow;
+    if (next < ntiles && next * 32 + lane < n_total) row_next = probe_lane(t0, __ldg(ids + next * 32 + lane));
+    mbar_wait(mbar, parity);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the zero rows (generic proxy) before the bulk store reads them
+    __syncwarp();
+    if (lane == 0) bulk_s2g(out + (size_t)tile * 32 * (ROWB / 4), buf_s, (uint32_t)nvalid * ROWB);
+    tile = next;
+    row = row_next;
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the reads
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -628,6 +730,43 @@ static int max_dim_of(mono_mtable* mt, const CallSeg* h_segs, int nsegs) {
   return m;
 }
 
+// launcher: returns false when the TMA variant does not apply (the caller falls back to lookup_kernel)
+static bool try_lookup_tma(mono_mtable* mt, int k, const int64_t* ids_dev, int64_t n_total, float* out_dev,
+                           int64_t out_stride, int out_col, cudaStream_t s) {
+  static const int env_mode = [] {  // MONO_LOOKUP_TMA=0/1 presets mono_set_option("lookup_tma")
+    const char* e = std::getenv("MONO_LOOKUP_TMA");
+    if (e) g_opt_lookup_tma.store(std::atoi(e) != 0);
+    return 0;
+  }();
+  (void)env_mode;
+  if (g_opt_lookup_tma.load(std::memory_order_relaxed) == 0) return false;
+  const HostTable& ht = mt->tables[k];
+  const int D = ht.dim;
+  const int rowb = D * 4;
+  if ((D & 3) || (rowb != 64 && rowb != 128 && rowb != 256)) return false;
+  if (out_col != 0 || (out_stride > 0 && out_stride != D) || (reinterpret_cast<uintptr_t>(out_dev) & 15)) return false;
+  if (ht.dev.emb_stride != (uint32_t)D) return false;  // rows are 16-byte aligned and contiguous when dim % 4 == 0
+  const TableDev* t = mt->d_tables + k;
+  constexpr int NW = kThreads / 32;
+#define LT(RB)                                                                                         \
+  do {                                                                                                 \
+    const size_t smem = (size_t)NW * 2 * 32 * RB + NW * 2 * 8;                                         \
+    static bool attr = false;                                                                          \
+    if (!attr) {                                                                                       \
+      MONO_CUDA(cudaFuncSetAttribute(lookup_tma_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      attr = true;                                                                                     \
+    }                                                                                                  \
+    lookup_tma_kernel<RB><<<resident_grid(lookup_tma_kernel<RB>, (n_total + 31) / 32, NW, kThreads, smem), kThreads, smem, s>>>( \
+        t, ids_dev, n_total, out_dev);                                                                 \
+  } while (0)
+  if (rowb == 64) LT(64);
+  else if (rowb == 128) LT(128);
+  else LT(256);
+#undef LT
+  MONO_CHECK_LAUNCH();
+  return true;
+}
+
 static void launch_lookup_staged(mono_mtable* mt, const CallSeg* d_segs, int nsegs, int G,
                                  const int64_t* ids_dev, int64_t n_total, float* out_dev,
                                  int64_t out_stride, int out_col, cudaStream_t s) {
@@ -669,6 +808,9 @@ void launch_lookup(mono_mtable* mt, const CallSeg* h_segs, int nsegs, const int6
   }
   h_segs = merged.data();
   nsegs = (int)merged.size();
+  if (nsegs == 1 && h_segs[0].id_begin == 0 &&
+      try_lookup_tma(mt, h_segs[0].table, ids_dev, n_total, out_dev + h_segs[0].val_off, 0, 0, s))
+    return;
   CallBlob cb = stage_call(mt, h_segs, nsegs, nullptr, 0, s);
   launch_lookup_staged(mt, cb.segs, nsegs, pick_group(max_dim_of(mt, h_segs, nsegs)), ids_dev, n_total,
                        out_dev, 0, 0, s);
@@ -708,6 +850,7 @@ void launch_lookup_pool(mono_mtable* mt, int k, const int64_t* fids_dev, const i
   const int nv = (D + 4 * G - 1) / (4 * G);
   if (row_offsets == nullptr) {
     // one FID per pooled row: SUM and MEAN are the identity (x / 1 == x): probe + gather only
+    if (try_lookup_tma(mt, k, fids_dev, n_rows, out, out_stride, out_col, s)) return;
     CallSeg sg;
     sg.id_begin = 0;
     sg.id_end = n_rows;

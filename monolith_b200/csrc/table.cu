@@ -8,6 +8,7 @@
 namespace mono {
 
 std::atomic<int64_t> g_launches{0};
+std::atomic<int> g_opt_lookup_tma{0};
 
 // ------------------------------------------------------------------------------------------
 // StageRing

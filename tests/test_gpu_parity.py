@@ -921,3 +921,36 @@ def test_hot_fid_gradient_sum_is_closer_to_fp64_than_the_sequential_cpu_sum(dev)
   assert err_gpu <= 1e-5 * np.abs(exact).max(), (err_gpu, np.abs(exact).max())
   assert err_gpu <= 5e-7 * scale
   assert err_gpu <= err_seq + 1e-12, (err_gpu, err_seq)
+
+
+# ------------------------------------------------------------------------------------------------
+# TMA-staged lookup (bulk row copies global -> shared -> global) == the register-path kernel == the oracle
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim", [16, 32, 64])
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 5000, 70001])
+def test_lookup_tma_vs_register_path_and_oracle(dim, n, dev):
+  import ctypes as C
+  from monolith_b200 import _lib, entry
+  lib = _lib.load()
+  rng = np.random.default_rng(dim * 1000 + n)
+  cfg = {"t": table([(dim, "sgd", {})], [0.1], capacity=64, init=entry.RandomUniformInitializer(-1.0, 1.0), init_seed=3)}
+  gpu, cpu = pair(cfg, dev)
+  vocab = np.unique(rand_fids(rng, 3000, 100000))
+  vals = rng.standard_normal((vocab.size, dim)).astype(np.float32)
+  gpu.assign({"t": (T(vocab, dev), T(vals, dev))})
+  cpu.assign({"t": (vocab, vals)})
+  ids = rng.choice(np.concatenate([vocab, vocab[:200] + 7]), size=n)          # ~6 % absent -> zero rows
+  want = cpu.lookup({"t": ids})["t"]
+  old = lib.mono_get_option(b"lookup_tma")
+  try:
+    outs = []
+    for mode in (0, 1):
+      assert lib.mono_set_option(b"lookup_tma", mode) == 0
+      outs.append(gpu.lookup({"t": T(ids, dev)})["t"].cpu().numpy())
+      pooled = gpu.lookup_pool("t", T(ids, dev), None, "sum").cpu().numpy()
+      np.testing.assert_array_equal(pooled.view(np.uint32), want.view(np.uint32))
+    np.testing.assert_array_equal(outs[0].view(np.uint32), want.view(np.uint32))
+    np.testing.assert_array_equal(outs[1].view(np.uint32), want.view(np.uint32))
+  finally:
+    lib.mono_set_option(b"lookup_tma", old)
+  assert lib.mono_set_option(b"no_such_option", 1) != 0
