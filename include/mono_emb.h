@@ -220,6 +220,17 @@ int mono_mtable_reinitialize(mono_mtable_t* t, int32_t k, const int64_t* ids_dev
  * from a background thread (tf_bridge.cc:73-104); here the caller drives it. */
 int mono_mtable_evict(mono_mtable_t* t, int32_t k, int64_t max_update_time, void* stream);
 
+/* Counting admission filter of table k (ref: monolith::hash_filter::HashFilter<uint16_t>, RT/hash_filter/
+ * hash_filter.h:34-165; created by hash_filter_ops.create_hash_filters; thresholds from
+ * SlotOccurrenceThresholdConfig, embedding_hash_table.proto:100-110).  A FID that is ABSENT from the table is only
+ * inserted by optimize / assign / the fused backward once the filter has counted `threshold(slot)` earlier
+ * occurrences of it (ref call sites: RT/ops/embedding_hash_table_tf_bridge.cc:181-185,208-240,296-326);
+ * assign_add consults the filter for every id, present or not (AssignAdd2, :224-232).  threshold 0 never filters.
+ * Tables without a filter behave like the reference's DummyHashFilter.  SYNC (allocates). */
+int mono_mtable_set_hash_filter(mono_mtable_t* t, int32_t k, int64_t capacity, uint32_t default_threshold,
+                                const uint32_t* slot_ids_host, const uint32_t* slot_thresholds_host,
+                                int32_t n_slots, void* stream);
+
 /* Full row access for checkpoint/restore and parity tests (ref: EntryDump,
  * embedding_hash_table.proto:45-50; LookupEntry, cuckoo_embedding_hash_table.cc:173-183).
  * entry_out_dev is [n, dim + state_floats + 2]: emb, optimizer state (reference order), then

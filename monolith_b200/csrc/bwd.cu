@@ -915,6 +915,9 @@ claim_miss_kernel(const TableDev* __restrict__ t, Entry* set, const uint32_t* __
   const int64_t n = (int64_t)*miss_ctr;
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
     const uint32_t sl = miss_slots[q];
+    // admission filter: the backward hands every distinct FID once per step (count 1), as the reference's
+    // deduplicated optimize does; a FID below its slot's threshold gets no row (its run is skipped by the apply)
+    if (should_be_filtered(t, ld_entry_cg(set + sl).key, 1u)) continue;
     const uint32_t ticket = atomicAdd(t->ctrs + kCtrMiss, 1u);
     const uint32_t fc = t->ctrs[kCtrFree];  // stable during this kernel (finalize updates it)
     const uint32_t row = ticket < fc ? t->free_list[fc - 1 - ticket] : t->ctrs[kCtrBump] + (ticket - fc);

@@ -416,6 +416,19 @@ int mono_mtable_evict(mono_mtable_t* t, int32_t k, int64_t max_update_time, void
   });
 }
 
+int mono_mtable_set_hash_filter(mono_mtable_t* t, int32_t k, int64_t capacity, uint32_t default_threshold,
+                                const uint32_t* slot_ids_host, const uint32_t* slot_thresholds_host,
+                                int32_t n_slots, void* stream) {
+  return guarded([&] {
+    require(t != nullptr && k >= 0 && k < (int)t->tables.size(), "bad table index");
+    require(capacity > 0, "hash filter capacity must be positive");
+    require(n_slots == 0 || (slot_ids_host && slot_thresholds_host), "set_hash_filter: null slot arrays");
+    HandleGuard hg_(t);
+    table_set_filter(t, k, (uint64_t)capacity, default_threshold, slot_ids_host, slot_thresholds_host, n_slots,
+                     (cudaStream_t)stream);
+  });
+}
+
 int mono_mtable_lookup_entry(mono_mtable_t* t, int32_t k, const int64_t* ids_dev, int64_t n,
                              float* entry_out_dev, void* stream) {
   return guarded([&] {

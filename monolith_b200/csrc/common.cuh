@@ -79,6 +79,12 @@ struct TableDev {
   int32_t n_slot_expire;
   const uint32_t* slot_expire;  // pairs (slot, days)
   uint64_t seed;
+  // counting admission filter (null = the dummy filter: never filters); see filter_add below
+  uint32_t* flt_cells;           // uint16 cells packed two per word, [flt_total + 64] cells
+  uint32_t flt_total;            // capacity * 1.5
+  uint32_t flt_default_thr;
+  int32_t n_slot_thr;
+  const uint32_t* slot_thr;      // pairs (slot, threshold)
   SegDev segs[kMaxSegs];
 };
 
@@ -422,6 +428,53 @@ __device__ __forceinline__ void probe_keys(const TableDev* __restrict__ t, const
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Counting admission filter — monolith::hash_filter::HashFilter<uint16_t> (ref: RT/hash_filter/hash_filter.h:34-165,
+// filter.h:60-61) on the device: open addressing over total = capacity * 1.5 (+ 64 spill) 16-bit cells, cell =
+// 12-bit signature << 4 | 4-bit saturating count, at most 64 probes.  filter_add returns the count BEFORE the
+// addition (0 for a new FID, 15 when the probe window is exhausted), like the reference's iterator add (:40-62).
+// Cells are updated with a 32-bit CAS on the word that holds them, so concurrent adds of different FIDs are safe;
+// the cell a FID lands in depends on the hash (the reference's absl::Hash is salted per process: unpinned there
+// too), the counts do not.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t filter_add(const TableDev* __restrict__ t, int64_t fid_, uint32_t count) {
+  constexpr uint32_t kMaxCount = 15, kMaxStep = 64;
+  const uint64_t fid = (uint64_t)fid_;
+  const uint32_t sign = (uint32_t)(((fid >> 17) | (fid << 15)) & 0x0FFFu);  // hash_filter.h:128
+  const uint32_t ncell = t->flt_total + kMaxStep;
+  uint32_t pos = (uint32_t)(mix64(fid) % (uint64_t)t->flt_total);
+  if (count > kMaxCount) count = kMaxCount;
+  for (uint32_t step = 0; step < kMaxStep; ++step) {
+    uint32_t* wp = t->flt_cells + (pos >> 1);
+    const uint32_t shift = (pos & 1u) * 16u;
+    uint32_t w = *reinterpret_cast<volatile uint32_t*>(wp);
+    while (true) {
+      const uint32_t v = (w >> shift) & 0xFFFFu;
+      if (v != 0 && (v >> 4) != sign) break;  // somebody else's cell: next probe
+      const uint32_t c = v & kMaxCount;
+      const uint32_t nv = v == 0 ? ((sign << 4) + count) : (c + count >= kMaxCount ? (v | kMaxCount) : v + count);
+      const uint32_t nw = (w & ~(0xFFFFu << shift)) | (nv << shift);
+      const uint32_t old = atomicCAS(wp, w, nw);
+      if (old == w) return v == 0 ? 0u : c;
+      w = old;  // the word changed under us (either half): look again
+    }
+    if (++pos == ncell) pos = 0;
+  }
+  return kMaxCount;
+}
+
+// ref: HashFilter::ShouldBeFiltered (hash_filter.h:137-144) with the per-slot occurrence thresholds
+// (SlotOccurrenceThresholdConfig, embedding_hash_table.proto:100-110): threshold 0 never filters
+__device__ __forceinline__ bool should_be_filtered(const TableDev* __restrict__ t, int64_t fid, uint32_t count) {
+  if (t->flt_cells == nullptr) return false;
+  uint32_t thr = t->flt_default_thr;
+  const uint32_t slot = slot_id_v2(fid);
+  for (int i = 0; i < t->n_slot_thr; ++i)
+    if (t->slot_thr[2 * i] == slot) thr = t->slot_thr[2 * i + 1];
+  if (thr == 0) return false;
+  return filter_add(t, fid, count) < thr;
 }
 
 // binary search: last segment with id_begin <= i (segments are sorted, non-overlapping)

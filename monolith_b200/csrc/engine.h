@@ -262,6 +262,8 @@ void grouping_reduce(mono_grouping* g, const float* pooled_grad, int64_t grad_st
 // table.cu
 void table_init(mono_mtable* mt, HostTable& t, const mono_table_cfg& cfg, cudaStream_t s);
 void table_free(HostTable& t);
+void table_set_filter(mono_mtable* mt, int k, uint64_t capacity, uint32_t default_thr, const uint32_t* slots,
+                      const uint32_t* thrs, int n_slots, cudaStream_t s);
 void upload_tables(mono_mtable* mt, cudaStream_t s);
 // make room for n_new more keys in table k (grows row slabs / rehashes buckets when needed)
 void ensure_capacity(mono_mtable* mt, int k, uint64_t n_new, cudaStream_t s);

@@ -458,6 +458,11 @@ struct UpsertArgs {
   uint32_t* rowidx;          // per item j: resolved row (bit 31 = freshly inserted)
   int32_t* status;           // reinitialize only
   int64_t pos0 = 0;          // apply pass without idx_list: item j is position pos0 + j
+  // admission filter (tables without one never filter): 0 = not consulted (reinitialize, restore); 1 = ids ABSENT
+  // from the table consult it (optimize: tf_bridge.cc:296-326; assign: :181-185); 2 = every id does (AssignAdd2
+  // has no Contains check, tf_bridge.cc:224-232)
+  int filter_mode = 0;
+  const uint32_t* occ_extra = nullptr;  // dedup path: occurrences of id position i beyond the first (count = 1 + occ_extra[i])
 };
 __device__ __forceinline__ uint32_t restore_ts(const UpsertArgs& a, const CallSeg& sg, const TableDev* t,
                                                int64_t i) {
@@ -485,6 +490,8 @@ __global__ void __launch_bounds__(kThreads) resolve_hit_kernel(UpsertArgs a) {
       const uint32_t row = probe_lane_slot(t, a.ids[i], &slot);
       if (row == kEmptyRow) {
         miss = true;
+      } else if (a.filter_mode == 2 && should_be_filtered(t, a.ids[i], 1)) {
+        a.rowidx[j] = kEmptyRow;  // AssignAdd2: filtered although present — the op is skipped for this id
       } else {
         slot->ts = RESTORE ? restore_ts(a, sg, t, i) : a.update_ts;
         a.rowidx[j] = row;
@@ -512,6 +519,10 @@ __global__ void __launch_bounds__(kThreads) resolve_miss_kernel(UpsertArgs a) {
     const int64_t i = a.idx_list ? (int64_t)a.idx_list[j] : j;
     const CallSeg sg = a.segs[a.nsegs > 1 ? find_seg(a.segs, a.nsegs, i) : 0];
     const TableDev* t = a.tables + sg.table;
+    if (a.filter_mode != 0 && should_be_filtered(t, a.ids[i], a.occ_extra ? 1u + a.occ_extra[i] : 1u)) {
+      a.rowidx[j] = kEmptyRow;  // not admitted yet: no row, the apply pass skips it
+      continue;
+    }
     const uint32_t ticket = atomicAdd(t->ctrs + kCtrMiss, 1u);
     const uint32_t fc = t->ctrs[kCtrFree];  // stable during this kernel (finalize updates it)
     const uint32_t row = ticket < fc ? t->free_list[fc - 1 - ticket] : t->ctrs[kCtrBump] + (ticket - fc);
@@ -672,7 +683,7 @@ __global__ void __launch_bounds__(kThreads)
 dup_accumulate_kernel(const TableDev* __restrict__ tables, const CallSeg* __restrict__ segs, int nsegs,
                       const uint32_t* __restrict__ items, const uint32_t* n_dev,
                       const uint32_t* __restrict__ leader_of, const float* __restrict__ vals,
-                      float* __restrict__ acc) {
+                      float* __restrict__ acc, uint32_t* __restrict__ occ_extra /* optional */) {
   const int64_t n = *n_dev;
   const int gl = Group<G>::gl();
   for (int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G; j < n;
@@ -685,6 +696,7 @@ dup_accumulate_kernel(const TableDev* __restrict__ tables, const CallSeg* __rest
     const float* src = vals + sg.val_off + (i - sg.id_begin) * D;
     float* dst = acc + sg.val_off + (l - sg.id_begin) * D;  // leader is in the same segment? see host
     for (int c = gl; c < D; c += G) dst[c] = __fadd_rn(dst[c], src[c]);
+    if (occ_extra && gl == 0) occ_extra[l] += 1u;  // one item per key and round: no race
   }
 }
 
@@ -979,6 +991,11 @@ void run_upsert(mono_mtable* mt, UpsertOp op, const CallSeg* h_segs, int nsegs,
   a.miss_list = miss_list;
   a.rowidx = rowidx;
   a.status = status_dev;
+  bool any_filter = false;
+  for (size_t k = 0; k < per_table.size(); ++k)
+    if (per_table[k] && mt->tables[k].dev.flt_cells) any_filter = true;
+  a.filter_mode = !any_filter ? 0 : (op == kOpOptimize || op == kOpAssign) ? 1 : (op == kOpAssignAdd ? 2 : 0);
+  uint32_t* occ_extra = nullptr;
 
   auto finalize = [&]() {
     upsert_finalize_kernel<<<(cb.ntab + 63) / 64, 64, 0, s>>>(mt->d_tables, cb.table_ids, cb.ntab,
@@ -1021,8 +1038,12 @@ void run_upsert(mono_mtable* mt, UpsertOp op, const CallSeg* h_segs, int nsegs,
                                                          mt->tables[h_segs[i].table].dim);
       leader_of = (uint32_t*)mt->ws_d.get(sizeof(uint32_t) * (size_t)n_total * 2, s);
       round0_leaders = leader_of + n_total;
-      acc = (float*)mt->ws_e.get(sizeof(float) * val_floats, s);
+      acc = (float*)mt->ws_e.get(sizeof(float) * val_floats + (any_filter ? 4 * (size_t)n_total + 256 : 0), s);
       MONO_CUDA(cudaMemcpyAsync(acc, vals_dev, sizeof(float) * val_floats, cudaMemcpyDeviceToDevice, s));
+      if (any_filter) {  // the dedup path hands the filter each id's occurrence count (tf_bridge.cc:296-310)
+        occ_extra = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(acc) + ((sizeof(float) * val_floats + 255) & ~(size_t)255));
+        MONO_CUDA(cudaMemsetAsync(occ_extra, 0, 4 * (size_t)n_total, s));
+      }
     }
     const uint32_t* pending = nullptr;
     int64_t n_pending = n_total;
@@ -1048,10 +1069,10 @@ void run_upsert(mono_mtable* mt, UpsertOp op, const CallSeg* h_segs, int nsegs,
           n_round0 = n_lead;
         } else {
           switch (G) {
-            case 4: dup_accumulate_kernel<4><<<grid_for(n_lead, kThreads / 4), kThreads, 0, s>>>(mt->d_tables, cb.segs, nsegs, leaders, ctr, leader_of, vals_dev, acc); break;
-            case 8: dup_accumulate_kernel<8><<<grid_for(n_lead, kThreads / 8), kThreads, 0, s>>>(mt->d_tables, cb.segs, nsegs, leaders, ctr, leader_of, vals_dev, acc); break;
-            case 16: dup_accumulate_kernel<16><<<grid_for(n_lead, kThreads / 16), kThreads, 0, s>>>(mt->d_tables, cb.segs, nsegs, leaders, ctr, leader_of, vals_dev, acc); break;
-            default: dup_accumulate_kernel<32><<<grid_for(n_lead, kThreads / 32), kThreads, 0, s>>>(mt->d_tables, cb.segs, nsegs, leaders, ctr, leader_of, vals_dev, acc); break;
+            case 4: dup_accumulate_kernel<4><<<grid_for(n_lead, kThreads / 4), kThreads, 0, s>>>(mt->d_tables, cb.segs, nsegs, leaders, ctr, leader_of, vals_dev, acc, occ_extra); break;
+            case 8: dup_accumulate_kernel<8><<<grid_for(n_lead, kThreads / 8), kThreads, 0, s>>>(mt->d_tables, cb.segs, nsegs, leaders, ctr, leader_of, vals_dev, acc, occ_extra); break;
+            case 16: dup_accumulate_kernel<16><<<grid_for(n_lead, kThreads / 16), kThreads, 0, s>>>(mt->d_tables, cb.segs, nsegs, leaders, ctr, leader_of, vals_dev, acc, occ_extra); break;
+            default: dup_accumulate_kernel<32><<<grid_for(n_lead, kThreads / 32), kThreads, 0, s>>>(mt->d_tables, cb.segs, nsegs, leaders, ctr, leader_of, vals_dev, acc, occ_extra); break;
           }
           MONO_CHECK_LAUNCH();
           // ctr is reused next round: the kernel above must finish reading it first (same stream)
@@ -1071,6 +1092,7 @@ void run_upsert(mono_mtable* mt, UpsertOp op, const CallSeg* h_segs, int nsegs,
       a.idx_list = round0_leaders;
       a.n = n_round0;
       a.vals = acc;
+      a.occ_extra = occ_extra;
       launch_upsert(op, G, a, n_round0, s);
       finalize();
     }
@@ -1139,6 +1161,8 @@ void run_upsert_groups(mono_mtable* mt, const CallSeg* h_segs, int nsegs, const 
   a.miss_list = miss_list;
   a.rowidx = rowidx;
   a.status = nullptr;
+  for (size_t k = 0; k < per_table.size(); ++k)
+    if (per_table[k] && mt->tables[k].dev.flt_cells) a.filter_mode = 1;
   resolve_hit_kernel<false><<<resident_grid(resolve_hit_kernel<false>, n_total, kThreads), kThreads, 0, s>>>(a);
   MONO_CHECK_LAUNCH();
   // misses are few in steady state: small grids, counts stay on the device

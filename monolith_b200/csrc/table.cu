@@ -202,6 +202,41 @@ void table_init(mono_mtable* mt, HostTable& t, const mono_table_cfg& cfg, cudaSt
   MONO_CUDA(cudaEventCreateWithFlags(&t.snap_ev, cudaEventDisableTiming));
 }
 
+// ref: hash_filter_ops.create_hash_filters + SlotOccurrenceThresholdConfig (embedding_hash_table.proto:100-110):
+// a counting filter of `capacity` FIDs with a default and per-slot occurrence thresholds (0 = never filter).
+void table_set_filter(mono_mtable* mt, int k, uint64_t capacity, uint32_t default_thr, const uint32_t* slots,
+                      const uint32_t* thrs, int n_slots, cudaStream_t s) {
+  HostTable& t = mt->tables[k];
+  TableDev& d = t.dev;
+  MONO_CUDA(cudaStreamSynchronize(s));
+  if (d.flt_cells) MONO_CUDA(cudaFree(d.flt_cells));
+  if (d.slot_thr) MONO_CUDA(cudaFree((void*)d.slot_thr));
+  d.flt_cells = nullptr;
+  d.slot_thr = nullptr;
+  d.n_slot_thr = 0;
+  uint64_t total = (uint64_t)(capacity * 1.5);  // hash_filter.h: total_size_ = capacity * 1.5
+  if (total == 0) total = 1;
+  if (total > 0xFFFFFF00ull) throw ArgError("hash filter capacity too large");
+  const size_t words = (size_t)((total + 64 + 1) / 2);
+  MONO_CUDA(cudaMalloc((void**)&d.flt_cells, words * sizeof(uint32_t)));
+  MONO_CUDA(cudaMemset(d.flt_cells, 0, words * sizeof(uint32_t)));
+  d.flt_total = (uint32_t)total;
+  d.flt_default_thr = default_thr;
+  if (n_slots > 0) {
+    std::vector<uint32_t> pairs;
+    for (int i = 0; i < n_slots; ++i) {
+      pairs.push_back(slots[i]);
+      pairs.push_back(thrs[i]);
+    }
+    uint32_t* p = nullptr;
+    MONO_CUDA(cudaMalloc((void**)&p, pairs.size() * sizeof(uint32_t)));
+    MONO_CUDA(cudaMemcpy(p, pairs.data(), pairs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    d.slot_thr = p;
+    d.n_slot_thr = n_slots;
+  }
+  mt->tables_dirty = true;
+}
+
 void table_free(HostTable& t) {
   TableDev& d = t.dev;
   cudaFree(d.ctrs);
@@ -211,6 +246,8 @@ void table_free(HostTable& t) {
   cudaFree(d.emb);
   if (d.state) cudaFree(d.state);
   if (d.slot_expire) cudaFree((void*)d.slot_expire);
+  if (d.flt_cells) cudaFree(d.flt_cells);
+  if (d.slot_thr) cudaFree((void*)d.slot_thr);
   if (t.h_snap) cudaFreeHost(t.h_snap);
   if (t.snap_ev) cudaEventDestroy(t.snap_ev);
   std::memset(&d, 0, sizeof(d));

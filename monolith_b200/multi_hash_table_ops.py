@@ -342,6 +342,18 @@ class MultiHashTable:
                                                    int(global_step), _stream(self._device)))
     return self
 
+  def set_hash_filter(self, slot: str, capacity: int, default_threshold: int, slot_thresholds: Optional[Dict[int, int]] = None):
+    """Attach a counting admission filter to table `slot` (ref: hash_filter_ops.create_hash_filters; thresholds:
+    HashTableConfigInstance slot_occurrence_threshold / SlotOccurrenceThresholdConfig): a FID absent from the table is
+    inserted only once it has been seen `threshold` times before (0 = never filter)."""
+    k = self._table_names.index(slot)
+    st = slot_thresholds or {}
+    ks = (C.c_uint32 * max(len(st), 1))(*[int(x) for x in st.keys()])
+    vs = (C.c_uint32 * max(len(st), 1))(*[int(x) for x in st.values()])
+    _lib.check(self._lib.mono_mtable_set_hash_filter(self._h, k, int(capacity), int(default_threshold), ks, vs, len(st),
+                                                     _stream(self._device)))
+    return self
+
   def contains(self, slot: str, ids: torch.Tensor) -> torch.Tensor:
     ids = _ids(ids, self._device)
     out = torch.empty(ids.numel(), dtype=torch.uint8, device=self._device)

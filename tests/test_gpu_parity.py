@@ -954,3 +954,93 @@ def test_lookup_tma_vs_register_path_and_oracle(dim, n, dev):
   finally:
     lib.mono_set_option(b"lookup_tma", old)
   assert lib.mono_set_option(b"no_such_option", 1) != 0
+
+
+# ------------------------------------------------------------------------------------------------
+# counting admission filter on the GPU vs the oracle's HashFilter restatement
+# ------------------------------------------------------------------------------------------------
+def test_hash_filter_threshold_schedule_golden_cuda(dev):
+  """The reference's test_gradients_with_hash_filter (NT/hash_table_ops_test.py:223-260) through the CUDA path: dim 1,
+  SGD lr 0.1, occurrence_threshold 3, ids [0, 0, 1] with gradient -1 applied four times."""
+  from monolith_b200 import MultiHashTable
+  t = MultiHashTable({"t": sgd_table(1, 0.1)}, device=dev)
+  t.set_hash_filter("t", capacity=1000, default_threshold=3)
+  ids = T(np.array([0, 0, 1], np.int64), dev)
+  g = T(-np.ones((3, 1), np.float32), dev)
+  for want in ([[0.0], [0.0]], [[0.1], [0.0]], [[0.3], [0.0]], [[0.5], [0.1]]):
+    t.apply_gradients({"t": (ids, g)})
+    np.testing.assert_allclose(gpu_lookup(t, {"t": [0, 1]}, dev)["t"], want, rtol=1e-6, atol=1e-7)
+
+
+def test_hash_filter_paths_vs_oracle(dev):
+  """Per-slot thresholds, the dedup path (occurrence counts), assign (absent ids only), assign_add (every id, present or
+  not: AssignAdd2 has no Contains check), the fused backward (one count per distinct FID and step) and threshold 0."""
+  D = 4
+  cfg = {"t": table([(D, "adagrad", {})], [0.1])}
+  rng = np.random.default_rng(9)
+  f = lambda slot, x: (np.int64(slot) << 48) | np.asarray(x, np.int64)
+
+  def both():
+    gpu, cpu = pair(cfg, dev)
+    for t in (gpu, cpu):
+      t.set_hash_filter("t", capacity=5000, default_threshold=2, slot_thresholds={7: 4, 9: 0})
+    return gpu, cpu
+
+  def same(gpu, cpu, ids):
+    assert gpu.size("t") == cpu.size("t")
+    got, want = gpu.lookup_entry("t", T(ids, dev))["raw"].cpu().numpy(), cpu.lookup_entry("t", ids)
+    np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
+
+  # (1) optimize, unique ids per step, three slots with thresholds 2 (default), 4 and 0
+  gpu, cpu = both()
+  ids = np.concatenate([f(3, np.arange(200)), f(7, np.arange(200)), f(9, np.arange(50))])
+  for step in range(6):
+    sel = ids[rng.random(ids.size) < 0.7]
+    g = rng.standard_normal((sel.size, D)).astype(np.float32)
+    gpu.apply_gradients({"t": (T(sel, dev), T(g, dev))}, req_time=step, ids_unique=True)
+    cpu.apply_gradients({"t": (sel, g)}, req_time=step)
+    same(gpu, cpu, ids)
+  # (2) dedup path: the filter is handed each id's occurrence count
+  gpu, cpu = both()
+  for step in range(3):
+    sel = rng.choice(f(3, np.arange(60)), 400)
+    g = rng.standard_normal((sel.size, D)).astype(np.float32)
+    gpu.apply_gradients({"t": (T(sel, dev), T(g, dev))}, req_time=step, enable_dedup=True)
+    cpu.apply_gradients({"t": (sel, g)}, req_time=step, enable_dedup=True)
+    u = np.unique(sel)
+    assert gpu.size("t") == cpu.size("t")
+    np.testing.assert_allclose(gpu_lookup(gpu, {"t": u}, dev)["t"], cpu.lookup({"t": u})["t"], rtol=1e-5, atol=1e-6)
+  # (3) duplicates without dedup: occurrence q of an absent id sees count c0 + q (sequential semantics)
+  gpu, cpu = both()
+  for step in range(4):
+    sel = rng.choice(f(7, np.arange(30)), 100)
+    g = rng.standard_normal((sel.size, D)).astype(np.float32)
+    gpu.apply_gradients({"t": (T(sel, dev), T(g, dev))}, req_time=step)
+    cpu.apply_gradients({"t": (sel, g)}, req_time=step)
+    same(gpu, cpu, f(7, np.arange(30)))
+  # (4) assign: absent ids consult the filter; assign_add: every id does
+  gpu, cpu = both()
+  ids4 = f(3, np.arange(40))
+  for step in range(4):
+    v = rng.standard_normal((ids4.size, D)).astype(np.float32)
+    gpu.assign({"t": (T(ids4, dev), T(v, dev))}, req_time=step, ids_unique=True)
+    cpu.assign({"t": (ids4, v)}, req_time=step)
+    same(gpu, cpu, ids4)
+  gpu, cpu = both()
+  ids5 = f(7, np.arange(40))
+  for step in range(7):
+    v = rng.standard_normal((ids5.size, D)).astype(np.float32)
+    gpu.assign_add({"t": (T(ids5, dev), T(v, dev))}, req_time=step, ids_unique=True)
+    cpu.assign_add({"t": (ids5, v)}, req_time=step)
+    same(gpu, cpu, ids5)
+  # (5) fused backward: every distinct FID of the batch counts once per step
+  gpu, cpu = both()
+  vocab = np.concatenate([f(3, np.arange(300)), f(7, np.arange(100))])
+  for step in range(6):
+    fids = rng.choice(vocab, 2000)
+    pg = rng.standard_normal((fids.size, D)).astype(np.float32)
+    gpu.pool_backward("t", T(fids, dev), T(pg, dev), None, "sum", req_time=step)
+    u, inv = orc.dedup(fids)
+    ug = orc.gather_pool_grad(pg, inv * D, D, u.size * D).reshape(-1, D)
+    cpu.apply_gradients({"t": (u, ug)}, req_time=step)
+    same(gpu, cpu, vocab)
