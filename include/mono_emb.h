@@ -460,6 +460,30 @@ uint32_t mono_ckpt_masked_crc32c(const void* data, int64_t n);
 int64_t mono_ckpt_snappy_compress(const void* in, int64_t n, void* out, int64_t out_cap);
 int64_t mono_ckpt_snappy_uncompress(const void* in, int64_t n, void* out, int64_t out_cap);
 
+/* ---- device-driven sharded step (replaces the orchestration of NT/distributed_ps.py:1501-2001 and
+ *      NT/distributed_ps_sync.py:95-512 for ONE table on the GPUs of one NVSwitch box) ------------------------------
+ * A whole sparse train step sharded by fid mod N with nothing returning to the host: FID buckets, rows and summed
+ * gradient rows travel through fixed per-source regions of the ranks' peer windows, arrival is signalled by
+ * directional flags (no all-rank barrier, no host count exchange), every loop is sized by device-side counts
+ * (csrc/xstep.cu).  Same results as mono_grouping_* + mono_peer_* + mono_mtable_fused_optimize driven from the host.
+ *   mono_xstep_window_bytes  bytes the window of every rank must have for capacity `cap_pair` (max FID occurrences
+ *                            of one rank's batch) — create the windows with mono_peer_create and attach them first
+ *   mono_xstep_forward       group the batch, exchange, pool: out[r] = pool of the rows of fids (CSR row_offsets or
+ *                            one FID per row), as mono_mtable_lookup_pool on the global table
+ *   mono_xstep_backward      gradient of that forward: per-FID sums to the owners, owners upsert + optimize, the
+ *                            requesters applied in rank order (ref: multi_hash_table_update_op.cc:286-300)
+ * Every rank must call forward / backward the same number of times; a forward must be followed by its backward. */
+typedef struct mono_xstep mono_xstep_t;
+int64_t mono_xstep_window_bytes(int32_t world, int64_t cap_pair, int32_t dim);
+int mono_xstep_create(mono_mtable_t* t, int32_t k, mono_peer_t* window, int64_t cap_pair, mono_xstep_t** out);
+int mono_xstep_destroy(mono_xstep_t* x);
+int mono_xstep_forward(mono_xstep_t* x, const int64_t* fids_dev, int64_t n_fids, const int32_t* row_offsets_dev,
+                       int64_t n_rows, int32_t pooling, float* out_dev, int64_t out_stride, int32_t out_col,
+                       void* stream);
+int mono_xstep_backward(mono_xstep_t* x, const float* pooled_grad_dev, int64_t grad_stride, int32_t grad_col,
+                        const int32_t* row_offsets_dev, int32_t pooling, const float* lr_host, int64_t update_time,
+                        void* stream);
+
 /* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */
 int64_t mono_kernel_launch_count(void);
 

@@ -42,6 +42,11 @@ SIGNATURES = {
     "mono_last_error": (C.c_char_p, []),
     "mono_abi_version": (_i32, []),
     "mono_kernel_launch_count": (_i64, []),
+    "mono_xstep_window_bytes": (_i64, [_i32, _i64, _i32]),
+    "mono_xstep_create": (C.c_int, [_p, _i32, _p, _i64, C.POINTER(_p)]),
+    "mono_xstep_destroy": (C.c_int, [_p]),
+    "mono_xstep_forward": (C.c_int, [_p, _p, _i64, _p, _i64, _i32, _p, _i64, _i32, _p]),
+    "mono_xstep_backward": (C.c_int, [_p, _p, _i64, _i32, _p, _i32, _p, _i64, _p]),
     "mono_set_option": (C.c_int, [C.c_char_p, _i64]),
     "mono_get_option": (_i64, [C.c_char_p]),
     "mono_mtable_create": (C.c_int, [C.POINTER(TableCfg), _i32, _i32, C.POINTER(_p)]),

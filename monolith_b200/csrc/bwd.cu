@@ -499,10 +499,11 @@ __device__ __forceinline__ void bwd_apply(const BwdArgs& a, uint32_t j, uint32_t
 
 // destination of run j's summed row: ugrad[j], or (po.n != 0: the sharded backward's fused gradient
 // exchange) row j of an owner-bucketed list whose part r lives in rank r's peer window.
-__device__ __forceinline__ float* run_dst(float* ugrad, const PeerOut& po, int64_t j, int D) {
+__device__ __forceinline__ float* run_dst(float* ugrad, const PeerOut& po, const int64_t* __restrict__ s_start, int64_t j,
+                                          int D) {
   if (po.n == 0) return ugrad + (size_t)j * D;
-  const int r = peer_part(po, j);
-  return reinterpret_cast<float*>(po.base[r]) + (j - po.start[r]) * D;
+  const int r = peer_part(s_start, po.n, j);
+  return reinterpret_cast<float*>(po.base[r]) + (j - s_start[r]) * D;
 }
 
 
@@ -594,6 +595,8 @@ enum { MODE_STORE = 0, MODE_APPLY = 1 };
 template <int G, int MODE, int OPT>
 __global__ void __launch_bounds__(kThreads, MODE == MODE_APPLY ? 2 : 3)
 seg_reduce_kernel(SegArgs sa, const PeerOut po) {
+  __shared__ int64_t s_start[kMaxPeers + 1];
+  peer_starts(po, s_start);
   constexpr int EPL = 32 / G;          // elements of a piece per lane
   constexpr int RPI = 32 / G;          // pieces per warp iteration
   constexpr int UNR = 4;               // gradient rows in flight per group
@@ -718,7 +721,7 @@ seg_reduce_kernel(SegArgs sa, const PeerOut po) {
           if (MODE == MODE_APPLY) {
             if (rrow[u] != kEmptyRow) bwd_apply<G, OPT>(a, j, rrow[u], acc, c, pre[u]);
           } else {
-            if (in) *reinterpret_cast<float4*>(run_dst(a.ugrad, po, j, D) + c) = acc;
+            if (in) *reinterpret_cast<float4*>(run_dst(a.ugrad, po, s_start, j, D) + c) = acc;
           }
         }
       }
@@ -761,6 +764,8 @@ tree_level_kernel(float* __restrict__ part, const SegMeta* __restrict__ meta, in
 template <int G, int MODE, int OPT>
 __global__ void __launch_bounds__(kThreads)
 long_finish_kernel(SegArgs sa, uint32_t top, const PeerOut po) {
+  __shared__ int64_t s_start[kMaxPeers + 1];
+  peer_starts(po, s_start);
   const BwdArgs& a = sa.b;
   const int gl = Group<G>::gl(), c = gl * 4;
   const int D = a.td.dim;
@@ -789,7 +794,7 @@ long_finish_kernel(SegArgs sa, uint32_t top, const PeerOut po) {
       const RowPre pre = bwd_prefetch<G, OPT>(a, ri, c);
       bwd_apply<G, OPT>(a, j, ri, acc, c, pre);
     } else {
-      if (c < D) *reinterpret_cast<float4*>(run_dst(a.ugrad, po, j, D) + c) = acc;
+      if (c < D) *reinterpret_cast<float4*>(run_dst(a.ugrad, po, s_start, j, D) + c) = acc;
     }
   }
 }
@@ -1257,6 +1262,7 @@ void grouping_build(mono_grouping* g, const int64_t* fids_dev, int64_t M, int N,
   g->dim = dim;
   g->sorted = nullptr;
   if (M == 0) {
+    if (!shard_counts_host) throw ArgError("grouping: the device-driven step needs a non-empty batch");
     for (int n = 0; n < N; ++n) shard_counts_host[n] = 0;
     if (n_unique_host) *n_unique_host = 0;
     return;
@@ -1310,23 +1316,31 @@ void grouping_build(mono_grouping* g, const int64_t* fids_dev, int64_t M, int N,
     fid_claim_kernel<false><<<resident_grid(fid_claim_kernel<false>, M, kThreads), kThreads, 0, s>>>(
         fids_dev, M, set, R, N, epoch, sw.k0, owner_cnt, ClaimResolve{});
     MONO_CHECK_LAUNCH();
-    // counts -> host on the side stream, while the sort below keeps the GPU busy
-    MONO_CUDA(cudaEventRecord(g->ev_claimed, s));
-    MONO_CUDA(cudaStreamWaitEvent(g->side, g->ev_claimed, 0));
-    MONO_CUDA(cudaMemcpyAsync(g->h_counts, owner_cnt, 4 * 257, cudaMemcpyDeviceToHost, g->side));
-    MONO_CUDA(cudaEventRecord(g->ev_copied, g->side));
+    // counts -> host on the side stream, while the sort below keeps the GPU busy.  Device-driven callers
+    // (shard_counts_host == nullptr: xstep.cu) never read them on the host: nothing waits, the per-owner counts stay
+    // in owner_cnt and a region overflow is left in owner_cnt[256] for the caller to check later.
+    const bool host_counts = shard_counts_host != nullptr;
+    if (host_counts) {
+      MONO_CUDA(cudaEventRecord(g->ev_claimed, s));
+      MONO_CUDA(cudaStreamWaitEvent(g->side, g->ev_claimed, 0));
+      MONO_CUDA(cudaMemcpyAsync(g->h_counts, owner_cnt, 4 * 257, cudaMemcpyDeviceToHost, g->side));
+      MONO_CUDA(cudaEventRecord(g->ev_copied, g->side));
+    }
     const uint2* sorted = sort_and_runs(sw, M, bits, 0, s);
     group_emit_kernel<<<resident_grid(group_emit_kernel, M, kThreads), kThreads, 0, s>>>(
         fids_dev, sorted, sw.run_of_sorted, sw.run_first_pos, ctr, M, dim, occ_offset_out, uniq_out);
     MONO_CHECK_LAUNCH();
-    MONO_CUDA(cudaEventSynchronize(g->ev_copied));
-    if (g->h_counts[256] != 0) continue;  // region overflow: redo with full-size regions
-    int64_t total = 0;
-    for (int n = 0; n < N; ++n) {
-      shard_counts_host[n] = (int32_t)g->h_counts[n];
-      total += g->h_counts[n];
+    g->owner_cnt = owner_cnt;
+    if (host_counts) {
+      MONO_CUDA(cudaEventSynchronize(g->ev_copied));
+      if (g->h_counts[256] != 0) continue;  // region overflow: redo with full-size regions
+      int64_t total = 0;
+      for (int n = 0; n < N; ++n) {
+        shard_counts_host[n] = (int32_t)g->h_counts[n];
+        total += g->h_counts[n];
+      }
+      if (n_unique_host) *n_unique_host = total;
     }
-    if (n_unique_host) *n_unique_host = total;
     g->sorted = sorted;
     g->run_start = sw.run_start;
     g->run_first_pos = sw.run_first_pos;

@@ -630,6 +630,45 @@ int mono_grouping_reduce_push(mono_grouping_t* g, const float* pooled_grad_dev, 
   });
 }
 
+int64_t mono_xstep_window_bytes(int32_t world, int64_t cap_pair, int32_t dim) {
+  if (world < 1 || world > kMaxPeers || cap_pair <= 0 || dim <= 0) return -1;
+  return xstep_window_bytes(world, cap_pair, dim);
+}
+
+int mono_xstep_create(mono_mtable_t* t, int32_t k, mono_peer_t* window, int64_t cap_pair, mono_xstep_t** out) {
+  return guarded([&] {
+    require(t && window && out, "xstep_create: null argument");
+    require(k >= 0 && k < (int)t->tables.size(), "xstep_create: bad table index");
+    *out = xstep_create(t, k, window, cap_pair);
+  });
+}
+
+int mono_xstep_destroy(mono_xstep_t* x) {
+  return guarded([&] { xstep_destroy(x); });
+}
+
+int mono_xstep_forward(mono_xstep_t* x, const int64_t* fids_dev, int64_t n_fids, const int32_t* row_offsets_dev,
+                       int64_t n_rows, int32_t pooling, float* out_dev, int64_t out_stride, int32_t out_col,
+                       void* stream) {
+  return guarded([&] {
+    require(x && fids_dev && out_dev, "xstep_forward: null argument");
+    HandleGuard hg_(x->mt);
+    xstep_forward(x, fids_dev, n_fids, row_offsets_dev, n_rows, pooling, out_dev, out_stride, out_col,
+                  (cudaStream_t)stream);
+  });
+}
+
+int mono_xstep_backward(mono_xstep_t* x, const float* pooled_grad_dev, int64_t grad_stride, int32_t grad_col,
+                        const int32_t* row_offsets_dev, int32_t pooling, const float* lr_host, int64_t update_time,
+                        void* stream) {
+  return guarded([&] {
+    require(x && pooled_grad_dev && lr_host, "xstep_backward: null argument");
+    HandleGuard hg_(x->mt);
+    xstep_backward(x, pooled_grad_dev, grad_stride, grad_col, row_offsets_dev, pooling, lr_host, update_time,
+                   (cudaStream_t)stream);
+  });
+}
+
 int mono_gather_pool(int32_t device, const float* fused_emb_dev, const int32_t* emb_offset_dev,
                      const int32_t* row_offsets_dev, int64_t n_rows, int32_t dim, int32_t pooling,
                      float* out_dev, int64_t out_stride, int32_t out_col, void* stream) {

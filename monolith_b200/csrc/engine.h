@@ -197,6 +197,7 @@ struct mono_grouping {
   uint32_t* occ = nullptr;              // scratch of reduce(): occurrence -> pooled row
   float* part = nullptr;                // long-run block sums
   void* meta = nullptr;                 // SegMeta[2 * pieces]
+  uint32_t* owner_cnt = nullptr;        // device: distinct FIDs per owner [N], [256] = region-overflow flag
   uint32_t* h_counts = nullptr;  // pinned: per-owner distinct counts [256] + overflow flag
   cudaStream_t side = nullptr;   // carries the early counts copy while the sort runs on the caller's stream
   cudaEvent_t ev_claimed = nullptr, ev_copied = nullptr;
@@ -214,14 +215,30 @@ struct PeerOut {
   char* base[kMaxPeers];
   int64_t start[kMaxPeers + 1];
   int n;
+  const uint32_t* cnt_dev;  // optional: the part sizes live on the device (start[] is then ignored)
 };
-__device__ __forceinline__ int peer_part(const PeerOut& po, int64_t i) {
+#ifdef __CUDACC__
+// Part boundaries into shared memory (from the host-side start[] or as the prefix of the device counts); every
+// thread of the block must call it (it ends with a barrier).
+__device__ __forceinline__ void peer_starts(const PeerOut& po, int64_t* s_start /* shared [kMaxPeers + 1] */) {
+  if (po.n == 0) return;  // uniform: no peer output
+  if (threadIdx.x == 0) {
+    int64_t run = 0;
+    for (int r = 0; r <= kMaxPeers; ++r) {
+      s_start[r] = po.cnt_dev ? run : po.start[r];
+      if (po.cnt_dev && r < po.n) run += po.cnt_dev[r];
+    }
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ int peer_part(const int64_t* __restrict__ start, int n, int64_t i) {
   int r = 0;
 #pragma unroll
   for (int q = 1; q < kMaxPeers; ++q)
-    if (q < po.n && i >= po.start[q]) r = q;
+    if (q < n && i >= start[q]) r = q;
   return r;
 }
+#endif
 }  // namespace mono
 
 struct mono_peer {
@@ -231,7 +248,45 @@ struct mono_peer {
   char* base[mono::kMaxPeers] = {};      // base[r]: rank r's window as mapped into this process
   bool attached = false;
   uint64_t seq = 0;                      // barrier sequence number (same on every rank)
+  uint64_t phase_seq[4] = {0, 0, 0, 0};  // sequence numbers of the directional flags (peer_signal / peer_wait)
 };
+
+namespace mono {
+struct XWin {  // the exchange as the kernels see it (by value)
+  char* base[kMaxPeers];   // base[r]: rank r's window as mapped here (flag page first)
+  int N, me, D;
+  int64_t C;               // capacity of one (owner, source) sub-region, in items
+  int64_t off_ids[2], off_rows, off_grads;  // byte offsets of the regions behind the flag page
+  __device__ __forceinline__ uint64_t* flags(int r) const { return reinterpret_cast<uint64_t*>(base[r]); }
+  __device__ __forceinline__ int64_t* ids_in(int r, int par, int src) const {
+    return reinterpret_cast<int64_t*>(base[r] + kPeerFlagBytes + off_ids[par]) + (int64_t)src * C;
+  }
+  __device__ __forceinline__ float* rows_in(int r) const {
+    return reinterpret_cast<float*>(base[r] + kPeerFlagBytes + off_rows);
+  }
+  __device__ __forceinline__ float* grads_in(int r, int src) const {
+    return reinterpret_cast<float*>(base[r] + kPeerFlagBytes + off_grads) + (int64_t)src * C * D;
+  }
+};
+
+}  // namespace mono
+
+struct mono_xstep {
+  mono_mtable* mt = nullptr;
+  int k = 0;
+  mono_peer* win = nullptr;
+  mono_grouping* grouping = nullptr;  // owned
+  int64_t C = 0;
+  int N = 1, me = 0, D = 0;
+  mono::XWin w{};
+  uint64_t step = 0;               // steps started (forward calls)
+  uint64_t timeout_ns = 0;
+  mono::DevBuf uniq, offs, ws;     // bucketed unique list, per-occurrence row offsets, owner-side scratch
+  mono::ClaimSet miss_set;
+  int64_t last_m = 0, last_rows = 0;
+  bool fwd_done = false;
+};
+
 
 namespace mono {
 
@@ -258,6 +313,15 @@ void grouping_build(mono_grouping* g, const int64_t* fids_dev, int64_t M, int N,
                     int64_t* n_unique_host, cudaStream_t s);
 void grouping_reduce(mono_grouping* g, const float* pooled_grad, int64_t grad_stride, int grad_col,
                      const int32_t* row_offsets, int64_t n_rows, int pooling, float* out_rows, cudaStream_t s);
+
+// xstep.cu
+int64_t xstep_window_bytes(int N, int64_t C, int D);
+mono_xstep* xstep_create(mono_mtable* mt, int k, mono_peer* win, int64_t cap_pair);
+void xstep_destroy(mono_xstep* x);
+void xstep_forward(mono_xstep* x, const int64_t* fids_dev, int64_t M, const int32_t* row_offsets, int64_t n_rows,
+                   int pooling, float* out, int64_t out_stride, int out_col, cudaStream_t s);
+void xstep_backward(mono_xstep* x, const float* pooled_grad, int64_t grad_stride, int grad_col,
+                    const int32_t* row_offsets, int pooling, const float* lr_host, int64_t update_time, cudaStream_t s);
 
 // table.cu
 void table_init(mono_mtable* mt, HostTable& t, const mono_table_cfg& cfg, cudaStream_t s);

@@ -145,6 +145,8 @@ template <int G>
 __global__ void __launch_bounds__(kThreads, 6)
 lookup_push_kernel(const TableDev* __restrict__ t0, const int64_t* __restrict__ ids, int64_t n_total,
                    const PeerOut po) {
+  __shared__ int64_t s_start[kMaxPeers + 1];
+  peer_starts(po, s_start);
   constexpr int RPI = 32 / G;
   constexpr int ITERS = G;
   constexpr int UNR = 4;
@@ -175,8 +177,8 @@ lookup_push_kernel(const TableDev* __restrict__ t0, const int64_t* __restrict__ 
         const int64_t ir = wbase + src_lane;
         const uint32_t r_st = __shfl_sync(0xffffffffu, row, src_lane);
         if (ir >= n_total) continue;
-        const int pr = peer_part(po, ir);
-        float* dst = reinterpret_cast<float*>(po.base[pr]) + (ir - po.start[pr]) * D0;
+        const int pr = peer_part(s_start, po.n, ir);
+        float* dst = reinterpret_cast<float*>(po.base[pr]) + (ir - s_start[pr]) * D0;
         if (c < D0) *reinterpret_cast<float4*>(dst + c) = x[u];
         for (int cc = c + 4 * G; cc < D0; cc += 4 * G) {  // wide rows (dim > 128)
           float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -463,6 +465,10 @@ struct UpsertArgs {
   // has no Contains check, tf_bridge.cc:224-232)
   int filter_mode = 0;
   const uint32_t* occ_extra = nullptr;  // dedup path: occurrences of id position i beyond the first (count = 1 + occ_extra[i])
+  // apply pass of the device-driven sharded step: do not start before *wait_flag >= wait_seq (the requester's
+  // gradient rows have landed in this rank's window; acquire at system scope)
+  const uint64_t* wait_flag = nullptr;
+  uint64_t wait_seq = 0;
 };
 __device__ __forceinline__ uint32_t restore_ts(const UpsertArgs& a, const CallSeg& sg, const TableDev* t,
                                                int64_t i) {
@@ -564,6 +570,15 @@ __global__ void upsert_finalize_kernel(const TableDev* tables, const int32_t* ta
 // value rows: no hash logic left here).
 template <int G, int OP>
 __global__ void __launch_bounds__(kThreads) upsert_apply_kernel(UpsertArgs a) {
+  if (a.wait_flag) {
+    if (threadIdx.x == 0) {
+      uint64_t v;
+      do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.wait_flag) : "memory");
+      } while (v < a.wait_seq);
+    }
+    __syncthreads();
+  }
   const int gl = Group<G>::gl();
   const int64_t n = a.n_dev ? (int64_t)*a.n_dev : a.n;
   const int64_t gstride = (int64_t)gridDim.x * (kThreads / G);
@@ -1203,6 +1218,39 @@ void run_upsert_groups(mono_mtable* mt, const CallSeg* h_segs, int nsegs, const 
     t.max_update_ts = std::max<int64_t>(t.max_update_ts, update_time);
     request_snapshot(mt, (int)k, s);
   }
+}
+
+// Apply pass over one requester's segment of the owner-side window (device-driven sharded step): items are
+// positions pos0 .. pos0 + *n_dev of ids_base / grads_base (rows of dim floats), rows already resolved in rowidx.
+void launch_apply_window(mono_mtable* mt, int k, const CallBlob& cb, const int64_t* ids_base, const float* grads_base,
+                         int64_t pos0, const uint32_t* n_dev, int64_t n_upper, uint32_t* rowidx, uint32_t update_ts,
+                         const uint64_t* wait_flag, uint64_t wait_seq, cudaStream_t s) {
+  UpsertArgs a;
+  a.tables = mt->d_tables;
+  a.segs = cb.segs;
+  a.nsegs = 1;
+  a.ids = ids_base;
+  a.idx_list = nullptr;
+  a.n = n_upper;
+  a.n_dev = n_dev;
+  a.vals = grads_base;
+  a.lr = cb.lr;
+  a.update_ts = update_ts;
+  a.miss_ctr = nullptr;
+  a.miss_list = nullptr;
+  a.rowidx = rowidx + pos0;
+  a.status = nullptr;
+  a.pos0 = pos0;
+  a.wait_flag = wait_flag;
+  a.wait_seq = wait_seq;
+  const int G = pick_group(mt->tables[k].dim);
+  switch (G) {
+    case 4: upsert_apply_kernel<4, kOpOptimize><<<resident_grid(upsert_apply_kernel<4, kOpOptimize>, n_upper, kThreads / 4), kThreads, 0, s>>>(a); break;
+    case 8: upsert_apply_kernel<8, kOpOptimize><<<resident_grid(upsert_apply_kernel<8, kOpOptimize>, n_upper, kThreads / 8), kThreads, 0, s>>>(a); break;
+    case 16: upsert_apply_kernel<16, kOpOptimize><<<resident_grid(upsert_apply_kernel<16, kOpOptimize>, n_upper, kThreads / 16), kThreads, 0, s>>>(a); break;
+    default: upsert_apply_kernel<32, kOpOptimize><<<resident_grid(upsert_apply_kernel<32, kOpOptimize>, n_upper, kThreads / 32), kThreads, 0, s>>>(a); break;
+  }
+  MONO_CHECK_LAUNCH();
 }
 
 void launch_upsert_finalize(mono_mtable* mt, const CallBlob& cb, uint32_t* miss_ctr, uint32_t update_ts, cudaStream_t s) {

@@ -85,7 +85,7 @@ template <class V>
 __global__ void __launch_bounds__(kThreads) peer_put_kernel(PutArgs a) {
   const int64_t total = a.po.start[a.po.n];
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = peer_part(a.po, i);
+    const int r = peer_part(a.po.start, a.po.n, i);
     const int64_t q = i - a.po.start[r];
     const V v = __ldcs(reinterpret_cast<const V*>(a.src[r]) + q);
     reinterpret_cast<V*>(a.po.base[r])[q] = v;
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kThreads) peer_get_kernel(GetArgs a) {
       r[u] = 0;
       v[u] = make_uint4(0, 0, 0, 0);
       if (i < total) {
-        r[u] = peer_part(a.po, i);
+        r[u] = peer_part(a.po.start, a.po.n, i);
         v[u] = __ldcs(reinterpret_cast<const uint4*>(a.src[r[u]]) + (i - a.po.start[r[u]]));
       }
     }

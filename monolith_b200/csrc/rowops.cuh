@@ -325,6 +325,9 @@ struct CallBlob {  // device pointers into the staged per-call descriptor block
 };
 CallBlob stage_call(mono_mtable* mt, const CallSeg* h_segs, int nsegs, const float* lr_host, int n_lr, cudaStream_t s);
 int pick_group(int max_dim);
+void launch_apply_window(mono_mtable* mt, int k, const CallBlob& cb, const int64_t* ids_base, const float* grads_base,
+                         int64_t pos0, const uint32_t* n_dev, int64_t n_upper, uint32_t* rowidx, uint32_t update_ts,
+                         const uint64_t* wait_flag, uint64_t wait_seq, cudaStream_t s);
 // folds the call's per-table miss tickets into the allocator counters (upsert_finalize_kernel)
 void launch_upsert_finalize(mono_mtable* mt, const CallBlob& cb, uint32_t* miss_ctr, uint32_t update_ts, cudaStream_t s);
 

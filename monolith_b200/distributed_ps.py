@@ -322,8 +322,10 @@ class ShardedStep:
     self.K = len(table.table_names)
     self.phases = _Phases(os.environ.get("MONO_TIMING", "0") in ("1", "2"))
     self.exchange = exchange or os.environ.get("MONO_EXCHANGE", "peer")
-    if self.exchange not in ("peer", "nccl"):
-      raise ValueError("exchange must be 'peer' or 'nccl'")
+    if self.exchange not in ("peer", "nccl", "direct"):
+      raise ValueError("exchange must be 'direct', 'peer' or 'nccl'")
+    self.xstep = None        # exchange == "direct": the device-driven step (csrc/xstep.cu), two C calls per step
+    self.cap_pair = 0
     # bulk rows / gradients: "push" = the producing kernel stores them into the consumer's window (fused
     # lookup+send / reduce+send; default), "pull" = the producer writes its own window and the consumer
     # copies it over with remote loads (one more pass; measured slower on 2 GPUs at both 1/2 and 7/8 remote
@@ -333,6 +335,7 @@ class ShardedStep:
       raise ValueError("MONO_PEER_BULK must be 'pull' or 'push'")
     self.window = None
     self.hostx = HostCounts(world, rank, world + 1, group) if self.exchange == "peer" else None
+    self.direct_steps = 0
     self.cap_rows = self.cap_recv = self._base_m = 0
     self.peer_steps = self.nccl_steps = 0
 
@@ -418,6 +421,73 @@ class ShardedStep:
     self.peer_steps += 1
     return uniq.numel()
 
+  # ---- exchange == "direct": nothing returns to the host inside a step (csrc/xstep.cu) ----------------------
+  def _make_xstep(self, m: int):
+    """(Re)create the fixed-capacity window and the step object; collective: the capacity is the largest batch of
+    any rank (+ 25 % headroom), so every rank decides the same."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    self.close_direct()
+    cap = int(m)
+    if self.N > 1:
+      t = torch.tensor([cap], dtype=torch.int64, device=self.device)
+      dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+      cap = int(t.item())
+    cap = int(cap * 1.25) + 1024
+    nbytes = lib.mono_xstep_window_bytes(self.N, cap, self.dim)
+    if nbytes <= 0:
+      raise ValueError("xstep: bad window geometry")
+    self.window = self.dops.PeerWindow(self.device, self.N, self.rank, nbytes, self.group)
+    h = C.c_void_p()
+    _lib.check(lib.mono_xstep_create(self.table.handle, self.k, self.window._h, cap, C.byref(h)))
+    self.xstep, self.cap_pair = h, cap
+
+  def close_direct(self):
+    from . import _lib
+    if self.xstep is not None:
+      torch.cuda.synchronize(self.device)
+      _lib.check(_lib.load().mono_xstep_destroy(self.xstep))
+      self.xstep = None
+    if self.window is not None:
+      torch.cuda.synchronize(self.device)
+      self.window.close(self.group)
+      self.window = None
+
+  def _step_direct(self, fids, pooled_grad, out, req_time, row_offsets, pooling):
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    fids = fids.reshape(-1)
+    if fids.dtype != torch.int64 or not fids.is_contiguous():
+      fids = fids.to(torch.int64).contiguous()
+    m = fids.numel()
+    if self.xstep is None or m > self.cap_pair:
+      # NOTE collective: every rank must come here in the same step (constant batch sizes never do after step 1)
+      self._make_xstep(m)
+    pool = {"sum": _lib.POOL_SUM, "mean": _lib.POOL_MEAN}[pooling]
+    ro = None
+    n_rows = m
+    if row_offsets is not None:
+      row_offsets = row_offsets.to(device=self.device, dtype=torch.int32).contiguous()
+      ro, n_rows = C.c_void_p(row_offsets.data_ptr()), row_offsets.numel() - 1
+    stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+    _lib.check(lib.mono_xstep_forward(self.xstep, C.c_void_p(fids.data_ptr()), m, ro, n_rows, pool,
+                                      C.c_void_p(out.data_ptr()), out.stride(0) if out.dim() == 2 else self.dim, 0, stream))
+    if callable(pooled_grad):   # forward enqueued: the caller's dense tower / host round trip goes here
+      pooled_grad = pooled_grad()
+    if pooled_grad.dtype != torch.float32 or pooled_grad.stride(-1) != 1:
+      pooled_grad = pooled_grad.to(torch.float32).contiguous()
+    lr = self.table.configs[self.name].call_learning_rate_fns()
+    lr_arr = (C.c_float * len(lr))(*lr)
+    stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+    _lib.check(lib.mono_xstep_backward(self.xstep, C.c_void_p(pooled_grad.data_ptr()),
+                                       pooled_grad.stride(0) if pooled_grad.dim() == 2 else self.dim, 0, ro, pool, lr_arr,
+                                       int(req_time), stream))
+    self._keep = (fids, pooled_grad, row_offsets)   # alive until the kernels have consumed them
+    self.direct_steps += 1
+    return 0
+
   def _slot(self, per_shard):
     """per-(shard, table) sizes with only this table populated."""
     out = [0] * (self.N * self.K)
@@ -430,6 +500,8 @@ class ShardedStep:
     """One sparse train step.  `pooled_grad` is the gradient w.r.t. the pooled rows written to `out`, or a
     callable returning it: the callable runs once the forward has been enqueued (what produces the gradient —
     the dense tower, or a round trip of `out` to the host — belongs there)."""
+    if self.exchange == "direct":
+      return self._step_direct(fids, pooled_grad, out, req_time, row_offsets, pooling)
     if self.exchange == "peer":
       return self._step_peer(fids, pooled_grad, out, req_time, row_offsets, pooling)
     N, D, dev, ph = self.N, self.dim, fids.device, self.phases

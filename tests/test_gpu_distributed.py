@@ -148,6 +148,8 @@ def _fast_worker(rank, world, port, q, exchange="peer"):
     o = np.argsort(ks)
     q.put((rank, pooled_all, (ks[o], rows[o])))
     dist.barrier()
+    if exchange == "direct":
+      st.close_direct()
     dist.destroy_process_group()
   except Exception:
     import traceback
@@ -155,7 +157,7 @@ def _fast_worker(rank, world, port, q, exchange="peer"):
     raise
 
 
-@pytest.mark.parametrize("exchange", ["peer-pull", "peer-push", "nccl"])
+@pytest.mark.parametrize("exchange", ["direct", "peer-pull", "peer-push", "nccl"])
 def test_sharded_fast_step_two_gpus(exchange):
   """ShardedStep on 2 GPUs == one global oracle table; exchange over NVLink peer windows (bulk data pulled
   by the consumer, or pushed by the fused lookup+send / reduce+send kernels; flag barriers) and over NCCL."""
@@ -166,7 +168,7 @@ def test_sharded_fast_step_two_gpus(exchange):
   world = 2
   ctx = mp.get_context("spawn")
   q = ctx.Queue()
-  port = 29900 + (os.getpid() % 90) + {"peer-pull": 0, "peer-push": 3, "nccl": 7}[exchange]
+  port = 29900 + (os.getpid() % 90) + {"peer-pull": 0, "peer-push": 3, "nccl": 7, "direct": 11}[exchange]
   procs = [ctx.Process(target=_fast_worker, args=(r, world, port, q, exchange)) for r in range(world)]
   for p in procs:
     p.start()

@@ -1044,3 +1044,59 @@ def test_hash_filter_paths_vs_oracle(dev):
     ug = orc.gather_pool_grad(pg, inv * D, D, u.size * D).reshape(-1, D)
     cpu.apply_gradients({"t": (u, ug)}, req_time=step)
     same(gpu, cpu, vocab)
+
+
+# ------------------------------------------------------------------------------------------------
+# device-driven sharded step (csrc/xstep.cu) with world = 1: the whole flag / header / window protocol against itself
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["one_fid_per_row", "csr_mean"])
+def test_sharded_direct_step_world1_vs_oracle(mode, dev):
+  from monolith_b200 import MultiHashTable
+  from monolith_b200.distributed_ps import ShardedStep
+  D = 16
+  cfg = {"t": table([(D, "adagrad", {})], [0.1])}
+  gpu, cpu = pair(cfg, dev)
+  st = ShardedStep(gpu, "t", D, 1, 0, dev, exchange="direct")
+  rng = np.random.default_rng(31)
+  hot = fid(5, 3)
+  try:
+    for step in range(4):
+      n = 6000 + 500 * step                                        # growing batches: the window is re-created once
+      ids = rng.integers(0, 900 + 50 * step, n)
+      ids[rng.random(n) < 0.25] = 3                                # hot FID: a > 64-occurrence run (tree-reduced)
+      fids = (np.int64(5) << 48) | ids.astype(np.int64)
+      if mode == "csr_mean":
+        lens = rng.integers(0, 5, n)
+        ro = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+        ro = ro[ro <= n]
+        ro[-1] = n
+        R, pool = ro.size - 1, "mean"
+      else:
+        ro, R, pool = None, n, "sum"
+      g = rng.standard_normal((R, D)).astype(np.float32)
+      out = torch.empty(R, D, device=dev)
+      st.step(T(fids, dev), T(g, dev), out, 20 + step, None if ro is None else T(ro, dev), pool)
+      want = cpu.lookup_pool("t", fids, ro, pool)
+      got = out.cpu().numpy()
+      if ro is None:
+        cold = fids != hot
+        np.testing.assert_array_equal(got[cold].view(np.uint32), want[cold].view(np.uint32))
+        np.testing.assert_allclose(got[~cold], want[~cold], rtol=2e-3, atol=2e-3)
+      else:
+        np.testing.assert_allclose(got, want, rtol=2e-3, atol=2e-3)
+      u, inv = orc.dedup(fids)
+      ug = orc.gather_pool_grad(g, inv * D, D, u.size * D, ro, pool).reshape(-1, D)
+      cpu.apply_gradients({"t": (u, ug)}, req_time=20 + step)
+    keys = cpu.keys("t")
+    assert gpu.size("t") == keys.size
+    got = gpu.lookup_entry("t", T(keys, dev))["raw"].cpu().numpy()
+    want = cpu.lookup_entry("t", keys)
+    cold = keys != hot
+    if mode == "one_fid_per_row":
+      np.testing.assert_array_equal(got[cold].view(np.uint32), want[cold].view(np.uint32))
+    else:
+      np.testing.assert_allclose(got[cold][:, :-2], want[cold][:, :-2], rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(got[~cold][:, :-2], want[~cold][:, :-2], rtol=2e-3, atol=2e-3)
+    np.testing.assert_array_equal(got[:, -2:].view(np.uint32), want[:, -2:].view(np.uint32))
+  finally:
+    st.close_direct()
