@@ -64,8 +64,9 @@ def parse():
   ap.add_argument("--sharded", action="store_true", help="run the sharded step (ShardedStep) even at N=1 (profiling)")
   ap.add_argument("--remote-frac", type=float, default=None,
                   help="experiment: fraction of a rank's FID occurrences owned by other ranks (default: natural 1 - 1/N)")
-  ap.add_argument("--exchange", default=None, choices=["peer", "nccl"],
-                  help="exchange of the sharded step: NVLink peer windows (default) or NCCL all-to-all")
+  ap.add_argument("--exchange", default=None, choices=["direct", "peer", "nccl"],
+                  help="exchange of the sharded step: 'direct' = device-driven (fixed window regions, directional flags, no host "
+                       "round trip), 'peer' = host-driven NVLink peer windows with flag barriers, 'nccl' = NCCL all-to-all")
   return ap.parse_args()
 
 
