@@ -44,11 +44,15 @@ UNIT = "lookups/s"
 def parse():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"],
+                  help="c2 (default; BASELINE.json configs[1], the metric's config): MovieLens-shaped, 1 table dim 32, 2 slots, 10 M keys; "
+                       "c3: Criteo-shaped, 26 slots dim 16 in one table, 26 M keys, batch 65 536 per GPU; "
+                       "c5: table sweep dim 8..128 (lookup and lookup+Adagrad GB/s), single GPU")
   ap.add_argument("--steps", type=int, default=20)
   ap.add_argument("--warmup", type=int, default=5)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-  ap.add_argument("--batch", type=int, default=1 << 20, help="samples per GPU per step")
-  ap.add_argument("--keys", type=int, default=10_000_000, help="resident keys per GPU-shard set (total at N=1)")
+  ap.add_argument("--batch", type=int, default=None, help="samples per GPU per step (default: 1 048 576 for c2, 65 536 for c3)")
+  ap.add_argument("--keys", type=int, default=None, help="resident keys per GPU (default: 10 M for c2 / c5, 26 M for c3)")
   ap.add_argument("--cpu-batch", type=int, default=None,
                   help="samples per step of the CPU arm / cpu_baseline (default: --batch, so that both arms run the same config)")
   ap.add_argument("--cpu-threads", type=int, default=0,
@@ -67,7 +71,16 @@ def parse():
   ap.add_argument("--exchange", default=None, choices=["direct", "peer", "nccl"],
                   help="exchange of the sharded step: 'direct' = device-driven (fixed window regions, directional flags, no host "
                        "round trip), 'peer' = host-driven NVLink peer windows with flag barriers, 'nccl' = NCCL all-to-all")
-  return ap.parse_args()
+  args = ap.parse_args()
+  global DIM, SLOTS
+  if args.workload == "c3":
+    DIM, SLOTS = 16, 26
+    args.batch = args.batch or (1 << 16)
+    args.keys = args.keys or 26_000_000
+  else:
+    args.batch = args.batch or (1 << 20)
+    args.keys = args.keys or 10_000_000
+  return args
 
 
 # ---------------------------------------------------------------------------------------------
@@ -107,13 +120,15 @@ def make_batches(n_batches, batch, keys_per_slot, seed, zipf_s=ZIPF_S, remote=No
   return out
 
 
-def fwd_bytes(M, U, D=DIM):
+def fwd_bytes(M, U, D=None):
   """8*M (FIDs) + U*(32 (bucket sector) + 4D (row)) + 4*D*R (pooled rows), R == M here."""
+  D = DIM if D is None else D
   return 8 * M + U * (32 + 4 * D) + 4 * D * M
 
 
-def bwd_bytes(M, U, D=DIM):
+def bwd_bytes(M, U, D=None):
   """SURVEY.md §8(d) backward (scatter + Adagrad): 4*D*R + U*(32 + 16*D + 8)."""
+  D = DIM if D is None else D
   return 4 * D * M + U * (32 + 16 * D + 8)
 
 
@@ -272,9 +287,10 @@ def run_reference(args):
 
 
 def workload_config(args, batch):
+  head = ("C3 Criteo-shaped DeepFM sparse step: 26 slots dim 16 in one table, Adagrad, " if getattr(args, "workload", "c2") == "c3"
+          else "C2 MovieLens-shaped DSSM sparse step: 1 table dim 32 Adagrad, 10M resident keys, 2 slots/sample, ")
   return {
-      "workload": "C2 MovieLens-shaped DSSM sparse step: 1 table dim 32 Adagrad, 10M resident keys, 2 slots/sample, "
-                  "Zipf(1.05) FIDs; step = fused lookup+pool fwd + fused backward (group FIDs, deterministic per-FID grad "
+      "workload": head + "Zipf(1.05) FIDs; step = fused lookup+pool fwd + fused backward (group FIDs, deterministic per-FID grad "
                   "reduce, Adagrad upsert with expiry bump)" + (
                       "; sharded: group by owner, FID/row/grad exchange over NVLink peer windows (fused lookup+send, reduce+send)"
                       if (args.gpus > 1 or getattr(args, "sharded", False)) else ""),
@@ -748,8 +764,63 @@ def run_ours(args):
     dist.destroy_process_group()
 
 
+def run_c5(args):
+  """Hash-table sweep (BASELINE.json configs[4], single GPU): dim 8..128, `keys` resident keys, uniform and Zipf FIDs;
+  lookup-only and lookup + Adagrad update, as achieved algorithmic GB/s and fraction of the measured HBM peak."""
+  import torch
+  from monolith_b200 import MultiHashTable, _lib, entry
+  torch.cuda.set_device(0)
+  dev = torch.device("cuda", 0)
+  lib = _lib.load()
+  try:
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs") or 6650.0
+  except Exception:
+    peak = 6650.0
+  M = 1 << 21
+  rows = []
+  for dim in (8, 16, 32, 64, 128):
+    seg = entry.CombineAsSegment(dim, entry.RandomUniformInitializer(-0.05, 0.05), entry.AdagradOptimizer(LR, INIT_ACC))
+    table = MultiHashTable({"t": entry.HashTableConfigInstance(
+        entry.TableConfig([seg], initial_capacity=int(args.keys * 1.05), init_seed=1), [LR])}, device=dev)
+    for lo in range(0, args.keys, 1 << 22):
+      ids = torch.arange(lo, min(args.keys, lo + (1 << 22)), device=dev, dtype=torch.int64) | (1 << 48)
+      table.assign_add({"t": (ids, torch.zeros(ids.numel(), dim, device=dev))}, req_time=1, ids_unique=True)
+    out = torch.empty(M, dim, device=dev)
+    g = torch.randn(M, dim, device=dev)
+    for name, zipf in (("uniform", 0.0), ("zipf1.05", ZIPF_S)):
+      rng = np.random.default_rng(3)
+      z = Zipf(args.keys, zipf)
+      fl = [torch.from_numpy(((z.sample(rng, M) * 2654435761) % args.keys) | (1 << 48)).to(dev) for _ in range(2)]
+      U = float(np.mean([torch.unique(f).numel() for f in fl]))
+
+      def timeit(fn, n=10, w=3):
+        for i in range(w):
+          fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+          fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+      fms = timeit(lambda i: table.lookup_pool("t", fl[i & 1], None, "sum", out=out))
+      sms = timeit(lambda i: (table.lookup_pool("t", fl[i & 1], None, "sum", out=out),
+                              table.pool_backward("t", fl[i & 1], g, None, "sum", req_time=100 + i)))
+      fb, sb = fwd_bytes(M, U, dim), fwd_bytes(M, U, dim) + bwd_bytes(M, U, dim)
+      rows.append({"dim": dim, "fids": name, "U": U, "lookup_ms": fms, "lookup_GBps": fb / fms / 1e6, "lookup_frac": fb / fms / 1e6 / peak,
+                   "lookup_update_ms": sms, "lookup_update_GBps": sb / sms / 1e6, "lookup_update_frac": sb / sms / 1e6 / peak,
+                   "lookups_per_s": M / fms * 1e3, "updates_per_s": M / sms * 1e3})
+    table.close()
+  print(json.dumps({"metric": "table_sweep_GBps", "workload": "c5", "keys": args.keys, "fids_per_launch": M, "peak_GBps": peak,
+                    "rows": rows, "gpu_launches": int(lib.mono_kernel_launch_count())}), flush=True)
+
+
 def main():
   args = parse()
+  if args.workload == "c5" and args.impl != "reference":
+    return run_c5(args)
   if args.impl == "reference":
     run_reference(args)
   else:
