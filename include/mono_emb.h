@@ -50,7 +50,14 @@ typedef enum mono_opt_type {
   MONO_OPT_SGD = 0,     /* ref: RT/hash_table/optimizer/sgd_optimizer.cc:42-49      */
   MONO_OPT_ADAGRAD = 1, /* ref: optimizer/adagrad_optimizer.cc:54-60, avx_utils.h   */
   MONO_OPT_FTRL = 2,    /* ref: optimizer/ftrl_optimizer.cc:56-76                   */
-  MONO_OPT_ADAM = 3     /* ref: optimizer/adam_optimizer.cc:57-84                   */
+  MONO_OPT_ADAM = 3,    /* ref: optimizer/adam_optimizer.cc:57-84                   */
+  /* further optimizers of RT/hash_table/optimizer/optimizer.proto:210-227: served by the
+   * generic per-element apply path (any segment mix), not by the single-segment vector fast paths */
+  MONO_OPT_MOMENTUM = 4,  /* ref: optimizer/momentum_optimizer.cc:52-72              */
+  MONO_OPT_RMSPROP = 5,   /* ref: optimizer/rmsprop_optimizer.cc:49-68 (double arithmetic, CONFIG learning rate) */
+  MONO_OPT_RMSPROPV2 = 6, /* ref: optimizer/rmsprop_optimizer.cc:121-141             */
+  MONO_OPT_ADADELTA = 7,  /* ref: optimizer/adadelta_optimizer.cc:51-72              */
+  MONO_OPT_AMSGRAD = 8    /* ref: optimizer/amsgrad_optimizer.cc:58-88               */
 } mono_opt_type;
 
 typedef enum mono_init_type {
@@ -68,6 +75,11 @@ typedef enum mono_init_type {
  *   ADAGRAD  : [0] initial_accumulator_value, [1] weight_decay_factor
  *   FTRL     : [0] initial_accumulator_value, [1] beta, [2] l1, [3] l2
  *   ADAM     : [0] beta1, [1] beta2, [2] epsilon, [3] weight_decay_factor, [4] use_nesterov(0/1)
+ *   MOMENTUM : [0] momentum, [1] weight_decay_factor, [2] use_nesterov(0/1)            state: n[dim]
+ *   RMSPROP  : [0] momentum, [1] weight_decay_factor, [2] learning_rate of the CONFIG  state: n[dim]
+ *   RMSPROPV2: [0] momentum, [1] weight_decay_factor                                   state: n[dim]
+ *   ADADELTA : [0] averaging_ratio, [1] epsilon, [2] weight_decay_factor               state: accum[dim], accum_update[dim]
+ *   AMSGRAD  : as ADAM                                                                 state: m, v, vhat [dim each], beta powers
  */
 typedef struct mono_segment_cfg {
   int32_t dim;

@@ -1030,7 +1030,8 @@ void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t 
   sg.lr_off = 0;
   CallBlob cb = stage_call(mt, &sg, 1, lr_host, ht.slices, s);
   const int G = pick_group(D);
-  const int opt_sel = ht.segs.size() == 1 ? ht.segs[0].opt_type : -1;
+  // the register-resident apply exists for the four vectorised optimizers; anything else: store + generic apply_row
+  const int opt_sel = (ht.segs.size() == 1 && ht.segs[0].opt_type <= MONO_OPT_ADAM) ? ht.segs[0].opt_type : -1;
 
   // ---- scratch layout ----
   uint32_t cap = 1024;

@@ -287,6 +287,9 @@ int state_floats_of(const mono_segment_cfg& s) {
     case MONO_OPT_ADAGRAD: return s.dim;
     case MONO_OPT_FTRL: return 2 * s.dim;
     case MONO_OPT_ADAM: return 2 * s.dim + 2;
+    case MONO_OPT_MOMENTUM: case MONO_OPT_RMSPROP: case MONO_OPT_RMSPROPV2: return s.dim;
+    case MONO_OPT_ADADELTA: return 2 * s.dim;
+    case MONO_OPT_AMSGRAD: return 3 * s.dim + 2;
     default: return 0;
   }
 }
@@ -314,6 +317,31 @@ std::string encode_single_opt(const mono_segment_cfg& s, const float* st) {
       put_float(&body, 4, st[2 * D + 1]);
       put_tag_len(&msg, 7, body);
       break;
+    case MONO_OPT_MOMENTUM:  // MomentumOptimizerDump { n = 1 } = field 9 (optimizer.proto:232-252)
+      put_floats_unpacked(&body, 1, st, D);
+      put_tag_len(&msg, 9, body);
+      break;
+    case MONO_OPT_RMSPROP:   // RmspropOptimizerDump { n = 1 } = field 11
+      put_floats_unpacked(&body, 1, st, D);
+      put_tag_len(&msg, 11, body);
+      break;
+    case MONO_OPT_RMSPROPV2:  // RmspropV2OptimizerDump { n = 1 } = field 12
+      put_floats_unpacked(&body, 1, st, D);
+      put_tag_len(&msg, 12, body);
+      break;
+    case MONO_OPT_ADADELTA:  // AdadeltaOptimizerDump { accum = 1, accum_update = 2 } = field 6
+      put_floats_unpacked(&body, 1, st, D);
+      put_floats_unpacked(&body, 2, st + D, D);
+      put_tag_len(&msg, 6, body);
+      break;
+    case MONO_OPT_AMSGRAD:  // AmsgradOptimizerDump { m = 1, v = 2, vhat = 3, beta1_power = 4, beta2_power = 5 } = field 8
+      put_floats_unpacked(&body, 1, st, D);
+      put_floats_unpacked(&body, 2, st + D, D);
+      put_floats_unpacked(&body, 3, st + 2 * D, D);
+      put_float(&body, 4, st[3 * D]);
+      put_float(&body, 5, st[3 * D + 1]);
+      put_tag_len(&msg, 8, body);
+      break;
     default:  // SGD: empty message, still present (sgd_optimizer.cc:51-55)
       put_tag_len(&msg, 2, body);
       break;
@@ -328,7 +356,9 @@ bool decode_single_opt(const uint8_t* p, size_t n, const mono_segment_cfg& s, fl
     const uint64_t tag = r.varint();
     const uint32_t field = (uint32_t)(tag >> 3), wt = (uint32_t)(tag & 7);
     const bool mine = (field == 1 && s.opt_type == MONO_OPT_ADAGRAD) || (field == 3 && s.opt_type == MONO_OPT_FTRL) ||
-                      (field == 7 && s.opt_type == MONO_OPT_ADAM);
+                      (field == 7 && s.opt_type == MONO_OPT_ADAM) || (field == 9 && s.opt_type == MONO_OPT_MOMENTUM) ||
+                      (field == 11 && s.opt_type == MONO_OPT_RMSPROP) || (field == 12 && s.opt_type == MONO_OPT_RMSPROPV2) ||
+                      (field == 6 && s.opt_type == MONO_OPT_ADADELTA) || (field == 8 && s.opt_type == MONO_OPT_AMSGRAD);
     if (!mine || wt != 2) {
       r.skip(wt);
       continue;
@@ -337,11 +367,21 @@ bool decode_single_opt(const uint8_t* p, size_t n, const mono_segment_cfg& s, fl
     const uint8_t* d;
     if (!r.ok || !r.bytes(len, &d)) return false;
     Reader b{d, d + len};
-    int n1 = 0, n2 = 0;
+    int n1 = 0, n2 = 0, n3 = 0;
+    const bool one_vec = s.opt_type == MONO_OPT_MOMENTUM || s.opt_type == MONO_OPT_RMSPROP || s.opt_type == MONO_OPT_RMSPROPV2;
     while (b.ok && b.p < b.end) {
       const uint64_t t2 = b.varint();
       const uint32_t f2 = (uint32_t)(t2 >> 3), w2 = (uint32_t)(t2 & 7);
-      if (s.opt_type == MONO_OPT_ADAGRAD && f2 == 1) read_floats(b, w2, st, D, &n1);
+      if (one_vec && f2 == 1) read_floats(b, w2, st, D, &n1);
+      else if (s.opt_type == MONO_OPT_ADADELTA && f2 == 1) read_floats(b, w2, st, D, &n1);
+      else if (s.opt_type == MONO_OPT_ADADELTA && f2 == 2) read_floats(b, w2, st + D, D, &n2);
+      else if (s.opt_type == MONO_OPT_AMSGRAD && f2 == 1) read_floats(b, w2, st, D, &n1);
+      else if (s.opt_type == MONO_OPT_AMSGRAD && f2 == 2) read_floats(b, w2, st + D, D, &n2);
+      else if (s.opt_type == MONO_OPT_AMSGRAD && f2 == 3) read_floats(b, w2, st + 2 * D, D, &n3);
+      else if (s.opt_type == MONO_OPT_AMSGRAD && (f2 == 4 || f2 == 5) && w2 == 5) {
+        const uint8_t* q;
+        if (b.bytes(4, &q)) std::memcpy(st + 3 * D + (f2 - 4), q, 4);
+      } else if (s.opt_type == MONO_OPT_ADAGRAD && f2 == 1) read_floats(b, w2, st, D, &n1);
       else if (s.opt_type == MONO_OPT_FTRL && f2 == 1) read_floats(b, w2, st + D, D, &n1);
       else if (s.opt_type == MONO_OPT_FTRL && f2 == 2) read_floats(b, w2, st, D, &n2);
       else if (s.opt_type == MONO_OPT_ADAM && f2 == 1) read_floats(b, w2, st, D, &n1);

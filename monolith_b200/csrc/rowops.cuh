@@ -15,6 +15,9 @@ __device__ __forceinline__ int state_floats_dev(const SegDev& s) {
     case MONO_OPT_ADAGRAD: return s.dim;
     case MONO_OPT_FTRL: return 2 * s.dim;
     case MONO_OPT_ADAM: return 2 * s.dim + 2;
+    case MONO_OPT_MOMENTUM: case MONO_OPT_RMSPROP: case MONO_OPT_RMSPROPV2: return s.dim;
+    case MONO_OPT_ADADELTA: return 2 * s.dim;
+    case MONO_OPT_AMSGRAD: return 3 * s.dim + 2;
     default: return 0;
   }
 }
@@ -36,7 +39,8 @@ __device__ __forceinline__ float init_state_value(const SegDev& s, int lj) {
     case MONO_OPT_ADAGRAD: return s.p[0];
     case MONO_OPT_FTRL: return lj < s.dim ? s.p[0] : 0.0f;
     case MONO_OPT_ADAM: return lj < 2 * s.dim ? 0.0f : (lj == 2 * s.dim ? s.p[0] : s.p[1]);
-    default: return 0.0f;
+    case MONO_OPT_AMSGRAD: return lj < 3 * s.dim ? 0.0f : (lj == 3 * s.dim ? s.p[0] : s.p[1]);  // amsgrad_optimizer.cc:44-56
+    default: return 0.0f;  // momentum / rmsprop / adadelta start from zero state
   }
 }
 
@@ -105,6 +109,63 @@ __device__ __forceinline__ void opt_elem(const SegDev& s, bool avx_form, float l
   }
 }
 
+// One element of the further optimizers (generic path only).  sp = the segment's state block, lc = local column.
+// Every step is an explicit IEEE operation in the reference's order (rmsprop computes in double, like the reference).
+__device__ __forceinline__ void opt_elem_more(const SegDev& s, int lc, float lr, float g, float& w, float* __restrict__ sp,
+                                              bool init_all, float lr_amsgrad) {
+  const int D = s.dim;
+  if (s.opt_type == MONO_OPT_MOMENTUM) {  // momentum_optimizer.cc:52-72
+    const float mom = s.p[0], wd = s.p[1];
+    const float n0 = init_all ? 0.0f : sp[lc];
+    const float dx = __fmul_rn(lr, __fadd_rn(g, __fmul_rn(wd, w)));
+    const float n1 = __fsub_rn(__fmul_rn(mom, n0), dx);
+    if (s.p[2] != 0.0f) w = __fadd_rn(w, __fadd_rn(__fmul_rn(-mom, n0), __fmul_rn(__fadd_rn(1.0f, mom), n1)));
+    else w = __fadd_rn(w, n1);
+    sp[lc] = n1;
+  } else if (s.opt_type == MONO_OPT_RMSPROP || s.opt_type == MONO_OPT_RMSPROPV2) {  // rmsprop_optimizer.cc:49-68,121-141
+    const double mom = (double)s.p[0], wd = (double)s.p[1];
+    const float n0 = init_all ? 0.0f : sp[lc];
+    const double dx = __dadd_rn((double)g, __dmul_rn(wd, (double)w));
+    float n1;
+    double eta;
+    if (s.opt_type == MONO_OPT_RMSPROP) {
+      n1 = (float)__dadd_rn(__dmul_rn(mom, (double)n0), __dmul_rn(__dmul_rn(__dsub_rn(1.0, mom), dx), dx));
+      eta = __ddiv_rn((double)s.p[2], __dadd_rn((double)__fsqrt_rn(n1), 1.0));   // the CONFIG's learning rate
+    } else {
+      n1 = (float)__dadd_rn(__dmul_rn(mom, (double)n0), __dmul_rn(dx, dx));
+      eta = __ddiv_rn((double)lr, __dadd_rn((double)__fsqrt_rn(n1), 1.0));
+    }
+    w = (float)__dsub_rn((double)w, __dmul_rn(eta, dx));
+    sp[lc] = n1;
+  } else if (s.opt_type == MONO_OPT_ADADELTA) {  // adadelta_optimizer.cc:51-72
+    const float rho = s.p[0], eps = s.p[1], wd = s.p[2];
+    const float a0 = init_all ? 0.0f : sp[lc], u0 = init_all ? 0.0f : sp[D + lc];
+    const float cg = __fadd_rn(g, __fmul_rn(wd, w));
+    const float a1 = __fadd_rn(__fmul_rn(a0, rho), __fmul_rn(__fmul_rn(cg, cg), __fsub_rn(1.0f, rho)));
+    const float upd = __fmul_rn(__fdiv_rn(__fsqrt_rn(__fadd_rn(u0, eps)), __fsqrt_rn(__fadd_rn(a1, eps))), cg);
+    w = __fsub_rn(w, __fmul_rn(upd, lr));
+    sp[lc] = a1;
+    sp[D + lc] = __fadd_rn(__fmul_rn(u0, rho), __fmul_rn(__fmul_rn(upd, upd), __fsub_rn(1.0f, rho)));
+  } else if (s.opt_type == MONO_OPT_AMSGRAD) {  // amsgrad_optimizer.cc:58-88 (lr_amsgrad: bias-corrected, per row)
+    const float beta1 = s.p[0], beta2 = s.p[1], eps = s.p[2], wd = s.p[3];
+    const float m0 = init_all ? 0.0f : sp[lc], v0 = init_all ? 0.0f : sp[D + lc], h0 = init_all ? 0.0f : sp[2 * D + lc];
+    const float cg = __fadd_rn(g, __fmul_rn(wd, w));
+    const float m1 = __fadd_rn(m0, __fmul_rn(__fsub_rn(cg, m0), __fsub_rn(1.0f, beta1)));
+    const float v1 = __fadd_rn(v0, __fmul_rn(__fsub_rn(__fmul_rn(cg, cg), v0), __fsub_rn(1.0f, beta2)));
+    const float h1 = fmaxf(h0, v1);
+    const float den = __fadd_rn(__fsqrt_rn(h1), eps);
+    if (s.p[4] != 0.0f) {
+      const float t1 = __fadd_rn(__fmul_rn(cg, __fsub_rn(1.0f, beta1)), __fmul_rn(beta1, m1));
+      w = __fsub_rn(w, __fdiv_rn(__fmul_rn(t1, lr_amsgrad), den));
+    } else {
+      w = __fsub_rn(w, __fdiv_rn(__fmul_rn(m1, lr_amsgrad), den));
+    }
+    sp[lc] = m1;
+    sp[D + lc] = v1;
+    sp[2 * D + lc] = h1;
+  }
+}
+
 __device__ __forceinline__ float adam_lr(float lr0, float b1p, float b2p) {  // adam_optimizer.cc:63
   return __fdiv_rn(__fmul_rn(lr0, __fsqrt_rn(__fsub_rn(1.0f, b2p))), __fsub_rn(1.0f, b1p));
 }
@@ -138,7 +199,8 @@ __device__ __forceinline__ void apply_row(const TableDev* __restrict__ t, uint32
   if (OP == kOpOptimize) {
     // ---- fast path: one segment, dim % 4 == 0: 128-bit accesses on w, state and grad ----
     const SegDev& s0 = t->segs[0];
-    if (t->num_segs == 1 && (D & 3) == 0 && ((reinterpret_cast<uintptr_t>(vals) & 15) == 0)) {
+    if (t->num_segs == 1 && s0.opt_type <= MONO_OPT_ADAM && (D & 3) == 0 &&
+        ((reinterpret_cast<uintptr_t>(vals) & 15) == 0)) {
       const float lr0 = lr[0];
       float lrt = lr0;
       float b1p = 0.f, b2p = 0.f;
@@ -203,6 +265,14 @@ __device__ __forceinline__ void apply_row(const TableDev* __restrict__ t, uint32
     } else if (OP == kOpOptimize) {
       float a = 0.f, b = 0.f, lrt = lr[si];
       float* sp = s_row + s.state_off;
+      if (s.opt_type > MONO_OPT_ADAM) {
+        float lra = lrt;
+        if (s.opt_type == MONO_OPT_AMSGRAD)
+          lra = adam_lr(lrt, init_all ? s.p[0] : sp[3 * s.dim], init_all ? s.p[1] : sp[3 * s.dim + 1]);
+        opt_elem_more(s, lc, lrt, vals[c], w, sp, init_all, lra);
+        w_row[c] = w;
+        continue;
+      }
       if (s.opt_type == MONO_OPT_ADAGRAD) {
         a = init_all ? s.p[0] : sp[lc];
       } else if (s.opt_type == MONO_OPT_FTRL) {
@@ -231,12 +301,13 @@ __device__ __forceinline__ void apply_row(const TableDev* __restrict__ t, uint32
     if (gl == 0) {
       for (int si = 0; si < t->num_segs; ++si) {
         const SegDev& s = t->segs[si];
-        if (s.opt_type != MONO_OPT_ADAM) continue;
+        if (s.opt_type != MONO_OPT_ADAM && s.opt_type != MONO_OPT_AMSGRAD) continue;
         float* sp = s_row + s.state_off;
-        float b1p = init_all ? s.p[0] : sp[2 * s.dim];
-        float b2p = init_all ? s.p[1] : sp[2 * s.dim + 1];
-        sp[2 * s.dim] = __fmul_rn(b1p, s.p[0]);
-        sp[2 * s.dim + 1] = __fmul_rn(b2p, s.p[1]);
+        const int po = (s.opt_type == MONO_OPT_ADAM ? 2 : 3) * s.dim;  // where the beta powers live
+        float b1p = init_all ? s.p[0] : sp[po];
+        float b2p = init_all ? s.p[1] : sp[po + 1];
+        sp[po] = __fmul_rn(b1p, s.p[0]);
+        sp[po + 1] = __fmul_rn(b2p, s.p[1]);
       }
     }
   } else if (init_all) {

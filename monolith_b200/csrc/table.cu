@@ -119,6 +119,9 @@ static int state_floats(const mono_segment_cfg& s) {
     case MONO_OPT_ADAGRAD: return s.dim;
     case MONO_OPT_FTRL: return 2 * s.dim;
     case MONO_OPT_ADAM: return 2 * s.dim + 2;
+    case MONO_OPT_MOMENTUM: case MONO_OPT_RMSPROP: case MONO_OPT_RMSPROPV2: return s.dim;
+    case MONO_OPT_ADADELTA: return 2 * s.dim;
+    case MONO_OPT_AMSGRAD: return 3 * s.dim + 2;
   }
   throw ArgError("unknown optimizer type");
 }

@@ -83,7 +83,77 @@ class AdamOptimizer(Optimizer):
             1.0 if self.use_nesterov else 0.0, 0.0]
 
 
-_DEFAULT_LR = {_lib.OPT_SGD: 0.01, _lib.OPT_ADAGRAD: 0.001, _lib.OPT_FTRL: 0.01, _lib.OPT_ADAM: 0.01}
+@dataclasses.dataclass
+class MomentumOptimizer(Optimizer):
+  """ref: NT/entry.py:227-245 / MomentumOptimizerConfig (optimizer.proto)."""
+  learning_rate: Optional[float] = None  # 0.01
+  weight_decay_factor: float = 0.0
+  use_nesterov: bool = False
+  momentum: float = 0.9
+  warmup_steps: int = 0
+  opt_type = _lib.OPT_MOMENTUM
+
+  def params(self):
+    return [self.momentum, self.weight_decay_factor, 1.0 if self.use_nesterov else 0.0, 0.0, 0.0, 0.0]
+
+
+@dataclasses.dataclass
+class RmspropOptimizer(Optimizer):
+  """ref: NT/entry.py:259-271.  NOTE the reference kernel reads the CONFIG's learning rate, not the per-call one
+  (rmsprop_optimizer.cc:62)."""
+  learning_rate: Optional[float] = None  # 0.01
+  weight_decay_factor: float = 0.0
+  momentum: float = 0.9
+  opt_type = _lib.OPT_RMSPROP
+
+  def params(self):
+    return [self.momentum, self.weight_decay_factor, 0.01 if self.learning_rate is None else self.learning_rate, 0.0, 0.0, 0.0]
+
+
+@dataclasses.dataclass
+class RmspropV2Optimizer(Optimizer):
+  """ref: NT/entry.py:273-285."""
+  learning_rate: Optional[float] = None  # 0.01
+  weight_decay_factor: float = 0.0
+  momentum: float = 0.9
+  opt_type = _lib.OPT_RMSPROPV2
+
+  def params(self):
+    return [self.momentum, self.weight_decay_factor, 0.0, 0.0, 0.0, 0.0]
+
+
+@dataclasses.dataclass
+class AdadeltaOptimizer(Optimizer):
+  """ref: NT/entry.py:115-134."""
+  learning_rate: Optional[float] = None  # 0.01
+  weight_decay_factor: float = 0.0
+  averaging_ratio: float = 0.9
+  epsilon: float = 0.01
+  warmup_steps: int = 0
+  opt_type = _lib.OPT_ADADELTA
+
+  def params(self):
+    return [self.averaging_ratio, self.epsilon, self.weight_decay_factor, 0.0, 0.0, 0.0]
+
+
+@dataclasses.dataclass
+class AmsgradOptimizer(Optimizer):
+  """ref: NT/entry.py:182-205."""
+  learning_rate: Optional[float] = None  # 0.01
+  beta1: float = 0.9
+  beta2: float = 0.99
+  weight_decay_factor: float = 0.0
+  use_nesterov: bool = False
+  epsilon: float = 0.01
+  warmup_steps: int = 0
+  opt_type = _lib.OPT_AMSGRAD
+
+  def params(self):
+    return [self.beta1, self.beta2, self.epsilon, self.weight_decay_factor, 1.0 if self.use_nesterov else 0.0, 0.0]
+
+
+_DEFAULT_LR = {_lib.OPT_SGD: 0.01, _lib.OPT_ADAGRAD: 0.001, _lib.OPT_FTRL: 0.01, _lib.OPT_ADAM: 0.01, _lib.OPT_MOMENTUM: 0.01,
+               _lib.OPT_RMSPROP: 0.01, _lib.OPT_RMSPROPV2: 0.01, _lib.OPT_ADADELTA: 0.01, _lib.OPT_AMSGRAD: 0.01}
 
 
 class Initializer:

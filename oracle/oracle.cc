@@ -116,8 +116,82 @@ int StateFloats(const mono_segment_cfg& s) {
     case MONO_OPT_ADAGRAD: return s.dim;         // adagrad_optimizer.cc:31-33
     case MONO_OPT_FTRL: return 2 * s.dim;        // ftrl_optimizer.cc:31-33
     case MONO_OPT_ADAM: return 2 * s.dim + 2;    // adam_optimizer.cc:30-32
+    case MONO_OPT_MOMENTUM: case MONO_OPT_RMSPROP: case MONO_OPT_RMSPROPV2: return s.dim;  // momentum_optimizer.cc:29, rmsprop_optimizer.cc:29,99
+    case MONO_OPT_ADADELTA: return 2 * s.dim;    // adadelta_optimizer.cc:29-31
+    case MONO_OPT_AMSGRAD: return 3 * s.dim + 2; // amsgrad_optimizer.cc:30-32
   }
   return 0;
+}
+
+// ref: RT/hash_table/optimizer/momentum_optimizer.cc:52-72
+void MomentumOptimize(float* num, float* n, const float* grad, int dim, float lr, float momentum, float wd, bool nesterov) {
+  for (int i = 0; i < dim; ++i) {
+    float dx = lr * (grad[i] + wd * num[i]);
+    float new_n = n[i];
+    float new_w = num[i];
+    if (nesterov) {
+      float prev_n = new_n;
+      new_n = momentum * new_n - dx;
+      new_w += -momentum * prev_n + (1 + momentum) * new_n;
+    } else {
+      new_n = momentum * new_n - dx;
+      new_w += new_n;
+    }
+    n[i] = new_n;
+    num[i] = new_w;
+  }
+}
+
+// ref: RT/hash_table/optimizer/rmsprop_optimizer.cc:49-68 (v1: the CONFIG's learning rate, (1 - momentum) dx^2) and
+// :121-141 (v2: learning_rates[0], dx^2); both compute in double and store floats.
+void RmspropOptimize(float* num, float* n, const float* grad, int dim, float lr, float momentum, float wd, bool v2) {
+  for (int i = 0; i < dim; ++i) {
+    float new_n = n[i];
+    float new_w = num[i];
+    double dx = grad[i] + static_cast<double>(wd) * new_w;
+    if (v2) new_n = static_cast<double>(momentum) * new_n + dx * dx;
+    else new_n = static_cast<double>(momentum) * new_n + (1 - static_cast<double>(momentum)) * dx * dx;
+    double eta = static_cast<double>(lr) / (std::sqrt(new_n) + 1);
+    new_w -= eta * dx;
+    n[i] = new_n;
+    num[i] = new_w;
+  }
+}
+
+// ref: RT/hash_table/optimizer/adadelta_optimizer.cc:51-72
+void AdadeltaOptimize(float* num, float* accum, float* accum_update, const float* grad, int dim, float lr, float rho,
+                      float eps, float wd) {
+  for (int i = 0; i < dim; ++i) {
+    float cur_grad = grad[i] + wd * num[i];
+    float new_accum = accum[i] * rho + cur_grad * cur_grad * (1 - rho);
+    float update = std::sqrt(accum_update[i] + eps) / std::sqrt(new_accum + eps) * cur_grad;
+    float new_w = num[i] - update * lr;
+    float new_accum_update = accum_update[i] * rho + update * update * (1 - rho);
+    num[i] = new_w;
+    accum[i] = new_accum;
+    accum_update[i] = new_accum_update;
+  }
+}
+
+// ref: RT/hash_table/optimizer/amsgrad_optimizer.cc:58-88
+void AmsgradOptimize(float* num, float* m, float* v, float* vhat, float* b1p, float* b2p, const float* grad, int dim,
+                     float lr0, float beta1, float beta2, float eps, float wd, bool nesterov) {
+  float lr = lr0 * std::sqrt(1.0f - *b2p) / (1.0f - *b1p);
+  for (int i = 0; i < dim; ++i) {
+    float cur_grad = grad[i] + wd * num[i];
+    float new_m = m[i] + (cur_grad - m[i]) * (1.0f - beta1);
+    float new_v = v[i] + (cur_grad * cur_grad - v[i]) * (1.0f - beta2);
+    float new_vhat = std::max(vhat[i], new_v);
+    float new_w = num[i];
+    if (nesterov) new_w -= ((cur_grad * (1.0f - beta1) + beta1 * new_m) * lr) / (std::sqrt(new_vhat) + eps);
+    else new_w -= (new_m * lr) / (std::sqrt(new_vhat) + eps);
+    num[i] = new_w;
+    m[i] = new_m;
+    v[i] = new_v;
+    vhat[i] = new_vhat;
+  }
+  *b1p *= beta1;
+  *b2p *= beta2;
 }
 
 // splitmix64: used only for the counter-based uniform initializer, which is an engine-defined
@@ -234,6 +308,17 @@ struct Table {
           st[2 * s.dim] = s.opt_p[0];
           st[2 * s.dim + 1] = s.opt_p[1];
           break;
+        case MONO_OPT_AMSGRAD:  // amsgrad_optimizer.cc:44-56
+          for (int i = 0; i < 3 * s.dim; ++i) st[i] = 0.f;
+          st[3 * s.dim] = s.opt_p[0];
+          st[3 * s.dim + 1] = s.opt_p[1];
+          break;
+        case MONO_OPT_MOMENTUM: case MONO_OPT_RMSPROP: case MONO_OPT_RMSPROPV2:
+          for (int i = 0; i < s.dim; ++i) st[i] = 0.f;
+          break;
+        case MONO_OPT_ADADELTA:
+          for (int i = 0; i < 2 * s.dim; ++i) st[i] = 0.f;
+          break;
         default: break;
       }
       st += StateFloats(s);
@@ -261,6 +346,22 @@ struct Table {
           AdamOptimize(num + col, st, st + s.dim, st + 2 * s.dim, st + 2 * s.dim + 1, grad + col,
                        s.dim, lr[sl], s.opt_p[0], s.opt_p[1], s.opt_p[2], s.opt_p[3],
                        s.opt_p[4] != 0.f);
+          break;
+        case MONO_OPT_MOMENTUM:
+          MomentumOptimize(num + col, st, grad + col, s.dim, lr[sl], s.opt_p[0], s.opt_p[1], s.opt_p[2] != 0.f);
+          break;
+        case MONO_OPT_RMSPROP:  // the config's learning rate, not the call's (rmsprop_optimizer.cc:62)
+          RmspropOptimize(num + col, st, grad + col, s.dim, s.opt_p[2], s.opt_p[0], s.opt_p[1], false);
+          break;
+        case MONO_OPT_RMSPROPV2:
+          RmspropOptimize(num + col, st, grad + col, s.dim, lr[sl], s.opt_p[0], s.opt_p[1], true);
+          break;
+        case MONO_OPT_ADADELTA:
+          AdadeltaOptimize(num + col, st, st + s.dim, grad + col, s.dim, lr[sl], s.opt_p[0], s.opt_p[1], s.opt_p[2]);
+          break;
+        case MONO_OPT_AMSGRAD:
+          AmsgradOptimize(num + col, st, st + s.dim, st + 2 * s.dim, st + 3 * s.dim, st + 3 * s.dim + 1, grad + col, s.dim,
+                          lr[sl], s.opt_p[0], s.opt_p[1], s.opt_p[2], s.opt_p[3], s.opt_p[4] != 0.f);
           break;
       }
       st += StateFloats(s);

@@ -52,6 +52,31 @@ KNOWN = {
         # sgd_optimizer_test.cc:32-41
         {"name": "sgd_basic", "opt": "sgd", "dim": 1, "params": {},
          "steps": [{"grad": [1.0], "lr": [0.1], "expect": [-0.1]}], "tol": 1e-6},
+        # momentum_optimizer_test.cc:32-49,51-72 (proto defaults: momentum .9, no nesterov, wd 0)
+        {"name": "momentum_basic", "opt": "momentum", "dim": 1, "params": {},
+         "steps": [{"grad": [10.0], "lr": [0.01], "expect": [-0.1]},
+                   {"grad": [10.0], "lr": [0.01], "expect": [-0.29]}], "tol": 1e-6},
+        {"name": "momentum_list", "opt": "momentum", "dim": 2, "params": {},
+         "steps": [{"grad": [10.0, 1.0], "lr": [0.01], "expect": [-0.1, -0.01]},
+                   {"grad": [10.0, 1.0], "lr": [0.01], "expect": [-0.29, -0.029]}], "tol": 1e-6},
+        # rmsprop_optimizer_test.cc:32-49 (v1: the CONFIG's learning rate .01, momentum .9) and :51-72 (v2)
+        {"name": "rmsprop_basic", "opt": "rmsprop", "dim": 1, "params": {"learning_rate": 0.01},
+         "steps": [{"grad": [10.0], "lr": [0.01], "expect": [-0.024025]},
+                   {"grad": [10.0], "lr": [0.01], "expect": [-0.042686]}], "tol": 1e-6},
+        {"name": "rmspropv2_list", "opt": "rmspropv2", "dim": 2, "params": {},
+         "steps": [{"grad": [10.0, 1.0], "lr": [0.01], "expect": [-0.0090909, -0.005]},
+                   {"grad": [10.0, 1.0], "lr": [0.01], "expect": [-0.0158549, -0.0092045]}], "tol": 1e-6},
+        # adadelta_optimizer_test.cc:32-51 (proto defaults: averaging_ratio .9, epsilon .01)
+        {"name": "adadelta_basic", "opt": "adadelta", "dim": 1, "params": {},
+         "steps": [{"grad": [10.0], "lr": [0.01], "expect": [-0.0031607]},
+                   {"grad": [10.0], "lr": [0.01], "expect": [-0.0064035]}], "tol": 1e-6},
+        # amsgrad_optimizer_test.cc:32-51,53-73 (proto defaults as Adam)
+        {"name": "amsgrad_basic", "opt": "amsgrad", "dim": 1, "params": {},
+         "steps": [{"grad": [10.0], "lr": [0.01], "expect": [-0.00990099]},
+                   {"grad": [10.0], "lr": [0.01], "expect": [-0.01983060]}], "tol": 1e-6},
+        {"name": "amsgrad_list", "opt": "amsgrad", "dim": 2, "params": {},
+         "steps": [{"grad": [10.0, 1.0], "lr": [0.01], "expect": [-0.00990099, -0.00909091]},
+                   {"grad": [10.0, 1.0], "lr": [0.01], "expect": [-0.01983060, -0.01842895]}], "tol": 1e-6},
     ],
     # optimizer_combination_test.cc:30-60: adagrad(dim 1, acc 1) | adagrad(dim 2, acc 2), lrs {1, 2}
     "combination": {

@@ -18,6 +18,22 @@ def opt_from(name, params=None, lr=None):
                                epsilon=params.get("epsilon", 0.01),
                                weight_decay_factor=params.get("weight_decay_factor", 0.0),
                                use_nesterov=params.get("use_nesterov", False))
+  if name == "momentum":
+    return entry.MomentumOptimizer(learning_rate=lr, weight_decay_factor=params.get("weight_decay_factor", 0.0),
+                                   use_nesterov=params.get("use_nesterov", False), momentum=params.get("momentum", 0.9))
+  if name == "rmsprop":
+    return entry.RmspropOptimizer(learning_rate=params.get("learning_rate", lr), weight_decay_factor=params.get("weight_decay_factor", 0.0),
+                                  momentum=params.get("momentum", 0.9))
+  if name == "rmspropv2":
+    return entry.RmspropV2Optimizer(learning_rate=lr, weight_decay_factor=params.get("weight_decay_factor", 0.0),
+                                    momentum=params.get("momentum", 0.9))
+  if name == "adadelta":
+    return entry.AdadeltaOptimizer(learning_rate=lr, weight_decay_factor=params.get("weight_decay_factor", 0.0),
+                                   averaging_ratio=params.get("averaging_ratio", 0.9), epsilon=params.get("epsilon", 0.01))
+  if name == "amsgrad":
+    return entry.AmsgradOptimizer(learning_rate=lr, beta1=params.get("beta1", 0.9), beta2=params.get("beta2", 0.99),
+                                  epsilon=params.get("epsilon", 0.01), weight_decay_factor=params.get("weight_decay_factor", 0.0),
+                                  use_nesterov=params.get("use_nesterov", False))
   raise ValueError(name)
 
 
