@@ -450,3 +450,77 @@ def test_snappy_and_entry_codec_fuzz():
     L.mono_ckpt_snappy_uncompress(blob, len(blob), back, len(back))                                                 # any status
 
   decoder_never_crashes_on_garbage()
+
+
+def test_further_optimizer_dumps_wire_bytes_match_protobuf():
+  """Momentum / RMSprop / RMSpropV2 / Adadelta / AMSGrad state in EntryDump: byte for byte what the protobuf runtime
+  serializes for the reference's messages (optimizer.proto: MomentumOptimizerDump = SingleOptimizerDump field 9 {n},
+  Rmsprop = 11 {n}, RmspropV2 = 12 {n}, Adadelta = 6 {accum, accum_update}, Amsgrad = 8 {m, v, vhat, beta powers})."""
+  pytest.importorskip("google.protobuf")
+  from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+  F = descriptor_pb2.FieldDescriptorProto
+  fd = descriptor_pb2.FileDescriptorProto(name="mono_ckpt_more.proto", package="u", syntax="proto2")
+  OPT, REP = F.LABEL_OPTIONAL, F.LABEL_REPEATED
+
+  def msg(name, fields):
+    m = fd.message_type.add(name=name)
+    for fname, num, typ, label, tname in fields:
+      f = m.field.add(name=fname, number=num, type=typ, label=label)
+      if tname:
+        f.type_name = ".u." + tname
+
+  fl = lambda n, i, lab=REP: (n, i, F.TYPE_FLOAT, lab, None)
+  msg("MomentumOptimizerDump", [fl("n", 1)])
+  msg("RmspropOptimizerDump", [fl("n", 1)])
+  msg("RmspropV2OptimizerDump", [fl("n", 1)])
+  msg("AdadeltaOptimizerDump", [fl("accum", 1), fl("accum_update", 2)])
+  msg("AmsgradOptimizerDump", [fl("m", 1), fl("v", 2), fl("vhat", 3), fl("beta1_power", 4, OPT), fl("beta2_power", 5, OPT)])
+  msg("SingleOptimizerDump", [("adadelta", 6, F.TYPE_MESSAGE, OPT, "AdadeltaOptimizerDump"),
+                              ("amsgrad", 8, F.TYPE_MESSAGE, OPT, "AmsgradOptimizerDump"),
+                              ("momentum", 9, F.TYPE_MESSAGE, OPT, "MomentumOptimizerDump"),
+                              ("rmsprop", 11, F.TYPE_MESSAGE, OPT, "RmspropOptimizerDump"),
+                              ("rmspropv2", 12, F.TYPE_MESSAGE, OPT, "RmspropV2OptimizerDump")])
+  msg("OptimizerDump", [("dump", 1, F.TYPE_MESSAGE, REP, "SingleOptimizerDump")])
+  msg("EntryDump", [("id", 1, F.TYPE_SFIXED64, OPT, None), ("num", 2, F.TYPE_FLOAT, REP, None),
+                    ("opt", 3, F.TYPE_MESSAGE, OPT, "OptimizerDump"), ("last_update_ts_sec", 4, F.TYPE_INT64, OPT, None)])
+  pool = descriptor_pool.DescriptorPool()
+  pool.Add(fd)
+  Entry = message_factory.GetMessageClass(pool.FindMessageTypeByName("u.EntryDump"))
+  MOM, RMS, RMS2, ADD, AMS = _lib.OPT_MOMENTUM, _lib.OPT_RMSPROP, _lib.OPT_RMSPROPV2, _lib.OPT_ADADELTA, _lib.OPT_AMSGRAD
+  spec = [(2, MOM), (3, RMS), (1, RMS2), (2, ADD), (3, AMS)]
+  nstate = {MOM: 1, RMS: 1, RMS2: 1, ADD: 2}
+  dim = sum(d for d, _ in spec)
+  st_n = sum(3 * d + 2 if o == AMS else nstate[o] * d for d, o in spec)
+  rng = np.random.default_rng(8)
+  row = rng.standard_normal(dim + st_n + 2).astype(np.float32)
+  fid, ts = (9 << 48) | 12345, 1700000123
+  row[dim + st_n:] = np.array([1, ts], np.uint32).view(np.float32)
+  L, segs = lib(), segs_of(spec)
+  buf = C.create_string_buffer(4096)
+  n = L.mono_ckpt_encode_entry(segs, len(spec), fid, row.ctypes.data_as(C.c_void_p), buf, len(buf))
+  assert n > 0
+  m = Entry()
+  m.id = fid
+  m.num.extend(row[:dim].tolist())
+  st = row[dim:]
+  for d, o in spec:
+    s = m.opt.dump.add()
+    if o == MOM:
+      s.momentum.n.extend(st[:d].tolist()); st = st[d:]
+    elif o == RMS:
+      s.rmsprop.n.extend(st[:d].tolist()); st = st[d:]
+    elif o == RMS2:
+      s.rmspropv2.n.extend(st[:d].tolist()); st = st[d:]
+    elif o == ADD:
+      s.adadelta.accum.extend(st[:d].tolist()); s.adadelta.accum_update.extend(st[d:2 * d].tolist()); st = st[2 * d:]
+    else:
+      s.amsgrad.m.extend(st[:d].tolist()); s.amsgrad.v.extend(st[d:2 * d].tolist()); s.amsgrad.vhat.extend(st[2 * d:3 * d].tolist())
+      s.amsgrad.beta1_power, s.amsgrad.beta2_power = float(st[3 * d]), float(st[3 * d + 1]); st = st[3 * d + 2:]
+  m.last_update_ts_sec = ts
+  wire = m.SerializeToString()
+  assert buf.raw[:n] == wire
+  out = np.zeros_like(row)
+  fid_out = C.c_int64(0)
+  assert L.mono_ckpt_decode_entry(segs, len(spec), wire, len(wire), C.byref(fid_out), out.ctypes.data_as(C.c_void_p)) == 0
+  assert fid_out.value == fid
+  np.testing.assert_array_equal(out.view(np.uint32), row.view(np.uint32))
