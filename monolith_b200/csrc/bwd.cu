@@ -592,14 +592,39 @@ __device__ __forceinline__ void load_items(const uint2* __restrict__ src, int64_
 
 enum { MODE_STORE = 0, MODE_APPLY = 1 };
 
+// positions of the 4 consecutive elements e .. e+3 (e a multiple of 4, < 32) of a chunk held EPL-per-lane
+template <int G>
+__device__ __forceinline__ void fetch4(const uint32_t (&v)[32 / G], int e, uint32_t (&out)[4]) {
+  constexpr int EPL = 32 / G;
+  const uint32_t gmask = Group<G>::mask();
+  const int gb = Group<G>::base();
+  if (EPL == 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) out[u] = __shfl_sync(gmask, v[u % EPL], gb + e / 4);
+  } else if (EPL == 8) {
+    const bool hi = (e & 4) != 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) out[u] = __shfl_sync(gmask, hi ? v[(4 + u) % EPL] : v[u % EPL], gb + e / 8);
+  } else if (EPL == 2) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) out[u] = __shfl_sync(gmask, v[u % EPL], gb + e / 2 + u / 2);
+  } else {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) out[u] = __shfl_sync(gmask, v[0], gb + e + u);
+  }
+}
+
+// The reduction kernel (MODE_STORE): unit sums go to run_dst (short runs) / part (long-run blocks).  The stream of a
+// group is walked in batches of 4 elements aligned to 4, so that a batch's positions are ONE lane's vector of the
+// chunk: 4 shuffles fetch them, 4 gradient rows are requested back to back, then the adds run in order.
 template <int G, int MODE, int OPT>
-__global__ void __launch_bounds__(kThreads, MODE == MODE_APPLY ? 2 : 3)
+__global__ void __launch_bounds__(kThreads, 3)
 seg_reduce_kernel(SegArgs sa, const PeerOut po) {
+  static_assert(MODE == MODE_STORE, "the optimizer is applied by runs_apply_kernel");
   __shared__ int64_t s_start[kMaxPeers + 1];
   peer_starts(po, s_start);
   constexpr int EPL = 32 / G;          // elements of a piece per lane
   constexpr int RPI = 32 / G;          // pieces per warp iteration
-  constexpr int UNR = 4;               // gradient rows in flight per group
   const BwdArgs& a = sa.b;
   const int gl = Group<G>::gl(), grp = (threadIdx.x & 31) / G;
   const uint32_t gmask = Group<G>::mask();
@@ -634,11 +659,6 @@ seg_reduce_kernel(SegArgs sa, const PeerOut po) {
     const uint32_t rs_prev = j0 > 0 ? run_start[j0 - 1] : 0u;       // start of the run covering the piece start
     const uint32_t rs_0 = run_start[j0];                            // first head at / after the piece start
     const uint32_t rs_end = run_start[j0 + nheads];                 // end of the last run that starts in the piece
-    uint32_t ri[EPL];
-    if (MODE == MODE_APPLY) {
-#pragma unroll
-      for (int q = 0; q < EPL; ++q) ri[q] = gl * EPL + q < nheads ? a.rowidx[j0 + gl * EPL + q] : kEmptyRow;
-    }
     // ---- units of this piece ----
     const int e_first = H ? __ffs(H) - 1 : nvalid;                  // leading occurrences belong to run j0 - 1
     uint32_t S = H;                                                  // unit starts
@@ -678,52 +698,34 @@ seg_reduce_kernel(SegArgs sa, const PeerOut po) {
     if (e_stop > 2 * kPiece) load_items<G>(a.sorted, base + 2 * kPiece, M, kdrop, pm2);
 
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int e0 = e_begin; e0 < e_stop; e0 += UNR) {
-      float4 x[UNR];
-      RowPre pre[UNR];
-      uint32_t rrow[UNR];
-      bool is_end[UNR];
+    for (int e0 = e_begin & ~3; e0 < e_stop; e0 += 4) {
+      uint32_t m[4];
+      if (e0 < kPiece) fetch4<G>(pm0, e0, m);
+      else if (e0 < 2 * kPiece) fetch4<G>(pm1, e0 - kPiece, m);
+      else fetch4<G>(pm2, e0 - 2 * kPiece, m);
+      // unit starts at e0 + u, and at e0 + u + 1 (=> e0 + u ends a unit); no starts past the piece
+      const uint32_t st4 = e0 < kPiece ? (S >> e0) & 0xFu : 0u;
+      const uint32_t nx4 = e0 + 1 < kPiece ? (S >> (e0 + 1)) & 0xFu : 0u;
+      float4 x[4];
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) {
+      for (int u = 0; u < 4; ++u) {
         const int e = e0 + u;
-        const bool live = e < e_stop;
-        const int ee = min(e, 3 * kPiece - 1);
-        uint32_t m = chunk_elem<G>(pm0, ee & 31);
-        const uint32_t m1v = chunk_elem<G>(pm1, ee & 31), m2v = chunk_elem<G>(pm2, ee & 31);
-        if (ee >= kPiece) m = ee >= 2 * kPiece ? m2v : m1v;
         x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (live && in) x[u] = occ_grad4(gs, m);
-        is_end[u] = live && (e + 1 == e_stop || (e + 1 < kPiece && ((S >> (e + 1)) & 1u)));
-        if (MODE == MODE_APPLY) {
-          // the unit that ends here: a short run iff it is not the leading block and not a long last run
-          const int hr = e < kPiece ? __popc(H & (0xFFFFFFFFu >> (31 - e))) : nheads;  // heads at or before e
-          const uint32_t r_of = chunk_elem<G>(ri, max(hr - 1, 0) & 31);
-          rrow[u] = kEmptyRow;
-          const bool short_end = is_end[u] && hr > 0 && !(last_long && hr == nheads);
-          if (short_end) rrow[u] = r_of;
-          pre[u] = bwd_prefetch<G, OPT>(a, short_end && r_of != kEmptyRow ? r_of : kFreshBit, c);
-        }
+        if (e >= e_begin && e < e_stop && in) x[u] = occ_grad4(gs, m[u]);
       }
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) {
+      for (int u = 0; u < 4; ++u) {
         const int e = e0 + u;
-        if (e >= e_stop) break;
-        const bool starts = e < kPiece && ((S >> e) & 1u);
-        if (starts) acc = x[u]; else add4(acc, x[u]);
-        if (!is_end[u]) continue;
-        const int hr = e < kPiece ? __popc(H & (0xFFFFFFFFu >> (31 - e))) : nheads;
-        if (hr == 0) {                        // leading block of the long run that covers the piece start
-          if (in) *reinterpret_cast<float4*>(sa.part + (size_t)(2 * p) * D + c) = acc;
-        } else if (last_long && hr == nheads) {  // block 0 of a long run
-          if (in) *reinterpret_cast<float4*>(sa.part + (size_t)(2 * p + 1) * D + c) = acc;
-        } else {
-          const uint32_t j = j0 + hr - 1;
-          if (MODE == MODE_APPLY) {
-            if (rrow[u] != kEmptyRow) bwd_apply<G, OPT>(a, j, rrow[u], acc, c, pre[u]);
-          } else {
-            if (in) *reinterpret_cast<float4*>(run_dst(a.ugrad, po, s_start, j, D) + c) = acc;
-          }
-        }
+        if (e < e_begin || e >= e_stop) continue;
+        if ((st4 >> u) & 1u) acc = x[u]; else add4(acc, x[u]);
+        if (!(e + 1 == e_stop || ((nx4 >> u) & 1u))) continue;
+        // ---- a unit ends here ----
+        const int hr = e < kPiece ? __popc(H & (0xFFFFFFFFu >> (31 - e))) : nheads;  // heads at or before e
+        float* dst;
+        if (hr == 0) dst = sa.part + (size_t)(2 * p) * D;                          // leading block of a long run
+        else if (last_long && hr == nheads) dst = sa.part + (size_t)(2 * p + 1) * D;  // block 0 of a long run
+        else dst = run_dst(a.ugrad, po, s_start, (int64_t)j0 + hr - 1, D);          // a short run
+        if (in) *reinterpret_cast<float4*>(dst + c) = acc;
       }
     }
   }
@@ -956,9 +958,8 @@ struct ReduceScratch {  // sizes of the reduction scratch for M occurrences of d
   }
 };
 
-// opt: MONO_OPT_* to apply the optimizer from registers (single-segment table), or -1: store the summed rows
-// (run_dst: a.ugrad or the peer window)
-static void launch_reduce(const SegArgs& sa, int G, int opt, const PeerOut& po, cudaStream_t s) {
+// per-run gradient sums -> run_dst (a.ugrad, or the owners' peer windows)
+static void launch_reduce(const SegArgs& sa, int G, int /*unused*/, const PeerOut& po, cudaStream_t s) {
   const int64_t np = sa.n_pieces;
   if (np <= 0) return;
   int levels = 0;
@@ -983,14 +984,7 @@ static void launch_reduce(const SegArgs& sa, int G, int opt, const PeerOut& po, 
         <<<resident_grid(long_finish_kernel<GG, MODE, OO>, np, kThreads / GG), kThreads, 0, s>>>(sa, (uint32_t)top, po); \
     MONO_CHECK_LAUNCH();                                                                                            \
   } while (0)
-#define SEG_G(GG)                                                         \
-  switch (opt) {                                                          \
-    case MONO_OPT_SGD: SEG_GO(GG, MODE_APPLY, MONO_OPT_SGD); break;       \
-    case MONO_OPT_ADAGRAD: SEG_GO(GG, MODE_APPLY, MONO_OPT_ADAGRAD); break; \
-    case MONO_OPT_FTRL: SEG_GO(GG, MODE_APPLY, MONO_OPT_FTRL); break;     \
-    case MONO_OPT_ADAM: SEG_GO(GG, MODE_APPLY, MONO_OPT_ADAM); break;     \
-    default: SEG_GO(GG, MODE_STORE, 0); break;                            \
-  }
+#define SEG_G(GG) SEG_GO(GG, MODE_STORE, 0)
   switch (G) {
     case 4: SEG_G(4); break;
     case 8: SEG_G(8); break;
@@ -1049,7 +1043,7 @@ void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t 
   const size_t o_miss = take(4 * (size_t)M);
   const size_t o_occ = take(row_offsets ? 4 * (size_t)M : 0);
   const size_t o_prb = take(rs.prb_bytes), o_part = take(rs.part_bytes), o_meta = take(rs.meta_bytes);
-  const size_t o_ug = take(opt_sel < 0 ? sizeof(float) * (size_t)M * D : 0);
+  const size_t o_ug = take(sizeof(float) * (size_t)M * D);
   char* ws = (char*)mt->ws_a.get(off, s);
   uint32_t epoch = 0;
   Entry* set = (Entry*)mt->claim_set.get(sizeof(Entry) * (size_t)cap, s, &epoch);
@@ -1106,7 +1100,7 @@ void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t 
   a.grad_stride = grad_stride;
   a.grad_col = grad_col;
   a.lr = cb.lr;
-  a.ugrad = opt_sel < 0 ? (float*)(ws + o_ug) : nullptr;
+  a.ugrad = (float*)(ws + o_ug);
   a.scratch = a.ugrad;
   sa.piece_run_base = sw.piece_run_base;
   sa.part = (float*)(ws + o_part);
@@ -1118,19 +1112,27 @@ void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t 
     MONO_CHECK_LAUNCH();
     a.occ_row = occ;
   }
-  launch_reduce(sa, G, opt_sel, no_peer, s);
-  if (opt_sel < 0) {  // any segment mix: the summed rows were stored; generic apply_row per run
-#define BWD2(GG)                                                                                                  \
-  runs_apply_kernel<GG, -1><<<resident_grid(runs_apply_kernel<GG, -1>, M, kThreads / GG), kThreads, 0, s>>>(a);   \
+  launch_reduce(sa, G, -1, no_peer, s);
+  // 6 apply: one streaming pass over the runs — row index, summed gradient, w / optimizer state of every distinct FID
+#define BWD2(GG, OO)                                                                                             \
+  runs_apply_kernel<GG, OO><<<resident_grid(runs_apply_kernel<GG, OO>, M, kThreads / GG), kThreads, 0, s>>>(a);  \
   MONO_CHECK_LAUNCH()
-    switch (G) {
-      case 4: BWD2(4); break;
-      case 8: BWD2(8); break;
-      case 16: BWD2(16); break;
-      default: BWD2(32); break;
-    }
-#undef BWD2
+#define BWD(GG)                                                         \
+  switch (opt_sel) {                                                    \
+    case MONO_OPT_SGD: BWD2(GG, MONO_OPT_SGD); break;                   \
+    case MONO_OPT_ADAGRAD: BWD2(GG, MONO_OPT_ADAGRAD); break;           \
+    case MONO_OPT_FTRL: BWD2(GG, MONO_OPT_FTRL); break;                 \
+    case MONO_OPT_ADAM: BWD2(GG, MONO_OPT_ADAM); break;                 \
+    default: BWD2(GG, -1); break;                                       \
   }
+  switch (G) {
+    case 4: BWD(4); break;
+    case 8: BWD(8); break;
+    case 16: BWD(16); break;
+    default: BWD(32); break;
+  }
+#undef BWD2
+#undef BWD
   ht.issued_total += (uint64_t)M;
   ht.max_update_ts = std::max<int64_t>(ht.max_update_ts, update_time);
   request_snapshot(mt, k, s);

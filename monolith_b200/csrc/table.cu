@@ -148,6 +148,8 @@ void table_init(mono_mtable* mt, HostTable& t, const mono_table_cfg& cfg, cudaSt
     const mono_segment_cfg& sc = cfg.segments[i];
     if (sc.dim <= 0) throw ArgError("segment dim must be positive");
     if (sc.init_type < 0 || sc.init_type > 3) throw ArgError("unknown initializer type");
+    if (sc.opt_type < MONO_OPT_SGD || sc.opt_type > MONO_OPT_AMSGRAD)
+      throw ArgError("unknown optimizer type (built: sgd, adagrad, ftrl, adam, momentum, rmsprop, rmspropv2, adadelta, amsgrad)");
     t.segs.push_back(sc);
     SegDev& sd = d.segs[i];
     sd.col_begin = col;

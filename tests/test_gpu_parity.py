@@ -983,7 +983,10 @@ def test_hash_filter_paths_vs_oracle(dev):
   def both():
     gpu, cpu = pair(cfg, dev)
     for t in (gpu, cpu):
-      t.set_hash_filter("t", capacity=5000, default_threshold=2, slot_thresholds={7: 4, 9: 0})
+      # a large filter: two FIDs with the same 12-bit signature and overlapping probe windows share a counter, and WHICH
+      # ones do depends on the insertion order (sequential in the oracle, concurrent on the GPU) — unpinned in the
+      # reference too (absl::Hash is salted per process); 3 M cells make that improbable for a few hundred FIDs
+      t.set_hash_filter("t", capacity=2_000_000, default_threshold=2, slot_thresholds={7: 4, 9: 0})
     return gpu, cpu
 
   def same(gpu, cpu, ids):
