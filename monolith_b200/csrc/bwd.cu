@@ -535,7 +535,8 @@ __device__ __forceinline__ float* run_dst(float* ugrad, const PeerOut& po, const
 //               every operand by arithmetic on the slot index: meta[slot] = {run, block, #blocks, valid}.
 // ==========================================================================================
 constexpr int kPiece = 32;
-constexpr int kTreeFan = 32;
+constexpr int kTreeFan = 128;   // members summed by one tree node (in block order)
+constexpr int kFinishMax = 512; // blocks / nodes the final pass may still have to add up per run
 
 struct SegMeta {  // one per partial slot
   uint32_t run, blk, nblk, valid;
@@ -614,14 +615,26 @@ __device__ __forceinline__ void fetch4(const uint32_t (&v)[32 / G], int e, uint3
   }
 }
 
-// The reduction kernel (MODE_STORE): unit sums go to run_dst (short runs) / part (long-run blocks).  The stream of a
-// group is walked in batches of 4 elements aligned to 4, so that a batch's positions are ONE lane's vector of the
-// chunk: 4 shuffles fetch them, 4 gradient rows are requested back to back, then the adds run in order.
+// The reduction kernel (MODE_STORE): unit sums go to run_dst (short runs) / part (long-run blocks).
+// Memory-level parallelism is what bounds it (a dependent random HBM round trip costs ~2.5 us under load, so ~100 KB
+// must be in flight per SM): the gradient rows of a group's stream are requested kStage = 16 at a time with cp.async
+// (LDGSTS) into shared memory — every lane copies ITS 16-byte column slice of each row into a private slot, so nothing
+// but the thread's own cp.async.wait orders the data and no register holds a row in flight — then the adds run in
+// occurrence order out of shared memory.  3 blocks x 64 KB = 192 KB of gradient rows in flight per SM.
+constexpr int kStage = 16;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
 template <int G, int MODE, int OPT>
 __global__ void __launch_bounds__(kThreads, 3)
 seg_reduce_kernel(SegArgs sa, const PeerOut po) {
   static_assert(MODE == MODE_STORE, "the optimizer is applied by runs_apply_kernel");
   __shared__ int64_t s_start[kMaxPeers + 1];
+  extern __shared__ float4 stage_raw[];        // [kStage][kThreads]: [slot][thread], conflict-free 16-byte accesses
+  float4 (*stage)[kThreads] = reinterpret_cast<float4 (*)[kThreads]>(stage_raw);
   peer_starts(po, s_start);
   constexpr int EPL = 32 / G;          // elements of a piece per lane
   constexpr int RPI = 32 / G;          // pieces per warp iteration
@@ -690,42 +703,63 @@ seg_reduce_kernel(SegArgs sa, const PeerOut po) {
     }
     if (S == 0) continue;
     const int e_begin = __ffs(S) - 1;
-    // positions of the continuation past the piece (at most 63 occurrences)
-    uint32_t pm1[EPL], pm2[EPL], kdrop[EPL];
-#pragma unroll
-    for (int q = 0; q < EPL; ++q) pm1[q] = pm2[q] = 0;
-    if (e_stop > kPiece) load_items<G>(a.sorted, base + kPiece, M, kdrop, pm1);
-    if (e_stop > 2 * kPiece) load_items<G>(a.sorted, base + 2 * kPiece, M, kdrop, pm2);
 
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int e0 = e_begin & ~3; e0 < e_stop; e0 += 4) {
-      uint32_t m[4];
-      if (e0 < kPiece) fetch4<G>(pm0, e0, m);
-      else if (e0 < 2 * kPiece) fetch4<G>(pm1, e0 - kPiece, m);
-      else fetch4<G>(pm2, e0 - 2 * kPiece, m);
-      // unit starts at e0 + u, and at e0 + u + 1 (=> e0 + u ends a unit); no starts past the piece
-      const uint32_t st4 = e0 < kPiece ? (S >> e0) & 0xFu : 0u;
-      const uint32_t nx4 = e0 + 1 < kPiece ? (S >> (e0 + 1)) & 0xFu : 0u;
-      float4 x[4];
+    for (int e0 = e_begin & ~(kStage - 1); e0 < e_stop; e0 += kStage) {
+      // ---- request: up to 16 gradient rows, this lane's 16-byte slice of each ----
+      float mean_n[kStage / 4][4];   // MEAN pooling: divisor of the row (applied after the copy)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int e = e0 + u;
-        x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e >= e_begin && e < e_stop && in) x[u] = occ_grad4(gs, m[u]);
+      for (int b4 = 0; b4 < kStage; b4 += 4) {
+        const int eb = e0 + b4;
+        if (eb >= e_stop) break;
+        uint32_t m[4];
+        if (eb < kPiece) {
+          fetch4<G>(pm0, eb, m);
+        } else {  // continuation past the piece: the positions straight from memory (same address in every lane)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) m[u] = base + eb + u < M ? a.sorted[base + eb + u].y : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = eb + u;
+          mean_n[b4 / 4][u] = 1.0f;
+          if (e >= e_begin && e < e_stop && in) {
+            const uint32_t r = gs.occ_row ? gs.occ_row[m[u]] : m[u];
+            if (gs.mean) mean_n[b4 / 4][u] = (float)(gs.row_offsets[r + 1] - gs.row_offsets[r]);
+            cp_async16(&stage[b4 + u][threadIdx.x], gs.base + (size_t)r * gs.stride);
+          }
+        }
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      // ---- consume in occurrence order ----
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int e = e0 + u;
-        if (e < e_begin || e >= e_stop) continue;
-        if ((st4 >> u) & 1u) acc = x[u]; else add4(acc, x[u]);
-        if (!(e + 1 == e_stop || ((nx4 >> u) & 1u))) continue;
-        // ---- a unit ends here ----
-        const int hr = e < kPiece ? __popc(H & (0xFFFFFFFFu >> (31 - e))) : nheads;  // heads at or before e
-        float* dst;
-        if (hr == 0) dst = sa.part + (size_t)(2 * p) * D;                          // leading block of a long run
-        else if (last_long && hr == nheads) dst = sa.part + (size_t)(2 * p + 1) * D;  // block 0 of a long run
-        else dst = run_dst(a.ugrad, po, s_start, (int64_t)j0 + hr - 1, D);          // a short run
-        if (in) *reinterpret_cast<float4*>(dst + c) = acc;
+      for (int b4 = 0; b4 < kStage; b4 += 4) {
+        const int eb = e0 + b4;
+        if (eb >= e_stop) break;
+        // unit starts at eb + u, and at eb + u + 1 (=> eb + u ends a unit); no starts past the piece
+        const uint32_t st4 = eb < kPiece ? (S >> eb) & 0xFu : 0u;
+        const uint32_t nx4 = eb + 1 < kPiece ? (S >> (eb + 1)) & 0xFu : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = eb + u;
+          if (e < e_begin || e >= e_stop) continue;
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (in) x = stage[b4 + u][threadIdx.x];
+          if (gs.mean) {
+            const float fn = mean_n[b4 / 4][u];
+            x.x = __fdiv_rn(x.x, fn); x.y = __fdiv_rn(x.y, fn); x.z = __fdiv_rn(x.z, fn); x.w = __fdiv_rn(x.w, fn);
+          }
+          if ((st4 >> u) & 1u) acc = x; else add4(acc, x);
+          if (!(e + 1 == e_stop || ((nx4 >> u) & 1u))) continue;
+          // ---- a unit ends here ----
+          const int hr = e < kPiece ? __popc(H & (0xFFFFFFFFu >> (31 - e))) : nheads;  // heads at or before e
+          float* dst;
+          if (hr == 0) dst = sa.part + (size_t)(2 * p) * D;                          // leading block of a long run
+          else if (last_long && hr == nheads) dst = sa.part + (size_t)(2 * p + 1) * D;  // block 0 of a long run
+          else dst = run_dst(a.ugrad, po, s_start, (int64_t)j0 + hr - 1, D);          // a short run
+          if (in) *reinterpret_cast<float4*>(dst + c) = acc;
+        }
       }
     }
   }
@@ -736,6 +770,8 @@ seg_reduce_kernel(SegArgs sa, const PeerOut po) {
 template <int G>
 __global__ void __launch_bounds__(kThreads)
 tree_level_kernel(float* __restrict__ part, const SegMeta* __restrict__ meta, int64_t n_slots, uint32_t stride, int D) {
+  extern __shared__ float4 stage_raw[];  // [kStage][kThreads]
+  float4 (*stage)[kThreads] = reinterpret_cast<float4 (*)[kThreads]>(stage_raw);
   const int gl = Group<G>::gl(), c = gl * 4;
   const int64_t gstride = (int64_t)gridDim.x * (kThreads / G);
   for (int64_t q = (int64_t)blockIdx.x * (kThreads / G) + threadIdx.x / G; q < n_slots; q += gstride) {
@@ -744,18 +780,21 @@ tree_level_kernel(float* __restrict__ part, const SegMeta* __restrict__ meta, in
     if (c >= D) continue;
     const int64_t piece = q >> 1;
     float4 acc = *reinterpret_cast<const float4*>(part + (size_t)q * D + c);
-    for (int i0 = 1; i0 < kTreeFan; i0 += 8) {
-      float4 x[8];
+    for (int i0 = 1; i0 < kTreeFan; i0 += 16) {
+      if ((uint64_t)m.blk + (uint64_t)i0 * stride >= m.nblk) break;
+      // 16 UNCONDITIONAL loads (indices clamped to the node's own slot) so that all of them are in flight together
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const uint32_t kk = m.blk + (uint32_t)(i0 + u) * stride;
-        x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i0 + u < kTreeFan && kk < m.nblk)
-          x[u] = *reinterpret_cast<const float4*>(part + (size_t)(2 * (piece + (int64_t)(i0 + u) * stride)) * D + c);
+      for (int u = 0; u < 16; ++u) {  // (the compiler serialises plain loads behind the dependent adds; cp.async does not)
+        const uint64_t kk = (uint64_t)m.blk + (uint64_t)(i0 + u) * stride;
+        const bool ok = i0 + u < kTreeFan && kk < m.nblk;
+        const size_t slot = ok ? (size_t)(2 * (piece + (int64_t)(i0 + u) * stride)) : (size_t)q;
+        cp_async16(&stage[u][threadIdx.x], part + slot * D + c);
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (i0 + u < kTreeFan && m.blk + (uint32_t)(i0 + u) * stride < m.nblk) add4(acc, x[u]);
+      for (int u = 0; u < 16; ++u)
+        if (i0 + u < kTreeFan && (uint64_t)m.blk + (uint64_t)(i0 + u) * stride < m.nblk) add4(acc, stage[u][threadIdx.x]);
     }
     *reinterpret_cast<float4*>(part + (size_t)q * D + c) = acc;
   }
@@ -767,6 +806,8 @@ template <int G, int MODE, int OPT>
 __global__ void __launch_bounds__(kThreads)
 long_finish_kernel(SegArgs sa, uint32_t top, const PeerOut po) {
   __shared__ int64_t s_start[kMaxPeers + 1];
+  extern __shared__ float4 stage_raw[];  // [kStage][kThreads]
+  float4 (*stage)[kThreads] = reinterpret_cast<float4 (*)[kThreads]>(stage_raw);
   peer_starts(po, s_start);
   const BwdArgs& a = sa.b;
   const int gl = Group<G>::gl(), c = gl * 4;
@@ -777,17 +818,18 @@ long_finish_kernel(SegArgs sa, uint32_t top, const PeerOut po) {
     if (!m.valid) continue;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c < D) acc = *reinterpret_cast<const float4*>(sa.part + (size_t)(2 * p + 1) * D + c);
-    for (uint32_t k0 = top; k0 < m.nblk; k0 += 8 * top) {
-      float4 x[8];
+    for (uint32_t k0 = top; k0 < m.nblk; k0 += 16 * top) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < 16; ++u) {  // 16 requests in flight (clamped to the head slot)
         const uint64_t k = (uint64_t)k0 + (uint64_t)u * top;
-        x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k < m.nblk && c < D) x[u] = *reinterpret_cast<const float4*>(sa.part + (size_t)(2 * (p + (int64_t)k)) * D + c);
+        const size_t slot = k < m.nblk ? (size_t)(2 * (p + (int64_t)k)) : (size_t)(2 * p + 1);
+        cp_async16(&stage[u][threadIdx.x], sa.part + slot * D + (c < D ? c : 0));
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if ((uint64_t)k0 + (uint64_t)u * top < m.nblk) add4(acc, x[u]);
+      for (int u = 0; u < 16; ++u)
+        if ((uint64_t)k0 + (uint64_t)u * top < m.nblk) add4(acc, stage[u][threadIdx.x]);
     }
     const uint32_t j = m.run;
     if (MODE == MODE_APPLY) {
@@ -852,6 +894,50 @@ struct ClaimResolve {
   uint32_t* miss_slots;
 };
 
+// The kernel is a chain of dependent random accesses per occurrence (FID -> set entry -> [winner: CAS -> table bucket
+// -> timestamp / row stores]); a loaded round trip costs ~2.5 us, so the chain is software-pipelined over the
+// grid-stride iterations of a thread: while occurrence i is decided, the set entry of i + stride and the FID of
+// i + 2 stride are already in flight, and the table bucket a WINNER has to probe is requested in one iteration and
+// examined in the next.
+struct ClaimSlot {
+  Entry* p;
+  uint32_t base, idx, owner;
+};
+__device__ __forceinline__ ClaimSlot claim_slot(Entry* set, int64_t key, uint32_t R, int N) {
+  ClaimSlot s;
+  s.owner = N == 1 ? 0u : (uint32_t)((uint64_t)key % (uint64_t)N);
+  s.base = s.owner * R;
+  s.idx = __umulhi((uint32_t)(mix64((uint64_t)key) >> 24), R);
+  s.p = set + s.base + s.idx;
+  return s;
+}
+
+struct PendingResolve {  // a winner whose first table bucket is in flight
+  bool on;
+  int64_t key;
+  uint32_t set_slot;
+  Entry* bucket;
+  Entry e0, e1, e2, e3;
+};
+
+template <bool RESOLVE>
+__device__ __forceinline__ void finish_resolve(const PendingResolve& pd, Entry* set, const ClaimResolve& cr) {
+  if (!RESOLVE || !pd.on) return;
+  uint32_t row = kEmptyRow;
+  Entry* slot = nullptr;
+  if (pd.e0.key == pd.key && pd.e0.row < kTombRow) { row = pd.e0.row; slot = pd.bucket; }
+  if (pd.e1.key == pd.key && pd.e1.row < kTombRow) { row = pd.e1.row; slot = pd.bucket + 1; }
+  if (pd.e2.key == pd.key && pd.e2.row < kTombRow) { row = pd.e2.row; slot = pd.bucket + 2; }
+  if (pd.e3.key == pd.key && pd.e3.row < kTombRow) { row = pd.e3.row; slot = pd.bucket + 3; }
+  if (row == kEmptyRow) row = probe_lane_slot(cr.t, pd.key, &slot);  // second bucket / stash: the slow, rare path
+  if (row != kEmptyRow) {
+    slot->ts = cr.update_ts;
+    set[pd.set_slot].row = row;
+  } else {
+    cr.miss_slots[atomicAdd(cr.miss_ctr, 1u)] = pd.set_slot;
+  }
+}
+
 template <bool RESOLVE>
 __global__ void __launch_bounds__(kThreads)
 fid_claim_kernel(const int64_t* __restrict__ fids, int64_t n, Entry* set, uint32_t R, int N, uint32_t epoch,
@@ -860,16 +946,34 @@ fid_claim_kernel(const int64_t* __restrict__ fids, int64_t n, Entry* set, uint32
   __shared__ uint32_t cnt[256];
   for (int d = threadIdx.x; d < 256; d += blockDim.x) cnt[d] = 0;
   __syncthreads();
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t key = __ldg(fids + i);
-    const uint32_t owner = N == 1 ? 0u : (uint32_t)((uint64_t)key % (uint64_t)N);
-    const uint32_t base = owner * R;
-    uint32_t idx = __umulhi((uint32_t)(mix64((uint64_t)key) >> 24), R);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t i_first = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  // pipeline registers: item i (key k0, slot s0, first entry e0 loaded), item i + stride (key k1 loaded)
+  int64_t k0 = i_first < n ? __ldg(fids + i_first) : 0;
+  int64_t k1 = i_first + stride < n ? __ldg(fids + i_first + stride) : 0;
+  ClaimSlot s0 = claim_slot(set, k0, R, N);
+  Entry e0 = empty_entry();
+  if (i_first < n) e0 = ld_entry(s0.p);  // L1-cacheable
+  PendingResolve pd;
+  pd.on = false;
+  for (int64_t i = i_first; i < n; i += stride) {
+    // ---- requests for the following items go out first ----
+    const int64_t k2 = i + 2 * stride < n ? __ldg(fids + i + 2 * stride) : 0;
+    const ClaimSlot s1 = claim_slot(set, k1, R, N);
+    Entry e1 = empty_entry();
+    if (i + stride < n) e1 = ld_entry(s1.p);
+    // ---- the winner of the previous iteration: its table bucket has arrived ----
+    finish_resolve<RESOLVE>(pd, set, cr);
+    pd.on = false;
+    // ---- item i ----
+    const int64_t key = k0;
+    uint32_t idx = s0.idx;
     uint32_t found = 0xFFFFFFFFu;
     bool won = false;
+    Entry e = e0;
     for (uint32_t probes = 0; probes < R; ++probes) {
-      Entry* p = set + base + idx;
-      Entry e = ld_entry(p);  // L1-cacheable
+      Entry* p = set + s0.base + idx;
+      if (probes) e = ld_entry(p);
       while (e.ts != epoch) {  // empty as far as we can see: claim it (CAS against what we saw)
         Entry ne;
         ne.key = key;
@@ -884,31 +988,39 @@ fid_claim_kernel(const int64_t* __restrict__ fids, int64_t n, Entry* set, uint32
         }
       }
       if (e.key == key) {
-        found = base + idx;
+        found = s0.base + idx;
         break;
       }
       idx = idx + 1 == R ? 0 : idx + 1;
     }
     if (found == 0xFFFFFFFFu) {  // region full (owner skew): the host retries with larger regions
       owner_cnt[256] = 1;
-      found = base;
+      found = s0.base;
       won = false;
     }
     slot_of[i] = found;
     if (won) {
-      atomicAdd(&cnt[owner], 1u);
-      if (RESOLVE) {
-        Entry* slot = nullptr;
-        const uint32_t row = probe_lane_slot(cr.t, key, &slot);
-        if (row != kEmptyRow) {
-          slot->ts = cr.update_ts;
-          set[found].row = row;
-        } else {
-          cr.miss_slots[atomicAdd(cr.miss_ctr, 1u)] = found;
-        }
+      atomicAdd(&cnt[s0.owner], 1u);
+      if (RESOLVE) {  // request the FID's first table bucket; it is examined in the next iteration
+        uint32_t b1, b2;
+        bucket_pair(key, cr.t->num_buckets, b1, b2);
+        pd.on = true;
+        pd.key = key;
+        pd.set_slot = found;
+        pd.bucket = cr.t->buckets + (size_t)b1 * kBucketSlots;
+        pd.e0 = ld_entry(pd.bucket);
+        pd.e1 = ld_entry(pd.bucket + 1);
+        pd.e2 = ld_entry(pd.bucket + 2);
+        pd.e3 = ld_entry(pd.bucket + 3);
       }
     }
+    // ---- rotate the pipeline ----
+    k0 = k1;
+    k1 = k2;
+    s0 = s1;
+    e0 = e1;
   }
+  finish_resolve<RESOLVE>(pd, set, cr);
   __syncthreads();
   for (int d = threadIdx.x; d < N; d += blockDim.x)
     if (cnt[d]) atomicAdd(owner_cnt + d, cnt[d]);
@@ -964,24 +1076,37 @@ static void launch_reduce(const SegArgs& sa, int G, int /*unused*/, const PeerOu
   if (np <= 0) return;
   int levels = 0;
   uint64_t top = 1;
-  while (top * kTreeFan < (uint64_t)np) {
+  while ((uint64_t)np > top * kFinishMax) {  // the final pass adds up to kFinishMax nodes per run, 16 loads in flight
     top *= kTreeFan;
     ++levels;
   }
   const int D = sa.b.td.dim;
 #define SEG_GO(GG, MODE, OO)                                                                                        \
   do {                                                                                                              \
+    constexpr size_t kStageBytes = sizeof(float4) * kStage * kThreads;                                              \
+    static bool attr_set = false;                                                                                   \
+    if (!attr_set) {                                                                                                \
+      MONO_CUDA(cudaFuncSetAttribute(seg_reduce_kernel<GG, MODE, OO>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                     (int)kStageBytes));                                                            \
+      MONO_CUDA(cudaFuncSetAttribute(tree_level_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                     (int)kStageBytes));                                                            \
+      MONO_CUDA(cudaFuncSetAttribute(long_finish_kernel<GG, MODE, OO>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     (int)kStageBytes));                                                            \
+      attr_set = true;                                                                                              \
+    }                                                                                                               \
     seg_reduce_kernel<GG, MODE, OO>                                                                                 \
-        <<<resident_grid(seg_reduce_kernel<GG, MODE, OO>, np, (kThreads / 32) * (32 / GG)), kThreads, 0, s>>>(sa, po); \
+        <<<resident_grid(seg_reduce_kernel<GG, MODE, OO>, np, (kThreads / 32) * (32 / GG), kThreads, kStageBytes),  \
+           kThreads, kStageBytes, s>>>(sa, po);                                                                     \
     MONO_CHECK_LAUNCH();                                                                                            \
     uint32_t stride = 1;                                                                                            \
     for (int l = 0; l < levels; ++l, stride *= kTreeFan) {                                                          \
-      tree_level_kernel<GG><<<resident_grid(tree_level_kernel<GG>, 2 * np, kThreads / GG), kThreads, 0, s>>>(       \
-          sa.part, sa.meta, 2 * np, stride, D);                                                                     \
+      tree_level_kernel<GG><<<resident_grid(tree_level_kernel<GG>, 2 * np, kThreads / GG, kThreads, kStageBytes),   \
+                              kThreads, kStageBytes, s>>>(sa.part, sa.meta, 2 * np, stride, D);                     \
       MONO_CHECK_LAUNCH();                                                                                          \
     }                                                                                                               \
     long_finish_kernel<GG, MODE, OO>                                                                                \
-        <<<resident_grid(long_finish_kernel<GG, MODE, OO>, np, kThreads / GG), kThreads, 0, s>>>(sa, (uint32_t)top, po); \
+        <<<resident_grid(long_finish_kernel<GG, MODE, OO>, np, kThreads / GG, kThreads, kStageBytes), kThreads,     \
+           kStageBytes, s>>>(sa, (uint32_t)top, po);                                                                \
     MONO_CHECK_LAUNCH();                                                                                            \
   } while (0)
 #define SEG_G(GG) SEG_GO(GG, MODE_STORE, 0)
