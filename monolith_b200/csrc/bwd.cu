@@ -1026,6 +1026,71 @@ fid_claim_kernel(const int64_t* __restrict__ fids, int64_t n, Entry* set, uint32
     if (cnt[d]) atomicAdd(owner_cnt + d, cnt[d]);
 }
 
+// Non-pipelined variant (one occurrence at a time per thread, the winner probes the table on the spot): 32 registers,
+// full occupancy.  mono_set_option("claim_pipeline", 0) selects it.
+template <bool RESOLVE>
+__global__ void __launch_bounds__(kThreads)
+fid_claim_simple_kernel(const int64_t* __restrict__ fids, int64_t n, Entry* set, uint32_t R, int N, uint32_t epoch,
+                 uint32_t* __restrict__ slot_of, uint32_t* __restrict__ owner_cnt /* [N], [256] = overflow */,
+                 ClaimResolve cr) {
+  __shared__ uint32_t cnt[256];
+  for (int d = threadIdx.x; d < 256; d += blockDim.x) cnt[d] = 0;
+  __syncthreads();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t key = __ldg(fids + i);
+    const uint32_t owner = N == 1 ? 0u : (uint32_t)((uint64_t)key % (uint64_t)N);
+    const uint32_t base = owner * R;
+    uint32_t idx = __umulhi((uint32_t)(mix64((uint64_t)key) >> 24), R);
+    uint32_t found = 0xFFFFFFFFu;
+    bool won = false;
+    for (uint32_t probes = 0; probes < R; ++probes) {
+      Entry* p = set + base + idx;
+      Entry e = ld_entry(p);  // L1-cacheable
+      while (e.ts != epoch) {  // empty as far as we can see: claim it (CAS against what we saw)
+        Entry ne;
+        ne.key = key;
+        ne.row = kEmptyRow;
+        ne.ts = epoch;
+        const Entry old = cas_entry_old(p, e, ne);
+        if (old.key == e.key && old.row == e.row && old.ts == e.ts) {
+          won = true;
+          e = ne;
+        } else {
+          e = old;  // somebody else changed it: the true entry (claimed this epoch, or a different stale one)
+        }
+      }
+      if (e.key == key) {
+        found = base + idx;
+        break;
+      }
+      idx = idx + 1 == R ? 0 : idx + 1;
+    }
+    if (found == 0xFFFFFFFFu) {  // region full (owner skew): the host retries with larger regions
+      owner_cnt[256] = 1;
+      found = base;
+      won = false;
+    }
+    slot_of[i] = found;
+    if (won) {
+      atomicAdd(&cnt[owner], 1u);
+      if (RESOLVE) {
+        Entry* slot = nullptr;
+        const uint32_t row = probe_lane_slot(cr.t, key, &slot);
+        if (row != kEmptyRow) {
+          slot->ts = cr.update_ts;
+          set[found].row = row;
+        } else {
+          cr.miss_slots[atomicAdd(cr.miss_ctr, 1u)] = found;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < N; d += blockDim.x)
+    if (cnt[d]) atomicAdd(owner_cnt + d, cnt[d]);
+}
+
+
 // FIDs the claim found absent from the table (each exactly once): take a row (free list first, then the bump
 // allocator), publish {fid, row, ts} with the lock-free cuckoo insert and park row | fresh in the set entry.
 __global__ void __launch_bounds__(kThreads)
@@ -1183,8 +1248,12 @@ void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t 
   cr.update_ts = (uint32_t)update_time;
   cr.miss_ctr = ctr + 8;
   cr.miss_slots = (uint32_t*)(ws + o_miss);
-  fid_claim_kernel<true><<<resident_grid(fid_claim_kernel<true>, M, kThreads), kThreads, 0, s>>>(
-      fids_dev, M, set, cap, 1, epoch, k0, ctr + 512, cr);
+  if (g_opt_claim_pipeline.load(std::memory_order_relaxed))
+    fid_claim_kernel<true><<<resident_grid(fid_claim_kernel<true>, M, kThreads), kThreads, 0, s>>>(
+        fids_dev, M, set, cap, 1, epoch, k0, ctr + 512, cr);
+  else
+    fid_claim_simple_kernel<true><<<resident_grid(fid_claim_simple_kernel<true>, M, kThreads), kThreads, 0, s>>>(
+        fids_dev, M, set, cap, 1, epoch, k0, ctr + 512, cr);
   MONO_CHECK_LAUNCH();
   // 2 absent FIDs: allocate a row + lock-free insert (few in steady state; the count stays on the device)
   claim_miss_kernel<<<resident_grid(claim_miss_kernel, std::min<int64_t>(M, 148 * 2 * kThreads), kThreads), kThreads, 0, s>>>(
@@ -1441,8 +1510,12 @@ void grouping_build(mono_grouping* g, const int64_t* fids_dev, int64_t M, int N,
     sw.piece_run_base = (uint32_t*)(ws + o_prb);
     sw.n_runs = ctr;
     sw.run_of_sorted = (uint32_t*)(ws + o_ros);
-    fid_claim_kernel<false><<<resident_grid(fid_claim_kernel<false>, M, kThreads), kThreads, 0, s>>>(
-        fids_dev, M, set, R, N, epoch, sw.k0, owner_cnt, ClaimResolve{});
+    if (g_opt_claim_pipeline.load(std::memory_order_relaxed))
+      fid_claim_kernel<false><<<resident_grid(fid_claim_kernel<false>, M, kThreads), kThreads, 0, s>>>(
+          fids_dev, M, set, R, N, epoch, sw.k0, owner_cnt, ClaimResolve{});
+    else
+      fid_claim_simple_kernel<false><<<resident_grid(fid_claim_simple_kernel<false>, M, kThreads), kThreads, 0, s>>>(
+          fids_dev, M, set, R, N, epoch, sw.k0, owner_cnt, ClaimResolve{});
     MONO_CHECK_LAUNCH();
     // counts -> host on the side stream, while the sort below keeps the GPU busy.  Device-driven callers
     // (shard_counts_host == nullptr: xstep.cu) never read them on the host: nothing waits, the per-owner counts stay
