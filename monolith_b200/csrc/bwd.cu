@@ -888,6 +888,7 @@ __global__ void __launch_bounds__(kThreads) runs_emit_kernel(BwdArgs a, int shif
 // (ref: entry.SetTimestamp(update_time), cuckoo_embedding_hash_table.cc:243), row index parked in the set
 // entry; absent FIDs are queued (set slot) for claim_miss_kernel.  No separate resolve pass over the uniques.
 struct ClaimResolve {
+  int set_loads_cg;  // debug knob: read the claim set with ld.global.cg (L2) instead of L1-cacheable loads
   const TableDev* t;
   uint32_t update_ts;
   uint32_t* miss_ctr;
@@ -953,7 +954,7 @@ fid_claim_kernel(const int64_t* __restrict__ fids, int64_t n, Entry* set, uint32
   int64_t k1 = i_first + stride < n ? __ldg(fids + i_first + stride) : 0;
   ClaimSlot s0 = claim_slot(set, k0, R, N);
   Entry e0 = empty_entry();
-  if (i_first < n) e0 = ld_entry(s0.p);  // L1-cacheable
+  if (i_first < n) e0 = cr.set_loads_cg ? ld_entry_cg(s0.p) : ld_entry(s0.p);  // L1-cacheable
   PendingResolve pd;
   pd.on = false;
   for (int64_t i = i_first; i < n; i += stride) {
@@ -961,7 +962,7 @@ fid_claim_kernel(const int64_t* __restrict__ fids, int64_t n, Entry* set, uint32
     const int64_t k2 = i + 2 * stride < n ? __ldg(fids + i + 2 * stride) : 0;
     const ClaimSlot s1 = claim_slot(set, k1, R, N);
     Entry e1 = empty_entry();
-    if (i + stride < n) e1 = ld_entry(s1.p);
+    if (i + stride < n) e1 = cr.set_loads_cg ? ld_entry_cg(s1.p) : ld_entry(s1.p);
     // ---- the winner of the previous iteration: its table bucket has arrived ----
     finish_resolve<RESOLVE>(pd, set, cr);
     pd.on = false;
@@ -973,7 +974,7 @@ fid_claim_kernel(const int64_t* __restrict__ fids, int64_t n, Entry* set, uint32
     Entry e = e0;
     for (uint32_t probes = 0; probes < R; ++probes) {
       Entry* p = set + s0.base + idx;
-      if (probes) e = ld_entry(p);
+      if (probes) e = cr.set_loads_cg ? ld_entry_cg(p) : ld_entry(p);
       while (e.ts != epoch) {  // empty as far as we can see: claim it (CAS against what we saw)
         Entry ne;
         ne.key = key;
@@ -1045,7 +1046,7 @@ fid_claim_simple_kernel(const int64_t* __restrict__ fids, int64_t n, Entry* set,
     bool won = false;
     for (uint32_t probes = 0; probes < R; ++probes) {
       Entry* p = set + base + idx;
-      Entry e = ld_entry(p);  // L1-cacheable
+      Entry e = cr.set_loads_cg ? ld_entry_cg(p) : ld_entry(p);  // L1-cacheable
       while (e.ts != epoch) {  // empty as far as we can see: claim it (CAS against what we saw)
         Entry ne;
         ne.key = key;
@@ -1244,6 +1245,7 @@ void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t 
   //   the set entry, expiry timestamp bumped) or queues it as absent
   uint32_t* k0 = (uint32_t*)(ws + o_k0);
   ClaimResolve cr;
+  cr.set_loads_cg = g_opt_claim_cg.load(std::memory_order_relaxed);
   cr.t = mt->d_tables + k;
   cr.update_ts = (uint32_t)update_time;
   cr.miss_ctr = ctr + 8;
@@ -1512,10 +1514,10 @@ void grouping_build(mono_grouping* g, const int64_t* fids_dev, int64_t M, int N,
     sw.run_of_sorted = (uint32_t*)(ws + o_ros);
     if (g_opt_claim_pipeline.load(std::memory_order_relaxed))
       fid_claim_kernel<false><<<resident_grid(fid_claim_kernel<false>, M, kThreads), kThreads, 0, s>>>(
-          fids_dev, M, set, R, N, epoch, sw.k0, owner_cnt, ClaimResolve{});
+          fids_dev, M, set, R, N, epoch, sw.k0, owner_cnt, ClaimResolve{g_opt_claim_cg.load(std::memory_order_relaxed), nullptr, 0, nullptr, nullptr});
     else
       fid_claim_simple_kernel<false><<<resident_grid(fid_claim_simple_kernel<false>, M, kThreads), kThreads, 0, s>>>(
-          fids_dev, M, set, R, N, epoch, sw.k0, owner_cnt, ClaimResolve{});
+          fids_dev, M, set, R, N, epoch, sw.k0, owner_cnt, ClaimResolve{g_opt_claim_cg.load(std::memory_order_relaxed), nullptr, 0, nullptr, nullptr});
     MONO_CHECK_LAUNCH();
     // counts -> host on the side stream, while the sort below keeps the GPU busy.  Device-driven callers
     // (shard_counts_host == nullptr: xstep.cu) never read them on the host: nothing waits, the per-owner counts stay
