@@ -887,151 +887,25 @@ __global__ void __launch_bounds__(kThreads) runs_emit_kernel(BwdArgs a, int shif
 // resolves the FID in the table right away — lane-level probe, expiry-timestamp bump
 // (ref: entry.SetTimestamp(update_time), cuckoo_embedding_hash_table.cc:243), row index parked in the set
 // entry; absent FIDs are queued (set slot) for claim_miss_kernel.  No separate resolve pass over the uniques.
+__device__ unsigned long long g_claim_torn = 0ull;  // statistics of the confirm knob
+unsigned long long claim_torn_count() {
+  unsigned long long v = 0;
+  cudaMemcpyFromSymbol(&v, g_claim_torn, sizeof(v));
+  return v;
+}
+
 struct ClaimResolve {
   int set_loads_cg;  // debug knob: read the claim set with ld.global.cg (L2) instead of L1-cacheable loads
+  int confirm;       // debug knob: confirm "another FID's slot" with an atomic read before probing on
   const TableDev* t;
   uint32_t update_ts;
   uint32_t* miss_ctr;
   uint32_t* miss_slots;
 };
 
-// The kernel is a chain of dependent random accesses per occurrence (FID -> set entry -> [winner: CAS -> table bucket
-// -> timestamp / row stores]); a loaded round trip costs ~2.5 us, so the chain is software-pipelined over the
-// grid-stride iterations of a thread: while occurrence i is decided, the set entry of i + stride and the FID of
-// i + 2 stride are already in flight, and the table bucket a WINNER has to probe is requested in one iteration and
-// examined in the next.
-struct ClaimSlot {
-  Entry* p;
-  uint32_t base, idx, owner;
-};
-__device__ __forceinline__ ClaimSlot claim_slot(Entry* set, int64_t key, uint32_t R, int N) {
-  ClaimSlot s;
-  s.owner = N == 1 ? 0u : (uint32_t)((uint64_t)key % (uint64_t)N);
-  s.base = s.owner * R;
-  s.idx = __umulhi((uint32_t)(mix64((uint64_t)key) >> 24), R);
-  s.p = set + s.base + s.idx;
-  return s;
-}
-
-struct PendingResolve {  // a winner whose first table bucket is in flight
-  bool on;
-  int64_t key;
-  uint32_t set_slot;
-  Entry* bucket;
-  Entry e0, e1, e2, e3;
-};
-
-template <bool RESOLVE>
-__device__ __forceinline__ void finish_resolve(const PendingResolve& pd, Entry* set, const ClaimResolve& cr) {
-  if (!RESOLVE || !pd.on) return;
-  uint32_t row = kEmptyRow;
-  Entry* slot = nullptr;
-  if (pd.e0.key == pd.key && pd.e0.row < kTombRow) { row = pd.e0.row; slot = pd.bucket; }
-  if (pd.e1.key == pd.key && pd.e1.row < kTombRow) { row = pd.e1.row; slot = pd.bucket + 1; }
-  if (pd.e2.key == pd.key && pd.e2.row < kTombRow) { row = pd.e2.row; slot = pd.bucket + 2; }
-  if (pd.e3.key == pd.key && pd.e3.row < kTombRow) { row = pd.e3.row; slot = pd.bucket + 3; }
-  if (row == kEmptyRow) row = probe_lane_slot(cr.t, pd.key, &slot);  // second bucket / stash: the slow, rare path
-  if (row != kEmptyRow) {
-    slot->ts = cr.update_ts;
-    set[pd.set_slot].row = row;
-  } else {
-    cr.miss_slots[atomicAdd(cr.miss_ctr, 1u)] = pd.set_slot;
-  }
-}
-
 template <bool RESOLVE>
 __global__ void __launch_bounds__(kThreads)
 fid_claim_kernel(const int64_t* __restrict__ fids, int64_t n, Entry* set, uint32_t R, int N, uint32_t epoch,
-                 uint32_t* __restrict__ slot_of, uint32_t* __restrict__ owner_cnt /* [N], [256] = overflow */,
-                 ClaimResolve cr) {
-  __shared__ uint32_t cnt[256];
-  for (int d = threadIdx.x; d < 256; d += blockDim.x) cnt[d] = 0;
-  __syncthreads();
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t i_first = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  // pipeline registers: item i (key k0, slot s0, first entry e0 loaded), item i + stride (key k1 loaded)
-  int64_t k0 = i_first < n ? __ldg(fids + i_first) : 0;
-  int64_t k1 = i_first + stride < n ? __ldg(fids + i_first + stride) : 0;
-  ClaimSlot s0 = claim_slot(set, k0, R, N);
-  Entry e0 = empty_entry();
-  if (i_first < n) e0 = cr.set_loads_cg ? ld_entry_cg(s0.p) : ld_entry(s0.p);  // L1-cacheable
-  PendingResolve pd;
-  pd.on = false;
-  for (int64_t i = i_first; i < n; i += stride) {
-    // ---- requests for the following items go out first ----
-    const int64_t k2 = i + 2 * stride < n ? __ldg(fids + i + 2 * stride) : 0;
-    const ClaimSlot s1 = claim_slot(set, k1, R, N);
-    Entry e1 = empty_entry();
-    if (i + stride < n) e1 = cr.set_loads_cg ? ld_entry_cg(s1.p) : ld_entry(s1.p);
-    // ---- the winner of the previous iteration: its table bucket has arrived ----
-    finish_resolve<RESOLVE>(pd, set, cr);
-    pd.on = false;
-    // ---- item i ----
-    const int64_t key = k0;
-    uint32_t idx = s0.idx;
-    uint32_t found = 0xFFFFFFFFu;
-    bool won = false;
-    Entry e = e0;
-    for (uint32_t probes = 0; probes < R; ++probes) {
-      Entry* p = set + s0.base + idx;
-      if (probes) e = cr.set_loads_cg ? ld_entry_cg(p) : ld_entry(p);
-      while (e.ts != epoch) {  // empty as far as we can see: claim it (CAS against what we saw)
-        Entry ne;
-        ne.key = key;
-        ne.row = kEmptyRow;
-        ne.ts = epoch;
-        const Entry old = cas_entry_old(p, e, ne);
-        if (old.key == e.key && old.row == e.row && old.ts == e.ts) {
-          won = true;
-          e = ne;
-        } else {
-          e = old;  // somebody else changed it: the true entry (claimed this epoch, or a different stale one)
-        }
-      }
-      if (e.key == key) {
-        found = s0.base + idx;
-        break;
-      }
-      idx = idx + 1 == R ? 0 : idx + 1;
-    }
-    if (found == 0xFFFFFFFFu) {  // region full (owner skew): the host retries with larger regions
-      owner_cnt[256] = 1;
-      found = s0.base;
-      won = false;
-    }
-    slot_of[i] = found;
-    if (won) {
-      atomicAdd(&cnt[s0.owner], 1u);
-      if (RESOLVE) {  // request the FID's first table bucket; it is examined in the next iteration
-        uint32_t b1, b2;
-        bucket_pair(key, cr.t->num_buckets, b1, b2);
-        pd.on = true;
-        pd.key = key;
-        pd.set_slot = found;
-        pd.bucket = cr.t->buckets + (size_t)b1 * kBucketSlots;
-        pd.e0 = ld_entry(pd.bucket);
-        pd.e1 = ld_entry(pd.bucket + 1);
-        pd.e2 = ld_entry(pd.bucket + 2);
-        pd.e3 = ld_entry(pd.bucket + 3);
-      }
-    }
-    // ---- rotate the pipeline ----
-    k0 = k1;
-    k1 = k2;
-    s0 = s1;
-    e0 = e1;
-  }
-  finish_resolve<RESOLVE>(pd, set, cr);
-  __syncthreads();
-  for (int d = threadIdx.x; d < N; d += blockDim.x)
-    if (cnt[d]) atomicAdd(owner_cnt + d, cnt[d]);
-}
-
-// Non-pipelined variant (one occurrence at a time per thread, the winner probes the table on the spot): 32 registers,
-// full occupancy.  mono_set_option("claim_pipeline", 0) selects it.
-template <bool RESOLVE>
-__global__ void __launch_bounds__(kThreads)
-fid_claim_simple_kernel(const int64_t* __restrict__ fids, int64_t n, Entry* set, uint32_t R, int N, uint32_t epoch,
                  uint32_t* __restrict__ slot_of, uint32_t* __restrict__ owner_cnt /* [N], [256] = overflow */,
                  ClaimResolve cr) {
   __shared__ uint32_t cnt[256];
@@ -1058,6 +932,14 @@ fid_claim_simple_kernel(const int64_t* __restrict__ fids, int64_t n, Entry* set,
           e = ne;
         } else {
           e = old;  // somebody else changed it: the true entry (claimed this epoch, or a different stale one)
+        }
+      }
+      if (e.key != key && cr.confirm) {  // "another FID's slot": confirm with an atomic read before walking on
+        const Entry tr = cas_entry_old(p, e, e);
+        if (!(tr.key == e.key && tr.row == e.row && tr.ts == e.ts)) {
+          atomicAdd(&g_claim_torn, 1ull);  // a plain 128-bit read disagreed with the atomic one
+          --probes;                        // same slot again, the loop re-reads it
+          continue;
         }
       }
       if (e.key == key) {
@@ -1246,16 +1128,13 @@ void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t 
   uint32_t* k0 = (uint32_t*)(ws + o_k0);
   ClaimResolve cr;
   cr.set_loads_cg = g_opt_claim_cg.load(std::memory_order_relaxed);
+  cr.confirm = g_opt_claim_pipeline.load(std::memory_order_relaxed);  // (knob "claim_pipeline" reused as "claim_confirm")
   cr.t = mt->d_tables + k;
   cr.update_ts = (uint32_t)update_time;
   cr.miss_ctr = ctr + 8;
   cr.miss_slots = (uint32_t*)(ws + o_miss);
-  if (g_opt_claim_pipeline.load(std::memory_order_relaxed))
-    fid_claim_kernel<true><<<resident_grid(fid_claim_kernel<true>, M, kThreads), kThreads, 0, s>>>(
-        fids_dev, M, set, cap, 1, epoch, k0, ctr + 512, cr);
-  else
-    fid_claim_simple_kernel<true><<<resident_grid(fid_claim_simple_kernel<true>, M, kThreads), kThreads, 0, s>>>(
-        fids_dev, M, set, cap, 1, epoch, k0, ctr + 512, cr);
+  fid_claim_kernel<true><<<resident_grid(fid_claim_kernel<true>, M, kThreads), kThreads, 0, s>>>(
+      fids_dev, M, set, cap, 1, epoch, k0, ctr + 512, cr);
   MONO_CHECK_LAUNCH();
   // 2 absent FIDs: allocate a row + lock-free insert (few in steady state; the count stays on the device)
   claim_miss_kernel<<<resident_grid(claim_miss_kernel, std::min<int64_t>(M, 148 * 2 * kThreads), kThreads), kThreads, 0, s>>>(
@@ -1512,12 +1391,12 @@ void grouping_build(mono_grouping* g, const int64_t* fids_dev, int64_t M, int N,
     sw.piece_run_base = (uint32_t*)(ws + o_prb);
     sw.n_runs = ctr;
     sw.run_of_sorted = (uint32_t*)(ws + o_ros);
-    if (g_opt_claim_pipeline.load(std::memory_order_relaxed))
-      fid_claim_kernel<false><<<resident_grid(fid_claim_kernel<false>, M, kThreads), kThreads, 0, s>>>(
-          fids_dev, M, set, R, N, epoch, sw.k0, owner_cnt, ClaimResolve{g_opt_claim_cg.load(std::memory_order_relaxed), nullptr, 0, nullptr, nullptr});
-    else
-      fid_claim_simple_kernel<false><<<resident_grid(fid_claim_simple_kernel<false>, M, kThreads), kThreads, 0, s>>>(
-          fids_dev, M, set, R, N, epoch, sw.k0, owner_cnt, ClaimResolve{g_opt_claim_cg.load(std::memory_order_relaxed), nullptr, 0, nullptr, nullptr});
+    ClaimResolve cr0;
+    std::memset(&cr0, 0, sizeof(cr0));
+    cr0.set_loads_cg = g_opt_claim_cg.load(std::memory_order_relaxed);
+    cr0.confirm = g_opt_claim_pipeline.load(std::memory_order_relaxed);
+    fid_claim_kernel<false><<<resident_grid(fid_claim_kernel<false>, M, kThreads), kThreads, 0, s>>>(
+        fids_dev, M, set, R, N, epoch, sw.k0, owner_cnt, cr0);
     MONO_CHECK_LAUNCH();
     // counts -> host on the side stream, while the sort below keeps the GPU busy.  Device-driven callers
     // (shard_counts_host == nullptr: xstep.cu) never read them on the host: nothing waits, the per-owner counts stay

@@ -125,6 +125,7 @@ int64_t mono_get_option(const char* name) {
   if (name && std::strcmp(name, "lookup_tma") == 0) return g_opt_lookup_tma.load();
   if (name && std::strcmp(name, "claim_pipeline") == 0) return g_opt_claim_pipeline.load();
   if (name && std::strcmp(name, "claim_cg") == 0) return g_opt_claim_cg.load();
+  if (name && std::strcmp(name, "claim_torn") == 0) return (int64_t)claim_torn_count();
   return -1;
 }
 
