@@ -502,8 +502,6 @@ int64_t mono_kernel_launch_count(void);
 /* Engine tuning knobs (process-wide; no reference counterpart).  Known names:
  *   "lookup_tma"  0 / 1: single-table lookups with packed output rows use the TMA-staged kernel (bulk row copies
  *                 global -> shared -> global) instead of the register-path kernel.  Results are identical.
- *   "claim_pipeline" 0 / 1: the backward's claim kernel software-pipelines its dependent accesses over the grid-stride
- *                 iterations (1) or handles one occurrence at a time at full occupancy (0, default).  Same results.
  * Returns MONO_ERR_INVALID_ARGUMENT for an unknown name.  mono_get_option returns the current value (or -1). */
 int mono_set_option(const char* name, int64_t value);
 int64_t mono_get_option(const char* name);

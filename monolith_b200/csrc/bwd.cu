@@ -137,12 +137,16 @@ radix_scatter_kernel(const void* __restrict__ in, int64_t n, int shift, int pre_
     __syncthreads();
     // ---- phase 1: stable rank of every item among the equal digits of its warp's 512-item slice ----
     const int64_t wbeg = (int64_t)blk * kRadixTile + (int64_t)w * (kRadixTile / kRadixWarps);
-    uint32_t lr[kRadixIPT];
+    uint32_t dgv[kRadixIPT];   // all 16 digits first: 16 independent loads in flight (0xFFFFFFFF = past the end)
 #pragma unroll
     for (int r = 0; r < kRadixIPT; ++r) {
       const int64_t i = wbeg + r * 32 + lane;
-      const bool valid = i < n;
-      const uint32_t dg = valid ? (radix_load<FIRST>(in, i, pre_shift).x >> shift) & (kRadixBins - 1) : 0u;
+      dgv[r] = i < n ? (radix_load<FIRST>(in, i, pre_shift).x >> shift) & (kRadixBins - 1) : 0xFFFFFFFFu;
+    }
+#pragma unroll
+    for (int r = 0; r < kRadixIPT; ++r) {  // afterwards dgv[r] = digit | rank << 16 (rank < 1024)
+      const bool valid = dgv[r] != 0xFFFFFFFFu;
+      const uint32_t dg = valid ? dgv[r] : 0u;
       uint32_t peers = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
       for (int b = 0; b < kRadixBits; ++b) {
@@ -156,7 +160,7 @@ radix_scatter_kernel(const void* __restrict__ in, int64_t n, int shift, int pre_
         wc[w][dg] = (uint16_t)(old + __popc(peers));
       }
       old = __shfl_sync(0xffffffffu, old, max(leader, 0));
-      lr[r] = old + __popc(peers & lt);
+      if (valid) dgv[r] = dg | ((old + __popc(peers & lt)) << 16);
       __syncwarp();
     }
     __syncthreads();
@@ -174,14 +178,23 @@ radix_scatter_kernel(const void* __restrict__ in, int64_t n, int shift, int pre_
       bbase[d] = goff[(size_t)blk * kRadixBins + d] + dbase[q];
     }
     __syncthreads();
-    // ---- phase 2: scatter ----
+    // ---- phase 2: scatter (digit and rank are in registers; the items are read again, 8 loads in flight) ----
 #pragma unroll
-    for (int r = 0; r < kRadixIPT; ++r) {
-      const int64_t i = wbeg + r * 32 + lane;
-      if (i < n) {
-        const uint2 it = radix_load<FIRST>(in, i, pre_shift);
-        const uint32_t dg = (it.x >> shift) & (kRadixBins - 1);
-        out[bbase[dg] + wc[w][dg] + lr[r]] = it;
+    for (int h = 0; h < kRadixIPT; h += 8) {
+      uint2 itv[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int64_t i = wbeg + (h + r) * 32 + lane;
+        itv[r] = make_uint2(0u, 0u);
+        if (dgv[h + r] != 0xFFFFFFFFu) itv[r] = radix_load<FIRST>(in, i, pre_shift);
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const uint32_t v = dgv[h + r];
+        if (v != 0xFFFFFFFFu) {
+          const uint32_t dg = v & (kRadixBins - 1);
+          out[bbase[dg] + wc[w][dg] + (v >> 16)] = itv[r];
+        }
       }
     }
     __syncthreads();
@@ -707,8 +720,8 @@ seg_reduce_kernel(SegArgs sa, const PeerOut po) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int e0 = e_begin & ~(kStage - 1); e0 < e_stop; e0 += kStage) {
       // ---- request: up to 16 gradient rows, this lane's 16-byte slice of each ----
-      float mean_n[kStage / 4][4];   // MEAN pooling: divisor of the row (applied after the copy)
-#pragma unroll
+      // (the 4-element bodies are NOT unrolled 4x more: the kernel was instruction-fetch bound when they were)
+#pragma unroll 1
       for (int b4 = 0; b4 < kStage; b4 += 4) {
         const int eb = e0 + b4;
         if (eb >= e_stop) break;
@@ -722,10 +735,8 @@ seg_reduce_kernel(SegArgs sa, const PeerOut po) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int e = eb + u;
-          mean_n[b4 / 4][u] = 1.0f;
           if (e >= e_begin && e < e_stop && in) {
             const uint32_t r = gs.occ_row ? gs.occ_row[m[u]] : m[u];
-            if (gs.mean) mean_n[b4 / 4][u] = (float)(gs.row_offsets[r + 1] - gs.row_offsets[r]);
             cp_async16(&stage[b4 + u][threadIdx.x], gs.base + (size_t)r * gs.stride);
           }
         }
@@ -733,13 +744,28 @@ seg_reduce_kernel(SegArgs sa, const PeerOut po) {
       asm volatile("cp.async.commit_group;" ::: "memory");
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       // ---- consume in occurrence order ----
-#pragma unroll
+#pragma unroll 1
       for (int b4 = 0; b4 < kStage; b4 += 4) {
         const int eb = e0 + b4;
         if (eb >= e_stop) break;
         // unit starts at eb + u, and at eb + u + 1 (=> eb + u ends a unit); no starts past the piece
         const uint32_t st4 = eb < kPiece ? (S >> eb) & 0xFu : 0u;
         const uint32_t nx4 = eb + 1 < kPiece ? (S >> (eb + 1)) & 0xFu : 0u;
+        float fn[4] = {1.f, 1.f, 1.f, 1.f};
+        if (gs.mean) {  // MEAN pooling: the divisor of each row (positions fetched again: rare path)
+          uint32_t m[4];
+          if (eb < kPiece) {
+            fetch4<G>(pm0, eb, m);
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) m[u] = base + eb + u < M ? a.sorted[base + eb + u].y : 0u;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t r = gs.occ_row ? gs.occ_row[m[u]] : m[u];
+            fn[u] = (float)(gs.row_offsets[r + 1] - gs.row_offsets[r]);
+          }
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int e = eb + u;
@@ -747,8 +773,7 @@ seg_reduce_kernel(SegArgs sa, const PeerOut po) {
           float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
           if (in) x = stage[b4 + u][threadIdx.x];
           if (gs.mean) {
-            const float fn = mean_n[b4 / 4][u];
-            x.x = __fdiv_rn(x.x, fn); x.y = __fdiv_rn(x.y, fn); x.z = __fdiv_rn(x.z, fn); x.w = __fdiv_rn(x.w, fn);
+            x.x = __fdiv_rn(x.x, fn[u]); x.y = __fdiv_rn(x.y, fn[u]); x.z = __fdiv_rn(x.z, fn[u]); x.w = __fdiv_rn(x.w, fn[u]);
           }
           if ((st4 >> u) & 1u) acc = x; else add4(acc, x);
           if (!(e + 1 == e_stop || ((nx4 >> u) & 1u))) continue;
@@ -843,24 +868,43 @@ long_finish_kernel(SegArgs sa, uint32_t top, const PeerOut po) {
   }
 }
 
-// Apply: group per run; rowidx[j], ugrad[j] and the row's w / state are all independent loads.
+// Apply: one streaming pass over the runs.  A warp takes 32 consecutive runs: the row indices are fetched lane-parallel
+// (one coalesced load), then every lane group applies its runs two at a time — both runs' summed gradient, w and
+// optimizer-state rows are requested before the first optimizer step, so two independent row chains are in flight
+// per group.
 template <int G, int OPT>
 __global__ void __launch_bounds__(kThreads) runs_apply_kernel(BwdArgs a) {
-  const int gl = Group<G>::gl();
+  constexpr int RPI = 32 / G;
+  const int lane = threadIdx.x & 31, gl = Group<G>::gl(), grp = lane / G;
   const int c = gl * 4;
   const int64_t nr = *a.n_runs;
   const int D = a.td.dim;
-  const int64_t gstride = (int64_t)gridDim.x * (kThreads / G);
-  for (int64_t j = (int64_t)blockIdx.x * (kThreads / G) + threadIdx.x / G; j < nr; j += gstride) {
-    const uint32_t ri = a.rowidx[j];
-    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c < D) g4 = __ldcs(reinterpret_cast<const float4*>(a.ugrad + (size_t)j * D + c));
-    if (ri == kEmptyRow) continue;
-    const RowPre pre = bwd_prefetch<G, OPT>(a, ri, c);
-    bwd_apply<G, OPT>(a, (uint32_t)j, ri, g4, c, pre);
+  const int64_t wstride = (int64_t)gridDim.x * (kThreads / 32) * 32;
+  for (int64_t wbase = ((int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * 32; wbase < nr; wbase += wstride) {
+    const uint32_t ri_l = wbase + lane < nr ? a.rowidx[wbase + lane] : kEmptyRow;
+#pragma unroll 1
+    for (int it = 0; it < G; it += 2) {
+      uint32_t ri[2];
+      int64_t j[2];
+      float4 g4[2];
+      RowPre pre[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int src = (it + q) * RPI + grp;
+        ri[q] = __shfl_sync(0xffffffffu, ri_l, src);
+        j[q] = wbase + src;
+        g4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j[q] < nr && c < D) g4[q] = __ldcs(reinterpret_cast<const float4*>(a.ugrad + (size_t)j[q] * D + c));
+        pre[q] = bwd_prefetch<G, OPT>(a, (j[q] < nr && ri[q] != kEmptyRow) ? ri[q] : kFreshBit, c);
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (j[q] >= nr || ri[q] == kEmptyRow) continue;  // past the end / row slab overflow / not admitted by the filter
+        bwd_apply<G, OPT>(a, (uint32_t)j[q], ri[q], g4[q], c, pre[q]);
+      }
+    }
   }
 }
-
 
 // run j of the sorted offsets -> destination row: out_rows + (sorted key << shift)
 template <int G>
@@ -887,16 +931,7 @@ __global__ void __launch_bounds__(kThreads) runs_emit_kernel(BwdArgs a, int shif
 // resolves the FID in the table right away — lane-level probe, expiry-timestamp bump
 // (ref: entry.SetTimestamp(update_time), cuckoo_embedding_hash_table.cc:243), row index parked in the set
 // entry; absent FIDs are queued (set slot) for claim_miss_kernel.  No separate resolve pass over the uniques.
-__device__ unsigned long long g_claim_torn = 0ull;  // statistics of the confirm knob
-unsigned long long claim_torn_count() {
-  unsigned long long v = 0;
-  cudaMemcpyFromSymbol(&v, g_claim_torn, sizeof(v));
-  return v;
-}
-
 struct ClaimResolve {
-  int set_loads_cg;  // debug knob: read the claim set with ld.global.cg (L2) instead of L1-cacheable loads
-  int confirm;       // debug knob: confirm "another FID's slot" with an atomic read before probing on
   const TableDev* t;
   uint32_t update_ts;
   uint32_t* miss_ctr;
@@ -904,15 +939,21 @@ struct ClaimResolve {
 };
 
 template <bool RESOLVE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 8)
 fid_claim_kernel(const int64_t* __restrict__ fids, int64_t n, Entry* set, uint32_t R, int N, uint32_t epoch,
                  uint32_t* __restrict__ slot_of, uint32_t* __restrict__ owner_cnt /* [N], [256] = overflow */,
                  ClaimResolve cr) {
   __shared__ uint32_t cnt[256];
   for (int d = threadIdx.x; d < 256; d += blockDim.x) cnt[d] = 0;
   __syncthreads();
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t key = __ldg(fids + i);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  // the chain per occurrence is FID -> set entry (-> CAS -> table bucket for a winner), ~2.5 us per dependent round
+  // trip: the NEXT occurrence's FID is requested one iteration ahead, which takes it off the chain
+  int64_t key_next = i < n ? __ldg(fids + i) : 0;
+  for (; i < n; i += stride) {
+    const int64_t key = key_next;
+    if (i + stride < n) key_next = __ldg(fids + i + stride);
     const uint32_t owner = N == 1 ? 0u : (uint32_t)((uint64_t)key % (uint64_t)N);
     const uint32_t base = owner * R;
     uint32_t idx = __umulhi((uint32_t)(mix64((uint64_t)key) >> 24), R);
@@ -920,7 +961,7 @@ fid_claim_kernel(const int64_t* __restrict__ fids, int64_t n, Entry* set, uint32
     bool won = false;
     for (uint32_t probes = 0; probes < R; ++probes) {
       Entry* p = set + base + idx;
-      Entry e = cr.set_loads_cg ? ld_entry_cg(p) : ld_entry(p);  // L1-cacheable
+      Entry e = ld_entry(p);  // L1-cacheable
       while (e.ts != epoch) {  // empty as far as we can see: claim it (CAS against what we saw)
         Entry ne;
         ne.key = key;
@@ -932,14 +973,6 @@ fid_claim_kernel(const int64_t* __restrict__ fids, int64_t n, Entry* set, uint32
           e = ne;
         } else {
           e = old;  // somebody else changed it: the true entry (claimed this epoch, or a different stale one)
-        }
-      }
-      if (e.key != key && cr.confirm) {  // "another FID's slot": confirm with an atomic read before walking on
-        const Entry tr = cas_entry_old(p, e, e);
-        if (!(tr.key == e.key && tr.row == e.row && tr.ts == e.ts)) {
-          atomicAdd(&g_claim_torn, 1ull);  // a plain 128-bit read disagreed with the atomic one
-          --probes;                        // same slot again, the loop re-reads it
-          continue;
         }
       }
       if (e.key == key) {
@@ -972,7 +1005,6 @@ fid_claim_kernel(const int64_t* __restrict__ fids, int64_t n, Entry* set, uint32
   for (int d = threadIdx.x; d < N; d += blockDim.x)
     if (cnt[d]) atomicAdd(owner_cnt + d, cnt[d]);
 }
-
 
 // FIDs the claim found absent from the table (each exactly once): take a row (free list first, then the bump
 // allocator), publish {fid, row, ts} with the lock-free cuckoo insert and park row | fresh in the set entry.
@@ -1127,8 +1159,6 @@ void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t 
   //   the set entry, expiry timestamp bumped) or queues it as absent
   uint32_t* k0 = (uint32_t*)(ws + o_k0);
   ClaimResolve cr;
-  cr.set_loads_cg = g_opt_claim_cg.load(std::memory_order_relaxed);
-  cr.confirm = g_opt_claim_pipeline.load(std::memory_order_relaxed);  // (knob "claim_pipeline" reused as "claim_confirm")
   cr.t = mt->d_tables + k;
   cr.update_ts = (uint32_t)update_time;
   cr.miss_ctr = ctr + 8;
@@ -1393,8 +1423,6 @@ void grouping_build(mono_grouping* g, const int64_t* fids_dev, int64_t M, int N,
     sw.run_of_sorted = (uint32_t*)(ws + o_ros);
     ClaimResolve cr0;
     std::memset(&cr0, 0, sizeof(cr0));
-    cr0.set_loads_cg = g_opt_claim_cg.load(std::memory_order_relaxed);
-    cr0.confirm = g_opt_claim_pipeline.load(std::memory_order_relaxed);
     fid_claim_kernel<false><<<resident_grid(fid_claim_kernel<false>, M, kThreads), kThreads, 0, s>>>(
         fids_dev, M, set, R, N, epoch, sw.k0, owner_cnt, cr0);
     MONO_CHECK_LAUNCH();

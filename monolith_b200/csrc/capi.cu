@@ -116,16 +116,11 @@ int mono_set_option(const char* name, int64_t value) {
   return guarded([&] {
     require(name != nullptr, "set_option: null name");
     if (std::strcmp(name, "lookup_tma") == 0) g_opt_lookup_tma.store(value != 0 ? 1 : 0);
-    else if (std::strcmp(name, "claim_pipeline") == 0) g_opt_claim_pipeline.store(value != 0 ? 1 : 0);
-    else if (std::strcmp(name, "claim_cg") == 0) g_opt_claim_cg.store(value != 0 ? 1 : 0);
     else throw ArgError(std::string("unknown option: ") + name);
   });
 }
 int64_t mono_get_option(const char* name) {
   if (name && std::strcmp(name, "lookup_tma") == 0) return g_opt_lookup_tma.load();
-  if (name && std::strcmp(name, "claim_pipeline") == 0) return g_opt_claim_pipeline.load();
-  if (name && std::strcmp(name, "claim_cg") == 0) return g_opt_claim_cg.load();
-  if (name && std::strcmp(name, "claim_torn") == 0) return (int64_t)claim_torn_count();
   return -1;
 }
 

@@ -18,9 +18,6 @@ namespace mono {
 
 extern std::atomic<int64_t> g_launches;  // kernels launched by this library
 extern std::atomic<int> g_opt_lookup_tma; // mono_set_option("lookup_tma")
-extern std::atomic<int> g_opt_claim_pipeline;  // mono_set_option("claim_pipeline")
-extern std::atomic<int> g_opt_claim_cg;        // mono_set_option("claim_cg")
-unsigned long long claim_torn_count();
 #define MONO_COUNT_LAUNCH() (::mono::g_launches.fetch_add(1, std::memory_order_relaxed))
 
 struct CudaError : std::runtime_error {

@@ -9,8 +9,6 @@ namespace mono {
 
 std::atomic<int64_t> g_launches{0};
 std::atomic<int> g_opt_lookup_tma{0};
-std::atomic<int> g_opt_claim_pipeline{0};
-std::atomic<int> g_opt_claim_cg{0};
 
 // ------------------------------------------------------------------------------------------
 // StageRing
