@@ -868,41 +868,22 @@ long_finish_kernel(SegArgs sa, uint32_t top, const PeerOut po) {
   }
 }
 
-// Apply: one streaming pass over the runs.  A warp takes 32 consecutive runs: the row indices are fetched lane-parallel
-// (one coalesced load), then every lane group applies its runs two at a time — both runs' summed gradient, w and
-// optimizer-state rows are requested before the first optimizer step, so two independent row chains are in flight
-// per group.
+// Apply: group per run; rowidx[j], ugrad[j] and the row's w / state are all independent loads.
+// (A variant that handled two runs per group at a time was measured slower: 62 registers, 43 % occupancy.)
 template <int G, int OPT>
 __global__ void __launch_bounds__(kThreads) runs_apply_kernel(BwdArgs a) {
-  constexpr int RPI = 32 / G;
-  const int lane = threadIdx.x & 31, gl = Group<G>::gl(), grp = lane / G;
+  const int gl = Group<G>::gl();
   const int c = gl * 4;
   const int64_t nr = *a.n_runs;
   const int D = a.td.dim;
-  const int64_t wstride = (int64_t)gridDim.x * (kThreads / 32) * 32;
-  for (int64_t wbase = ((int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * 32; wbase < nr; wbase += wstride) {
-    const uint32_t ri_l = wbase + lane < nr ? a.rowidx[wbase + lane] : kEmptyRow;
-#pragma unroll 1
-    for (int it = 0; it < G; it += 2) {
-      uint32_t ri[2];
-      int64_t j[2];
-      float4 g4[2];
-      RowPre pre[2];
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int src = (it + q) * RPI + grp;
-        ri[q] = __shfl_sync(0xffffffffu, ri_l, src);
-        j[q] = wbase + src;
-        g4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j[q] < nr && c < D) g4[q] = __ldcs(reinterpret_cast<const float4*>(a.ugrad + (size_t)j[q] * D + c));
-        pre[q] = bwd_prefetch<G, OPT>(a, (j[q] < nr && ri[q] != kEmptyRow) ? ri[q] : kFreshBit, c);
-      }
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        if (j[q] >= nr || ri[q] == kEmptyRow) continue;  // past the end / row slab overflow / not admitted by the filter
-        bwd_apply<G, OPT>(a, (uint32_t)j[q], ri[q], g4[q], c, pre[q]);
-      }
-    }
+  const int64_t gstride = (int64_t)gridDim.x * (kThreads / G);
+  for (int64_t j = (int64_t)blockIdx.x * (kThreads / G) + threadIdx.x / G; j < nr; j += gstride) {
+    const uint32_t ri = a.rowidx[j];
+    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < D) g4 = __ldcs(reinterpret_cast<const float4*>(a.ugrad + (size_t)j * D + c));
+    if (ri == kEmptyRow) continue;
+    const RowPre pre = bwd_prefetch<G, OPT>(a, ri, c);
+    bwd_apply<G, OPT>(a, (uint32_t)j, ri, g4, c, pre);
   }
 }
 
@@ -939,7 +920,7 @@ struct ClaimResolve {
 };
 
 template <bool RESOLVE>
-__global__ void __launch_bounds__(kThreads, 8)
+__global__ void __launch_bounds__(kThreads)
 fid_claim_kernel(const int64_t* __restrict__ fids, int64_t n, Entry* set, uint32_t R, int N, uint32_t epoch,
                  uint32_t* __restrict__ slot_of, uint32_t* __restrict__ owner_cnt /* [N], [256] = overflow */,
                  ClaimResolve cr) {
