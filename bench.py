@@ -65,6 +65,8 @@ def parse():
   ap.add_argument("--no-e2e", action="store_true")
   ap.add_argument("--e2e-chunks", type=int, default=8,
                   help="e2e leg: slices of the pooled-rows D2H / gradient H2D round trip (1 = sequential copies)")
+  ap.add_argument("--no-prepare", action="store_true",
+                  help="exchange=direct: do NOT build the next batch's grouping on a side stream under the step in flight")
   ap.add_argument("--sharded", action="store_true", help="run the sharded step (ShardedStep) even at N=1 (profiling)")
   ap.add_argument("--remote-frac", type=float, default=None,
                   help="experiment: fraction of a rank's FID occurrences owned by other ranks (default: natural 1 - 1/N)")
@@ -572,8 +574,12 @@ def run_ours(args):
       regions.append(ms)
     return float(np.median(regions)), launches, regions
 
+  overlap = use_sharded and sharded.exchange == "direct" and not args.no_prepare
+
   def dev_step(i):
     step(i, fids_dev[i % NB], pgrad_dev, pooled)
+    if overlap:   # the input pipeline knows the next batch: its grouping is built under this step's exchange phases
+      sharded.prepare(fids_dev[(i + 1) % NB])
 
   with Clocks(local) as clk:
     ms, launches, regions = timed(dev_step, args.steps, args.warmup, args.repeats)

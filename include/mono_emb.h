@@ -489,6 +489,10 @@ typedef struct mono_xstep mono_xstep_t;
 int64_t mono_xstep_window_bytes(int32_t world, int64_t cap_pair, int32_t dim);
 int mono_xstep_create(mono_mtable_t* t, int32_t k, mono_peer_t* window, int64_t cap_pair, mono_xstep_t** out);
 int mono_xstep_destroy(mono_xstep_t* x);
+/* Optional: build the grouping of the NEXT batch on `stream2` while the step in flight runs on its own stream (the
+ * grouping depends on the batch only; ref pipelining: NT/distributed_ps_sync.py:199-204,270-275).  The next
+ * mono_xstep_forward must get the same fids pointer and count, otherwise it regroups inline. */
+int mono_xstep_prepare(mono_xstep_t* x, const int64_t* fids_next_dev, int64_t n_fids, void* stream2);
 int mono_xstep_forward(mono_xstep_t* x, const int64_t* fids_dev, int64_t n_fids, const int32_t* row_offsets_dev,
                        int64_t n_rows, int32_t pooling, float* out_dev, int64_t out_stride, int32_t out_col,
                        void* stream);

@@ -46,6 +46,7 @@ SIGNATURES = {
     "mono_xstep_window_bytes": (_i64, [_i32, _i64, _i32]),
     "mono_xstep_create": (C.c_int, [_p, _i32, _p, _i64, C.POINTER(_p)]),
     "mono_xstep_destroy": (C.c_int, [_p]),
+    "mono_xstep_prepare": (C.c_int, [_p, _p, _i64, _p]),
     "mono_xstep_forward": (C.c_int, [_p, _p, _i64, _p, _i64, _i32, _p, _i64, _i32, _p]),
     "mono_xstep_backward": (C.c_int, [_p, _p, _i64, _i32, _p, _i32, _p, _i64, _p]),
     "mono_set_option": (C.c_int, [C.c_char_p, _i64]),

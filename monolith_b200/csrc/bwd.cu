@@ -512,11 +512,11 @@ __device__ __forceinline__ void bwd_apply(const BwdArgs& a, uint32_t j, uint32_t
 
 // destination of run j's summed row: ugrad[j], or (po.n != 0: the sharded backward's fused gradient
 // exchange) row j of an owner-bucketed list whose part r lives in rank r's peer window.
-__device__ __forceinline__ float* run_dst(float* ugrad, const PeerOut& po, const int64_t* __restrict__ s_start, int64_t j,
-                                          int D) {
-  if (po.n == 0) return ugrad + (size_t)j * D;
-  const int r = peer_part(s_start, po.n, j);
-  return reinterpret_cast<float*>(po.base[r]) + (j - s_start[r]) * D;
+__device__ __forceinline__ float* run_dst(float* ugrad, int n_parts, const int64_t* __restrict__ s_start,
+                                          char* const* __restrict__ s_base, int64_t j, int D) {
+  if (n_parts == 0) return ugrad + (size_t)j * D;
+  const int r = peer_part(s_start, n_parts, j);
+  return reinterpret_cast<float*>(s_base[r]) + (j - s_start[r]) * D;
 }
 
 
@@ -646,9 +646,11 @@ __global__ void __launch_bounds__(kThreads, 3)
 seg_reduce_kernel(SegArgs sa, const PeerOut po) {
   static_assert(MODE == MODE_STORE, "the optimizer is applied by runs_apply_kernel");
   __shared__ int64_t s_start[kMaxPeers + 1];
+  __shared__ char* s_base[kMaxPeers];
   extern __shared__ float4 stage_raw[];        // [kStage][kThreads]: [slot][thread], conflict-free 16-byte accesses
   float4 (*stage)[kThreads] = reinterpret_cast<float4 (*)[kThreads]>(stage_raw);
-  peer_starts(po, s_start);
+  peer_starts(po, s_start, s_base);
+  const int n_parts = po.n;
   constexpr int EPL = 32 / G;          // elements of a piece per lane
   constexpr int RPI = 32 / G;          // pieces per warp iteration
   const BwdArgs& a = sa.b;
@@ -782,7 +784,7 @@ seg_reduce_kernel(SegArgs sa, const PeerOut po) {
           float* dst;
           if (hr == 0) dst = sa.part + (size_t)(2 * p) * D;                          // leading block of a long run
           else if (last_long && hr == nheads) dst = sa.part + (size_t)(2 * p + 1) * D;  // block 0 of a long run
-          else dst = run_dst(a.ugrad, po, s_start, (int64_t)j0 + hr - 1, D);          // a short run
+          else dst = run_dst(a.ugrad, n_parts, s_start, s_base, (int64_t)j0 + hr - 1, D);  // a short run
           if (in) *reinterpret_cast<float4*>(dst + c) = acc;
         }
       }
@@ -831,9 +833,10 @@ template <int G, int MODE, int OPT>
 __global__ void __launch_bounds__(kThreads)
 long_finish_kernel(SegArgs sa, uint32_t top, const PeerOut po) {
   __shared__ int64_t s_start[kMaxPeers + 1];
+  __shared__ char* s_base[kMaxPeers];
   extern __shared__ float4 stage_raw[];  // [kStage][kThreads]
   float4 (*stage)[kThreads] = reinterpret_cast<float4 (*)[kThreads]>(stage_raw);
-  peer_starts(po, s_start);
+  peer_starts(po, s_start, s_base);
   const BwdArgs& a = sa.b;
   const int gl = Group<G>::gl(), c = gl * 4;
   const int D = a.td.dim;
@@ -863,7 +866,7 @@ long_finish_kernel(SegArgs sa, uint32_t top, const PeerOut po) {
       const RowPre pre = bwd_prefetch<G, OPT>(a, ri, c);
       bwd_apply<G, OPT>(a, j, ri, acc, c, pre);
     } else {
-      if (c < D) *reinterpret_cast<float4*>(run_dst(a.ugrad, po, s_start, j, D) + c) = acc;
+      if (c < D) *reinterpret_cast<float4*>(run_dst(a.ugrad, po.n, s_start, s_base, j, D) + c) = acc;
     }
   }
 }

@@ -647,6 +647,14 @@ int mono_xstep_destroy(mono_xstep_t* x) {
   return guarded([&] { xstep_destroy(x); });
 }
 
+int mono_xstep_prepare(mono_xstep_t* x, const int64_t* fids_next_dev, int64_t n_fids, void* stream2) {
+  return guarded([&] {
+    require(x && fids_next_dev, "xstep_prepare: null argument");
+    HandleGuard hg_(x->mt);
+    xstep_prepare(x, fids_next_dev, n_fids, (cudaStream_t)stream2);
+  });
+}
+
 int mono_xstep_forward(mono_xstep_t* x, const int64_t* fids_dev, int64_t n_fids, const int32_t* row_offsets_dev,
                        int64_t n_rows, int32_t pooling, float* out_dev, int64_t out_stride, int32_t out_col,
                        void* stream) {

@@ -218,9 +218,9 @@ struct PeerOut {
   const uint32_t* cnt_dev;  // optional: the part sizes live on the device (start[] is then ignored)
 };
 #ifdef __CUDACC__
-// Part boundaries into shared memory (from the host-side start[] or as the prefix of the device counts); every
-// thread of the block must call it (it ends with a barrier).
-__device__ __forceinline__ void peer_starts(const PeerOut& po, int64_t* s_start /* shared [kMaxPeers + 1] */) {
+// Part boundaries (from the host-side start[] or as the prefix of the device counts) and part bases into shared
+// memory; every thread of the block must call it (it ends with a barrier).  s_start[kMaxPeers + 1], s_base[kMaxPeers].
+__device__ __forceinline__ void peer_starts(const PeerOut& po, int64_t* s_start, char** s_base = nullptr) {
   if (po.n == 0) return;  // uniform: no peer output
   if (threadIdx.x == 0) {
     int64_t run = 0;
@@ -229,6 +229,7 @@ __device__ __forceinline__ void peer_starts(const PeerOut& po, int64_t* s_start 
       if (po.cnt_dev && r < po.n) run += po.cnt_dev[r];
     }
   }
+  if (s_base && threadIdx.x < kMaxPeers) s_base[threadIdx.x] = po.base[threadIdx.x];
   __syncthreads();
 }
 __device__ __forceinline__ int peer_part(const int64_t* __restrict__ start, int n, int64_t i) {
@@ -275,13 +276,22 @@ struct mono_xstep {
   mono_mtable* mt = nullptr;
   int k = 0;
   mono_peer* win = nullptr;
-  mono_grouping* grouping = nullptr;  // owned
+  // two groupings (by step parity): while step e runs, the grouping of batch e + 1 can be built on another stream
+  // (mono_xstep_prepare) — it does not depend on the table
+  mono_grouping* grouping[2] = {nullptr, nullptr};  // owned
+  mono::DevBuf uniq[2], offs[2];                     // bucketed unique list, per-occurrence row offsets
+  cudaEvent_t ev_prep[2] = {nullptr, nullptr};       // grouping [slot] built (recorded on the prepare stream)
+  cudaEvent_t ev_bwd[2] = {nullptr, nullptr};        // backward of the step that used grouping [slot] enqueued
+  bool bwd_recorded[2] = {false, false};
+  uint64_t prep_seq = 0;                             // step the prepared grouping belongs to (0 = none)
+  const int64_t* prep_fids = nullptr;
+  int64_t prep_m = 0;
   int64_t C = 0;
   int N = 1, me = 0, D = 0;
   mono::XWin w{};
   uint64_t step = 0;               // steps started (forward calls)
   uint64_t timeout_ns = 0;
-  mono::DevBuf uniq, offs, ws;     // bucketed unique list, per-occurrence row offsets, owner-side scratch
+  mono::DevBuf ws;                 // owner-side scratch
   mono::ClaimSet miss_set;
   int64_t last_m = 0, last_rows = 0;
   bool fwd_done = false;
@@ -318,6 +328,7 @@ void grouping_reduce(mono_grouping* g, const float* pooled_grad, int64_t grad_st
 int64_t xstep_window_bytes(int N, int64_t C, int D);
 mono_xstep* xstep_create(mono_mtable* mt, int k, mono_peer* win, int64_t cap_pair);
 void xstep_destroy(mono_xstep* x);
+void xstep_prepare(mono_xstep* x, const int64_t* fids_next_dev, int64_t M, cudaStream_t s2);
 void xstep_forward(mono_xstep* x, const int64_t* fids_dev, int64_t M, const int32_t* row_offsets, int64_t n_rows,
                    int pooling, float* out, int64_t out_stride, int out_col, cudaStream_t s);
 void xstep_backward(mono_xstep* x, const float* pooled_grad, int64_t grad_stride, int grad_col,

@@ -338,8 +338,12 @@ mono_xstep* xstep_create(mono_mtable* mt, int k, mono_peer* win, int64_t cap_pai
   x->N = win->world;
   x->me = win->rank;
   x->D = D;
-  x->grouping = new mono_grouping();
-  x->grouping->device = mt->device;
+  for (int q = 0; q < 2; ++q) {
+    x->grouping[q] = new mono_grouping();
+    x->grouping[q]->device = mt->device;
+    MONO_CUDA(cudaEventCreateWithFlags(&x->ev_prep[q], cudaEventDisableTiming));
+    MONO_CUDA(cudaEventCreateWithFlags(&x->ev_bwd[q], cudaEventDisableTiming));
+  }
   XWin& w = x->w;
   std::memset(&w, 0, sizeof(w));
   for (int r = 0; r < x->N; ++r) w.base[r] = win->base[r];
@@ -361,12 +365,15 @@ void xstep_destroy(mono_xstep* x) {
   if (!x) return;
   cudaSetDevice(x->mt->device);
   cudaDeviceSynchronize();
-  x->uniq.release();
-  x->offs.release();
   x->ws.release();
   x->miss_set.release();
-  if (x->grouping) {
-    mono_grouping* g = x->grouping;
+  for (int q = 0; q < 2; ++q) {
+    x->uniq[q].release();
+    x->offs[q].release();
+    if (x->ev_prep[q]) cudaEventDestroy(x->ev_prep[q]);
+    if (x->ev_bwd[q]) cudaEventDestroy(x->ev_bwd[q]);
+    mono_grouping* g = x->grouping[q];
+    if (!g) continue;
     g->ws.release();
     g->claim_set.release();
     if (g->h_counts) cudaFreeHost(g->h_counts);
@@ -388,10 +395,21 @@ void xstep_forward(mono_xstep* x, const int64_t* fids_dev, int64_t M, const int3
   const XWin& w = x->w;
   const uint64_t seq = ++x->step;
   const int par = (int)(seq & 1);
-  int64_t* uniq = (int64_t*)x->uniq.get(8 * (size_t)M, s);
-  int32_t* offs = (int32_t*)x->offs.get(4 * (size_t)M, s);
-  grouping_build(x->grouping, fids_dev, M, x->N, x->D, uniq, offs, nullptr, nullptr, s);
-  const uint32_t* owner_cnt = x->grouping->owner_cnt;
+  mono_grouping* g = x->grouping[par];
+  int64_t* uniq;
+  int32_t* offs;
+  if (x->prep_seq == seq && x->prep_fids == fids_dev && x->prep_m == M) {
+    // the grouping of this batch was built ahead of time on another stream (xstep_prepare): just order after it
+    MONO_CUDA(cudaStreamWaitEvent(s, x->ev_prep[par], 0));
+    uniq = (int64_t*)x->uniq[par].p;
+    offs = (int32_t*)x->offs[par].p;
+  } else {
+    uniq = (int64_t*)x->uniq[par].get(8 * (size_t)M, s);
+    offs = (int32_t*)x->offs[par].get(4 * (size_t)M, s);
+    grouping_build(g, fids_dev, M, x->N, x->D, uniq, offs, nullptr, nullptr, s);
+  }
+  x->prep_seq = 0;
+  const uint32_t* owner_cnt = g->owner_cnt;
   xput_ids_kernel<<<resident_grid(xput_ids_kernel, M, kThreads), kThreads, 0, s>>>(uniq, owner_cnt, w, par);
   MONO_CHECK_LAUNCH();
   xsignal_kernel<<<1, 32, 0, s>>>(w, kPhaseIds, seq, owner_cnt);
@@ -438,8 +456,9 @@ void xstep_backward(mono_xstep* x, const float* pooled_grad, int64_t grad_stride
   po.n = x->N;
   for (int r = 0; r < x->N; ++r)
     po.base[r] = x->win->base[r] + kPeerFlagBytes + w.off_grads + (int64_t)x->me * x->C * x->D * 4;
-  po.cnt_dev = x->grouping->owner_cnt;
-  grouping_reduce_push(x->grouping, pooled_grad, grad_stride, grad_col, row_offsets, x->last_rows, pooling, po, s);
+  mono_grouping* g = x->grouping[par];
+  po.cnt_dev = g->owner_cnt;
+  grouping_reduce_push(g, pooled_grad, grad_stride, grad_col, row_offsets, x->last_rows, pooling, po, s);
   xsignal_kernel<<<1, 32, 0, s>>>(w, kPhaseGrads, seq, nullptr);
   MONO_CHECK_LAUNCH();
   // owner: resolve (+ insert) everything received, then apply source by source
@@ -498,6 +517,28 @@ void xstep_backward(mono_xstep* x, const float* pooled_grad, int64_t grad_stride
   ht.issued_total += (uint64_t)x->last_m;
   ht.max_update_ts = std::max<int64_t>(ht.max_update_ts, update_time);
   request_snapshot(mt, x->k, s);
+  MONO_CUDA(cudaEventRecord(x->ev_bwd[par], s));  // grouping [par] is free again once this point is reached
+  x->bwd_recorded[par] = true;
+}
+
+// Build the grouping of the NEXT batch on stream s2 while the current step runs on its own stream: the grouping
+// (claim, sort, run list, bucketed unique list) depends on the batch only, not on the table, so it may overlap the
+// NVLink-bound and flag-waiting phases of the step in flight (the reference pipelines the same way: the next batch's
+// id shuffling runs under the current batch's dense compute, NT/distributed_ps_sync.py:199-204,270-275).  The next
+// mono_xstep_forward must be called with the same fids pointer and count to use it.
+void xstep_prepare(mono_xstep* x, const int64_t* fids_next_dev, int64_t M, cudaStream_t s2) {
+  MONO_CUDA(cudaSetDevice(x->mt->device));
+  if (M <= 0 || M > x->C) throw ArgError("xstep_prepare: batch larger than the window capacity (or empty)");
+  const uint64_t seq = x->step + 1;
+  const int par = (int)(seq & 1);
+  if (x->bwd_recorded[par]) MONO_CUDA(cudaStreamWaitEvent(s2, x->ev_bwd[par], 0));  // last user of grouping [par]
+  int64_t* uniq = (int64_t*)x->uniq[par].get(8 * (size_t)M, s2);
+  int32_t* offs = (int32_t*)x->offs[par].get(4 * (size_t)M, s2);
+  grouping_build(x->grouping[par], fids_next_dev, M, x->N, x->D, uniq, offs, nullptr, nullptr, s2);
+  MONO_CUDA(cudaEventRecord(x->ev_prep[par], s2));
+  x->prep_seq = seq;
+  x->prep_fids = fids_next_dev;
+  x->prep_m = M;
 }
 
 }  // namespace mono

@@ -443,6 +443,23 @@ class ShardedStep:
     _lib.check(lib.mono_xstep_create(self.table.handle, self.k, self.window._h, cap, C.byref(h)))
     self.xstep, self.cap_pair = h, cap
 
+  def prepare(self, fids_next: torch.Tensor):
+    """exchange == "direct": build the grouping of the NEXT batch on a side stream while the step in flight runs
+    (no table dependency).  Pass the SAME tensor to the next step()."""
+    import ctypes as C
+    from . import _lib
+    if self.exchange != "direct" or self.xstep is None:
+      return
+    f = fids_next.reshape(-1)
+    if f.dtype != torch.int64 or not f.is_contiguous() or f.numel() > self.cap_pair or f.numel() == 0:
+      return
+    if getattr(self, "_side", None) is None:
+      self._side = torch.cuda.Stream(device=self.device)
+    self._side.wait_stream(torch.cuda.current_stream(self.device))   # fids_next may have been produced on the main stream
+    _lib.check(_lib.load().mono_xstep_prepare(self.xstep, C.c_void_p(f.data_ptr()), f.numel(),
+                                              C.c_void_p(self._side.cuda_stream)))
+    self._keep_prep = f
+
   def close_direct(self):
     from . import _lib
     if self.xstep is not None:

@@ -136,10 +136,13 @@ def _fast_worker(rank, world, port, q, exchange="peer"):
       exchange = "peer"
     st = ShardedStep(table, "t", 16, world, rank, dev, exchange=exchange)
     pooled_all = []
+    devb = [torch.from_numpy(_fast_batch(rank, step)[0]).to(dev) for step in range(3)]
     for step in range(3):
       fids, g = _fast_batch(rank, step)
       out = torch.empty(fids.size, 16, device=dev)
-      st.step(torch.from_numpy(fids).to(dev), torch.from_numpy(g).to(dev), out, 20 + step)
+      st.step(devb[step], torch.from_numpy(g).to(dev), out, 20 + step)
+      if exchange == "direct" and step + 1 < 3:
+        st.prepare(devb[step + 1])          # next batch's grouping on a side stream, under this step's exchange
       pooled_all.append(out.cpu().numpy())
     ks, rows = [], []
     for ids, raw in table.export("t", chunk=1 << 14):

@@ -1062,23 +1062,27 @@ def test_sharded_direct_step_world1_vs_oracle(mode, dev):
   st = ShardedStep(gpu, "t", D, 1, 0, dev, exchange="direct")
   rng = np.random.default_rng(31)
   hot = fid(5, 3)
+  batches = []
+  for step in range(5):
+    n = 6000 + (500 * step if step < 3 else 1000)                # growing batches: the window is re-created once or twice
+    ids = rng.integers(0, 900 + 50 * step, n)
+    ids[rng.random(n) < 0.25] = 3                                # hot FID: a > 64-occurrence run (tree-reduced)
+    fids = (np.int64(5) << 48) | ids.astype(np.int64)
+    if mode == "csr_mean":
+      lens = rng.integers(0, 5, n)
+      ro = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+      ro = ro[ro <= n]
+      ro[-1] = n
+      R, pool = ro.size - 1, "mean"
+    else:
+      ro, R, pool = None, n, "sum"
+    batches.append((fids, ro, R, pool, rng.standard_normal((R, D)).astype(np.float32), T(fids, dev)))
   try:
-    for step in range(4):
-      n = 6000 + 500 * step                                        # growing batches: the window is re-created once
-      ids = rng.integers(0, 900 + 50 * step, n)
-      ids[rng.random(n) < 0.25] = 3                                # hot FID: a > 64-occurrence run (tree-reduced)
-      fids = (np.int64(5) << 48) | ids.astype(np.int64)
-      if mode == "csr_mean":
-        lens = rng.integers(0, 5, n)
-        ro = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
-        ro = ro[ro <= n]
-        ro[-1] = n
-        R, pool = ro.size - 1, "mean"
-      else:
-        ro, R, pool = None, n, "sum"
-      g = rng.standard_normal((R, D)).astype(np.float32)
+    for step, (fids, ro, R, pool, g, f_dev) in enumerate(batches):
       out = torch.empty(R, D, device=dev)
-      st.step(T(fids, dev), T(g, dev), out, 20 + step, None if ro is None else T(ro, dev), pool)
+      st.step(f_dev, T(g, dev), out, 20 + step, None if ro is None else T(ro, dev), pool)
+      if step + 1 < len(batches):
+        st.prepare(batches[step + 1][5])                           # next batch's grouping on a side stream (same tensor object)
       want = cpu.lookup_pool("t", fids, ro, pool)
       got = out.cpu().numpy()
       if ro is None:
