@@ -294,12 +294,12 @@ def workload_config(args, batch):
   return {
       "workload": head + "Zipf(1.05) FIDs; step = fused lookup+pool fwd + fused backward (group FIDs, deterministic per-FID grad "
                   "reduce, Adagrad upsert with expiry bump)" + (
-                      "; sharded: group by owner, FID/row/grad exchange over NVLink peer windows (fused lookup+send, reduce+send)"
+                      "; sharded: group by owner, FID/row/grad exchange over NVLink peer windows (fused lookup+send, reduce+send; device-driven: fixed per-source regions, directional flags, no host round trip)"
                       if (args.gpus > 1 or getattr(args, "sharded", False)) else ""),
       **({"remote_frac_experiment": args.remote_frac} if getattr(args, "remote_frac", None) is not None else {}),
       "zipf_s": args.zipf, "keys": args.keys, "dim": DIM, "slots": SLOTS, "batch_per_gpu": batch, "fids_per_step_per_gpu": batch * SLOTS,
       "l2_hygiene": "inputs larger than L2: 2.6 GB table + 4 rotating batches, 268 MB pooled output per step",
-      "parallelism": (f"fid-hash sharding x{args.gpus}, exchange={getattr(args, 'exchange', None) or os.environ.get('MONO_EXCHANGE', 'peer')}"
+      "parallelism": (f"fid-hash sharding x{args.gpus}, exchange={getattr(args, 'exchange', None) or os.environ.get('MONO_EXCHANGE', 'direct')}"
                       if (args.gpus > 1 or getattr(args, "sharded", False)) else "single GPU"),
   }
 

@@ -65,15 +65,20 @@ lookup_kernel(const TableDev* __restrict__ tables, const CallSeg* __restrict__ s
   float* const base0 = out + segs[0].val_off - segs[0].id_begin * rs0 + out_col;
   const bool vec0 = (D0 & 3) == 0 && (rs0 & 3) == 0 && (reinterpret_cast<uintptr_t>(base0) & 15) == 0;
   const int64_t wstride = (int64_t)gridDim.x * (kThreads / 32) * 32;
-  for (int64_t wbase = ((int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * 32;
-       wbase < n_total; wbase += wstride) {
+  const int64_t wfirst = ((int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * 32;
+  // the chain per tile is FID -> bucket -> row (~2.5 us per dependent round trip under load): the NEXT tile's FIDs are
+  // requested one iteration ahead, which takes that round trip off the chain
+  int64_t key_next = wfirst + lane < n_total ? __ldg(ids + wfirst + lane) : 0;
+  for (int64_t wbase = wfirst; wbase < n_total; wbase += wstride) {
     // ---- phase A: lane-per-key probe ----
     const int64_t i = wbase + lane;
+    const int64_t key = key_next;
+    if (i + wstride < n_total) key_next = __ldg(ids + i + wstride);
     int si = 0;
     uint32_t row = kEmptyRow;
     if (i < n_total) {
       if (!SINGLE) si = find_seg(segs, nsegs, i);
-      row = probe_lane(SINGLE ? t0 : tables + segs[si].table, __ldg(ids + i));
+      row = probe_lane(SINGLE ? t0 : tables + segs[si].table, key);
     }
     // ---- phase B: group-per-row copy, UNR rows in flight ----
 #pragma unroll
@@ -257,6 +262,8 @@ lookup_tma_kernel(const TableDev* __restrict__ t0, const int64_t* __restrict__ i
   int64_t tile = (int64_t)blockIdx.x * NW + w;
   uint32_t row = kEmptyRow;
   if (tile < ntiles && tile * 32 + lane < n_total) row = probe_lane(t0, __ldg(ids + tile * 32 + lane));
+  // FIDs of the tile after this one: requested one iteration before they are probed (off the dependent chain)
+  int64_t key_next = (tile + tstride < ntiles && (tile + tstride) * 32 + lane < n_total) ? __ldg(ids + (tile + tstride) * 32 + lane) : 0;
   for (uint32_t it = 0; tile < ntiles; ++it) {
     const int b = it & 1;
     const uint32_t parity = (it >> 1) & 1u;
@@ -278,8 +285,10 @@ lookup_tma_kernel(const TableDev* __restrict__ t0, const int64_t* __restrict__ i
     }
     // ---- the next tile's probe chain runs while this tile's rows are in flight ----
     const int64_t next = tile + tstride;
+    const int64_t key_cur = key_next;
+    if (next + tstride < ntiles && (next + tstride) * 32 + lane < n_total) key_next = __ldg(ids + (next + tstride) * 32 + lane);
     uint32_t row_next = kEmptyRow;
-    if (next < ntiles && next * 32 + lane < n_total) row_next = probe_lane(t0, __ldg(ids + next * 32 + lane));
+    if (next < ntiles && next * 32 + lane < n_total) row_next = probe_lane(t0, key_cur);
     mbar_wait(mbar, parity);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the zero rows (generic proxy) before the bulk store reads them
     __syncwarp();

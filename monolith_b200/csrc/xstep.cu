@@ -164,10 +164,14 @@ xlookup_push_kernel(const TableDev* __restrict__ t0, XWin w, int par, uint64_t s
     const int64_t* __restrict__ ids = w.ids_in(w.me, par, src);
     float* __restrict__ dst_rows = w.rows_in(src) + dst_off * D0;
     const int64_t wstride = (int64_t)gridDim.x * (kThreads / 32) * 32;
-    for (int64_t wbase = ((int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * 32; wbase < n_src; wbase += wstride) {
+    const int64_t wfirst = ((int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * 32;
+    int64_t key_next = wfirst + lane < n_src ? ids[wfirst + lane] : 0;  // next tile's FIDs one iteration ahead
+    for (int64_t wbase = wfirst; wbase < n_src; wbase += wstride) {
       const int64_t i = wbase + lane;
+      const int64_t key = key_next;
+      if (i + wstride < n_src) key_next = ids[i + wstride];
       uint32_t row = kEmptyRow;
-      if (i < n_src) row = probe_lane(t0, ids[i]);
+      if (i < n_src) row = probe_lane(t0, key);
 #pragma unroll
       for (int it0 = 0; it0 < ITERS; it0 += UNR) {
         float4 x[UNR];

@@ -321,7 +321,8 @@ class ShardedStep:
     self.k = table.table_names.index(name)
     self.K = len(table.table_names)
     self.phases = _Phases(os.environ.get("MONO_TIMING", "0") in ("1", "2"))
-    self.exchange = exchange or os.environ.get("MONO_EXCHANGE", "peer")
+    # default: the device-driven exchange (validated against ONE global oracle table on 2 and 8 GPUs, round 2)
+    self.exchange = exchange or os.environ.get("MONO_EXCHANGE", "direct" if torch.device(device).type == "cuda" else "nccl")
     if self.exchange not in ("peer", "nccl", "direct"):
       raise ValueError("exchange must be 'direct', 'peer' or 'nccl'")
     self.xstep = None        # exchange == "direct": the device-driven step (csrc/xstep.cu), two C calls per step

@@ -30,3 +30,12 @@ PY
 if [ -n "$2" ]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$2" -s ${3:-6} -c ${4:-8} -o $O/${T}_full python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-parity --no-extras --repeats 1 > $O/${T}_ncu_f.log 2>&1; tail -1 $O/${T}_ncu_f.log
 fi
+for V in 0 1; do
+  MONO_LOOKUP_TMA=$V timeout 600 python bench.py --no-cpu-baseline --no-e2e --no-parity --steps 10 --repeats 2 > $O/${T}_fwd_tma$V.json 2> $O/${T}_fwd_tma$V.err
+  python - <<PY
+import json
+d = json.loads(open("gpurun_out/${T}_fwd_tma$V.json").read().strip().splitlines()[-1])
+r = d["roofline"]
+print("lookup_tma=$V: step", round(d["ms_per_step"], 4), "fwd zipf ms", round(r["launch_ms"], 4), "frac", round(r["frac"], 3), {k: (round(v["ms"], 4), round(v.get("frac", 0), 3)) for k, v in (r.get("extras") or {}).items()})
+PY
+done
