@@ -240,7 +240,8 @@ def cpu_arm(keys, batch, steps, warmup, threads, zipf_s=ZIPF_S, candidates=(1, 8
     for c in cand:
       ps, _, keep = _fastps(lib, keys, c)
       one(ps, 0)
-      dt = min(one(ps, 1)[0], one(ps, 2)[0])
+      one(ps, 1)
+      dt = min(one(ps, 2)[0], one(ps, 3)[0])
       lib.orc_fastps_destroy(ps)
       sweep[c] = M / dt
       if best is None or dt < best[0]:
@@ -248,14 +249,16 @@ def cpu_arm(keys, batch, steps, warmup, threads, zipf_s=ZIPF_S, candidates=(1, 8
     threads = best[1]
   ps, fill_s, keep = _fastps(lib, keys, threads)
   times, uniq = [], []
+  warmup = max(warmup, 3)
   for i in range(warmup + steps):
     dt, u = one(ps, i)
     if i >= warmup:
       times.append(dt)
       uniq.append(u)
   lib.orc_fastps_destroy(ps)
-  total = float(np.sum(times))
-  return {"value": M * steps / total, "ms_per_step": 1e3 * total / steps, "fill_s": fill_s, "batch": batch,
+  # the value is the MEDIAN step (host timing jitters: page faults of the growing scratch vectors, other tenants)
+  med = float(np.median(times))
+  return {"value": M / med, "ms_per_step": 1e3 * med, "ms_per_step_mean": 1e3 * float(np.mean(times)), "fill_s": fill_s, "batch": batch,
           "M": M, "U_mean": float(np.mean(uniq)), "threads": threads, "host_cores": cores,
           "thread_sweep_lookups_per_s": {str(k): v for k, v in sweep.items()},
           "ms_per_step_min": 1e3 * float(np.min(times)), "ms_per_step_max": 1e3 * float(np.max(times))}
@@ -435,7 +438,7 @@ def bind_numa(local):
 
 class Tower:
   """Stand-in dense tower of the DSSM (ref model: markdown/demo/demo_model.py:47-84): pooled [B, 2*32] -> bf16 MLP
-  64 -> 256 -> 1 -> logistic loss against labels; forward + backward produce the gradient w.r.t. the pooled rows.
+  64 -> 64 -> 1 -> logistic loss against labels; forward + backward produce the gradient w.r.t. the pooled rows.
   Dense layers are out of scope: plain torch / cuBLAS on tensor cores, used only to close the e2e loop on
   the device and as the thing the exchange overlaps with."""
 
@@ -443,8 +446,8 @@ class Tower:
     import torch
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
-    self.w1 = (torch.randn(SLOTS * DIM, 256, device=dev, generator=g) * 0.05).to(torch.bfloat16).requires_grad_(True)
-    self.w2 = (torch.randn(256, 1, device=dev, generator=g) * 0.05).to(torch.bfloat16).requires_grad_(True)
+    self.w1 = (torch.randn(SLOTS * DIM, 64, device=dev, generator=g) * 0.05).to(torch.bfloat16).requires_grad_(True)
+    self.w2 = (torch.randn(64, 1, device=dev, generator=g) * 0.05).to(torch.bfloat16).requires_grad_(True)
     self.batch = batch
 
   def grad(self, pooled, labels, grad_out):
@@ -594,39 +597,64 @@ def run_ours(args):
     labels_pin = (torch.rand(args.batch) < 0.3).float().pin_memory()
     loss_pin = torch.empty(1).pin_memory()
     d_f = [torch.empty(M, dtype=torch.int64, device=dev) for _ in range(2)]
-    d_lab = torch.empty(args.batch, device=dev)
     d_g = torch.empty(M, DIM, device=dev)
     tower = Tower(dev, args.batch)
 
+    copy_stream = torch.cuda.Stream(device=dev)
+    ev_in = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_free = [torch.cuda.Event(), torch.cuda.Event()]
+    d_labs = [torch.empty(args.batch, device=dev) for _ in range(2)]
+    state = {"primed": -1}
+
+    def enqueue_inputs(i):
+      """H2D of step i's inputs (pinned host FIDs + labels) on the copy stream: the input pipeline runs one step
+      ahead of the trainer, as any data loader does; every step's copy is inside the timed region."""
+      b = i & 1
+      with torch.cuda.stream(copy_stream):
+        copy_stream.wait_event(ev_free[b])            # the step that last used buffer b has consumed it
+        d_f[b].copy_(fids_pin[i % NB], non_blocking=True)
+        d_labs[b].copy_(labels_pin, non_blocking=True)
+        ev_in[b].record(copy_stream)
+
     def e2e_step(i):
-      """What a training job does per step: the input pipeline hands over HOST FIDs + labels; forward, dense tower
-      forward/backward on the device, sparse backward; the loss comes back to the host."""
+      """What a training job does per step: the input pipeline hands over HOST FIDs + labels (copied H2D while the
+      previous step computes); forward, dense tower forward/backward on the device, sparse backward; the loss comes
+      back to the host."""
       main = torch.cuda.current_stream()
-      f = d_f[i & 1]
-      f.copy_(fids_pin[i % NB], non_blocking=True)
-      d_lab.copy_(labels_pin, non_blocking=True)
+      if state["primed"] != i:
+        enqueue_inputs(i)                              # first step of a region: nothing was prefetched
+      b = i & 1
+      main.wait_event(ev_in[b])
+      enqueue_inputs(i + 1)
+      state["primed"] = i + 1
+      f, lab = d_f[b], d_labs[b]
       loss = []
 
       def grads():
-        loss.append(tower.grad(pooled, d_lab, d_g))
+        loss.append(tower.grad(pooled, lab, d_g))
         return d_g
 
       step(i, f, grads, pooled)
+      ev_free[b].record(main)
       loss_pin.copy_(loss[0].reshape(1), non_blocking=True)
       main.synchronize()  # the loss is on the host, the update is applied
+
+    for e_ in ev_free:
+      e_.record(torch.cuda.current_stream())
 
     es, ew = max(3, args.steps // 2), 3
     ems, _, eregions = timed(e2e_step, es, ew, max(1, min(3, args.repeats)))
 
     def tower_only(i):  # context: how much of the e2e step is not the sparse path
-      tower.grad(pooled, d_lab, d_g)
+      tower.grad(pooled, d_labs[0], d_g)
 
     tms, _, _ = timed(tower_only, 10, 3)
     e2e = {"value": M * world * es / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * M + 4 * args.batch,
            "d2h_bytes_per_step": 4, "ms_per_step": ems / es, "ms_per_step_regions": [r / es for r in eregions],
            "dense_tower_ms": tms / 10,
-           "pipeline": "per step: H2D of the step's FIDs (pinned int64[M]) and labels, fused lookup+pool forward, stand-in "
-                       "DSSM tower (bf16 MLP 64-256-1 + logistic loss, torch/cuBLAS) forward+backward on the device, fused sparse "
+           "pipeline": "per step: H2D of the step's FIDs (pinned int64[M]) and labels on a copy stream one step ahead (input "
+                       "prefetch), fused lookup+pool forward, stand-in "
+                       "DSSM tower (bf16 MLP 64-64-1 + logistic loss, torch/cuBLAS) forward+backward on the device, fused sparse "
                        "backward, D2H of the loss; the host synchronises every step"}
 
     # round-1 variant for continuity: a HOST-resident tower (pooled rows D2H, gradients H2D: 553 MB over PCIe per step)

@@ -634,12 +634,6 @@ __device__ __forceinline__ void fetch4(const uint32_t (&v)[32 / G], int e, uint3
 // (LDGSTS) into shared memory — every lane copies ITS 16-byte column slice of each row into a private slot, so nothing
 // but the thread's own cp.async.wait orders the data and no register holds a row in flight — then the adds run in
 // occurrence order out of shared memory.  3 blocks x 64 KB = 192 KB of gradient rows in flight per SM.
-constexpr int kStage = 16;
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
 
 template <int G, int MODE, int OPT>
 __global__ void __launch_bounds__(kThreads, 3)

@@ -387,6 +387,13 @@ __device__ __forceinline__ uint32_t probe_lane_slot(const TableDev* __restrict__
 }
 
 
+// ---- cp.async staging: rows requested kStage at a time into per-thread shared-memory slots (zero register cost) ----
+constexpr int kStage = 16;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
 // ---- host helpers implemented in ops.cu ----
 struct CallBlob {  // device pointers into the staged per-call descriptor block
   const CallSeg* segs;
