@@ -458,7 +458,7 @@ lookup_pool_kernel(const TableDev* __restrict__ t, const int64_t* __restrict__ f
 // shared memory: three round trips per 16 FIDs instead of two per FID.  Longer lists are walked in chunks of 16 with
 // the accumulators carried.  Terms are added in FID order: bit-exact with the CPU reference's pooling.
 template <int G>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, 2)
 lookup_pool_staged_kernel(const TableDev* __restrict__ t, const int64_t* __restrict__ fids,
                           const int32_t* __restrict__ row_offsets, int64_t n_rows, int pooling,
                           float* __restrict__ out, int64_t out_stride, int out_col) {
@@ -489,12 +489,34 @@ lookup_pool_staged_kernel(const TableDev* __restrict__ t, const int64_t* __restr
     for (int64_t f0 = f_begin; f0 < f_end; f0 += kStage) {
       const int cnt = (int)min((int64_t)kStage, f_end - f0);
       // ---- probe: lane gl takes flat entries gl, gl + G, ... ----
+      // (all key loads first, then all first-bucket loads: the KPL probe chains of a lane overlap instead of queueing)
       uint32_t rk[KPL];
+      int64_t key[KPL];
+      const Entry* bk[KPL];
+      Entry e0[KPL], e1[KPL], e2[KPL], e3[KPL];
 #pragma unroll
       for (int s = 0; s < KPL; ++s) {
         const int k = s * G + gl;
-        rk[s] = kEmptyRow;
-        if (k < cnt && k < kStage) rk[s] = probe_lane(t, __ldg(fids + f0 + k));
+        key[s] = (k < cnt && k < kStage) ? __ldg(fids + f0 + k) : 0;
+      }
+#pragma unroll
+      for (int s = 0; s < KPL; ++s) {
+        uint32_t b1, b2;
+        bucket_pair(key[s], t->num_buckets, b1, b2);
+        bk[s] = t->buckets + (size_t)b1 * kBucketSlots;
+        e0[s] = ld_entry_nc(bk[s]); e1[s] = ld_entry_nc(bk[s] + 1); e2[s] = ld_entry_nc(bk[s] + 2); e3[s] = ld_entry_nc(bk[s] + 3);
+      }
+#pragma unroll
+      for (int s = 0; s < KPL; ++s) {
+        const int k = s * G + gl;
+        uint32_t row = kEmptyRow;
+        if (e0[s].key == key[s] && e0[s].row < kTombRow) row = e0[s].row;
+        if (e1[s].key == key[s] && e1[s].row < kTombRow) row = e1[s].row;
+        if (e2[s].key == key[s] && e2[s].row < kTombRow) row = e2[s].row;
+        if (e3[s].key == key[s] && e3[s].row < kTombRow) row = e3[s].row;
+        const bool live = k < cnt && k < kStage;
+        if (live && row == kEmptyRow) row = probe_lane(t, key[s]);  // second bucket / stash: the full probe
+        rk[s] = live ? row : kEmptyRow;
       }
       // ---- request every row of the chunk ----
 #pragma unroll
