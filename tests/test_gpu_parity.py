@@ -1107,3 +1107,92 @@ def test_sharded_direct_step_world1_vs_oracle(mode, dev):
     np.testing.assert_array_equal(got[:, -2:].view(np.uint32), want[:, -2:].view(np.uint32))
   finally:
     st.close_direct()
+
+
+# ------------------------------------------------------------------------------------------------
+# the bench's batch shape (M = 2 097 152 occurrences, Zipf, dim 32, Adagrad) against the oracle
+# ------------------------------------------------------------------------------------------------
+def test_bench_shape_step_vs_oracle(dev):
+  """One full sparse step at the benchmark's batch shape (C2: 1 048 576 samples x 2 slots, Zipf(1.05) ranks, dim 32,
+  Adagrad) over a 1 M-key vocabulary: pooled rows bit for bit; after the fused backward every entry whose FID occurs
+  <= 64 times bit for bit (reference summation order), the hot FIDs within 1e-5 of the row's scale (tree vs sequential
+  fp32 sums; see the fp64 test above)."""
+  import bench
+  D = 32
+  from monolith_b200 import entry
+  cfg = {"t": table([(D, "adagrad", {"initial_accumulator_value": 0.1})], [0.05], capacity=1 << 20,
+                    init=entry.RandomUniformInitializer(-0.05, 0.05), init_seed=1)}
+  gpu, cpu = pair(cfg, dev)
+  fids = bench.make_batches(1, 1 << 20, 500_000, seed=11)[0]
+  M = fids.size
+  rng = np.random.default_rng(3)
+  vocab = np.unique(fids)
+  pre = vocab[rng.random(vocab.size) < 0.9]                       # 10 % of the FIDs are new in this step (upserts)
+  z = np.zeros((pre.size, D), np.float32)
+  gpu.assign_add({"t": (T(pre, dev), T(z, dev))}, req_time=1, ids_unique=True)
+  cpu.assign_add({"t": (pre, z)}, req_time=1)
+  pooled = gpu.lookup_pool("t", T(fids, dev), None, "sum").cpu().numpy()
+  np.testing.assert_array_equal(pooled.view(np.uint32), cpu.lookup_pool("t", fids, None, "sum").view(np.uint32))
+  pg = rng.standard_normal((M, D)).astype(np.float32)
+  gpu.pool_backward("t", T(fids, dev), T(pg, dev), None, "sum", req_time=7)
+  u, inv = orc.dedup(fids)
+  ug = orc.gather_pool_grad(pg, inv * D, D, u.size * D).reshape(-1, D)
+  cpu.apply_gradients({"t": (u, ug)}, req_time=7)
+  assert gpu.size("t") == cpu.size("t") == vocab.size
+  got = gpu.lookup_entry("t", T(vocab, dev))["raw"].cpu().numpy()
+  want = cpu.lookup_entry("t", vocab)
+  cnt = np.bincount(np.searchsorted(vocab, fids), minlength=vocab.size)
+  cold = cnt <= 64
+  assert cold.sum() > 0.95 * vocab.size and (~cold).sum() > 100
+  np.testing.assert_array_equal(got[cold].view(np.uint32), want[cold].view(np.uint32))
+  np.testing.assert_array_equal(got[~cold][:, -2:].view(np.uint32), want[~cold][:, -2:].view(np.uint32))
+  scale = np.abs(want[~cold][:, :-2]).max(axis=1, keepdims=True) + 1e-3
+  assert float((np.abs(got[~cold][:, :-2] - want[~cold][:, :-2]) / scale).max()) < 2e-3
+
+
+def test_two_host_threads_share_one_handle(dev):
+  """Two host threads drive ONE table handle concurrently (lookups against updates of disjoint FID sets, each on its
+  own stream): the per-handle lock of the C ABI serialises them; results equal the sequential ones (ref: TF runs the
+  ops of one resource from several inter-op threads)."""
+  import threading
+  D = 16
+  cfg = {"t": table([(D, "adagrad", {})], [0.1])}
+  gpu, cpu = pair(cfg, dev)
+  rng = np.random.default_rng(5)
+  a_ids, b_ids = fid(1, np.arange(20000)), fid(2, np.arange(20000))
+  va = rng.standard_normal((a_ids.size, D)).astype(np.float32)
+  gpu.assign({"t": (T(a_ids, dev), T(va, dev))}, ids_unique=True)
+  cpu.assign({"t": (a_ids, va)})
+  torch.cuda.synchronize()
+  errs, looked = [], []
+  grads = [rng.standard_normal((b_ids.size, D)).astype(np.float32) for _ in range(6)]
+
+  def reader():
+    try:
+      with torch.cuda.stream(torch.cuda.Stream(device=dev)):
+        for _ in range(30):
+          looked.append(gpu.lookup({"t": T(a_ids, dev)})["t"].cpu().numpy())
+    except Exception as e:  # pragma: no cover
+      errs.append(e)
+
+  def writer():
+    try:
+      with torch.cuda.stream(torch.cuda.Stream(device=dev)):
+        for k, g in enumerate(grads):
+          gpu.apply_gradients({"t": (T(b_ids, dev), T(g, dev))}, req_time=10 + k, ids_unique=True)
+        torch.cuda.current_stream().synchronize()
+    except Exception as e:  # pragma: no cover
+      errs.append(e)
+
+  ts = [threading.Thread(target=reader), threading.Thread(target=writer)]
+  for t in ts:
+    t.start()
+  for t in ts:
+    t.join()
+  assert not errs, errs
+  for k, g in enumerate(grads):
+    cpu.apply_gradients({"t": (b_ids, g)}, req_time=10 + k)
+  for x in looked:                                               # rows of set A never change: every lookup saw them all
+    np.testing.assert_array_equal(x.view(np.uint32), va.view(np.uint32))
+  both = np.concatenate([a_ids, b_ids])
+  np.testing.assert_array_equal(gpu_lookup(gpu, {"t": both}, dev)["t"].view(np.uint32), cpu.lookup({"t": both})["t"].view(np.uint32))
