@@ -395,7 +395,6 @@ struct BwdArgs {
   int grad_col;
   const float* lr;              // device, slice learning rates of the table
   float* ugrad;                 // [runs][D] summed gradient of every run (= unique FID), run order (MODE_STORE)
-  int skip_long;                // runs_apply: leave the runs of > kShortRun occurrences to long_finish_kernel<MODE_APPLY>
   float* scratch;               // alias of ugrad for the generic (multi-segment) apply path
 };
 
@@ -877,8 +876,6 @@ __global__ void __launch_bounds__(kThreads) runs_apply_kernel(BwdArgs a) {
   const int64_t gstride = (int64_t)gridDim.x * (kThreads / G);
   for (int64_t j = (int64_t)blockIdx.x * (kThreads / G) + threadIdx.x / G; j < nr; j += gstride) {
     const uint32_t ri = a.rowidx[j];
-    // hot FIDs (> kShortRun occurrences) are applied by long_finish_kernel<MODE_APPLY>, which runs beside this kernel
-    if (a.skip_long && a.run_start[j + 1] - a.run_start[j] > (uint32_t)kShortRun) continue;
     float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c < D) g4 = __ldcs(reinterpret_cast<const float4*>(a.ugrad + (size_t)j * D + c));
     if (ri == kEmptyRow) continue;
@@ -1031,12 +1028,8 @@ struct ReduceScratch {  // sizes of the reduction scratch for M occurrences of d
   }
 };
 
-// per-run gradient sums -> run_dst (a.ugrad, or the owners' peer windows).
-// finish_opt >= 0 (single-GPU fused backward, one of the four vectorised optimizers): the hot FIDs' tree and their
-// optimizer step (long_finish_kernel<MODE_APPLY>) go to stream `s_long`, forked after the segmented reduce, so that they
-// run beside the caller's streaming apply of the short runs; the caller joins on `ev_join`.
-static void launch_reduce(const SegArgs& sa, int G, int finish_opt, const PeerOut& po, cudaStream_t s,
-                          cudaStream_t s_long = nullptr, cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr) {
+// per-run gradient sums -> run_dst (a.ugrad, or the owners' peer windows)
+static void launch_reduce(const SegArgs& sa, int G, int /*unused*/, const PeerOut& po, cudaStream_t s) {
   const int64_t np = sa.n_pieces;
   if (np <= 0) return;
   int levels = 0;
@@ -1046,52 +1039,35 @@ static void launch_reduce(const SegArgs& sa, int G, int finish_opt, const PeerOu
     ++levels;
   }
   const int D = sa.b.td.dim;
-  constexpr size_t kStageBytes = sizeof(float4) * kStage * kThreads;
-  const bool fork = finish_opt >= 0 && s_long != nullptr;
-  cudaStream_t sl = fork ? s_long : s;
-#define SEG_ATTR(KERNEL)                                                                                            \
+#define SEG_GO(GG, MODE, OO)                                                                                        \
   do {                                                                                                              \
+    constexpr size_t kStageBytes = sizeof(float4) * kStage * kThreads;                                              \
     static bool attr_set = false;                                                                                   \
     if (!attr_set) {                                                                                                \
-      MONO_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageBytes));       \
+      MONO_CUDA(cudaFuncSetAttribute(seg_reduce_kernel<GG, MODE, OO>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                     (int)kStageBytes));                                                            \
+      MONO_CUDA(cudaFuncSetAttribute(tree_level_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                     (int)kStageBytes));                                                            \
+      MONO_CUDA(cudaFuncSetAttribute(long_finish_kernel<GG, MODE, OO>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     (int)kStageBytes));                                                            \
       attr_set = true;                                                                                              \
     }                                                                                                               \
-  } while (0)
-#define FIN_GO(GG, MODE, OO)                                                                                        \
-  do {                                                                                                              \
-    SEG_ATTR((long_finish_kernel<GG, MODE, OO>));                                                                   \
-    long_finish_kernel<GG, MODE, OO>                                                                                \
-        <<<resident_grid(long_finish_kernel<GG, MODE, OO>, np, kThreads / GG, kThreads, kStageBytes), kThreads,     \
-           kStageBytes, sl>>>(sa, (uint32_t)top, po);                                                               \
-    MONO_CHECK_LAUNCH();                                                                                            \
-  } while (0)
-#define SEG_G(GG)                                                                                                   \
-  do {                                                                                                              \
-    SEG_ATTR((seg_reduce_kernel<GG, MODE_STORE, 0>));                                                               \
-    SEG_ATTR((tree_level_kernel<GG>));                                                                              \
-    seg_reduce_kernel<GG, MODE_STORE, 0>                                                                            \
-        <<<resident_grid(seg_reduce_kernel<GG, MODE_STORE, 0>, np, (kThreads / 32) * (32 / GG), kThreads, kStageBytes), \
+    seg_reduce_kernel<GG, MODE, OO>                                                                                 \
+        <<<resident_grid(seg_reduce_kernel<GG, MODE, OO>, np, (kThreads / 32) * (32 / GG), kThreads, kStageBytes),  \
            kThreads, kStageBytes, s>>>(sa, po);                                                                     \
     MONO_CHECK_LAUNCH();                                                                                            \
-    if (fork) {                                                                                                     \
-      MONO_CUDA(cudaEventRecord(ev_fork, s));                                                                       \
-      MONO_CUDA(cudaStreamWaitEvent(sl, ev_fork, 0));                                                               \
-    }                                                                                                               \
     uint32_t stride = 1;                                                                                            \
     for (int l = 0; l < levels; ++l, stride *= kTreeFan) {                                                          \
       tree_level_kernel<GG><<<resident_grid(tree_level_kernel<GG>, 2 * np, kThreads / GG, kThreads, kStageBytes),   \
-                              kThreads, kStageBytes, sl>>>(sa.part, sa.meta, 2 * np, stride, D);                    \
+                              kThreads, kStageBytes, s>>>(sa.part, sa.meta, 2 * np, stride, D);                     \
       MONO_CHECK_LAUNCH();                                                                                          \
     }                                                                                                               \
-    switch (fork ? finish_opt : -1) {                                                                               \
-      case MONO_OPT_SGD: FIN_GO(GG, MODE_APPLY, MONO_OPT_SGD); break;                                               \
-      case MONO_OPT_ADAGRAD: FIN_GO(GG, MODE_APPLY, MONO_OPT_ADAGRAD); break;                                       \
-      case MONO_OPT_FTRL: FIN_GO(GG, MODE_APPLY, MONO_OPT_FTRL); break;                                             \
-      case MONO_OPT_ADAM: FIN_GO(GG, MODE_APPLY, MONO_OPT_ADAM); break;                                             \
-      default: FIN_GO(GG, MODE_STORE, 0); break;                                                                    \
-    }                                                                                                               \
-    if (fork) MONO_CUDA(cudaEventRecord(ev_join, sl));                                                              \
+    long_finish_kernel<GG, MODE, OO>                                                                                \
+        <<<resident_grid(long_finish_kernel<GG, MODE, OO>, np, kThreads / GG, kThreads, kStageBytes), kThreads,     \
+           kStageBytes, s>>>(sa, (uint32_t)top, po);                                                                \
+    MONO_CHECK_LAUNCH();                                                                                            \
   } while (0)
+#define SEG_G(GG) SEG_GO(GG, MODE_STORE, 0)
   switch (G) {
     case 4: SEG_G(4); break;
     case 8: SEG_G(8); break;
@@ -1099,8 +1075,7 @@ static void launch_reduce(const SegArgs& sa, int G, int finish_opt, const PeerOu
     default: SEG_G(32); break;
   }
 #undef SEG_G
-#undef FIN_GO
-#undef SEG_ATTR
+#undef SEG_GO
 }
 
 static int bits_for(uint64_t cap) {
@@ -1220,15 +1195,7 @@ void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t 
     MONO_CHECK_LAUNCH();
     a.occ_row = occ;
   }
-  // hot FIDs: tree + optimizer step on the table's side stream, beside the streaming apply of the short runs below
-  if (!mt->side_stream) {
-    MONO_CUDA(cudaStreamCreateWithFlags(&mt->side_stream, cudaStreamNonBlocking));
-    MONO_CUDA(cudaEventCreateWithFlags(&mt->ev_fork, cudaEventDisableTiming));
-    MONO_CUDA(cudaEventCreateWithFlags(&mt->ev_join, cudaEventDisableTiming));
-  }
-  const bool fork = opt_sel >= 0;
-  a.skip_long = fork ? 1 : 0;
-  launch_reduce(sa, G, opt_sel, no_peer, s, mt->side_stream, mt->ev_fork, mt->ev_join);
+  launch_reduce(sa, G, -1, no_peer, s);
   // 6 apply: one streaming pass over the runs — row index, summed gradient, w / optimizer state of every distinct FID
 #define BWD2(GG, OO)                                                                                             \
   runs_apply_kernel<GG, OO><<<resident_grid(runs_apply_kernel<GG, OO>, M, kThreads / GG), kThreads, 0, s>>>(a);  \
@@ -1249,7 +1216,6 @@ void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t 
   }
 #undef BWD2
 #undef BWD
-  if (fork) MONO_CUDA(cudaStreamWaitEvent(s, mt->ev_join, 0));  // join: the hot FIDs are applied too
   ht.issued_total += (uint64_t)M;
   ht.max_update_ts = std::max<int64_t>(ht.max_update_ts, update_time);
   request_snapshot(mt, k, s);

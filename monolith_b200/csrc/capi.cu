@@ -179,9 +179,6 @@ int mono_mtable_destroy(mono_mtable_t* t) {
   if (t->pinned_out) cudaFreeHost(t->pinned_out);
   if (t->h_flag) cudaFreeHost(t->h_flag);
   if (t->own_stream) cudaStreamDestroy(t->own_stream);
-  if (t->side_stream) cudaStreamDestroy(t->side_stream);
-  if (t->ev_fork) cudaEventDestroy(t->ev_fork);
-  if (t->ev_join) cudaEventDestroy(t->ev_join);
   delete t;
   return MONO_OK;
 }

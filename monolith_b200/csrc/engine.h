@@ -178,8 +178,6 @@ struct mono_mtable {
   void* pinned_out = nullptr;
   size_t pinned_out_cap = 0;
   cudaStream_t own_stream = nullptr;  // used by the *_host entry points
-  cudaStream_t side_stream = nullptr; // fused backward: the hot FIDs' tree + optimizer step run beside the main apply
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   uint32_t* h_flag = nullptr;         // pinned scratch for small D2H reads
 };
 
