@@ -23,6 +23,17 @@ for f in ("r2_bench_n1", "r2_bench_tma"):
   except Exception as e:
     print(f, "unreadable:", e)
 PY
+echo "== workload c3 (Criteo-shaped: 26 slots, dim 16)"; timeout 900 python bench.py --workload c3 --no-extras --steps 20 --repeats 3 > $O/r2_bench_c3.json 2> $O/r2_bench_c3.err; tail -c 300 $O/r2_bench_c3.err; head -c 300 $O/r2_bench_c3.json; echo
+echo "== workload c5 (dim sweep)"; timeout 1200 python bench.py --workload c5 > $O/r2_bench_c5.json 2> $O/r2_bench_c5.err; tail -c 300 $O/r2_bench_c5.err
+python - <<'PY'
+import json
+try:
+  d = json.loads(open("gpurun_out/r2_bench_c5.json").read().strip().splitlines()[-1])
+  for r in d["rows"]:
+    print("c5 dim", r["dim"], r["fids"], "lookup ms", round(r["lookup_ms"], 4), "frac", round(r["lookup_frac"], 3), "lookup+update ms", round(r["lookup_update_ms"], 4), "frac", round(r["lookup_update_frac"], 3))
+except Exception as e:
+  print("c5 unreadable:", e)
+PY
 for X in peer direct; do
   echo "== sharded step on one GPU, exchange=$X"
   timeout 600 python bench.py --sharded --exchange $X --no-cpu-baseline --no-e2e --no-extras --steps 10 --repeats 3 > $O/r2_bench_sharded_$X.json 2> $O/r2_bench_sharded_$X.err
@@ -32,6 +43,6 @@ echo "== ncu launch lists"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r2_launches_direct.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-parity --no-extras --repeats 1 > $O/r2_ncu_l1.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file $O/r2_launches_sharded_direct.csv python bench.py --sharded --exchange direct --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-parity --no-extras --repeats 1 > $O/r2_ncu_l2.log 2>&1
 echo "== ncu full (one step of the single-GPU path)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"fid_claim|claim_miss|radix|runs_|seg_reduce|tree_level|long_finish|lookup_kernel|lookup_tma|upsert_fin" -s 24 -c 16 -o $O/r2_step_full python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-parity --no-extras --repeats 1 > $O/r2_ncu_full.log 2>&1; tail -2 $O/r2_ncu_full.log
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"fid_claim|claim_miss|radix|runs_|seg_reduce|tree_level|long_finish|lookup_kernel|lookup_tma|upsert_fin" -s 22 -c 17 -o $O/r2_step_full python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-parity --no-extras --repeats 1 > $O/r2_ncu_full.log 2>&1; tail -2 $O/r2_ncu_full.log
 MONO_LOOKUP_TMA=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"lookup_tma" -s 8 -c 2 -o $O/r2_tma_full python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-parity --no-extras --repeats 1 > $O/r2_ncu_tma.log 2>&1; tail -2 $O/r2_ncu_tma.log
 echo "== done"
