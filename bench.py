@@ -256,8 +256,9 @@ def cpu_arm(keys, batch, steps, warmup, threads, zipf_s=ZIPF_S, candidates=(1, 8
       times.append(dt)
       uniq.append(u)
   lib.orc_fastps_destroy(ps)
-  # the value is the MEDIAN step (host timing jitters: page faults of the growing scratch vectors, other tenants)
-  med = float(np.median(times))
+  # the value is the BEST step: the host is shared with other tenants and its timing jitters by 2x; the minimum is the
+  # number most favourable to the CPU baseline
+  med = float(np.min(times))
   return {"value": M / med, "ms_per_step": 1e3 * med, "ms_per_step_mean": 1e3 * float(np.mean(times)), "fill_s": fill_s, "batch": batch,
           "M": M, "U_mean": float(np.mean(uniq)), "threads": threads, "host_cores": cores,
           "thread_sweep_lookups_per_s": {str(k): v for k, v in sweep.items()},
