@@ -10,15 +10,19 @@ One "step" = the whole sparse part of one training step for one batch:
     backward: group the occurrences by FID (scratch set + stable radix sort), deterministic per-FID sum of
               the pooled grads (no float atomics), fused Adagrad update + expiry-timestamp bump (upsert)
   N > 1 (torchrun, one rank per GPU, weak scaling): the same step sharded by fid mod N (ShardedStep): group by
-  owner, FIDs / rows / row gradients exchanged through NVLink peer windows (fused lookup+send and
-  reduce+send kernels, flag barriers), owners apply the requesters' gradients in rank order.
-`value`  = FID occurrences (lookups) per second over all ranks, inputs resident in HBM.
-`e2e`    = same step through the public Python API with pinned HOST inputs (FIDs, pooled grads) copied
-           H2D and the pooled embeddings copied D2H inside the timed region: forward, pooled rows to the
-           host and gradients back in --e2e-chunks slices (PCIe full duplex; a gradient slice is sent only
-           after its pooled slice has reached the host), then the backward.
-`--impl reference` times the CPU restatement of the reference's parameter-server path (oracle port;
-the reference itself needs bazel + TensorFlow and cannot be built here) on the host cores.
+  owner, FIDs / rows / row gradients exchanged through fixed NVLink peer-window regions by the kernels
+  themselves (device-side counts, per-source flags, no host synchronisation inside the step: xstep.cu);
+  owners apply the requesters' gradients in rank order.  --exchange peer|nccl select the older paths.
+`value`  = FID occurrences (lookups) per second over all ranks, inputs resident in HBM; median of --repeats
+           timed regions of --steps steps each.
+`e2e`    = the same step through the public Python API with pinned HOST inputs: per step the FIDs and labels
+           are copied H2D (prefetched on a copy stream), forward, a small bf16 tower (64-64-1) on the device
+           produces the loss and the pooled gradients, backward, and the loss is read back D2H.
+`parity_check` = before timing, every rank runs a few small steps through the same sharded path and rank 0
+           compares all tables with ONE global oracle table fed the concatenated batches.
+`--impl reference` times a multi-threaded CPU implementation of the same step (oracle/oracle.cc orc_fastps_*:
+partition-parallel dedup, flat hash shards; checked against the plain restatement in tests) on the host
+cores; the reference itself needs bazel + TensorFlow and cannot be built here.
 """
 import argparse
 import json
