@@ -503,9 +503,22 @@ int mono_xstep_backward(mono_xstep_t* x, const float* pooled_grad_dev, int64_t g
 /* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */
 int64_t mono_kernel_launch_count(void);
 
+/* Stand-in dense tower of bench.py's end-to-end step (NOT part of the reference's embedding interface; dense layers
+ * are out of scope): pooled[batch][64] fp32 (device) -> relu(x W1) -> . w2 -> mean BCE-with-logits against labels[batch];
+ * writes d loss / d pooled into grad_out[batch][64] fp32 and the loss into *loss_out (device scalar).  w1: bf16 [64 in][64
+ * out] row-major, w2: bf16 [64].  scratch: device floats, at least mono_bench_tower_scratch_floats().  One fused kernel
+ * (bf16 tensor-core MMA, fp32 accumulate) + a 1-block loss reduction, asynchronous on `stream`. */
+int64_t mono_bench_tower_scratch_floats(void);
+int mono_bench_tower_grad(const float* pooled, int64_t batch, const float* labels, const void* w1_bf16,
+                          const void* w2_bf16, float* grad_out, float* loss_out, float* scratch,
+                          int64_t scratch_floats, void* stream);
+
 /* Engine tuning knobs (process-wide; no reference counterpart).  Known names:
  *   "lookup_tma"  0 / 1: single-table lookups with packed output rows use the TMA-staged kernel (bulk row copies
  *                 global -> shared -> global) instead of the register-path kernel.  Results are identical.
+ *   "claim_pf" "apply_pf" "lookup_pf" (L2 prefetch of the next item's lines), "seg_vpl" (1 | 2), "seg_ahead",
+ *   "claim_dual" "lookup_dual" (both candidate buckets requested together): A/B switches between two implementations
+ *   of the same result; defaults are the measured winners (profiles/r2_ab.txt).
  * Returns MONO_ERR_INVALID_ARGUMENT for an unknown name.  mono_get_option returns the current value (or -1). */
 int mono_set_option(const char* name, int64_t value);
 int64_t mono_get_option(const char* name);

@@ -49,6 +49,8 @@ SIGNATURES = {
     "mono_xstep_prepare": (C.c_int, [_p, _p, _i64, _p]),
     "mono_xstep_forward": (C.c_int, [_p, _p, _i64, _p, _i64, _i32, _p, _i64, _i32, _p]),
     "mono_xstep_backward": (C.c_int, [_p, _p, _i64, _i32, _p, _i32, _p, _i64, _p]),
+    "mono_bench_tower_scratch_floats": (_i64, []),
+    "mono_bench_tower_grad": (C.c_int, [_p, _i64, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "mono_set_option": (C.c_int, [C.c_char_p, _i64]),
     "mono_get_option": (_i64, [C.c_char_p]),
     "mono_mtable_create": (C.c_int, [C.POINTER(TableCfg), _i32, _i32, C.POINTER(_p)]),

@@ -27,7 +27,7 @@ namespace mono {
 // Items travel as uint2 {key, position} (ONE 8-byte scattered store per item and pass); the first pass reads the
 // bare keys (position = index).  Per pass: tile histograms (shared-memory atomics) -> column scan over the tiles
 // -> stable scatter.  The scatter kernel ranks an item among the equal digits in front of it inside its tile
-// with ballots (11 votes give the lane mask of equal digits; lanes are consecutive positions, so the count of
+// with a warp match (the lane mask of equal digits; lanes are consecutive positions, so the count of
 // lower lanes is the stable rank) and per-warp digit counters in shared memory; tiles are ordered by the scanned
 // histograms, so no atomic ever decides an output position.
 // ==========================================================================================
@@ -147,12 +147,8 @@ radix_scatter_kernel(const void* __restrict__ in, int64_t n, int shift, int pre_
     for (int r = 0; r < kRadixIPT; ++r) {  // afterwards dgv[r] = digit | rank << 16 (rank < 1024)
       const bool valid = dgv[r] != 0xFFFFFFFFu;
       const uint32_t dg = valid ? dgv[r] : 0u;
-      uint32_t peers = __ballot_sync(0xffffffffu, valid);
-#pragma unroll
-      for (int b = 0; b < kRadixBits; ++b) {
-        const uint32_t bal = __ballot_sync(0xffffffffu, (dg >> b) & 1u);
-        peers &= ((dg >> b) & 1u) ? bal : ~bal;
-      }
+      // lanes holding the same digit: one MATCH.ANY (11 ballots + mask logic made this kernel issue-bound)
+      const uint32_t peers = __match_any_sync(0xffffffffu, dgv[r]);
       const int leader = __ffs(peers) - 1;
       uint32_t old = 0;
       if (valid && lane == leader) {
@@ -635,10 +631,13 @@ __device__ __forceinline__ void fetch4(const uint32_t (&v)[32 / G], int e, uint3
 // but the thread's own cp.async.wait orders the data and no register holds a row in flight — then the adds run in
 // occurrence order out of shared memory.  3 blocks x 64 KB = 192 KB of gradient rows in flight per SM.
 
-template <int G, int MODE, int OPT>
+// G = lanes per group, VPL = 16-byte vectors of the row per lane (lane gl owns columns (gl + v * G) * 4 ..): VPL = 2 halves
+// the warp instructions per occurrence (the kernel issues ~50 of them per occurrence at VPL = 1 and was issue-bound,
+// profiles/r2_ncu_kernels_summary.txt) at the same bytes in flight (kStage / VPL rows of VPL vectors per thread).
+// PLAIN = SUM pooling over identity occurrence rows (no CSR indirection, no MEAN divisor): compiled out.
+template <int G, int VPL, bool PLAIN, bool AHEAD>
 __global__ void __launch_bounds__(kThreads, 3)
 seg_reduce_kernel(SegArgs sa, const PeerOut po) {
-  static_assert(MODE == MODE_STORE, "the optimizer is applied by runs_apply_kernel");
   __shared__ int64_t s_start[kMaxPeers + 1];
   __shared__ char* s_base[kMaxPeers];
   extern __shared__ float4 stage_raw[];        // [kStage][kThreads]: [slot][thread], conflict-free 16-byte accesses
@@ -647,12 +646,15 @@ seg_reduce_kernel(SegArgs sa, const PeerOut po) {
   const int n_parts = po.n;
   constexpr int EPL = 32 / G;          // elements of a piece per lane
   constexpr int RPI = 32 / G;          // pieces per warp iteration
+  constexpr int RS = kStage / VPL;     // gradient rows requested per stage
   const BwdArgs& a = sa.b;
   const int gl = Group<G>::gl(), grp = (threadIdx.x & 31) / G;
   const uint32_t gmask = Group<G>::mask();
   const int c = gl * 4;
   const int D = a.td.dim;
-  const bool in = c < D;
+  bool in[VPL];
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) in[v] = c + v * G * 4 < D;
   const int64_t M = a.n;
   const GradSrc gs = make_grad_src(a, c);
   const uint32_t* __restrict__ run_start = a.run_start;
@@ -664,6 +666,14 @@ seg_reduce_kernel(SegArgs sa, const PeerOut po) {
     // ---- lane-parallel loads: the piece's sort keys and positions, the run index in front of the piece ----
     uint32_t pm0[EPL], sk[EPL];
     load_items<G>(a.sorted, base, M, sk, pm0);
+    // AHEAD: the positions of the next two pieces too (a group may stream up to 63 occurrences past its piece), so the
+    // continuation never waits for a dependent position load in front of its gradient-row request
+    uint32_t pm1[AHEAD ? EPL : 1], pm2[AHEAD ? EPL : 1];
+    if (AHEAD) {
+      uint32_t skx[EPL];
+      load_items<G>(a.sorted, base + kPiece, M, skx, reinterpret_cast<uint32_t (&)[EPL]>(pm1));
+      load_items<G>(a.sorted, base + 2 * kPiece, M, skx, reinterpret_cast<uint32_t (&)[EPL]>(pm2));
+    }
     const uint32_t j0 = sa.piece_run_base[p];
     uint32_t sk_prev = __shfl_up_sync(gmask, sk[EPL - 1], 1, G);
     if (gl == 0) sk_prev = base > 0 ? a.sorted[base - 1].x : ~sk[0];
@@ -713,17 +723,22 @@ seg_reduce_kernel(SegArgs sa, const PeerOut po) {
     if (S == 0) continue;
     const int e_begin = __ffs(S) - 1;
 
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int e0 = e_begin & ~(kStage - 1); e0 < e_stop; e0 += kStage) {
-      // ---- request: up to 16 gradient rows, this lane's 16-byte slice of each ----
+    float4 acc[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e0 = e_begin & ~(RS - 1); e0 < e_stop; e0 += RS) {
+      // ---- request: up to RS gradient rows, this lane's 16-byte slices of each ----
       // (the 4-element bodies are NOT unrolled 4x more: the kernel was instruction-fetch bound when they were)
 #pragma unroll 1
-      for (int b4 = 0; b4 < kStage; b4 += 4) {
+      for (int b4 = 0; b4 < RS; b4 += 4) {
         const int eb = e0 + b4;
         if (eb >= e_stop) break;
         uint32_t m[4];
         if (eb < kPiece) {
           fetch4<G>(pm0, eb, m);
+        } else if (AHEAD) {
+          if (eb < 2 * kPiece) fetch4<G>(reinterpret_cast<const uint32_t (&)[EPL]>(pm1), eb - kPiece, m);
+          else fetch4<G>(reinterpret_cast<const uint32_t (&)[EPL]>(pm2), eb - 2 * kPiece, m);
         } else {  // continuation past the piece: the positions straight from memory (same address in every lane)
 #pragma unroll
           for (int u = 0; u < 4; ++u) m[u] = base + eb + u < M ? a.sorted[base + eb + u].y : 0u;
@@ -731,9 +746,12 @@ seg_reduce_kernel(SegArgs sa, const PeerOut po) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int e = eb + u;
-          if (e >= e_begin && e < e_stop && in) {
-            const uint32_t r = gs.occ_row ? gs.occ_row[m[u]] : m[u];
-            cp_async16(&stage[b4 + u][threadIdx.x], gs.base + (size_t)r * gs.stride);
+          if (e >= e_begin && e < e_stop) {
+            const uint32_t r = (!PLAIN && gs.occ_row) ? gs.occ_row[m[u]] : m[u];
+            const float* src = gs.base + (size_t)r * gs.stride;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v)
+              if (in[v]) cp_async16(&stage[(b4 + u) * VPL + v][threadIdx.x], src + v * G * 4);
           }
         }
       }
@@ -741,14 +759,14 @@ seg_reduce_kernel(SegArgs sa, const PeerOut po) {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       // ---- consume in occurrence order ----
 #pragma unroll 1
-      for (int b4 = 0; b4 < kStage; b4 += 4) {
+      for (int b4 = 0; b4 < RS; b4 += 4) {
         const int eb = e0 + b4;
         if (eb >= e_stop) break;
         // unit starts at eb + u, and at eb + u + 1 (=> eb + u ends a unit); no starts past the piece
         const uint32_t st4 = eb < kPiece ? (S >> eb) & 0xFu : 0u;
         const uint32_t nx4 = eb + 1 < kPiece ? (S >> (eb + 1)) & 0xFu : 0u;
         float fn[4] = {1.f, 1.f, 1.f, 1.f};
-        if (gs.mean) {  // MEAN pooling: the divisor of each row (positions fetched again: rare path)
+        if (!PLAIN && gs.mean) {  // MEAN pooling: the divisor of each row (positions fetched again: rare path)
           uint32_t m[4];
           if (eb < kPiece) {
             fetch4<G>(pm0, eb, m);
@@ -766,12 +784,15 @@ seg_reduce_kernel(SegArgs sa, const PeerOut po) {
         for (int u = 0; u < 4; ++u) {
           const int e = eb + u;
           if (e < e_begin || e >= e_stop) continue;
-          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (in) x = stage[b4 + u][threadIdx.x];
-          if (gs.mean) {
-            x.x = __fdiv_rn(x.x, fn[u]); x.y = __fdiv_rn(x.y, fn[u]); x.z = __fdiv_rn(x.z, fn[u]); x.w = __fdiv_rn(x.w, fn[u]);
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) {
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (in[v]) x = stage[(b4 + u) * VPL + v][threadIdx.x];
+            if (!PLAIN && gs.mean) {
+              x.x = __fdiv_rn(x.x, fn[u]); x.y = __fdiv_rn(x.y, fn[u]); x.z = __fdiv_rn(x.z, fn[u]); x.w = __fdiv_rn(x.w, fn[u]);
+            }
+            if ((st4 >> u) & 1u) acc[v] = x; else add4(acc[v], x);
           }
-          if ((st4 >> u) & 1u) acc = x; else add4(acc, x);
           if (!(e + 1 == e_stop || ((nx4 >> u) & 1u))) continue;
           // ---- a unit ends here ----
           const int hr = e < kPiece ? __popc(H & (0xFFFFFFFFu >> (31 - e))) : nheads;  // heads at or before e
@@ -779,45 +800,80 @@ seg_reduce_kernel(SegArgs sa, const PeerOut po) {
           if (hr == 0) dst = sa.part + (size_t)(2 * p) * D;                          // leading block of a long run
           else if (last_long && hr == nheads) dst = sa.part + (size_t)(2 * p + 1) * D;  // block 0 of a long run
           else dst = run_dst(a.ugrad, n_parts, s_start, s_base, (int64_t)j0 + hr - 1, D);  // a short run
-          if (in) *reinterpret_cast<float4*>(dst + c) = acc;
+#pragma unroll
+          for (int v = 0; v < VPL; ++v)
+            if (in[v]) *reinterpret_cast<float4*>(dst + c + v * G * 4) = acc[v];
         }
       }
     }
   }
 }
 
-// One level of the fixed 32-ary tree over the block index of the long runs: the slot of block k, k a multiple of
-// 32 * stride, receives (in place) the sum, in block order, of the slots of blocks k, k + stride, ..., k + 31 * stride.
+// One level of the fixed tree over the block index of the long runs: the slot of block k, k a multiple of
+// kTreeFan * stride, receives (in place) the sum of the slots of blocks k, k + stride, ..., k + (kTreeFan - 1) * stride.
+// A WARP owns a node: its 32 / G lane groups each sum a contiguous quarter (kTreeFan * G / 32 members, in block
+// order, 16 requests in flight per lane), then the group sums are added in group order through shuffles — the
+// association is a function of (run length, row width) only, so results are run-to-run bit-stable.  (One lane group
+// per node, 8 dependent stages of 16 loads, took 28 us on the C2 batch: the hottest FIDs' chains were the kernel.)
 template <int G>
 __global__ void __launch_bounds__(kThreads)
 tree_level_kernel(float* __restrict__ part, const SegMeta* __restrict__ meta, int64_t n_slots, uint32_t stride, int D) {
   extern __shared__ float4 stage_raw[];  // [kStage][kThreads]
   float4 (*stage)[kThreads] = reinterpret_cast<float4 (*)[kThreads]>(stage_raw);
-  const int gl = Group<G>::gl(), c = gl * 4;
-  const int64_t gstride = (int64_t)gridDim.x * (kThreads / G);
-  for (int64_t q = (int64_t)blockIdx.x * (kThreads / G) + threadIdx.x / G; q < n_slots; q += gstride) {
-    const SegMeta m = meta[q];
-    if (!m.valid || m.blk % (kTreeFan * stride) != 0 || m.blk + stride >= m.nblk) continue;
-    if (c >= D) continue;
-    const int64_t piece = q >> 1;
-    float4 acc = *reinterpret_cast<const float4*>(part + (size_t)q * D + c);
-    for (int i0 = 1; i0 < kTreeFan; i0 += 16) {
-      if ((uint64_t)m.blk + (uint64_t)i0 * stride >= m.nblk) break;
-      // 16 UNCONDITIONAL loads (indices clamped to the node's own slot) so that all of them are in flight together
+  constexpr int NG = 32 / G;                 // lane groups per warp = slots scanned per warp iteration
+  constexpr int PER = kTreeFan / NG;         // members per lane group
+  static_assert(PER % 16 == 0 || PER == kTreeFan, "members per group must fill whole stages");
+  const int gl = Group<G>::gl(), c = gl * 4, grp = (threadIdx.x & 31) / G;
+  const bool in = c < D;
+  const int lane = threadIdx.x & 31;
+  const int64_t wstride = (int64_t)gridDim.x * (kThreads / 32) * 32;
+  for (int64_t q0 = ((int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * 32; q0 < n_slots; q0 += wstride) {
+    // every lane inspects one slot; node heads are then processed one at a time by the whole warp
+    SegMeta mine;
+    mine.run = mine.blk = mine.nblk = mine.valid = 0;
+    if (q0 + lane < n_slots) mine = meta[q0 + lane];
+    const bool head = mine.valid && mine.blk % (kTreeFan * stride) == 0 && (uint64_t)mine.blk + stride < mine.nblk;
+    uint32_t heads = __ballot_sync(0xFFFFFFFFu, head);
+    while (heads) {
+      const int src = __ffs(heads) - 1;       // the lane that saw this head
+      heads &= heads - 1;
+      const uint32_t blk = __shfl_sync(0xFFFFFFFFu, mine.blk, src);
+      const uint32_t nblk = __shfl_sync(0xFFFFFFFFu, mine.nblk, src);
+      const int64_t q = q0 + src;
+      const int64_t piece = q >> 1;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      // member i of the node lives in slot q (i = 0) or 2 * (piece + i * stride): block k + i*stride starts i*stride pieces on
+      for (int i0 = grp * PER; i0 < (grp + 1) * PER; i0 += 16) {
+        if ((uint64_t)blk + (uint64_t)i0 * stride >= nblk) break;
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {  // (the compiler serialises plain loads behind the dependent adds; cp.async does not)
-        const uint64_t kk = (uint64_t)m.blk + (uint64_t)(i0 + u) * stride;
-        const bool ok = i0 + u < kTreeFan && kk < m.nblk;
-        const size_t slot = ok ? (size_t)(2 * (piece + (int64_t)(i0 + u) * stride)) : (size_t)q;
-        cp_async16(&stage[u][threadIdx.x], part + slot * D + c);
+        for (int u = 0; u < 16; ++u) {  // 16 UNCONDITIONAL requests (clamped to the node's own slot): all in flight together
+          const int i = i0 + u;
+          const bool ok = i > 0 && (uint64_t)blk + (uint64_t)i * stride < nblk;
+          const size_t slot = ok ? (size_t)(2 * (piece + (int64_t)i * stride)) : (size_t)q;
+          cp_async16(&stage[u][threadIdx.x], part + slot * D + (in ? c : 0));
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int i = i0 + u;
+          if ((uint64_t)blk + (uint64_t)i * stride < nblk) add4(acc, stage[u][threadIdx.x]);
+        }
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      // group sums -> group 0, in group order
+      float4 tot = acc;
 #pragma unroll
-      for (int u = 0; u < 16; ++u)
-        if (i0 + u < kTreeFan && (uint64_t)m.blk + (uint64_t)(i0 + u) * stride < m.nblk) add4(acc, stage[u][threadIdx.x]);
+      for (int g = 1; g < NG; ++g) {
+        float4 o;
+        o.x = __shfl_sync(0xFFFFFFFFu, acc.x, g * G + gl);
+        o.y = __shfl_sync(0xFFFFFFFFu, acc.y, g * G + gl);
+        o.z = __shfl_sync(0xFFFFFFFFu, acc.z, g * G + gl);
+        o.w = __shfl_sync(0xFFFFFFFFu, acc.w, g * G + gl);
+        if ((uint64_t)blk + (uint64_t)(g * PER) * stride < nblk) add4(tot, o);
+      }
+      __syncwarp();  // every group has read its members (slot q among them) before the node is overwritten
+      if (grp == 0 && in) *reinterpret_cast<float4*>(part + (size_t)q * D + c) = tot;
     }
-    *reinterpret_cast<float4*>(part + (size_t)q * D + c) = acc;
   }
 }
 
@@ -867,15 +923,31 @@ long_finish_kernel(SegArgs sa, uint32_t top, const PeerOut po) {
 
 // Apply: group per run; rowidx[j], ugrad[j] and the row's w / state are all independent loads.
 // (A variant that handled two runs per group at a time was measured slower: 62 registers, 43 % occupancy.)
+// prefetch != 0: the NEXT run's row index is read one iteration ahead and its weight / state rows are pulled into L2
+// meanwhile, which takes the random row fetch (~2.5 us from HBM) off the per-iteration chain.
 template <int G, int OPT>
-__global__ void __launch_bounds__(kThreads) runs_apply_kernel(BwdArgs a) {
+__global__ void __launch_bounds__(kThreads) runs_apply_kernel(BwdArgs a, int prefetch) {
   const int gl = Group<G>::gl();
   const int c = gl * 4;
   const int64_t nr = *a.n_runs;
   const int D = a.td.dim;
   const int64_t gstride = (int64_t)gridDim.x * (kThreads / G);
-  for (int64_t j = (int64_t)blockIdx.x * (kThreads / G) + threadIdx.x / G; j < nr; j += gstride) {
-    const uint32_t ri = a.rowidx[j];
+  int64_t j = (int64_t)blockIdx.x * (kThreads / G) + threadIdx.x / G;
+  uint32_t ri_next = j < nr ? a.rowidx[j] : kEmptyRow;
+  for (; j < nr; j += gstride) {
+    const uint32_t ri = ri_next;
+    if (j + gstride < nr) {
+      ri_next = a.rowidx[j + gstride];
+      if (prefetch && OPT >= 0 && ri_next != kEmptyRow && !(ri_next & kFreshBit) && c < D) {
+        const uint32_t row = ri_next & ~kFreshBit;
+        prefetch_l2(a.td.emb + (size_t)row * a.td.emb_stride + c);
+        if (OPT != MONO_OPT_SGD) {
+          const float* s_row = a.td.state + (size_t)row * a.td.state_stride;
+          prefetch_l2(s_row + c);
+          if (OPT == MONO_OPT_FTRL || OPT == MONO_OPT_ADAM) prefetch_l2(s_row + D + c);
+        }
+      }
+    }
     float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c < D) g4 = __ldcs(reinterpret_cast<const float4*>(a.ugrad + (size_t)j * D + c));
     if (ri == kEmptyRow) continue;
@@ -916,11 +988,11 @@ struct ClaimResolve {
   uint32_t* miss_slots;
 };
 
-template <bool RESOLVE>
+template <bool RESOLVE, bool DUAL = false>
 __global__ void __launch_bounds__(kThreads)
 fid_claim_kernel(const int64_t* __restrict__ fids, int64_t n, Entry* set, uint32_t R, int N, uint32_t epoch,
                  uint32_t* __restrict__ slot_of, uint32_t* __restrict__ owner_cnt /* [N], [256] = overflow */,
-                 ClaimResolve cr) {
+                 ClaimResolve cr, int prefetch) {
   __shared__ uint32_t cnt[256];
   for (int d = threadIdx.x; d < 256; d += blockDim.x) cnt[d] = 0;
   __syncthreads();
@@ -928,10 +1000,29 @@ fid_claim_kernel(const int64_t* __restrict__ fids, int64_t n, Entry* set, uint32
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   // the chain per occurrence is FID -> set entry (-> CAS -> table bucket for a winner), ~2.5 us per dependent round
   // trip: the NEXT occurrence's FID is requested one iteration ahead, which takes it off the chain
+  // ... and so are (prefetch != 0) its scratch-set slot and, for RESOLVE, its first table bucket: both are pulled into
+  // L2 while this iteration's chain runs, so the next iteration's two dependent reads are L2 hits.
   int64_t key_next = i < n ? __ldg(fids + i) : 0;
+  const Entry* pf_buckets = nullptr;
+  uint32_t pf_nb = 0;
+  if (RESOLVE && prefetch) {
+    pf_buckets = cr.t->buckets;
+    pf_nb = cr.t->num_buckets;
+  }
   for (; i < n; i += stride) {
     const int64_t key = key_next;
-    if (i + stride < n) key_next = __ldg(fids + i + stride);
+    if (i + stride < n) {
+      key_next = __ldg(fids + i + stride);
+      if (prefetch) {
+        const uint32_t o_n = N == 1 ? 0u : (uint32_t)((uint64_t)key_next % (uint64_t)N);
+        prefetch_l2(set + o_n * R + __umulhi((uint32_t)(mix64((uint64_t)key_next) >> 24), R));
+        if (RESOLVE) {
+          uint32_t b1, b2;
+          bucket_pair(key_next, pf_nb, b1, b2);
+          prefetch_l2(pf_buckets + (size_t)b1 * kBucketSlots);
+        }
+      }
+    }
     const uint32_t owner = N == 1 ? 0u : (uint32_t)((uint64_t)key % (uint64_t)N);
     const uint32_t base = owner * R;
     uint32_t idx = __umulhi((uint32_t)(mix64((uint64_t)key) >> 24), R);
@@ -969,7 +1060,7 @@ fid_claim_kernel(const int64_t* __restrict__ fids, int64_t n, Entry* set, uint32
       atomicAdd(&cnt[owner], 1u);
       if (RESOLVE) {
         Entry* slot = nullptr;
-        const uint32_t row = probe_lane_slot(cr.t, key, &slot);
+        const uint32_t row = probe_lane_slot<DUAL>(cr.t, key, &slot);
         if (row != kEmptyRow) {
           slot->ts = cr.update_ts;
           set[found].row = row;
@@ -1028,6 +1119,27 @@ struct ReduceScratch {  // sizes of the reduction scratch for M occurrences of d
   }
 };
 
+constexpr size_t kStageBytes = sizeof(float4) * kStage * kThreads;
+template <int GL, int VPL, bool PLAIN, bool AHEAD>
+static void launch_seg2(const SegArgs& sa, const PeerOut& po, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    MONO_CUDA(cudaFuncSetAttribute(seg_reduce_kernel<GL, VPL, PLAIN, AHEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)kStageBytes));
+    attr_set = true;
+  }
+  seg_reduce_kernel<GL, VPL, PLAIN, AHEAD>
+      <<<resident_grid(seg_reduce_kernel<GL, VPL, PLAIN, AHEAD>, sa.n_pieces, (kThreads / 32) * (32 / GL), kThreads,
+                       kStageBytes),
+         kThreads, kStageBytes, s>>>(sa, po);
+  MONO_CHECK_LAUNCH();
+}
+template <int GL, int VPL, bool PLAIN>
+static void launch_seg(const SegArgs& sa, const PeerOut& po, cudaStream_t s) {
+  if (knob(KNOB_SEG_AHEAD)) launch_seg2<GL, VPL, PLAIN, true>(sa, po, s);
+  else launch_seg2<GL, VPL, PLAIN, false>(sa, po, s);
+}
+
 // per-run gradient sums -> run_dst (a.ugrad, or the owners' peer windows)
 static void launch_reduce(const SegArgs& sa, int G, int /*unused*/, const PeerOut& po, cudaStream_t s) {
   const int64_t np = sa.n_pieces;
@@ -1039,26 +1151,28 @@ static void launch_reduce(const SegArgs& sa, int G, int /*unused*/, const PeerOu
     ++levels;
   }
   const int D = sa.b.td.dim;
+  const bool plain = sa.b.occ_row == nullptr && !(sa.b.pooling == MONO_POOL_MEAN && sa.b.row_offsets != nullptr);
+  const bool two = knob(KNOB_SEG_VPL) == 2;
 #define SEG_GO(GG, MODE, OO)                                                                                        \
   do {                                                                                                              \
-    constexpr size_t kStageBytes = sizeof(float4) * kStage * kThreads;                                              \
     static bool attr_set = false;                                                                                   \
     if (!attr_set) {                                                                                                \
-      MONO_CUDA(cudaFuncSetAttribute(seg_reduce_kernel<GG, MODE, OO>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                     (int)kStageBytes));                                                            \
       MONO_CUDA(cudaFuncSetAttribute(tree_level_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
                                      (int)kStageBytes));                                                            \
       MONO_CUDA(cudaFuncSetAttribute(long_finish_kernel<GG, MODE, OO>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      (int)kStageBytes));                                                            \
       attr_set = true;                                                                                              \
     }                                                                                                               \
-    seg_reduce_kernel<GG, MODE, OO>                                                                                 \
-        <<<resident_grid(seg_reduce_kernel<GG, MODE, OO>, np, (kThreads / 32) * (32 / GG), kThreads, kStageBytes),  \
-           kThreads, kStageBytes, s>>>(sa, po);                                                                     \
-    MONO_CHECK_LAUNCH();                                                                                            \
+    if (two && GG >= 8) {                                                                                           \
+      if (plain) launch_seg<(GG >= 8 ? GG / 2 : GG), (GG >= 8 ? 2 : 1), true>(sa, po, s);                           \
+      else launch_seg<(GG >= 8 ? GG / 2 : GG), (GG >= 8 ? 2 : 1), false>(sa, po, s);                                \
+    } else {                                                                                                        \
+      if (plain) launch_seg<GG, 1, true>(sa, po, s);                                                                \
+      else launch_seg<GG, 1, false>(sa, po, s);                                                                     \
+    }                                                                                                               \
     uint32_t stride = 1;                                                                                            \
     for (int l = 0; l < levels; ++l, stride *= kTreeFan) {                                                          \
-      tree_level_kernel<GG><<<resident_grid(tree_level_kernel<GG>, 2 * np, kThreads / GG, kThreads, kStageBytes),   \
+      tree_level_kernel<GG><<<resident_grid(tree_level_kernel<GG>, 2 * np, kThreads, kThreads, kStageBytes),        \
                               kThreads, kStageBytes, s>>>(sa.part, sa.meta, 2 * np, stride, D);                     \
       MONO_CHECK_LAUNCH();                                                                                          \
     }                                                                                                               \
@@ -1141,8 +1255,12 @@ void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t 
   cr.update_ts = (uint32_t)update_time;
   cr.miss_ctr = ctr + 8;
   cr.miss_slots = (uint32_t*)(ws + o_miss);
-  fid_claim_kernel<true><<<resident_grid(fid_claim_kernel<true>, M, kThreads), kThreads, 0, s>>>(
-      fids_dev, M, set, cap, 1, epoch, k0, ctr + 512, cr);
+  if (knob(KNOB_CLAIM_DUAL))
+    fid_claim_kernel<true, true><<<resident_grid(fid_claim_kernel<true, true>, M, kThreads), kThreads, 0, s>>>(
+        fids_dev, M, set, cap, 1, epoch, k0, ctr + 512, cr, knob(KNOB_CLAIM_PF));
+  else
+    fid_claim_kernel<true><<<resident_grid(fid_claim_kernel<true>, M, kThreads), kThreads, 0, s>>>(
+        fids_dev, M, set, cap, 1, epoch, k0, ctr + 512, cr, knob(KNOB_CLAIM_PF));
   MONO_CHECK_LAUNCH();
   // 2 absent FIDs: allocate a row + lock-free insert (few in steady state; the count stays on the device)
   claim_miss_kernel<<<resident_grid(claim_miss_kernel, std::min<int64_t>(M, 148 * 2 * kThreads), kThreads), kThreads, 0, s>>>(
@@ -1197,8 +1315,9 @@ void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t 
   }
   launch_reduce(sa, G, -1, no_peer, s);
   // 6 apply: one streaming pass over the runs — row index, summed gradient, w / optimizer state of every distinct FID
+  const int pf = knob(KNOB_APPLY_PF);
 #define BWD2(GG, OO)                                                                                             \
-  runs_apply_kernel<GG, OO><<<resident_grid(runs_apply_kernel<GG, OO>, M, kThreads / GG), kThreads, 0, s>>>(a);  \
+  runs_apply_kernel<GG, OO><<<resident_grid(runs_apply_kernel<GG, OO>, M, kThreads / GG), kThreads, 0, s>>>(a, pf);  \
   MONO_CHECK_LAUNCH()
 #define BWD(GG)                                                         \
   switch (opt_sel) {                                                    \
@@ -1402,7 +1521,7 @@ void grouping_build(mono_grouping* g, const int64_t* fids_dev, int64_t M, int N,
     ClaimResolve cr0;
     std::memset(&cr0, 0, sizeof(cr0));
     fid_claim_kernel<false><<<resident_grid(fid_claim_kernel<false>, M, kThreads), kThreads, 0, s>>>(
-        fids_dev, M, set, R, N, epoch, sw.k0, owner_cnt, cr0);
+        fids_dev, M, set, R, N, epoch, sw.k0, owner_cnt, cr0, knob(KNOB_CLAIM_PF));
     MONO_CHECK_LAUNCH();
     // counts -> host on the side stream, while the sort below keeps the GPU busy.  Device-driven callers
     // (shard_counts_host == nullptr: xstep.cu) never read them on the host: nothing waits, the per-owner counts stay

@@ -116,12 +116,25 @@ int mono_set_option(const char* name, int64_t value) {
   return guarded([&] {
     require(name != nullptr, "set_option: null name");
     if (std::strcmp(name, "lookup_tma") == 0) g_opt_lookup_tma.store(value != 0 ? 1 : 0);
+    else if (knob_id(name) >= 0) knob_set(knob_id(name), (int)value);
     else throw ArgError(std::string("unknown option: ") + name);
   });
 }
 int64_t mono_get_option(const char* name) {
   if (name && std::strcmp(name, "lookup_tma") == 0) return g_opt_lookup_tma.load();
+  if (knob_id(name) >= 0) return knob(knob_id(name));
   return -1;
+}
+
+int64_t mono_bench_tower_scratch_floats(void) { return tower_scratch_floats(); }
+int mono_bench_tower_grad(const float* pooled, int64_t batch, const float* labels, const void* w1_bf16,
+                          const void* w2_bf16, float* grad_out, float* loss_out, float* scratch,
+                          int64_t scratch_floats, void* stream) {
+  return guarded([&] {
+    require(pooled && labels && w1_bf16 && w2_bf16 && grad_out && loss_out && scratch, "bench_tower_grad: null argument");
+    require(batch >= 0 && scratch_floats >= tower_scratch_floats(), "bench_tower_grad: scratch too small");
+    tower_grad(pooled, batch, labels, w1_bf16, w2_bf16, grad_out, loss_out, scratch, (cudaStream_t)stream);
+  });
 }
 
 int mono_mtable_create(const mono_table_cfg* cfgs, int32_t n_tables, int32_t device,

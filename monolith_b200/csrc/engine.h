@@ -18,6 +18,17 @@ namespace mono {
 
 extern std::atomic<int64_t> g_launches;  // kernels launched by this library
 extern std::atomic<int> g_opt_lookup_tma; // mono_set_option("lookup_tma")
+// Tuning knobs (mono_set_option(name) / env MONO_KNOBS="name=value,..."): each selects between two implementations of
+// the same result, kept switchable so that a bench run can A/B them in one session.
+enum Knob { KNOB_CLAIM_PF = 0, KNOB_SEG_VPL, KNOB_APPLY_PF, KNOB_LOOKUP_PF, KNOB_CLAIM_DUAL, KNOB_LOOKUP_DUAL, KNOB_SEG_AHEAD, KNOB_COUNT };
+int knob(int id);
+int knob_id(const char* name);            // -1: unknown
+void knob_set(int id, int value);
+
+// tower.cu: the e2e bench's stand-in dense tower (64-64-1 bf16 MLP + logistic loss), forward + input gradient in one kernel
+int tower_scratch_floats();
+void tower_grad(const float* x, int64_t batch, const float* labels, const void* w1_bf16, const void* w2_bf16, float* dx,
+                float* loss, float* scratch, cudaStream_t s);
 #define MONO_COUNT_LAUNCH() (::mono::g_launches.fetch_add(1, std::memory_order_relaxed))
 
 struct CudaError : std::runtime_error {

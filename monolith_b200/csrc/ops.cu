@@ -46,11 +46,11 @@ __device__ __forceinline__ void store_vec(float* dst, int c, int D, const float4
 
 // SINGLE: the call has one segment (one table): table fields and the output base are warp-uniform
 // and hoisted, which keeps the kernel at ~40 registers => 6 resident blocks (48 warps) per SM.
-template <int G, bool SINGLE>
-__global__ void __launch_bounds__(kThreads, SINGLE ? 6 : 4)
+template <int G, bool SINGLE, bool DUAL = false>
+__global__ void __launch_bounds__(kThreads, SINGLE && !DUAL ? 6 : 4)
 lookup_kernel(const TableDev* __restrict__ tables, const CallSeg* __restrict__ segs, int nsegs,
               const int64_t* __restrict__ ids, int64_t n_total, float* __restrict__ out,
-              int64_t out_stride /* <= 0: rows packed at dim floats */, int out_col) {
+              int64_t out_stride /* <= 0: rows packed at dim floats */, int out_col, int prefetch) {
   constexpr int RPI = 32 / G;   // rows copied per iteration of a warp
   constexpr int ITERS = G;      // iterations to drain the 32 resolved rows
   constexpr int UNR = 4;        // row loads in flight per lane
@@ -73,12 +73,19 @@ lookup_kernel(const TableDev* __restrict__ tables, const CallSeg* __restrict__ s
     // ---- phase A: lane-per-key probe ----
     const int64_t i = wbase + lane;
     const int64_t key = key_next;
-    if (i + wstride < n_total) key_next = __ldg(ids + i + wstride);
+    if (i + wstride < n_total) {
+      key_next = __ldg(ids + i + wstride);
+      if (SINGLE && prefetch) {  // knob lookup_pf: the next tile's first buckets into L2
+        uint32_t b1, b2;
+        bucket_pair(key_next, t0->num_buckets, b1, b2);
+        prefetch_l2(t0->buckets + (size_t)b1 * kBucketSlots);
+      }
+    }
     int si = 0;
     uint32_t row = kEmptyRow;
     if (i < n_total) {
       if (!SINGLE) si = find_seg(segs, nsegs, i);
-      row = probe_lane(SINGLE ? t0 : tables + segs[si].table, key);
+      row = probe_lane<DUAL>(SINGLE ? t0 : tables + segs[si].table, key);
     }
     // ---- phase B: group-per-row copy, UNR rows in flight ----
 #pragma unroll
@@ -921,12 +928,16 @@ static void launch_lookup_staged(mono_mtable* mt, const CallSeg* d_segs, int nse
                                  const int64_t* ids_dev, int64_t n_total, float* out_dev,
                                  int64_t out_stride, int out_col, cudaStream_t s) {
 #define L(GG)                                                                                      \
-  if (nsegs == 1)                                                                                  \
+  if (nsegs == 1 && knob(KNOB_LOOKUP_DUAL))                                                        \
+    lookup_kernel<GG, true, true><<<resident_grid(lookup_kernel<GG, true, true>, n_total, kThreads), kThreads, 0, s>>>( \
+        mt->d_tables, d_segs, nsegs, ids_dev, n_total, out_dev, out_stride, out_col, pf);          \
+  else if (nsegs == 1)                                                                             \
     lookup_kernel<GG, true><<<resident_grid(lookup_kernel<GG, true>, n_total, kThreads), kThreads, 0, s>>>( \
-        mt->d_tables, d_segs, nsegs, ids_dev, n_total, out_dev, out_stride, out_col);              \
+        mt->d_tables, d_segs, nsegs, ids_dev, n_total, out_dev, out_stride, out_col, pf);          \
   else                                                                                             \
     lookup_kernel<GG, false><<<resident_grid(lookup_kernel<GG, false>, n_total, kThreads), kThreads, 0, s>>>( \
-        mt->d_tables, d_segs, nsegs, ids_dev, n_total, out_dev, out_stride, out_col)
+        mt->d_tables, d_segs, nsegs, ids_dev, n_total, out_dev, out_stride, out_col, pf)
+  const int pf = knob(KNOB_LOOKUP_PF);
   switch (G) {
     case 4: L(4); break;
     case 8: L(8); break;

@@ -320,11 +320,39 @@ __device__ __forceinline__ void apply_row(const TableDev* __restrict__ t, uint32
 }
 
 // lane-per-key probe of the bucketised table: the whole 64-byte bucket with 4 x LDG.128 per lane
+// DUAL: both candidate buckets are requested together (8 x LDG.128).  A warp-tile of 32 probes almost always holds a
+// key that lives in its second bucket, so the sequential form costs the WARP two dependent round trips; DUAL trades
+// 64 extra bytes per key for one round trip (knobs lookup_dual / claim_dual).
+template <bool DUAL = false>
 __device__ __forceinline__ uint32_t probe_lane(const TableDev* __restrict__ t, int64_t key) {
   const Entry* __restrict__ buckets = t->buckets;
   uint32_t b1, b2;
   bucket_pair(key, t->num_buckets, b1, b2);
   uint32_t row = kEmptyRow;
+  if (DUAL) {
+    const Entry* p = buckets + (size_t)b1 * kBucketSlots;
+    const Entry* q = buckets + (size_t)b2 * kBucketSlots;
+    Entry e0 = ld_entry_nc(p), e1 = ld_entry_nc(p + 1), e2 = ld_entry_nc(p + 2), e3 = ld_entry_nc(p + 3);
+    Entry f0 = ld_entry_nc(q), f1 = ld_entry_nc(q + 1), f2 = ld_entry_nc(q + 2), f3 = ld_entry_nc(q + 3);
+    if (f0.key == key && f0.row < kTombRow) row = f0.row;
+    if (f1.key == key && f1.row < kTombRow) row = f1.row;
+    if (f2.key == key && f2.row < kTombRow) row = f2.row;
+    if (f3.key == key && f3.row < kTombRow) row = f3.row;
+    if (e0.key == key && e0.row < kTombRow) row = e0.row;
+    if (e1.key == key && e1.row < kTombRow) row = e1.row;
+    if (e2.key == key && e2.row < kTombRow) row = e2.row;
+    if (e3.key == key && e3.row < kTombRow) row = e3.row;
+    if (row == kEmptyRow && t->ctrs[kCtrStash] != 0) {
+      const uint32_t mask = t->stash_cap - 1;
+      const uint32_t s = (uint32_t)(mix64((uint64_t)key) >> 17) & mask;
+      for (uint32_t i = 0; i <= mask; ++i) {
+        Entry e = ld_entry_cg(t->stash + ((s + i) & mask));
+        if (e.row == kEmptyRow) break;
+        if (e.key == key && e.row < kTombRow) { row = e.row; break; }
+      }
+    }
+    return row;
+  }
   {
     const Entry* p = buckets + (size_t)b1 * kBucketSlots;
     Entry e0 = ld_entry_nc(p), e1 = ld_entry_nc(p + 1), e2 = ld_entry_nc(p + 2), e3 = ld_entry_nc(p + 3);
@@ -357,21 +385,38 @@ __device__ __forceinline__ uint32_t probe_lane(const TableDev* __restrict__ t, i
 constexpr uint32_t kFreshBit = 0x80000000u;
 
 // probe that also returns the matching entry's address (for the timestamp bump)
+template <bool DUAL = false>
 __device__ __forceinline__ uint32_t probe_lane_slot(const TableDev* __restrict__ t, int64_t key,
                                                     Entry** slot) {
   Entry* buckets = t->buckets;
   uint32_t b1, b2;
   bucket_pair(key, t->num_buckets, b1, b2);
   uint32_t row = kEmptyRow;
-#pragma unroll
-  for (int round = 0; round < 2; ++round) {
-    Entry* p = buckets + (size_t)(round == 0 ? b1 : b2) * kBucketSlots;
+  if (DUAL) {
+    Entry* p = buckets + (size_t)b1 * kBucketSlots;
+    Entry* q = buckets + (size_t)b2 * kBucketSlots;
     Entry e0 = ld_entry(p), e1 = ld_entry(p + 1), e2 = ld_entry(p + 2), e3 = ld_entry(p + 3);
+    Entry f0 = ld_entry(q), f1 = ld_entry(q + 1), f2 = ld_entry(q + 2), f3 = ld_entry(q + 3);
+    if (f0.key == key && f0.row < kTombRow) { row = f0.row; *slot = q; }
+    if (f1.key == key && f1.row < kTombRow) { row = f1.row; *slot = q + 1; }
+    if (f2.key == key && f2.row < kTombRow) { row = f2.row; *slot = q + 2; }
+    if (f3.key == key && f3.row < kTombRow) { row = f3.row; *slot = q + 3; }
     if (e0.key == key && e0.row < kTombRow) { row = e0.row; *slot = p; }
     if (e1.key == key && e1.row < kTombRow) { row = e1.row; *slot = p + 1; }
     if (e2.key == key && e2.row < kTombRow) { row = e2.row; *slot = p + 2; }
     if (e3.key == key && e3.row < kTombRow) { row = e3.row; *slot = p + 3; }
     if (row != kEmptyRow) return row;
+  } else {
+#pragma unroll
+    for (int round = 0; round < 2; ++round) {
+      Entry* p = buckets + (size_t)(round == 0 ? b1 : b2) * kBucketSlots;
+      Entry e0 = ld_entry(p), e1 = ld_entry(p + 1), e2 = ld_entry(p + 2), e3 = ld_entry(p + 3);
+      if (e0.key == key && e0.row < kTombRow) { row = e0.row; *slot = p; }
+      if (e1.key == key && e1.row < kTombRow) { row = e1.row; *slot = p + 1; }
+      if (e2.key == key && e2.row < kTombRow) { row = e2.row; *slot = p + 2; }
+      if (e3.key == key && e3.row < kTombRow) { row = e3.row; *slot = p + 3; }
+      if (row != kEmptyRow) return row;
+    }
   }
   if (t->ctrs[kCtrStash] != 0) {
     const uint32_t mask = t->stash_cap - 1;
@@ -386,6 +431,10 @@ __device__ __forceinline__ uint32_t probe_lane_slot(const TableDev* __restrict__
   return kEmptyRow;
 }
 
+
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
 // ---- cp.async staging: rows requested kStage at a time into per-thread shared-memory slots (zero register cost) ----
 constexpr int kStage = 16;

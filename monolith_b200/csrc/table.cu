@@ -1,6 +1,7 @@
 // table.cu — storage management of the collisionless table: creation, growth (row slabs and
 // bucket array), TTL eviction, export.  The probe / insert primitives are in common.cuh.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "engine.h"
@@ -9,6 +10,53 @@ namespace mono {
 
 std::atomic<int64_t> g_launches{0};
 std::atomic<int> g_opt_lookup_tma{0};
+
+namespace {
+struct KnobDef { const char* name; int dflt; };
+// claim_pf  : the claim kernel prefetches (L2) the NEXT occurrence's scratch-set slot and table bucket
+// seg_vpl   : 16-byte vectors of a gradient row per lane in seg_reduce_kernel (1 | 2)
+// apply_pf  : runs_apply_kernel prefetches (L2) the next run's weight / optimizer-state rows
+// lookup_pf : the lookup kernels prefetch (L2) the next occurrence's table bucket
+// seg_ahead : seg_reduce_kernel loads the positions of the two following pieces up front (no dependent position load)
+// claim_dual / lookup_dual : both candidate buckets of a key are requested together (rowops.cuh probe_lane<DUAL>)
+// Measured on B200 (profiles/r2_ab.txt): every L2-prefetch variant LOSES (claim 68 -> 110 us, apply 61 -> 83 us,
+// lookup +30 us) and seg_vpl = 2 is a wash: they stay available but off.
+const KnobDef kKnobs[KNOB_COUNT] = {{"claim_pf", 0}, {"seg_vpl", 1}, {"apply_pf", 0}, {"lookup_pf", 0},
+                                    {"claim_dual", 0}, {"lookup_dual", 0}, {"seg_ahead", 1}};
+std::atomic<int> g_knob[KNOB_COUNT];
+std::once_flag g_knob_once;
+void knob_init() {
+  for (int i = 0; i < KNOB_COUNT; ++i) g_knob[i].store(kKnobs[i].dflt);
+  const char* e = std::getenv("MONO_KNOBS");
+  if (!e) return;
+  std::string str(e);
+  size_t pos = 0;
+  while (pos < str.size()) {
+    size_t end = str.find(',', pos);
+    if (end == std::string::npos) end = str.size();
+    const std::string kv = str.substr(pos, end - pos);
+    const size_t eq = kv.find('=');
+    if (eq != std::string::npos) {
+      const int id = knob_id(kv.substr(0, eq).c_str());
+      if (id >= 0) g_knob[id].store(std::atoi(kv.c_str() + eq + 1));
+    }
+    pos = end + 1;
+  }
+}
+}  // namespace
+int knob_id(const char* name) {
+  for (int i = 0; i < KNOB_COUNT; ++i)
+    if (name && std::strcmp(name, kKnobs[i].name) == 0) return i;
+  return -1;
+}
+int knob(int id) {
+  std::call_once(g_knob_once, knob_init);
+  return g_knob[id].load(std::memory_order_relaxed);
+}
+void knob_set(int id, int value) {
+  std::call_once(g_knob_once, knob_init);
+  g_knob[id].store(value);
+}
 
 // ------------------------------------------------------------------------------------------
 // StageRing

@@ -1196,3 +1196,35 @@ def test_two_host_threads_share_one_handle(dev):
     np.testing.assert_array_equal(x.view(np.uint32), va.view(np.uint32))
   both = np.concatenate([a_ids, b_ids])
   np.testing.assert_array_equal(gpu_lookup(gpu, {"t": both}, dev)["t"].view(np.uint32), cpu.lookup({"t": both})["t"].view(np.uint32))
+
+
+# ------------------------------------------------------------------------------------------------
+# the e2e bench's stand-in dense tower: the fused kernel (csrc/tower.cu) against torch.autograd
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("batch", [16, 5000, 65536 + 7])
+def test_bench_tower_fused_vs_autograd(dev, batch):
+  """floating point, bf16 operands: loss within 1e-3 relative, input gradient within 2 % in relative L2 norm (the two
+  sides round to bf16 at the same points but accumulate in different orders, so a ReLU mask can flip on a unit whose
+  pre-activation is ~0)."""
+  import bench
+  from monolith_b200 import _lib
+  lib = _lib.load()
+  torch.manual_seed(batch)
+  fused = bench.Tower(dev, batch, seed=3, lib=lib)
+  ref = bench.Tower(dev, batch, seed=3)
+  pooled = torch.randn(batch * bench.SLOTS, bench.DIM, device=dev)
+  labels = (torch.rand(batch, device=dev) < 0.3).float()
+  g = torch.full((batch * bench.SLOTS, bench.DIM), 7.0, device=dev)
+  loss = fused.grad(pooled, labels, g).clone()
+  loss_ref, gx = ref.grad_autograd(pooled, labels)
+  torch.cuda.synchronize()
+  assert abs(float(loss) - float(loss_ref)) <= 1e-3 * abs(float(loss_ref))
+  got = g.view(batch, bench.SLOTS * bench.DIM).double()
+  want = gx.double()
+  rel = float((got - want).norm() / want.norm())
+  assert rel < 2e-2, rel
+  # the torch formulation with the hand-written backward agrees with autograd too
+  g2 = torch.empty_like(g)
+  loss2 = ref.grad_torch(pooled, labels, g2)
+  assert abs(float(loss2) - float(loss_ref)) <= 1e-3 * abs(float(loss_ref))
+  assert float((g2.view(batch, -1).double() - want).norm() / want.norm()) < 2e-2
