@@ -48,9 +48,12 @@ UNIT = "lookups/s"
 def parse():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
-  ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"],
+  ap.add_argument("--new-frac", type=float, default=0.05, help="c4: fraction of a step's FID occurrences that are never-seen FIDs")
+  ap.add_argument("--evict-every", type=int, default=8, help="c4: steps between TTL eviction scans")
+  ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
                   help="c2 (default; BASELINE.json configs[1], the metric's config): MovieLens-shaped, 1 table dim 32, 2 slots, 10 M keys; "
                        "c3: Criteo-shaped, 26 slots dim 16 in one table, 26 M keys, batch 65 536 per GPU; "
+                       "c4: streaming insert+evict, 200 slots dim 16, 125 M keys per GPU, batch 8192 per GPU; "
                        "c5: table sweep dim 8..128 (lookup and lookup+Adagrad GB/s), single GPU")
   ap.add_argument("--steps", type=int, default=20)
   ap.add_argument("--warmup", type=int, default=5)
@@ -85,6 +88,9 @@ def parse():
     DIM, SLOTS = 16, 26
     args.batch = args.batch or (1 << 16)
     args.keys = args.keys or 26_000_000
+  elif args.workload == "c4":
+    args.batch = args.batch or (1 << 13)
+    args.keys = args.keys or 125_000_000
   else:
     args.batch = args.batch or (1 << 20)
     args.keys = args.keys or 10_000_000
@@ -692,11 +698,22 @@ def run_ours(args):
       f, lab = d_f[b], d_labs[b]
       loss = []
 
+      tr = state.get("trace")                          # phase trace (one untimed region): CUDA events on the main stream
+      if tr is not None:
+        tr.append([torch.cuda.Event(enable_timing=True) for _ in range(4)])
+        tr[-1][0].record(main)                         # inputs have arrived, the forward starts
+
       def grads():
+        if tr is not None:
+          tr[-1][1].record(main)                       # forward done
         loss.append(tower.grad(pooled, lab, d_g))
+        if tr is not None:
+          tr[-1][2].record(main)                       # tower done
         return d_g
 
       step(i, f, grads, pooled)
+      if tr is not None:
+        tr[-1][3].record(main)                         # backward done
       ev_free[b].record(main)
       loss_pin[b:b + 1].copy_(loss[0].reshape(1), non_blocking=True)   # D2H of this step's loss, every step
       ev_loss[b].record(main)
@@ -711,6 +728,20 @@ def run_ours(args):
     es, ew = max(3, args.steps // 2), 3
     ems, _, eregions = timed(e2e_step, es, ew, max(1, min(3, args.repeats)))
 
+    # where an e2e step's time goes on the device (separate untimed region; world 1 only: the sharded step takes the
+    # gradient callable at a different point)
+    phases = None
+    if not use_sharded:
+      state["trace"] = []
+      timed(e2e_step, 12, 2)
+      tr = state.pop("trace")[4:]
+      torch.cuda.synchronize()
+      phases = {"forward_ms": float(np.mean([t[0].elapsed_time(t[1]) for t in tr])),
+                "tower_ms": float(np.mean([t[1].elapsed_time(t[2]) for t in tr])),
+                "backward_ms": float(np.mean([t[2].elapsed_time(t[3]) for t in tr])),
+                "between_steps_ms": float(np.mean([a[3].elapsed_time(b_[0]) for a, b_ in zip(tr[:-1], tr[1:])]))}
+      state["trace"] = None
+
     def tower_only(i):  # context: how much of the e2e step is not the sparse path
       tower.grad(pooled, d_labs[0], d_g)
 
@@ -718,7 +749,7 @@ def run_ours(args):
     ttms, _, _ = timed(lambda i: tower_torch.grad(pooled, d_labs[0], d_g), 5, 2)
     e2e = {"value": M * world * es / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * M + 4 * args.batch,
            "d2h_bytes_per_step": 4, "ms_per_step": ems / es, "ms_per_step_regions": [r / es for r in eregions],
-           "dense_tower_ms": tms / 10, "dense_tower_torch_ms": ttms / 5,
+           "dense_tower_ms": tms / 10, "dense_tower_torch_ms": ttms / 5, "device_phases": phases,
            "pipeline": "per step: H2D of the step's FIDs (pinned int64[M]) and labels on a copy stream one step ahead (input "
                        "prefetch), fused lookup+pool forward, stand-in "
                        "DSSM tower (bf16 MLP 64-64-1 + logistic loss; one fused mma.sync kernel, csrc/tower.cu) on the device, fused sparse "
@@ -920,10 +951,156 @@ def run_c5(args):
                     "rows": rows, "gpu_launches": int(lib.mono_kernel_launch_count())}), flush=True)
 
 
+def run_c4(args):
+  """Streaming insert + evict (BASELINE.json configs[3], DCN-v2-shaped): 200 slots x dim 16 in one collisionless table,
+  `--keys` resident keys PER GPU (default 125 M: the 1 B-key table over 8 GPUs), Adagrad.  Every step a fraction
+  `--new-frac` of the occurrences are FIDs never seen before (inserted by the backward with their initial row), the rest
+  are Zipf-distributed over the resident population; every `--evict-every` steps the table drops every key whose
+  last-update time is older than the TTL window (ref: CuckooEmbeddingHashTable::Evict, a full-table scan).  The resident
+  keys are prefilled with last-update times spread uniformly over the window, so the stream is in steady state:
+  keys inserted per step ~= keys evicted per step.  N > 1: the same stream through the sharded step (FID-hash exchange);
+  every rank owns keys/GPU resident keys and evicts its own shard."""
+  import torch
+  import torch.distributed as dist
+  from monolith_b200 import MultiHashTable, _lib, entry
+  global DIM, SLOTS
+  DIM, SLOTS = 16, 200
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  torch.cuda.set_device(local)
+  dev = torch.device("cuda", local)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+  lib = _lib.load()
+  keys = args.keys
+  batch = args.batch
+  M = batch * SLOTS
+  n_new = int(M * args.new_frac)
+  window = max(args.evict_every, int(round(keys / max(1, n_new))))       # TTL in steps: insert rate == evict rate
+  seg = entry.CombineAsSegment(DIM, entry.RandomUniformInitializer(-0.05, 0.05), entry.AdagradOptimizer(LR, INIT_ACC))
+  table = MultiHashTable({"item": entry.HashTableConfigInstance(
+      entry.TableConfig([seg], initial_capacity=int(keys * 1.15), init_seed=1), [LR])}, device=dev)
+  gkeys = keys * world                                                     # global resident population
+  t_fill0 = time.time()
+  CH = 1 << 22
+  n_ch = (gkeys + CH - 1) // CH
+  for c in range(n_ch):                                                    # chunk c gets last-update time in [0, window)
+    ids = torch.arange(c * CH, min(gkeys, (c + 1) * CH), device=dev, dtype=torch.int64)
+    ids = ((ids % SLOTS + 1) << 48) | (ids // SLOTS)
+    if world > 1:
+      ids = ids[(ids % world) == rank]
+    table.assign_add({"item": (ids, torch.zeros(ids.numel(), DIM, device=dev))}, req_time=int(c * window / n_ch), ids_unique=True)
+  torch.cuda.synchronize()
+  fill_s = time.time() - t_fill0
+  size0 = int(table.size("item"))
+
+  use_sharded = world > 1
+  if use_sharded:
+    from monolith_b200.distributed_ps import ShardedStep
+    sharded = ShardedStep(table, "item", DIM, world, rank, dev, exchange=args.exchange)
+
+  rng = np.random.default_rng(11 + rank)
+  per_slot = gkeys // SLOTS
+  fresh_next = [per_slot + 1 + rank]                                       # fresh ranks, disjoint over the ranks
+
+  def make_batch():
+    # continuous-power-law approximation of Zipf(1.05) over the resident ranks of a slot (no 1 GB CDF for 1 B keys)
+    u = rng.random(M)
+    a = 1.0 - ZIPF_S
+    r = np.floor(((per_slot ** a - 1.0) * u + 1.0) ** (1.0 / a)).astype(np.int64) - 1
+    ident = (np.clip(r, 0, per_slot - 1) * 2654435761) % per_slot
+    slots = np.tile(np.arange(1, SLOTS + 1, dtype=np.int64), batch)
+    fid = (slots << np.int64(48)) | ident
+    pos = rng.choice(M, n_new, replace=False)
+    fid[pos] = (slots[pos] << np.int64(48)) | (fresh_next[0] + np.arange(n_new, dtype=np.int64) * world)
+    fresh_next[0] += n_new * world
+    return fid
+
+  total_steps = args.warmup + args.steps * max(1, args.repeats)
+  fids_dev = [torch.from_numpy(make_batch()).to(dev) for _ in range(total_steps)]   # every batch brings NEW fresh FIDs
+  gen = torch.Generator(device=dev)
+  gen.manual_seed(5 + rank)
+  pgrad = torch.randn(M, DIM, device=dev, generator=gen)
+  pooled = torch.empty(M, DIM, device=dev)
+  ev = {"n": 0, "ms": 0.0}
+
+  def step(i):
+    now = window + i
+    if use_sharded:
+      sharded.step(fids_dev[i], pgrad, pooled, now)
+    else:
+      table.lookup_pool("item", fids_dev[i], None, "sum", out=pooled)
+      table.pool_backward("item", fids_dev[i], pgrad, None, "sum", req_time=now)
+    if (i + 1) % args.evict_every == 0:
+      table.evict("item", now - window)
+      ev["n"] += 1
+
+  for i in range(args.warmup):
+    step(i)
+  i0 = args.warmup
+  regions, sizes = [], []
+  with Clocks(local) as clk:
+    for r in range(max(1, args.repeats)):
+      torch.cuda.synchronize()
+      if world > 1:
+        dist.barrier()
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      l0 = lib.mono_kernel_launch_count()
+      e0.record()
+      for k in range(args.steps):
+        step(i0 + r * args.steps + k)
+      e1.record()
+      torch.cuda.synchronize()
+      launches = lib.mono_kernel_launch_count() - l0
+      ms = e0.elapsed_time(e1)
+      if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+      regions.append(ms)
+      sizes.append(int(table.size("item")))
+  ms = float(np.median(regions))
+  # one eviction scan alone (outside the timed regions), for the report
+  torch.cuda.synchronize()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  table.evict("item", 0)     # threshold 0: a pure scan, nothing qualifies any more
+  e1.record()
+  torch.cuda.synchronize()
+  scan_ms = e0.elapsed_time(e1)
+  try:
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs") or 6650.0
+  except Exception:
+    peak = 6650.0
+  if rank == 0:
+    print(json.dumps({
+        "metric": METRIC, "value": M * world * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C4 streaming insert+evict: {SLOTS} slots x dim {DIM}, {keys} resident keys per GPU ({gkeys} global), "
+                               f"batch {batch} samples ({M} FID occurrences) per GPU, {args.new_frac:.3f} of them never-seen FIDs "
+                               f"({n_new} inserts per step and GPU), evict every {args.evict_every} steps with a TTL window of {window} steps; "
+                               "inputs larger than L2 (every batch distinct)",
+                   "exchange": (sharded.exchange if use_sharded else None)},
+        "repeats": {"n": len(regions), "statistic": "median", "ms_per_step_all": [r / args.steps for r in regions]},
+        "inserts_per_sec": n_new * world * args.steps / (ms * 1e-3),
+        "table_size": {"after_fill": size0, "after_each_region": sizes},
+        "evict": {"scans_in_timed_regions": ev["n"], "full_scan_ms": scan_ms,
+                  "scan_GBps": 16.0 * table.size("item") / 0.5 / scan_ms / 1e6 if scan_ms > 0 else None,
+                  "scan_note": "bucket array only (16 B per slot at ~50 % load) / scan time; peak " + str(peak)},
+        "fill_s": fill_s, "clocks": clk.summary(), "gpu_launches": int(launches),
+    }), flush=True)
+  if world > 1:
+    dist.destroy_process_group()
+
+
 def main():
   args = parse()
   if args.workload == "c5" and args.impl != "reference":
     return run_c5(args)
+  if args.workload == "c4" and args.impl != "reference":
+    return run_c4(args)
   if args.impl == "reference":
     run_reference(args)
   else:

@@ -47,7 +47,8 @@ enum Ctr {
   kCtrMiss = 5,      // scratch: misses of the current upsert call
   kCtrAux = 6,       // scratch
   kCtrMaxTs = 7,     // max update time seen (low 32 bits; ref tf_bridge.cc:202-206 truncates to int)
-  kNumCtrs = 8
+  kCtrMoves = 8,     // cuckoo displacements ever made (readers on other streams use it to confirm a miss)
+  kNumCtrs = 16
 };
 
 struct SegDev {  // one EntryConfig.Segment (ref: embedding_hash_table.proto:23-33)
@@ -308,9 +309,21 @@ __device__ __forceinline__ Probe probe_key(const TableDev* __restrict__ t, int64
 // Lock-free cuckoo insert of a key known to be ABSENT (callers resolve hits first and keys are
 // unique within a call).  One thread per key.  Bucketised (4-slot) 2-choice cuckoo, as libcuckoo
 // (ref: cuckoohash_map.hpp:574-588 uprase_fn, :1432 BFS depth) but with 128-bit CAS/EXCH instead of
-// bucket locks: claim an empty slot with CAS; when both buckets are full, swap the entry with a
-// victim via EXCH and carry the victim to its alternate bucket.  A chain longer than
-// kMaxEvictions parks the carried entry in the stash.
+// bucket locks: claim an empty slot with CAS; when both buckets are full, move a victim to its alternate
+// bucket (copy-first, below).  A chain longer than kMaxEvictions parks the carried entry in the stash.
+__device__ __forceinline__ bool same_entry(const Entry& a, const Entry& b) {
+  return a.key == b.key && a.row == b.row && a.ts == b.ts;
+}
+
+// Lock-free insert of a key that is NOT in the table (callers guarantee one inserter per key).
+// Displacement is COPY-FIRST: when both buckets of `e` are full, a victim of the current bucket is first copied
+// into a free slot of ITS alternate bucket (for a moment it is present twice, with the same row), and only then
+// is its old slot overwritten with `e` by a 128-bit CAS.  A lookup running at the same time on another stream
+// therefore never misses a key that is in the table (the reference's readers hold bucket locks for the same
+// guarantee: cuckoohash_map.hpp:66-67 find under lock).  If the CAS loses (somebody moved / removed the victim, or
+// bumped its timestamp), the copy is withdrawn and the step is retried.  Only when the alternate buckets of ALL
+// four victims are full does the insert fall back to the classic exchange chain, where the displaced entry is
+// carried in a register between two atomics (at <= 60 % load that is a ~1e-5 event per displacement).
 __device__ __forceinline__ void cuckoo_insert(const TableDev* __restrict__ t, Entry e) {
   const uint32_t nb = t->num_buckets;
   Entry* buckets = t->buckets;
@@ -329,9 +342,53 @@ __device__ __forceinline__ void cuckoo_insert(const TableDev* __restrict__ t, En
         if (o.row == kEmptyRow && cas_entry(base + s, empty, e)) return;
       }
     }
-    // evict: deterministic victim choice from the key hash and the iteration
-    uint32_t vs = (uint32_t)(mix64((uint64_t)e.key + it) >> 7) & (kBucketSlots - 1);
-    Entry* vp = buckets + (size_t)cur * kBucketSlots + vs;
+    // ---- copy-first displacement of one entry of `cur` ----
+    const uint32_t v0 = (uint32_t)(mix64((uint64_t)e.key + it) >> 7) & (kBucketSlots - 1);  // deterministic first victim
+    bool changed = false;
+    for (int k = 0; k < kBucketSlots && !changed; ++k) {
+      Entry* vp = buckets + (size_t)cur * kBucketSlots + ((v0 + k) & (kBucketSlots - 1));
+      const Entry v = ld_entry_cg(vp);
+      if (v.row == kEmptyRow) {  // freed meanwhile
+        if (cas_entry(vp, empty, e)) return;
+        changed = true;
+        break;
+      }
+      uint32_t a1, a2;
+      bucket_pair(v.key, nb, a1, a2);
+      const uint32_t va = cur == a1 ? a2 : a1;
+      Entry* ab = buckets + (size_t)va * kBucketSlots;
+      for (int s = 0; s < kBucketSlots; ++s) {
+        const Entry o = ld_entry_cg(ab + s);
+        if (o.row != kEmptyRow || !cas_entry(ab + s, empty, v)) continue;
+        // the victim now lives in both of its buckets.  Announce the move BEFORE its old slot goes away: a reader that
+        // probed the alternate bucket before the copy and the old slot after the overwrite sees the counter change
+        // between the two and probes again (rowops.cuh probe_lane_confirm_miss)
+        __threadfence();
+        atomicAdd(t->ctrs + kCtrMoves, 1u);
+        __threadfence();
+        Entry seen = v;
+        for (int tries = 0; tries < 16; ++tries) {
+          const Entry old = cas_entry_old(vp, seen, e);
+          if (same_entry(old, seen)) return;                       // placed; the victim lives on in `va`
+          if (old.key != v.key || old.row != v.row) break;         // the victim left this slot
+          seen = old;                                              // only its timestamp moved: again
+        }
+        // lost the slot: withdraw the copy (its timestamp may have been bumped by a concurrent update)
+        Entry c = v;
+        for (int tries = 0; tries < 16; ++tries) {
+          const Entry old = cas_entry_old(ab + s, c, empty);
+          if (same_entry(old, c) || old.key != v.key || old.row != v.row) break;
+          c = old;
+        }
+        changed = true;
+        break;
+      }
+    }
+    if (changed) continue;  // the bucket changed under us: rescan it
+    // ---- every victim's alternate bucket is full: classic exchange step ----
+    Entry* vp = buckets + (size_t)cur * kBucketSlots + v0;
+    atomicAdd(t->ctrs + kCtrMoves, 1u);
+    __threadfence();
     Entry victim = exch_entry(vp, e);
     if (victim.row == kEmptyRow) return;  // slot was freed meanwhile: we just filled it
     e = victim;

@@ -323,7 +323,8 @@ __device__ __forceinline__ void apply_row(const TableDev* __restrict__ t, uint32
 // DUAL: both candidate buckets are requested together (8 x LDG.128).  A warp-tile of 32 probes almost always holds a
 // key that lives in its second bucket, so the sequential form costs the WARP two dependent round trips; DUAL trades
 // 64 extra bytes per key for one round trip (knobs lookup_dual / claim_dual).
-template <bool DUAL = false>
+// LD = 0: read-only (non-coherent, L1) loads; LD = 1: loads coherent at L2 (the confirm-a-miss path below)
+template <bool DUAL = false, int LD = 0>
 __device__ __forceinline__ uint32_t probe_lane(const TableDev* __restrict__ t, int64_t key) {
   const Entry* __restrict__ buckets = t->buckets;
   uint32_t b1, b2;
@@ -332,8 +333,8 @@ __device__ __forceinline__ uint32_t probe_lane(const TableDev* __restrict__ t, i
   if (DUAL) {
     const Entry* p = buckets + (size_t)b1 * kBucketSlots;
     const Entry* q = buckets + (size_t)b2 * kBucketSlots;
-    Entry e0 = ld_entry_nc(p), e1 = ld_entry_nc(p + 1), e2 = ld_entry_nc(p + 2), e3 = ld_entry_nc(p + 3);
-    Entry f0 = ld_entry_nc(q), f1 = ld_entry_nc(q + 1), f2 = ld_entry_nc(q + 2), f3 = ld_entry_nc(q + 3);
+    Entry e0 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(p), e1 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(p + 1), e2 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(p + 2), e3 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(p + 3);
+    Entry f0 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(q), f1 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(q + 1), f2 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(q + 2), f3 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(q + 3);
     if (f0.key == key && f0.row < kTombRow) row = f0.row;
     if (f1.key == key && f1.row < kTombRow) row = f1.row;
     if (f2.key == key && f2.row < kTombRow) row = f2.row;
@@ -355,7 +356,7 @@ __device__ __forceinline__ uint32_t probe_lane(const TableDev* __restrict__ t, i
   }
   {
     const Entry* p = buckets + (size_t)b1 * kBucketSlots;
-    Entry e0 = ld_entry_nc(p), e1 = ld_entry_nc(p + 1), e2 = ld_entry_nc(p + 2), e3 = ld_entry_nc(p + 3);
+    Entry e0 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(p), e1 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(p + 1), e2 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(p + 2), e3 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(p + 3);
     if (e0.key == key && e0.row < kTombRow) row = e0.row;
     if (e1.key == key && e1.row < kTombRow) row = e1.row;
     if (e2.key == key && e2.row < kTombRow) row = e2.row;
@@ -363,7 +364,7 @@ __device__ __forceinline__ uint32_t probe_lane(const TableDev* __restrict__ t, i
   }
   if (row == kEmptyRow) {
     const Entry* p = buckets + (size_t)b2 * kBucketSlots;
-    Entry e0 = ld_entry_nc(p), e1 = ld_entry_nc(p + 1), e2 = ld_entry_nc(p + 2), e3 = ld_entry_nc(p + 3);
+    Entry e0 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(p), e1 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(p + 1), e2 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(p + 2), e3 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(p + 3);
     if (e0.key == key && e0.row < kTombRow) row = e0.row;
     if (e1.key == key && e1.row < kTombRow) row = e1.row;
     if (e2.key == key && e2.row < kTombRow) row = e2.row;
@@ -381,6 +382,33 @@ __device__ __forceinline__ uint32_t probe_lane(const TableDev* __restrict__ t, i
   return row;
 }
 
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// A lookup that missed while ANOTHER STREAM may be inserting.  cuckoo_insert moves a resident entry between its two
+// buckets copy-first and bumps ctrs[kCtrMoves] between the copy and the overwrite of the old slot, so a reader can
+// only miss a resident key if the counter changes between its two bucket reads.  m0 = the counter when the kernel
+// started (~0u: not sampled): equal => nothing has moved since, the key is absent (one L2-hit load per miss, the
+// steady-state cost).  Otherwise probe again with coherent loads, bracketed by counter reads, until a probe runs
+// with no move in between.
+static __device__ __noinline__ uint32_t probe_lane_confirm_miss(const TableDev* __restrict__ t, int64_t key, uint32_t m0) {
+  const uint32_t* mv = t->ctrs + kCtrMoves;
+  uint32_t ma = ld_acquire_u32(mv);
+  if (ma == m0) return kEmptyRow;
+  for (int tries = 0; tries < 8; ++tries) {
+    const uint32_t row = probe_lane<false, 1>(t, key);
+    if (row != kEmptyRow) return row;
+    __threadfence();
+    const uint32_t mb = ld_acquire_u32(mv);
+    if (mb == ma) return kEmptyRow;
+    ma = mb;
+  }
+  return kEmptyRow;
+}
 
 constexpr uint32_t kFreshBit = 0x80000000u;
 

@@ -61,28 +61,38 @@ tower_grad_kernel(const float* __restrict__ x, int64_t B, const float* __restric
   const float inv_b = 1.0f / (float)B;
   float loss_acc = 0.f;
   const int64_t n_tiles = (B + 15) / 16;
-  for (int64_t tile = (int64_t)blockIdx.x * (kTowerThreads / 32) + w; tile < n_tiles;
-       tile += (int64_t)gridDim.x * (kTowerThreads / 32)) {
+  // the x fragment of the NEXT tile is requested before the current tile is computed: 16 independent 8-byte loads per
+  // lane stay in flight under the two GEMMs and the stores (the kernel is a stream: nothing else hides HBM latency)
+  float2 v[4][4];
+  float yv[2];
+  auto request = [&](int64_t t) {
+    const int64_t a0 = t * 16 + qr, a1 = a0 + 8;
+    const bool k0 = a0 < B, k1 = a1 < B;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int c0 = ks * 16 + qc;
+      v[ks][0] = k0 ? __ldcs(reinterpret_cast<const float2*>(x + a0 * kTowerIn + c0)) : make_float2(0.f, 0.f);
+      v[ks][1] = k1 ? __ldcs(reinterpret_cast<const float2*>(x + a1 * kTowerIn + c0)) : make_float2(0.f, 0.f);
+      v[ks][2] = k0 ? __ldcs(reinterpret_cast<const float2*>(x + a0 * kTowerIn + c0 + 8)) : make_float2(0.f, 0.f);
+      v[ks][3] = k1 ? __ldcs(reinterpret_cast<const float2*>(x + a1 * kTowerIn + c0 + 8)) : make_float2(0.f, 0.f);
+    }
+    yv[0] = k0 ? labels[a0] : 0.f;
+    yv[1] = k1 ? labels[a1] : 0.f;
+  };
+  const int64_t tstride = (int64_t)gridDim.x * (kTowerThreads / 32);
+  int64_t tile = (int64_t)blockIdx.x * (kTowerThreads / 32) + w;
+  if (tile < n_tiles) request(tile);
+  for (; tile < n_tiles; tile += tstride) {
     const int64_t r0 = tile * 16 + qr, r1 = r0 + 8;
     const bool ok0 = r0 < B, ok1 = r1 < B;
-    // ---- x fragment: 4 k-steps x {row r0 | r1} x {cols k, k+8}: 16 independent 8-byte loads ----
+    // ---- x fragment: 4 k-steps x {row r0 | r1} x {cols k, k+8} ----
     uint32_t xa[4][4];
-    {
-      float2 v[4][4];
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const int c0 = ks * 16 + qc;
-        v[ks][0] = ok0 ? __ldcs(reinterpret_cast<const float2*>(x + r0 * kTowerIn + c0)) : make_float2(0.f, 0.f);
-        v[ks][1] = ok1 ? __ldcs(reinterpret_cast<const float2*>(x + r1 * kTowerIn + c0)) : make_float2(0.f, 0.f);
-        v[ks][2] = ok0 ? __ldcs(reinterpret_cast<const float2*>(x + r0 * kTowerIn + c0 + 8)) : make_float2(0.f, 0.f);
-        v[ks][3] = ok1 ? __ldcs(reinterpret_cast<const float2*>(x + r1 * kTowerIn + c0 + 8)) : make_float2(0.f, 0.f);
-      }
+    for (int ks = 0; ks < 4; ++ks)
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) xa[ks][q] = pack_bf16(v[ks][q].x, v[ks][q].y);
-    }
-    const float y0 = ok0 ? labels[r0] : 0.f, y1 = ok1 ? labels[r1] : 0.f;
+      for (int q = 0; q < 4; ++q) xa[ks][q] = pack_bf16(v[ks][q].x, v[ks][q].y);
+    const float y0 = yv[0], y1 = yv[1];
+    if (tile + tstride < n_tiles) request(tile + tstride);
     // ---- h = relu(x W1): 8 n-tiles of 8 hidden units ----
     float h[8][4];
 #pragma unroll
@@ -175,7 +185,8 @@ void tower_grad(const float* x, int64_t batch, const float* labels, const void* 
                 float* dx, float* loss, float* scratch, cudaStream_t s) {
   if (batch <= 0) return;
   const int64_t tiles = (batch + 15) / 16;
-  const int grid = (int)std::min<int64_t>((tiles + (kTowerThreads / 32) - 1) / (kTowerThreads / 32), tower_scratch_floats());
+  // persistent: two resident blocks per SM, every warp walks its tiles with the next one's loads in flight
+  const int grid = (int)std::min<int64_t>((tiles + (kTowerThreads / 32) - 1) / (kTowerThreads / 32), 148 * 2);
   tower_grad_kernel<<<grid, kTowerThreads, 0, s>>>(x, batch, labels, (const __nv_bfloat16*)w1_bf16,
                                                    (const __nv_bfloat16*)w2_bf16, dx, scratch);
   MONO_CHECK_LAUNCH();

@@ -1228,3 +1228,63 @@ def test_bench_tower_fused_vs_autograd(dev, batch):
   loss2 = ref.grad_torch(pooled, labels, g2)
   assert abs(float(loss2) - float(loss_ref)) <= 1e-3 * abs(float(loss_ref))
   assert float((g2.view(batch, -1).double() - want).norm() / want.norm()) < 2e-2
+
+
+def test_lookup_never_misses_during_inserts_on_another_stream(dev):
+  """Readers vs. structural change: one host thread looks up a resident FID set on its own stream while another thread
+  INSERTS new FIDs (which displaces resident entries between their two buckets) on a second stream.  Every lookup must
+  see every resident row: the cuckoo displacement copies a victim into its alternate bucket BEFORE its old slot is
+  overwritten (csrc/common.cuh cuckoo_insert; the reference gives readers the same guarantee with bucket locks,
+  cuckoohash_map.hpp find / uprase under lock).  Capacity is preallocated so that the table does not grow (growth
+  swaps the bucket array and is stream-ordered by contract)."""
+  import threading
+  D = 8
+  n_a, n_b = 300_000, 420_000
+  cfg = {"t": sgd_table(D, capacity=n_a + n_b)}
+  gpu, cpu = pair(cfg, dev)
+  rng = np.random.default_rng(9)
+  a_ids, b_ids = fid(1, np.arange(n_a)), fid(2, np.arange(n_b))
+  va = rng.standard_normal((n_a, D)).astype(np.float32)
+  vb = rng.standard_normal((n_b, D)).astype(np.float32)
+  gpu.assign({"t": (T(a_ids, dev), T(va, dev))}, ids_unique=True)
+  torch.cuda.synchronize()
+  a_dev = T(a_ids, dev)
+  va_dev = T(va, dev)
+  errs, bad = [], []
+  stop = threading.Event()
+
+  def reader():
+    try:
+      with torch.cuda.stream(torch.cuda.Stream(device=dev)):
+        n = 0
+        while not stop.is_set() or n < 5:
+          got = gpu.lookup({"t": a_dev})["t"]
+          bad.append(int((got != va_dev).any(dim=1).sum().item()))
+          n += 1
+    except Exception as e:  # pragma: no cover
+      errs.append(e)
+
+  def writer():
+    try:
+      with torch.cuda.stream(torch.cuda.Stream(device=dev)):
+        for lo in range(0, n_b, 20_000):
+          sl = slice(lo, lo + 20_000)
+          gpu.assign({"t": (T(b_ids[sl], dev), T(vb[sl], dev))}, ids_unique=True)
+        torch.cuda.current_stream().synchronize()
+    except Exception as e:  # pragma: no cover
+      errs.append(e)
+    finally:
+      stop.set()
+
+  ts = [threading.Thread(target=reader), threading.Thread(target=writer)]
+  for t in ts:
+    t.start()
+  for t in ts:
+    t.join()
+  assert not errs, errs
+  assert len(bad) >= 5 and sum(bad) == 0, (len(bad), sum(bad), max(bad))
+  cpu.assign({"t": (a_ids, va)})
+  cpu.assign({"t": (b_ids, vb)})
+  both = np.concatenate([a_ids, b_ids])
+  np.testing.assert_array_equal(gpu_lookup(gpu, {"t": both}, dev)["t"].view(np.uint32), cpu.lookup({"t": both})["t"].view(np.uint32))
+  assert gpu.size("t") == n_a + n_b
