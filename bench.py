@@ -680,14 +680,16 @@ def run_ours(args):
       b = i & 1
       with torch.cuda.stream(copy_stream):
         copy_stream.wait_event(ev_free[b])            # the step that last used buffer b has consumed it
-        d_f[b].copy_(fids_pin[i % NB], non_blocking=True)
-        d_labs[b].copy_(labels_pin, non_blocking=True)
+        if not state.get("nocopy"):   # "nocopy" is a diagnostic region only: what the copies cost the step
+          d_f[b].copy_(fids_pin[i % NB], non_blocking=True)
+          d_labs[b].copy_(labels_pin, non_blocking=True)
         ev_in[b].record(copy_stream)
 
     def e2e_step(i):
       """What a training job does per step: the input pipeline hands over HOST FIDs + labels (copied H2D while the
       previous step computes); forward, dense tower forward/backward on the device, sparse backward; the loss comes
       back to the host."""
+      t_host0 = time.perf_counter()
       main = torch.cuda.current_stream()
       if state["primed"] != i:
         enqueue_inputs(i)                              # first step of a region: nothing was prefetched
@@ -717,6 +719,8 @@ def run_ours(args):
       ev_free[b].record(main)
       loss_pin[b:b + 1].copy_(loss[0].reshape(1), non_blocking=True)   # D2H of this step's loss, every step
       ev_loss[b].record(main)
+      state["host_s"] = state.get("host_s", 0.0) + (time.perf_counter() - t_host0)   # host time to queue one step
+      state["host_n"] = state.get("host_n", 0) + 1
       # the host reads step i-1's loss while step i runs on the device (asynchronous logging): it never waits for the
       # step it has just queued, so the launch queue stays one step deep; the region's closing synchronize covers the last
       ev_loss[b ^ 1].synchronize()
@@ -739,8 +743,15 @@ def run_ours(args):
       phases = {"forward_ms": float(np.mean([t[0].elapsed_time(t[1]) for t in tr])),
                 "tower_ms": float(np.mean([t[1].elapsed_time(t[2]) for t in tr])),
                 "backward_ms": float(np.mean([t[2].elapsed_time(t[3]) for t in tr])),
-                "between_steps_ms": float(np.mean([a[3].elapsed_time(b_[0]) for a, b_ in zip(tr[:-1], tr[1:])]))}
+                "between_steps_ms": float(np.mean([a[3].elapsed_time(b_[0]) for a, b_ in zip(tr[:-1], tr[1:])])),
+                "host_queue_ms_per_step": 1e3 * state["host_s"] / max(1, state["host_n"])}
       state["trace"] = None
+
+    # diagnostic: the same loop with the per-step H2D copies switched off (inputs of an earlier step stay in the device
+    # buffers): the difference is what the copy engine's traffic costs the kernels that run beside it
+    state["nocopy"] = True
+    ncms, _, _ = timed(e2e_step, es, 2)
+    state["nocopy"] = False
 
     def tower_only(i):  # context: how much of the e2e step is not the sparse path
       tower.grad(pooled, d_labs[0], d_g)
@@ -750,6 +761,7 @@ def run_ours(args):
     e2e = {"value": M * world * es / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * M + 4 * args.batch,
            "d2h_bytes_per_step": 4, "ms_per_step": ems / es, "ms_per_step_regions": [r / es for r in eregions],
            "dense_tower_ms": tms / 10, "dense_tower_torch_ms": ttms / 5, "device_phases": phases,
+           "ms_per_step_without_input_copies": ncms / es,
            "pipeline": "per step: H2D of the step's FIDs (pinned int64[M]) and labels on a copy stream one step ahead (input "
                        "prefetch), fused lookup+pool forward, stand-in "
                        "DSSM tower (bf16 MLP 64-64-1 + logistic loss; one fused mma.sync kernel, csrc/tower.cu) on the device, fused sparse "
