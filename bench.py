@@ -991,18 +991,22 @@ def run_c4(args):
   n_new = int(M * args.new_frac)
   window = max(args.evict_every, int(round(keys / max(1, n_new))))       # TTL in steps: insert rate == evict rate
   seg = entry.CombineAsSegment(DIM, entry.RandomUniformInitializer(-0.05, 0.05), entry.AdagradOptimizer(LR, INIT_ACC))
+  # time: the TTL is ONE DAY (SlotExpireTimeConfig counts days; the reference evicts entries with max_update_time - ts >=
+  # expire days, cuckoo_embedding_hash_table.cc:251-264); a step advances the clock by dt seconds so that the window is a day
+  DAY = 86400
+  dt = max(1, int(round(DAY / window)))
   table = MultiHashTable({"item": entry.HashTableConfigInstance(
-      entry.TableConfig([seg], initial_capacity=int(keys * 1.15), init_seed=1), [LR])}, device=dev)
+      entry.TableConfig([seg], initial_capacity=int(keys * 1.15), init_seed=1, default_expire_time=1), [LR])}, device=dev)
   gkeys = keys * world                                                     # global resident population
   t_fill0 = time.time()
-  CH = 1 << 22
+  CH = 1 << 20   # fine-grained last-update times: every eviction scan finds about as many expired keys as were inserted
   n_ch = (gkeys + CH - 1) // CH
-  for c in range(n_ch):                                                    # chunk c gets last-update time in [0, window)
+  for c in range(n_ch):                                                    # chunk c gets last-update time in [0, one day)
     ids = torch.arange(c * CH, min(gkeys, (c + 1) * CH), device=dev, dtype=torch.int64)
     ids = ((ids % SLOTS + 1) << 48) | (ids // SLOTS)
     if world > 1:
       ids = ids[(ids % world) == rank]
-    table.assign_add({"item": (ids, torch.zeros(ids.numel(), DIM, device=dev))}, req_time=int(c * window / n_ch), ids_unique=True)
+    table.assign_add({"item": (ids, torch.zeros(ids.numel(), DIM, device=dev))}, req_time=int(c * DAY / n_ch), ids_unique=True)
   torch.cuda.synchronize()
   fill_s = time.time() - t_fill0
   size0 = int(table.size("item"))
@@ -1038,14 +1042,14 @@ def run_c4(args):
   ev = {"n": 0, "ms": 0.0}
 
   def step(i):
-    now = window + i
+    now = DAY + (i + 1) * dt
     if use_sharded:
       sharded.step(fids_dev[i], pgrad, pooled, now)
     else:
       table.lookup_pool("item", fids_dev[i], None, "sum", out=pooled)
       table.pool_backward("item", fids_dev[i], pgrad, None, "sum", req_time=now)
     if (i + 1) % args.evict_every == 0:
-      table.evict("item", now - window)
+      table.evict("item", now)              # drops every key not updated for a day
       ev["n"] += 1
 
   for i in range(args.warmup):
@@ -1092,7 +1096,7 @@ def run_c4(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"C4 streaming insert+evict: {SLOTS} slots x dim {DIM}, {keys} resident keys per GPU ({gkeys} global), "
                                f"batch {batch} samples ({M} FID occurrences) per GPU, {args.new_frac:.3f} of them never-seen FIDs "
-                               f"({n_new} inserts per step and GPU), evict every {args.evict_every} steps with a TTL window of {window} steps; "
+                               f"({n_new} inserts per step and GPU), evict every {args.evict_every} steps, TTL one day = {window} steps of {dt} s; "
                                "inputs larger than L2 (every batch distinct)",
                    "exchange": (sharded.exchange if use_sharded else None)},
         "repeats": {"n": len(regions), "statistic": "median", "ms_per_step_all": [r / args.steps for r in regions]},

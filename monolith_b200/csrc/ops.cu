@@ -64,7 +64,6 @@ lookup_kernel(const TableDev* __restrict__ tables, const CallSeg* __restrict__ s
   const int64_t rs0 = out_stride > 0 ? out_stride : D0;
   float* const base0 = out + segs[0].val_off - segs[0].id_begin * rs0 + out_col;
   const bool vec0 = (D0 & 3) == 0 && (rs0 & 3) == 0 && (reinterpret_cast<uintptr_t>(base0) & 15) == 0;
-  const uint32_t moves0 = SINGLE ? ld_acquire_u32(t0->ctrs + kCtrMoves) : ~0u;  // displacement counter at kernel start
   const int64_t wstride = (int64_t)gridDim.x * (kThreads / 32) * 32;
   const int64_t wfirst = ((int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * 32;
   // the chain per tile is FID -> bucket -> row (~2.5 us per dependent round trip under load): the NEXT tile's FIDs are
@@ -88,7 +87,7 @@ lookup_kernel(const TableDev* __restrict__ tables, const CallSeg* __restrict__ s
       if (!SINGLE) si = find_seg(segs, nsegs, i);
       const TableDev* tk = SINGLE ? t0 : tables + segs[si].table;
       row = probe_lane<DUAL>(tk, key);
-      if (row == kEmptyRow) row = probe_lane_confirm_miss(tk, key, SINGLE ? moves0 : ~0u);  // inserts on another stream
+      if (row == kEmptyRow) row = probe_lane_confirm_miss(tk, key);  // inserts on another stream
     }
     // ---- phase B: group-per-row copy, UNR rows in flight ----
 #pragma unroll
@@ -170,7 +169,6 @@ lookup_push_kernel(const TableDev* __restrict__ t0, const int64_t* __restrict__ 
   const int D0 = t0->dim;
   const float* __restrict__ emb0 = t0->emb;
   const uint32_t stride0 = t0->emb_stride;
-  const uint32_t moves0 = ld_acquire_u32(t0->ctrs + kCtrMoves);
   const int64_t wstride = (int64_t)gridDim.x * (kThreads / 32) * 32;
   for (int64_t wbase = ((int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * 32;
        wbase < n_total; wbase += wstride) {
@@ -179,7 +177,7 @@ lookup_push_kernel(const TableDev* __restrict__ t0, const int64_t* __restrict__ 
     if (i < n_total) {
       const int64_t key = __ldg(ids + i);
       row = probe_lane(t0, key);
-      if (row == kEmptyRow) row = probe_lane_confirm_miss(t0, key, moves0);
+      if (row == kEmptyRow) row = probe_lane_confirm_miss(t0, key);
     }
 #pragma unroll
     for (int it0 = 0; it0 < ITERS; it0 += UNR) {
@@ -275,12 +273,11 @@ lookup_tma_kernel(const TableDev* __restrict__ t0, const int64_t* __restrict__ i
   const int64_t ntiles = (n_total + 31) / 32;
   const int64_t tstride = (int64_t)gridDim.x * NW;
   int64_t tile = (int64_t)blockIdx.x * NW + w;
-  const uint32_t moves0 = ld_acquire_u32(t0->ctrs + kCtrMoves);
   uint32_t row = kEmptyRow;
   if (tile < ntiles && tile * 32 + lane < n_total) {
     const int64_t key0 = __ldg(ids + tile * 32 + lane);
     row = probe_lane(t0, key0);
-    if (row == kEmptyRow) row = probe_lane_confirm_miss(t0, key0, moves0);
+    if (row == kEmptyRow) row = probe_lane_confirm_miss(t0, key0);
   }
   // FIDs of the tile after this one: requested one iteration before they are probed (off the dependent chain)
   int64_t key_next = (tile + tstride < ntiles && (tile + tstride) * 32 + lane < n_total) ? __ldg(ids + (tile + tstride) * 32 + lane) : 0;
@@ -310,7 +307,7 @@ lookup_tma_kernel(const TableDev* __restrict__ t0, const int64_t* __restrict__ i
     uint32_t row_next = kEmptyRow;
     if (next < ntiles && next * 32 + lane < n_total) {
       row_next = probe_lane(t0, key_cur);
-      if (row_next == kEmptyRow) row_next = probe_lane_confirm_miss(t0, key_cur, moves0);
+      if (row_next == kEmptyRow) row_next = probe_lane_confirm_miss(t0, key_cur);
     }
     mbar_wait(mbar, parity);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the zero rows (generic proxy) before the bulk store reads them
@@ -386,7 +383,6 @@ lookup_pool_kernel(const TableDev* __restrict__ t, const int64_t* __restrict__ f
   const int lane = threadIdx.x & 31, gl = Group<G>::gl();
   const int D = t->dim;
   const uint32_t stash = t->ctrs[kCtrStash];
-  const uint32_t moves0 = ld_acquire_u32(t->ctrs + kCtrMoves);
   const float* __restrict__ emb = t->emb;
   const uint32_t stride = t->emb_stride;
   // a warp owns GPW*U consecutive pooled rows per iteration; group g takes rows g, g+GPW, ...
@@ -429,7 +425,7 @@ lookup_pool_kernel(const TableDev* __restrict__ t, const int64_t* __restrict__ f
         const bool miss = active[q] && row[q] == kEmptyRow;
         if (!__any_sync(0xffffffffu, miss)) continue;
         uint32_t r2 = kEmptyRow;
-        if (miss && gl == 0) r2 = probe_lane_confirm_miss(t, key[q], moves0);
+        if (miss && gl == 0) r2 = probe_lane_confirm_miss(t, key[q]);
         r2 = __shfl_sync(0xffffffffu, r2, Group<G>::base());
         if (miss) row[q] = r2;
       }
@@ -508,7 +504,6 @@ lookup_pool_staged_kernel(const TableDev* __restrict__ t, const int64_t* __restr
   const float* __restrict__ emb = t->emb;
   const uint32_t stride = t->emb_stride;
   const bool in = c < D;
-  const uint32_t moves0 = ld_acquire_u32(t->ctrs + kCtrMoves);
   const int64_t gstride = (int64_t)gridDim.x * (kThreads / 32) * GPW * U;
   for (int64_t r0 = (((int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * GPW + lane / G) * U; r0 < n_rows;
        r0 += gstride) {
@@ -550,7 +545,7 @@ lookup_pool_staged_kernel(const TableDev* __restrict__ t, const int64_t* __restr
         if (e3[s].key == key[s] && e3[s].row < kTombRow) row = e3[s].row;
         const bool live = k < cnt && k < kStage;
         if (live && row == kEmptyRow) row = probe_lane(t, key[s]);  // second bucket / stash: the full probe
-        if (live && row == kEmptyRow) row = probe_lane_confirm_miss(t, key[s], moves0);  // inserts on another stream
+        if (live && row == kEmptyRow) row = probe_lane_confirm_miss(t, key[s]);  // inserts on another stream
         rk[s] = live ? row : kEmptyRow;
       }
       // ---- request every row of the chunk ----

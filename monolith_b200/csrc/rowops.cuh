@@ -391,14 +391,13 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
 
 // A lookup that missed while ANOTHER STREAM may be inserting.  cuckoo_insert moves a resident entry between its two
 // buckets copy-first and bumps ctrs[kCtrMoves] between the copy and the overwrite of the old slot, so a reader can
-// only miss a resident key if the counter changes between its two bucket reads.  m0 = the counter when the kernel
-// started (~0u: not sampled): equal => nothing has moved since, the key is absent (one L2-hit load per miss, the
-// steady-state cost).  Otherwise probe again with coherent loads, bracketed by counter reads, until a probe runs
-// with no move in between.
-static __device__ __noinline__ uint32_t probe_lane_confirm_miss(const TableDev* __restrict__ t, int64_t key, uint32_t m0) {
+// only miss a resident key if the counter changes between its two bucket reads.  The fast probe cannot be trusted for
+// that (its non-coherent loads may be served by an L1 line that is older than the move), so every miss is confirmed:
+// probe again with loads that are coherent at L2, bracketed by counter reads, until one probe runs with no move in
+// between.  Cost: two L2-hit loads and one extra probe per MISS (absent FIDs only; resident FIDs never come here).
+static __device__ __noinline__ uint32_t probe_lane_confirm_miss(const TableDev* __restrict__ t, int64_t key) {
   const uint32_t* mv = t->ctrs + kCtrMoves;
   uint32_t ma = ld_acquire_u32(mv);
-  if (ma == m0) return kEmptyRow;
   for (int tries = 0; tries < 8; ++tries) {
     const uint32_t row = probe_lane<false, 1>(t, key);
     if (row != kEmptyRow) return row;

@@ -173,7 +173,7 @@ xlookup_push_kernel(const TableDev* __restrict__ t0, XWin w, int par, uint64_t s
       uint32_t row = kEmptyRow;
       if (i < n_src) {
         row = probe_lane(t0, key);
-        if (row == kEmptyRow) row = probe_lane_confirm_miss(t0, key, ~0u);  // inserts on another stream (rowops.cuh)
+        if (row == kEmptyRow) row = probe_lane_confirm_miss(t0, key);  // inserts on another stream (rowops.cuh)
       }
 #pragma unroll
       for (int it0 = 0; it0 < ITERS; it0 += UNR) {
