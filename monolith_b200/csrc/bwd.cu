@@ -1206,6 +1206,7 @@ void run_pool_backward(mono_mtable* mt, int k, const int64_t* fids_dev, int64_t 
                        const int32_t* row_offsets, int64_t n_rows, int pooling,
                        const float* pooled_grad, int64_t grad_stride, int grad_col,
                        const float* lr_host, int64_t update_time, cudaStream_t s) {
+  mt->note_insert(s);
   if (n_fids <= 0) return;
   if (n_fids > ((int64_t)1 << 30)) throw ArgError("more than 2^30 fids in one call");
   if (pooling != MONO_POOL_SUM && pooling != MONO_POOL_MEAN) throw ArgError("pool_backward: SUM or MEAN");

@@ -190,6 +190,17 @@ struct mono_mtable {
   size_t pinned_out_cap = 0;
   cudaStream_t own_stream = nullptr;  // used by the *_host entry points
   uint32_t* h_flag = nullptr;         // pinned scratch for small D2H reads
+  // Which stream inserts come from.  A lookup launched on the SAME stream is ordered behind them; one launched on another
+  // stream may run beside an insert and must confirm its misses (rowops.cuh probe_lane_confirm_miss).  Sticky once two
+  // different streams have been seen.
+  cudaStream_t insert_stream = nullptr;
+  bool any_insert = false, confirm_always = false;
+  void note_insert(cudaStream_t s) {
+    if (any_insert && insert_stream != s) confirm_always = true;
+    insert_stream = s;
+    any_insert = true;
+  }
+  bool lookup_must_confirm(cudaStream_t s) const { return confirm_always || (any_insert && insert_stream != s); }
 };
 
 // one reusable grouping of a batch (see ops.cu "Owner grouping")

@@ -46,7 +46,8 @@ __device__ __forceinline__ void store_vec(float* dst, int c, int D, const float4
 
 // SINGLE: the call has one segment (one table): table fields and the output base are warp-uniform
 // and hoisted, which keeps the kernel at ~40 registers => 6 resident blocks (48 warps) per SM.
-template <int G, bool SINGLE, bool DUAL = false>
+// CONFIRM: the call may run beside inserts of another stream (mono_mtable::lookup_must_confirm): misses are confirmed.
+template <int G, bool SINGLE, bool DUAL = false, bool CONFIRM = true>
 __global__ void __launch_bounds__(kThreads, SINGLE && !DUAL ? 6 : 4)
 lookup_kernel(const TableDev* __restrict__ tables, const CallSeg* __restrict__ segs, int nsegs,
               const int64_t* __restrict__ ids, int64_t n_total, float* __restrict__ out,
@@ -87,7 +88,7 @@ lookup_kernel(const TableDev* __restrict__ tables, const CallSeg* __restrict__ s
       if (!SINGLE) si = find_seg(segs, nsegs, i);
       const TableDev* tk = SINGLE ? t0 : tables + segs[si].table;
       row = probe_lane<DUAL>(tk, key);
-      if (row == kEmptyRow) row = probe_lane_confirm_miss(tk, key);  // inserts on another stream
+      if (CONFIRM && row == kEmptyRow) row = probe_lane_confirm_miss(tk, key);  // inserts on another stream
     }
     // ---- phase B: group-per-row copy, UNR rows in flight ----
 #pragma unroll
@@ -954,6 +955,9 @@ static void launch_lookup_staged(mono_mtable* mt, const CallSeg* d_segs, int nse
   if (nsegs == 1 && knob(KNOB_LOOKUP_DUAL))                                                        \
     lookup_kernel<GG, true, true><<<resident_grid(lookup_kernel<GG, true, true>, n_total, kThreads), kThreads, 0, s>>>( \
         mt->d_tables, d_segs, nsegs, ids_dev, n_total, out_dev, out_stride, out_col, pf);          \
+  else if (nsegs == 1 && !mt->lookup_must_confirm(s))                                              \
+    lookup_kernel<GG, true, false, false><<<resident_grid(lookup_kernel<GG, true, false, false>, n_total, kThreads), kThreads, 0, s>>>( \
+        mt->d_tables, d_segs, nsegs, ids_dev, n_total, out_dev, out_stride, out_col, pf);          \
   else if (nsegs == 1)                                                                             \
     lookup_kernel<GG, true><<<resident_grid(lookup_kernel<GG, true>, n_total, kThreads), kThreads, 0, s>>>( \
         mt->d_tables, d_segs, nsegs, ids_dev, n_total, out_dev, out_stride, out_col, pf);          \
@@ -1138,6 +1142,7 @@ void run_upsert(mono_mtable* mt, UpsertOp op, const CallSeg* h_segs, int nsegs,
                 const int64_t* ids_dev, int64_t n_total, const float* vals_dev,
                 const float* lr_host, int n_lr, int64_t update_time, bool unique, bool dedup_sum,
                 int32_t* status_dev, cudaStream_t s) {
+  mt->note_insert(s);
   if (n_total <= 0 || nsegs <= 0) return;
   // The kernels walk positions [0, n): rebase the call on the id range its segments cover
   // (fused_optimize passes one shard's segments of a larger id array).
@@ -1311,6 +1316,7 @@ void run_upsert(mono_mtable* mt, UpsertOp op, const CallSeg* h_segs, int nsegs,
 void run_upsert_groups(mono_mtable* mt, const CallSeg* h_segs, int nsegs, const int64_t* group_begin,
                        int ngroups, const int64_t* ids_dev, const float* vals_dev, const float* lr_host,
                        int n_lr, int64_t update_time, cudaStream_t s) {
+  mt->note_insert(s);
   if (nsegs <= 0 || ngroups <= 0) return;
   const int64_t n_total = h_segs[nsegs - 1].id_end;
   if (n_total <= 0) return;
@@ -1407,6 +1413,7 @@ void run_upsert_groups(mono_mtable* mt, const CallSeg* h_segs, int nsegs, const 
 void launch_apply_window(mono_mtable* mt, int k, const CallBlob& cb, const int64_t* ids_base, const float* grads_base,
                          int64_t pos0, const uint32_t* n_dev, int64_t n_upper, uint32_t* rowidx, uint32_t update_ts,
                          const uint64_t* wait_flag, uint64_t wait_seq, cudaStream_t s) {
+  mt->note_insert(s);
   UpsertArgs a;
   a.tables = mt->d_tables;
   a.segs = cb.segs;

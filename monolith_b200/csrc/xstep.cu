@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(32) xwait_kernel(XWin w, int phase, uint64_t s
 // 2 owner: lookup fused with the row exchange, source by source as the FID buckets arrive.  Every block visits all
 // sources (starting at a block-dependent one, taking whichever has arrived first) and grid-strides over the
 // source's warp tiles; rows go straight into the requester's rows_in (one 128-bit NVLink store per lane).
-template <int G>
+template <int G, bool CONFIRM>
 __global__ void __launch_bounds__(kThreads, 6)
 xlookup_push_kernel(const TableDev* __restrict__ t0, XWin w, int par, uint64_t seq, uint64_t timeout_ns) {
   constexpr int RPI = 32 / G;
@@ -173,7 +173,7 @@ xlookup_push_kernel(const TableDev* __restrict__ t0, XWin w, int par, uint64_t s
       uint32_t row = kEmptyRow;
       if (i < n_src) {
         row = probe_lane(t0, key);
-        if (row == kEmptyRow) row = probe_lane_confirm_miss(t0, key);  // inserts on another stream (rowops.cuh)
+        if (CONFIRM && row == kEmptyRow) row = probe_lane_confirm_miss(t0, key);  // inserts on another stream (rowops.cuh)
       }
 #pragma unroll
       for (int it0 = 0; it0 < ITERS; it0 += UNR) {
@@ -423,9 +423,14 @@ void xstep_forward(mono_xstep* x, const int64_t* fids_dev, int64_t M, const int3
   MONO_CHECK_LAUNCH();
   const TableDev* t = mt->d_tables + x->k;
   // the grid is sized for the capacity bound; the kernel loops over what actually arrived
-#define XLP(GG)                                                                                               \
-  xlookup_push_kernel<GG><<<resident_grid(xlookup_push_kernel<GG>, M, kThreads), kThreads, 0, s>>>(t, w, par, seq, \
-                                                                                                  x->timeout_ns)
+  const bool confirm = mt->lookup_must_confirm(s);  // inserts may be running on another stream
+#define XLP(GG)                                                                                                        \
+  if (confirm)                                                                                                         \
+    xlookup_push_kernel<GG, true><<<resident_grid(xlookup_push_kernel<GG, true>, M, kThreads), kThreads, 0, s>>>(     \
+        t, w, par, seq, x->timeout_ns);                                                                                \
+  else                                                                                                                 \
+    xlookup_push_kernel<GG, false><<<resident_grid(xlookup_push_kernel<GG, false>, M, kThreads), kThreads, 0, s>>>(   \
+        t, w, par, seq, x->timeout_ns)
   switch (pick_group(x->D)) {
     case 4: XLP(4); break;
     case 8: XLP(8); break;
@@ -453,6 +458,7 @@ void xstep_backward(mono_xstep* x, const float* pooled_grad, int64_t grad_stride
   if (!x->fwd_done) throw ArgError("xstep_backward without a forward");
   x->fwd_done = false;
   mono_mtable* mt = x->mt;
+  mt->note_insert(s);
   HostTable& ht = mt->tables[x->k];
   const XWin& w = x->w;
   const uint64_t seq = x->step;
