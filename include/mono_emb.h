@@ -57,7 +57,10 @@ typedef enum mono_opt_type {
   MONO_OPT_RMSPROP = 5,   /* ref: optimizer/rmsprop_optimizer.cc:49-68 (double arithmetic, CONFIG learning rate) */
   MONO_OPT_RMSPROPV2 = 6, /* ref: optimizer/rmsprop_optimizer.cc:121-141             */
   MONO_OPT_ADADELTA = 7,  /* ref: optimizer/adadelta_optimizer.cc:51-72              */
-  MONO_OPT_AMSGRAD = 8    /* ref: optimizer/amsgrad_optimizer.cc:58-88               */
+  MONO_OPT_AMSGRAD = 8,   /* ref: optimizer/amsgrad_optimizer.cc:58-88               */
+  MONO_OPT_MOVING_AVERAGE = 9, /* ref: optimizer/moving_average_optimizer.cc:44-52 (no state, no learning rate) */
+  MONO_OPT_GROUP_ADAGRAD = 10  /* ref: optimizer/group_adagrad_optimizer.cc:50-89 (one float of state per segment;
+                                  the whole segment is one group: max-gradient accumulator, L2 group shrinkage) */
 } mono_opt_type;
 
 typedef enum mono_init_type {
@@ -80,6 +83,9 @@ typedef enum mono_init_type {
  *   RMSPROPV2: [0] momentum, [1] weight_decay_factor                                   state: n[dim]
  *   ADADELTA : [0] averaging_ratio, [1] epsilon, [2] weight_decay_factor               state: accum[dim], accum_update[dim]
  *   AMSGRAD  : as ADAM                                                                 state: m, v, vhat [dim each], beta powers
+ *   MOVING_AVERAGE: [0] momentum                                                       state: none
+ *   GROUP_ADAGRAD : [0] initial_accumulator_value, [1] weight_decay_factor, [2] beta,
+ *                   [3] l2_regularization_strength                                     state: grad_square_sum (1 float)
  */
 typedef struct mono_segment_cfg {
   int32_t dim;

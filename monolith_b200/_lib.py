@@ -31,6 +31,7 @@ class SliceTask(C.Structure):  # mono_slice_task
 
 OPT_SGD, OPT_ADAGRAD, OPT_FTRL, OPT_ADAM = 0, 1, 2, 3
 OPT_MOMENTUM, OPT_RMSPROP, OPT_RMSPROPV2, OPT_ADADELTA, OPT_AMSGRAD = 4, 5, 6, 7, 8
+OPT_MOVING_AVERAGE, OPT_GROUP_ADAGRAD = 9, 10
 INIT_ZEROS, INIT_ONES, INIT_CONSTANT, INIT_UNIFORM = 0, 1, 2, 3
 POOL_SUM, POOL_MEAN, POOL_FIRSTN = 0, 1, 2
 FLAG_IDS_UNIQUE, FLAG_DEDUP_SUM = 1, 2

@@ -290,6 +290,7 @@ int state_floats_of(const mono_segment_cfg& s) {
     case MONO_OPT_MOMENTUM: case MONO_OPT_RMSPROP: case MONO_OPT_RMSPROPV2: return s.dim;
     case MONO_OPT_ADADELTA: return 2 * s.dim;
     case MONO_OPT_AMSGRAD: return 3 * s.dim + 2;
+    case MONO_OPT_GROUP_ADAGRAD: return 1;
     default: return 0;
   }
 }
@@ -342,6 +343,10 @@ std::string encode_single_opt(const mono_segment_cfg& s, const float* st) {
       put_float(&body, 5, st[3 * D + 1]);
       put_tag_len(&msg, 8, body);
       break;
+    case MONO_OPT_GROUP_ADAGRAD:  // GroupAdaGradOptimizerDump { grad_square_sum = 1 } = field 15
+      put_float(&body, 1, st[0]);
+      put_tag_len(&msg, 15, body);
+      break;
     default:  // SGD: empty message, still present (sgd_optimizer.cc:51-55)
       put_tag_len(&msg, 2, body);
       break;
@@ -358,7 +363,8 @@ bool decode_single_opt(const uint8_t* p, size_t n, const mono_segment_cfg& s, fl
     const bool mine = (field == 1 && s.opt_type == MONO_OPT_ADAGRAD) || (field == 3 && s.opt_type == MONO_OPT_FTRL) ||
                       (field == 7 && s.opt_type == MONO_OPT_ADAM) || (field == 9 && s.opt_type == MONO_OPT_MOMENTUM) ||
                       (field == 11 && s.opt_type == MONO_OPT_RMSPROP) || (field == 12 && s.opt_type == MONO_OPT_RMSPROPV2) ||
-                      (field == 6 && s.opt_type == MONO_OPT_ADADELTA) || (field == 8 && s.opt_type == MONO_OPT_AMSGRAD);
+                      (field == 6 && s.opt_type == MONO_OPT_ADADELTA) || (field == 8 && s.opt_type == MONO_OPT_AMSGRAD) ||
+                      (field == 15 && s.opt_type == MONO_OPT_GROUP_ADAGRAD);
     if (!mine || wt != 2) {
       r.skip(wt);
       continue;
@@ -381,6 +387,9 @@ bool decode_single_opt(const uint8_t* p, size_t n, const mono_segment_cfg& s, fl
       else if (s.opt_type == MONO_OPT_AMSGRAD && (f2 == 4 || f2 == 5) && w2 == 5) {
         const uint8_t* q;
         if (b.bytes(4, &q)) std::memcpy(st + 3 * D + (f2 - 4), q, 4);
+      } else if (s.opt_type == MONO_OPT_GROUP_ADAGRAD && f2 == 1 && w2 == 5) {
+        const uint8_t* q;
+        if (b.bytes(4, &q)) std::memcpy(st, q, 4);
       } else if (s.opt_type == MONO_OPT_ADAGRAD && f2 == 1) read_floats(b, w2, st, D, &n1);
       else if (s.opt_type == MONO_OPT_FTRL && f2 == 1) read_floats(b, w2, st + D, D, &n1);
       else if (s.opt_type == MONO_OPT_FTRL && f2 == 2) read_floats(b, w2, st, D, &n2);
@@ -599,7 +608,8 @@ int64_t mono_ckpt_encode_entry(const mono_segment_cfg* segs, int32_t nsegs, int6
     std::string opt;
     const float* st = row + dim;
     for (const auto& s : sv) {
-      put_tag_len(&opt, 1, encode_single_opt(s, st));
+      // MovingAverage::Save returns an empty OptimizerDump (moving_average_optimizer.cc:54-57): nothing is appended
+      if (s.opt_type != MONO_OPT_MOVING_AVERAGE) put_tag_len(&opt, 1, encode_single_opt(s, st));
       st += state_floats_of(s);
     }
     put_tag_len(&rec, 3, opt);
@@ -646,6 +656,7 @@ int mono_ckpt_decode_entry(const mono_segment_cfg* segs, int32_t nsegs, const vo
             const uint64_t l2 = o.varint();
             const uint8_t* q;
             if (!o.ok || !o.bytes(l2, &q)) break;
+            while (si < sv.size() && sv[si].opt_type == MONO_OPT_MOVING_AVERAGE) ++si;  // contributes no dump, no state
             if (si < sv.size()) {
               if (!decode_single_opt(q, l2, sv[si], st)) throw std::runtime_error("checkpoint: bad OptimizerDump");
               st += state_floats_of(sv[si]);
@@ -725,7 +736,7 @@ int mono_ckpt_writer_add(mono_ckpt_writer* w, const int64_t* ids, const float* r
       put_floats_unpacked(&rec, 2, row, w->dim);
       const float* st = row + w->dim;
       for (const auto& s : w->segs) {
-        put_tag_len(&opt, 1, encode_single_opt(s, st));
+        if (s.opt_type != MONO_OPT_MOVING_AVERAGE) put_tag_len(&opt, 1, encode_single_opt(s, st));
         st += state_floats_of(s);
       }
       put_tag_len(&rec, 3, opt);

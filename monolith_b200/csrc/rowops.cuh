@@ -18,6 +18,7 @@ __device__ __forceinline__ int state_floats_dev(const SegDev& s) {
     case MONO_OPT_MOMENTUM: case MONO_OPT_RMSPROP: case MONO_OPT_RMSPROPV2: return s.dim;
     case MONO_OPT_ADADELTA: return 2 * s.dim;
     case MONO_OPT_AMSGRAD: return 3 * s.dim + 2;
+    case MONO_OPT_GROUP_ADAGRAD: return 1;
     default: return 0;
   }
 }
@@ -40,6 +41,7 @@ __device__ __forceinline__ float init_state_value(const SegDev& s, int lj) {
     case MONO_OPT_FTRL: return lj < s.dim ? s.p[0] : 0.0f;
     case MONO_OPT_ADAM: return lj < 2 * s.dim ? 0.0f : (lj == 2 * s.dim ? s.p[0] : s.p[1]);
     case MONO_OPT_AMSGRAD: return lj < 3 * s.dim ? 0.0f : (lj == 3 * s.dim ? s.p[0] : s.p[1]);  // amsgrad_optimizer.cc:44-56
+    case MONO_OPT_GROUP_ADAGRAD: return s.p[0];  // group_adagrad_optimizer.cc:45-48
     default: return 0.0f;  // momentum / rmsprop / adadelta start from zero state
   }
 }
@@ -163,6 +165,45 @@ __device__ __forceinline__ void opt_elem_more(const SegDev& s, int lc, float lr,
     sp[lc] = m1;
     sp[D + lc] = v1;
     sp[2 * D + lc] = h1;
+  } else if (s.opt_type == MONO_OPT_MOVING_AVERAGE) {  // moving_average_optimizer.cc:44-52 (no learning rate, no state)
+    const float mom = s.p[0];
+    w = __fadd_rn(__fmul_rn(mom, w), __fmul_rn(__fsub_rn(1.0f, mom), g));
+  }
+}
+
+// GroupAdaGrad (group_adagrad_optimizer.cc:50-89): the segment is ONE group — the accumulator grows by the largest
+// squared (decayed) gradient of the group, and the new weights are the group-shrunk z.  The two reductions (max, and
+// the sum of squares in column order) make it a whole-segment step: one lane walks the segment, in the reference's
+// order, so the result is bit-exact with the oracle.  w = the segment's dim weights (in place), sp = its 1-float state.
+__device__ __forceinline__ void group_adagrad_segment(const SegDev& s, float lr, const float* __restrict__ g,
+                                                      float* __restrict__ w, float* __restrict__ sp, bool init_all,
+                                                      const TableDev* t, int64_t key) {
+  const float wd = s.p[1], beta = s.p[2], l2 = s.p[3];
+  const int D = s.dim;
+  float maxsq = 0.0f;
+  for (int i = 0; i < D; ++i) {
+    const float wi = init_all ? init_emb_value(t, s, key, s.col_begin + i) : w[i];
+    const float gd = __fadd_rn(g[i], __fmul_rn(wd, wi));
+    const float sq = __fmul_rn(gd, gd);
+    if (sq > maxsq) maxsq = sq;
+  }
+  const float acc = __fadd_rn(init_all ? s.p[0] : sp[0], maxsq);
+  sp[0] = acc;
+  const float eff = __fdiv_rn(lr, __fadd_rn(beta, __fsqrt_rn(acc)));
+  float zn = 0.0f;
+  for (int i = 0; i < D; ++i) {
+    const float wi = init_all ? init_emb_value(t, s, key, s.col_begin + i) : w[i];
+    const float gd = __fadd_rn(g[i], __fmul_rn(wd, wi));
+    const float z = __fsub_rn(gd, __fdiv_rn(wi, eff));
+    w[i] = z;
+    zn = __fadd_rn(zn, __fmul_rn(z, z));
+  }
+  zn = __fsqrt_rn(zn);
+  if (zn < l2) {
+    for (int i = 0; i < D; ++i) w[i] = 0.0f;
+  } else {
+    const float coef = __fdiv_rn(__fmul_rn(-eff, __fsub_rn(zn, l2)), zn);
+    for (int i = 0; i < D; ++i) w[i] = __fmul_rn(coef, w[i]);
   }
 }
 
@@ -253,10 +294,18 @@ __device__ __forceinline__ void apply_row(const TableDev* __restrict__ t, uint32
     for (int j = gl; j < t->state_dim; j += G) s_row[j] = vals[D + j];
     return;
   }
+  if (OP == kOpOptimize) {  // whole-segment optimizers: one lane per segment, ahead of the per-column loop
+    for (int si = gl; si < t->num_segs; si += G) {
+      const SegDev& s = t->segs[si];
+      if (s.opt_type == MONO_OPT_GROUP_ADAGRAD)
+        group_adagrad_segment(s, lr[si], vals + s.col_begin, w_row + s.col_begin, s_row + s.state_off, init_all, t, key);
+    }
+  }
   for (int c = gl; c < D; c += G) {
     const int si = seg_of_col(t, c);
     const SegDev& s = t->segs[si];
     const int lc = c - s.col_begin;
+    if (OP == kOpOptimize && s.opt_type == MONO_OPT_GROUP_ADAGRAD) continue;  // done above
     float w = init_all ? init_emb_value(t, s, key, c) : w_row[c];
     if (OP == kOpAssign) {
       w = vals[c];

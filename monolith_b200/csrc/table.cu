@@ -170,6 +170,7 @@ static int state_floats(const mono_segment_cfg& s) {
     case MONO_OPT_MOMENTUM: case MONO_OPT_RMSPROP: case MONO_OPT_RMSPROPV2: return s.dim;
     case MONO_OPT_ADADELTA: return 2 * s.dim;
     case MONO_OPT_AMSGRAD: return 3 * s.dim + 2;
+    case MONO_OPT_GROUP_ADAGRAD: return 1;
   }
   throw ArgError("unknown optimizer type");
 }
@@ -196,8 +197,8 @@ void table_init(mono_mtable* mt, HostTable& t, const mono_table_cfg& cfg, cudaSt
     const mono_segment_cfg& sc = cfg.segments[i];
     if (sc.dim <= 0) throw ArgError("segment dim must be positive");
     if (sc.init_type < 0 || sc.init_type > 3) throw ArgError("unknown initializer type");
-    if (sc.opt_type < MONO_OPT_SGD || sc.opt_type > MONO_OPT_AMSGRAD)
-      throw ArgError("unknown optimizer type (built: sgd, adagrad, ftrl, adam, momentum, rmsprop, rmspropv2, adadelta, amsgrad)");
+    if (sc.opt_type < MONO_OPT_SGD || sc.opt_type > MONO_OPT_GROUP_ADAGRAD)
+      throw ArgError("unknown optimizer type (built: sgd, adagrad, ftrl, adam, momentum, rmsprop, rmspropv2, adadelta, amsgrad, moving_average, group_adagrad)");
     t.segs.push_back(sc);
     SegDev& sd = d.segs[i];
     sd.col_begin = col;

@@ -152,7 +152,35 @@ class AmsgradOptimizer(Optimizer):
     return [self.beta1, self.beta2, self.epsilon, self.weight_decay_factor, 1.0 if self.use_nesterov else 0.0, 0.0]
 
 
-_DEFAULT_LR = {_lib.OPT_SGD: 0.01, _lib.OPT_ADAGRAD: 0.001, _lib.OPT_FTRL: 0.01, _lib.OPT_ADAM: 0.01, _lib.OPT_MOMENTUM: 0.01,
+@dataclasses.dataclass
+class MovingAverageOptimizer(Optimizer):
+  """ref: NT/entry.py:247-255 / moving_average_optimizer.cc:44-52: w = momentum * w + (1 - momentum) * grad; no state, the
+  learning rate is ignored."""
+  momentum: float = 0.9
+  learning_rate: Optional[float] = None
+  opt_type = _lib.OPT_MOVING_AVERAGE
+
+  def params(self):
+    return [self.momentum, 0.0, 0.0, 0.0, 0.0, 0.0]
+
+
+@dataclasses.dataclass
+class GroupAdaGradOptimizer(Optimizer):
+  """ref: GroupAdaGradOptimizerConfig (optimizer.proto:90-98) / group_adagrad_optimizer.cc:50-89 (no Python wrapper in
+  the reference's entry.py; reachable there through the proto).  The segment is one group."""
+  learning_rate: Optional[float] = None  # 0.01
+  beta: float = 0.0
+  initial_accumulator_value: float = 0.1
+  l2_regularization_strength: float = 0.0
+  weight_decay_factor: float = 0.0
+  warmup_steps: int = 0
+  opt_type = _lib.OPT_GROUP_ADAGRAD
+
+  def params(self):
+    return [self.initial_accumulator_value, self.weight_decay_factor, self.beta, self.l2_regularization_strength, 0.0, 0.0]
+
+
+_DEFAULT_LR = {_lib.OPT_MOVING_AVERAGE: 0.01, _lib.OPT_GROUP_ADAGRAD: 0.01, _lib.OPT_SGD: 0.01, _lib.OPT_ADAGRAD: 0.001, _lib.OPT_FTRL: 0.01, _lib.OPT_ADAM: 0.01, _lib.OPT_MOMENTUM: 0.01,
                _lib.OPT_RMSPROP: 0.01, _lib.OPT_RMSPROPV2: 0.01, _lib.OPT_ADADELTA: 0.01, _lib.OPT_AMSGRAD: 0.01}
 
 

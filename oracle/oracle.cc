@@ -110,6 +110,40 @@ void SgdOptimize(float* num, const float* grad, int dim, float lr) {
   for (int i = 0; i < dim; ++i) num[i] -= lr * grad[i];
 }
 
+// ref: RT/hash_table/optimizer/moving_average_optimizer.cc:44-52
+void MovingAverageOptimize(float* num, const float* grad, int dim, float momentum) {
+  for (int i = 0; i < dim; ++i) {
+    float new_w = momentum * num[i] + (1 - momentum) * grad[i];
+    num[i] = new_w;
+  }
+}
+
+// ref: RT/hash_table/optimizer/group_adagrad_optimizer.cc:50-89
+void GroupAdagradOptimize(float* num, float* grad_square_sum, const float* grad, int dim, float effective_lr, float wd,
+                          float beta, float l2) {
+  float max_grad_square = 0.0f;
+  std::vector<float> g_decayed(dim);
+  for (int i = 0; i < dim; ++i) {
+    float g = grad[i] + wd * num[i];
+    if (g * g > max_grad_square) max_grad_square = g * g;
+    g_decayed[i] = g;
+  }
+  *grad_square_sum = *grad_square_sum + max_grad_square;
+  float lr = effective_lr / (beta + std::sqrt(*grad_square_sum));
+  float z_norm = 0.0f;
+  for (int i = 0; i < dim; ++i) {
+    num[i] = g_decayed[i] - num[i] / lr;
+    z_norm += num[i] * num[i];
+  }
+  z_norm = std::sqrt(z_norm);
+  if (z_norm < l2) {
+    for (int i = 0; i < dim; ++i) num[i] = 0;
+  } else {
+    float coeffi = -lr * (z_norm - l2) / z_norm;
+    for (int i = 0; i < dim; ++i) num[i] = coeffi * num[i];
+  }
+}
+
 int StateFloats(const mono_segment_cfg& s) {
   switch (s.opt_type) {
     case MONO_OPT_SGD: return 0;                 // sgd_optimizer.cc:28
@@ -119,6 +153,8 @@ int StateFloats(const mono_segment_cfg& s) {
     case MONO_OPT_MOMENTUM: case MONO_OPT_RMSPROP: case MONO_OPT_RMSPROPV2: return s.dim;  // momentum_optimizer.cc:29, rmsprop_optimizer.cc:29,99
     case MONO_OPT_ADADELTA: return 2 * s.dim;    // adadelta_optimizer.cc:29-31
     case MONO_OPT_AMSGRAD: return 3 * s.dim + 2; // amsgrad_optimizer.cc:30-32
+    case MONO_OPT_MOVING_AVERAGE: return 0;      // moving_average_optimizer.cc:30
+    case MONO_OPT_GROUP_ADAGRAD: return 1;       // group_adagrad_optimizer.cc:31 (one float: grad_square_sum)
   }
   return 0;
 }
@@ -319,6 +355,9 @@ struct Table {
         case MONO_OPT_ADADELTA:
           for (int i = 0; i < 2 * s.dim; ++i) st[i] = 0.f;
           break;
+        case MONO_OPT_GROUP_ADAGRAD:  // group_adagrad_optimizer.cc:45-48
+          st[0] = s.opt_p[0];
+          break;
         default: break;
       }
       st += StateFloats(s);
@@ -362,6 +401,12 @@ struct Table {
         case MONO_OPT_AMSGRAD:
           AmsgradOptimize(num + col, st, st + s.dim, st + 2 * s.dim, st + 3 * s.dim, st + 3 * s.dim + 1, grad + col, s.dim,
                           lr[sl], s.opt_p[0], s.opt_p[1], s.opt_p[2], s.opt_p[3], s.opt_p[4] != 0.f);
+          break;
+        case MONO_OPT_MOVING_AVERAGE:
+          MovingAverageOptimize(num + col, grad + col, s.dim, s.opt_p[0]);
+          break;
+        case MONO_OPT_GROUP_ADAGRAD:
+          GroupAdagradOptimize(num + col, st, grad + col, s.dim, lr[sl], s.opt_p[1], s.opt_p[2], s.opt_p[3]);
           break;
       }
       st += StateFloats(s);

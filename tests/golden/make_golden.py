@@ -77,6 +77,28 @@ KNOWN = {
         {"name": "amsgrad_list", "opt": "amsgrad", "dim": 2, "params": {},
          "steps": [{"grad": [10.0, 1.0], "lr": [0.01], "expect": [-0.00990099, -0.00909091]},
                    {"grad": [10.0, 1.0], "lr": [0.01], "expect": [-0.01983060, -0.01842895]}], "tol": 1e-6},
+        # moving_average_optimizer_test.cc:32-49,51-74 (proto default momentum .9; the learning rate is ignored)
+        {"name": "moving_average_basic", "opt": "moving_average", "dim": 1, "params": {},
+         "steps": [{"grad": [10.0], "lr": [0.01], "expect": [1.0]},
+                   {"grad": [10.0], "lr": [0.01], "expect": [1.9]}], "tol": 1e-6},
+        {"name": "moving_average_list", "opt": "moving_average", "dim": 2, "params": {},
+         "steps": [{"grad": [10.0, 1.0], "lr": [0.01], "expect": [1.0, 0.1]},
+                   {"grad": [10.0, 1.0], "lr": [0.01], "expect": [1.9, 0.19]}], "tol": 1e-6},
+        # group_adagrad_optimizer_test.cc:32-54 (Basic), :56-80 (ListUpdate), :82-96 (ZeroLambda), :98-112 (SetZero)
+        {"name": "group_adagrad_basic", "opt": "group_adagrad", "dim": 1,
+         "params": {"l2": 1.0, "beta": 1.0, "initial_accumulator_value": 0.0},
+         "steps": [{"grad": [10.0], "lr": [0.01], "expect": [-0.008182]},
+                   {"grad": [10.0], "lr": [0.01], "expect": [-0.014125]}], "tol": 1e-6},
+        {"name": "group_adagrad_list", "opt": "group_adagrad", "dim": 2,
+         "params": {"l2": 0.5, "beta": 1.0, "initial_accumulator_value": 0.0},
+         "steps": [{"grad": [10.0, 1.0], "lr": [0.01], "expect": [-0.008639, -0.000864]},
+                   {"grad": [1.0, 5.0], "lr": [0.01], "expect": [-0.009096, -0.004778]}], "tol": 1e-6},
+        {"name": "group_adagrad_zero_lambda", "opt": "group_adagrad", "dim": 2,
+         "params": {"l2": 0.0, "beta": 1.0, "initial_accumulator_value": 0.0},
+         "steps": [{"grad": [10.0, 1.0], "lr": [0.01], "expect": [-0.009091, -0.000909]}], "tol": 1e-6},
+        {"name": "group_adagrad_set_zero", "opt": "group_adagrad", "dim": 2,
+         "params": {"l2": 1000.0, "beta": 1.0, "initial_accumulator_value": 0.0},
+         "steps": [{"grad": [10.0, 1.0], "lr": [0.01], "expect": [0.0, 0.0]}], "tol": 1e-6},
     ],
     # optimizer_combination_test.cc:30-60: adagrad(dim 1, acc 1) | adagrad(dim 2, acc 2), lrs {1, 2}
     "combination": {

@@ -34,6 +34,13 @@ def opt_from(name, params=None, lr=None):
     return entry.AmsgradOptimizer(learning_rate=lr, beta1=params.get("beta1", 0.9), beta2=params.get("beta2", 0.99),
                                   epsilon=params.get("epsilon", 0.01), weight_decay_factor=params.get("weight_decay_factor", 0.0),
                                   use_nesterov=params.get("use_nesterov", False))
+  if name == "moving_average":
+    return entry.MovingAverageOptimizer(momentum=params.get("momentum", 0.9), learning_rate=lr)
+  if name == "group_adagrad":
+    return entry.GroupAdaGradOptimizer(learning_rate=lr, beta=params.get("beta", 0.0),
+                                       initial_accumulator_value=params.get("initial_accumulator_value", 0.1),
+                                       l2_regularization_strength=params.get("l2", 0.0),
+                                       weight_decay_factor=params.get("weight_decay_factor", 0.0))
   raise ValueError(name)
 
 

@@ -524,3 +524,56 @@ def test_further_optimizer_dumps_wire_bytes_match_protobuf():
   assert L.mono_ckpt_decode_entry(segs, len(spec), wire, len(wire), C.byref(fid_out), out.ctypes.data_as(C.c_void_p)) == 0
   assert fid_out.value == fid
   np.testing.assert_array_equal(out.view(np.uint32), row.view(np.uint32))
+
+
+def test_group_adagrad_and_moving_average_dump_wire_bytes():
+  """GroupAdaGrad state = SingleOptimizerDump field 15 {grad_square_sum = 1 (float)} (optimizer.proto:100-102,245);
+  MovingAverage::Save returns an EMPTY OptimizerDump (moving_average_optimizer.cc:54-57), so a moving-average segment
+  contributes no SingleOptimizerDump at all and the following segments' dumps move up."""
+  pytest.importorskip("google.protobuf")
+  from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+  F = descriptor_pb2.FieldDescriptorProto
+  fd = descriptor_pb2.FileDescriptorProto(name="mono_ckpt_group.proto", package="g", syntax="proto2")
+  OPT, REP = F.LABEL_OPTIONAL, F.LABEL_REPEATED
+
+  def msg(name, fields):
+    m = fd.message_type.add(name=name)
+    for fname, num, typ, label, tname in fields:
+      f = m.field.add(name=fname, number=num, type=typ, label=label)
+      if tname:
+        f.type_name = ".g." + tname
+
+  msg("AdagradOptimizerDump", [("norm", 1, F.TYPE_FLOAT, REP, None)])
+  msg("GroupAdaGradOptimizerDump", [("grad_square_sum", 1, F.TYPE_FLOAT, OPT, None)])
+  msg("SingleOptimizerDump", [("adagrad", 1, F.TYPE_MESSAGE, OPT, "AdagradOptimizerDump"),
+                              ("group_adagrad", 15, F.TYPE_MESSAGE, OPT, "GroupAdaGradOptimizerDump")])
+  msg("OptimizerDump", [("dump", 1, F.TYPE_MESSAGE, REP, "SingleOptimizerDump")])
+  msg("EntryDump", [("id", 1, F.TYPE_SFIXED64, OPT, None), ("num", 2, F.TYPE_FLOAT, REP, None),
+                    ("opt", 3, F.TYPE_MESSAGE, OPT, "OptimizerDump"), ("last_update_ts_sec", 4, F.TYPE_INT64, OPT, None)])
+  pool = descriptor_pool.DescriptorPool()
+  pool.Add(fd)
+  Entry = message_factory.GetMessageClass(pool.FindMessageTypeByName("g.EntryDump"))
+  GA, MA, AG = _lib.OPT_GROUP_ADAGRAD, _lib.OPT_MOVING_AVERAGE, _lib.OPT_ADAGRAD
+  spec = [(3, GA), (2, MA), (2, AG)]            # state: 1 | 0 | 2
+  dim, st_n = 7, 3
+  rng = np.random.default_rng(4)
+  row = rng.standard_normal(dim + st_n + 2).astype(np.float32)
+  fid, ts = (5 << 48) | 77, 1700000999
+  row[dim + st_n:] = np.array([1, ts], np.uint32).view(np.float32)
+  L, segs = lib(), segs_of(spec)
+  buf = C.create_string_buffer(2048)
+  n = L.mono_ckpt_encode_entry(segs, len(spec), fid, row.ctypes.data_as(C.c_void_p), buf, len(buf))
+  assert n > 0
+  m = Entry()
+  m.id = fid
+  m.num.extend(row[:dim].tolist())
+  m.opt.dump.add().group_adagrad.grad_square_sum = float(row[dim])
+  m.opt.dump.add().adagrad.norm.extend(row[dim + 1:dim + 3].tolist())
+  m.last_update_ts_sec = ts
+  wire = m.SerializeToString()
+  assert buf.raw[:n] == wire
+  out = np.zeros_like(row)
+  fid_out = C.c_int64(0)
+  assert L.mono_ckpt_decode_entry(segs, len(spec), wire, len(wire), C.byref(fid_out), out.ctypes.data_as(C.c_void_p)) == 0
+  assert fid_out.value == fid
+  np.testing.assert_array_equal(out.view(np.uint32), row.view(np.uint32))

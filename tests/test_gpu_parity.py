@@ -195,6 +195,52 @@ def test_update_and_lookup_bit_exact(dim, opt, dev):
   np.testing.assert_array_equal(eg.view(np.uint32), cpu.lookup_entry("t", vocab[:500]).view(np.uint32))
 
 
+FURTHER_OPT_CASES = [
+    ("momentum", {}), ("momentum", {"use_nesterov": True, "weight_decay_factor": 0.01}),
+    ("rmsprop", {"learning_rate": 0.02}), ("rmspropv2", {"weight_decay_factor": 0.001}),
+    ("adadelta", {}), ("amsgrad", {}), ("moving_average", {"momentum": 0.8}),
+    ("group_adagrad", {"l2": 0.05, "beta": 1.0, "initial_accumulator_value": 0.1, "weight_decay_factor": 0.01}),
+]
+
+
+@pytest.mark.parametrize("dim", [1, 8, 20])
+@pytest.mark.parametrize("opt", FURTHER_OPT_CASES, ids=lambda o: o[0] + ("+" if len(o[1]) > 1 else ""))
+def test_further_optimizers_bit_exact(dim, opt, dev):
+  """The optimizers served by the generic per-element path (and the whole-segment GroupAdaGrad) against the oracle's
+  restatement of the reference .cc files: random rows, repeated updates, fresh and resident FIDs; bit for bit."""
+  rng = np.random.default_rng(dim * 17 + len(opt[0]))
+  from monolith_b200 import entry
+  cfg = {"t": table([(dim, opt[0], opt[1])], [0.03], capacity=64, init=entry.RandomUniformInitializer(-0.1, 0.1),
+                    init_seed=5)}
+  gpu, cpu = pair(cfg, dev)
+  vocab = np.unique(rand_fids(rng, 800, 1 << 40))
+  for step in range(4):
+    ids = rng.choice(vocab, size=400, replace=False)
+    g = rng.standard_normal((ids.size, dim)).astype(np.float32)
+    gpu.apply_gradients({"t": (T(ids, dev), T(g, dev))}, req_time=10 + step, ids_unique=True)
+    cpu.apply_gradients({"t": (ids, g)}, req_time=10 + step)
+  got = gpu_lookup(gpu, {"t": vocab}, dev)["t"]
+  np.testing.assert_array_equal(got.view(np.uint32), cpu.lookup({"t": vocab})["t"].view(np.uint32))
+  eg = gpu.lookup_entry("t", T(vocab[:300], dev))["raw"].cpu().numpy()
+  np.testing.assert_array_equal(eg.view(np.uint32), cpu.lookup_entry("t", vocab[:300]).view(np.uint32))
+
+
+def test_group_adagrad_next_to_other_segments(dev):
+  """A whole-segment optimizer between per-element ones in one table (segment = group)."""
+  rng = np.random.default_rng(3)
+  cfg = {"t": table([(3, "adagrad", {}), (6, "group_adagrad", {"l2": 0.01, "beta": 0.5}), (2, "moving_average", {}),
+                     (4, "sgd", {})], [0.1, 0.05, 0.0, 0.2])}
+  gpu, cpu = pair(cfg, dev)
+  ids = fid(3, np.arange(500))
+  for step in range(3):
+    g = rng.standard_normal((ids.size, 15)).astype(np.float32)
+    gpu.apply_gradients({"t": (T(ids, dev), T(g, dev))}, req_time=step, ids_unique=True)
+    cpu.apply_gradients({"t": (ids, g)}, req_time=step)
+  np.testing.assert_array_equal(gpu_lookup(gpu, {"t": ids}, dev)["t"].view(np.uint32), cpu.lookup({"t": ids})["t"].view(np.uint32))
+  eg = gpu.lookup_entry("t", T(ids, dev))["raw"].cpu().numpy()
+  np.testing.assert_array_equal(eg.view(np.uint32), cpu.lookup_entry("t", ids).view(np.uint32))
+
+
 def test_multi_table_multi_segment_parity(dev):
   """bias (dim 1, FTRL) + vec (dim 16, Adagrad) in one table, next to SGD / Adam tables: the demo model's
   shape (ref: NT/model.py:88-115) through one MultiHashTable."""

@@ -21,3 +21,8 @@ except Exception as e:
   print("unreadable:", e)
 PY
 done
+if [ -n "$4" ]; then   # C4 streaming insert+evict through the sharded step: $4 = resident keys per GPU
+  echo "== c4 N=$N keys/GPU=$4"
+  timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --workload c4 --gpus $N --keys $4 --steps 16 --repeats 2 > $O/r2_c4_n${N}.json 2> $O/r2_c4_n${N}.err
+  tail -c 400 $O/r2_c4_n${N}.err; cut -c1-1600 $O/r2_c4_n${N}.json
+fi
