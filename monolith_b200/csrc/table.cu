@@ -163,7 +163,7 @@ export_kernel(const TableDev* __restrict__ t, uint64_t slot0, uint64_t slot1, in
 // ------------------------------------------------------------------------------------------
 static int state_floats(const mono_segment_cfg& s) {
   switch (s.opt_type) {
-    case MONO_OPT_SGD: return 0;
+    case MONO_OPT_SGD: case MONO_OPT_MOVING_AVERAGE: return 0;
     case MONO_OPT_ADAGRAD: return s.dim;
     case MONO_OPT_FTRL: return 2 * s.dim;
     case MONO_OPT_ADAM: return 2 * s.dim + 2;
