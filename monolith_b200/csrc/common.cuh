@@ -32,6 +32,10 @@ static_assert(sizeof(Entry) == 16, "entry must be 16 bytes");
 
 constexpr uint32_t kEmptyRow = 0xFFFFFFFFu;  // all-ones entry == empty (cudaMemset 0xFF)
 constexpr uint32_t kTombRow = 0xFFFFFFFEu;   // deleted stash slot (keeps probe chains intact)
+// Bit 31 of a LIVE entry's row marks "being moved by a cuckoo displacement" (cuckoo_insert): the entry is still valid
+// (readers strip the bit), other inserters leave it alone.  Row indices are < 2^31.
+constexpr uint32_t kMovingBit = 0x80000000u;
+constexpr uint32_t kRowMask = 0x7FFFFFFFu;
 constexpr int kBucketSlots = 4;
 constexpr int kMaxEvictions = 48;
 constexpr int kMaxSegs = 8;
@@ -273,7 +277,7 @@ __device__ __forceinline__ Probe probe_key(const TableDev* __restrict__ t, int64
     bool hit = pending && gl < kBucketSlots && e.key == key && e.row < kTombRow;
     uint32_t bal = Group<G>::bits(__ballot_sync(0xffffffffu, hit));
     int src = Group<G>::base() + (bal ? (__ffs(bal) - 1) : 0);
-    uint32_t row = __shfl_sync(0xffffffffu, e.row, src);
+    uint32_t row = __shfl_sync(0xffffffffu, e.row, src) & kRowMask;
     unsigned long long pp = __shfl_sync(0xffffffffu, (unsigned long long)p, src);
     if (pending && bal) {
       r.row = row;
@@ -292,7 +296,7 @@ __device__ __forceinline__ Probe probe_key(const TableDev* __restrict__ t, int64
         Entry* p = t->stash + ((s + i) & mask);
         Entry e = ld_entry_cg(p);
         if (e.row == kEmptyRow) break;
-        if (e.key == key && e.row < kTombRow) { row = e.row; sp = p; break; }
+        if (e.key == key && e.row < kTombRow) { row = e.row & kRowMask; sp = p; break; }
       }
     }
     int src = Group<G>::base();
@@ -316,14 +320,23 @@ __device__ __forceinline__ bool same_entry(const Entry& a, const Entry& b) {
 }
 
 // Lock-free insert of a key that is NOT in the table (callers guarantee one inserter per key).
-// Displacement is COPY-FIRST: when both buckets of `e` are full, a victim of the current bucket is first copied
-// into a free slot of ITS alternate bucket (for a moment it is present twice, with the same row), and only then
-// is its old slot overwritten with `e` by a 128-bit CAS.  A lookup running at the same time on another stream
-// therefore never misses a key that is in the table (the reference's readers hold bucket locks for the same
-// guarantee: cuckoohash_map.hpp:66-67 find under lock).  If the CAS loses (somebody moved / removed the victim, or
-// bumped its timestamp), the copy is withdrawn and the step is retried.  Only when the alternate buckets of ALL
-// four victims are full does the insert fall back to the classic exchange chain, where the displaced entry is
-// carried in a register between two atomics (at <= 60 % load that is a ~1e-5 event per displacement).
+// Displacement is COPY-FIRST and exclusive per victim:
+//   1. the victim's slot is MARKED (kMovingBit in its row, one 128-bit CAS): readers strip the bit and still find the
+//      entry; other inserters leave a marked entry alone, so exactly one mover works on a victim at a time;
+//   2. the victim (unmarked) is CAS-copied into a free slot of ITS alternate bucket — for a moment it is present twice,
+//      with the same row;
+//   3. the displacement counter is bumped (a reader that probed the alternate bucket before the copy and the old slot
+//      after step 4 sees the counter change between its two reads and probes again: rowops.cuh probe_lane_confirm_miss);
+//   4. the marked slot is overwritten with `e` (CAS; only a concurrent timestamp bump can make it retry).
+// A lookup running at the same time on another stream therefore never misses a key that is in the table (the
+// reference's readers hold bucket locks for the same guarantee: cuckoohash_map.hpp find / uprase under lock), and no
+// interleaving of movers can leave a key in the table twice: the original stays until ITS mover replaces it, and only
+// that mover creates a copy.  If the alternate bucket has no free slot the mark is taken back and the next victim is
+// tried; only when all four fail does the insert fall back to the classic step — swap `e` with an (unmarked) victim
+// and carry it to its alternate bucket, where it is briefly in a register only (at <= 60 % load a ~1e-5 event).
+__device__ __forceinline__ bool same_key_row(const Entry& a, const Entry& b) {
+  return a.key == b.key && ((a.row ^ b.row) & kRowMask) == 0;
+}
 __device__ __forceinline__ void cuckoo_insert(const TableDev* __restrict__ t, Entry e) {
   const uint32_t nb = t->num_buckets;
   Entry* buckets = t->buckets;
@@ -344,53 +357,63 @@ __device__ __forceinline__ void cuckoo_insert(const TableDev* __restrict__ t, En
     }
     // ---- copy-first displacement of one entry of `cur` ----
     const uint32_t v0 = (uint32_t)(mix64((uint64_t)e.key + it) >> 7) & (kBucketSlots - 1);  // deterministic first victim
-    bool changed = false;
-    for (int k = 0; k < kBucketSlots && !changed; ++k) {
+    bool rescan = false;
+    for (int k = 0; k < kBucketSlots && !rescan; ++k) {
       Entry* vp = buckets + (size_t)cur * kBucketSlots + ((v0 + k) & (kBucketSlots - 1));
       const Entry v = ld_entry_cg(vp);
       if (v.row == kEmptyRow) {  // freed meanwhile
         if (cas_entry(vp, empty, e)) return;
-        changed = true;
+        rescan = true;
+        break;
+      }
+      if (v.row & kMovingBit) continue;       // another mover owns this victim
+      Entry marked = v;
+      marked.row |= kMovingBit;
+      if (!cas_entry(vp, v, marked)) {        // changed under us (timestamp bump, another mover, ...): look again
+        rescan = true;
         break;
       }
       uint32_t a1, a2;
       bucket_pair(v.key, nb, a1, a2);
       const uint32_t va = cur == a1 ? a2 : a1;
       Entry* ab = buckets + (size_t)va * kBucketSlots;
-      for (int s = 0; s < kBucketSlots; ++s) {
+      bool copied = false;
+      for (int s = 0; s < kBucketSlots && !copied; ++s) {
         const Entry o = ld_entry_cg(ab + s);
-        if (o.row != kEmptyRow || !cas_entry(ab + s, empty, v)) continue;
-        // the victim now lives in both of its buckets.  Announce the move BEFORE its old slot goes away: a reader that
-        // probed the alternate bucket before the copy and the old slot after the overwrite sees the counter change
-        // between the two and probes again (rowops.cuh probe_lane_confirm_miss)
+        if (o.row == kEmptyRow && cas_entry(ab + s, empty, v)) copied = true;
+      }
+      if (copied) {
         __threadfence();
         atomicAdd(t->ctrs + kCtrMoves, 1u);
         __threadfence();
-        Entry seen = v;
-        for (int tries = 0; tries < 16; ++tries) {
-          const Entry old = cas_entry_old(vp, seen, e);
-          if (same_entry(old, seen)) return;                       // placed; the victim lives on in `va`
-          if (old.key != v.key || old.row != v.row) break;         // the victim left this slot
-          seen = old;                                              // only its timestamp moved: again
-        }
-        // lost the slot: withdraw the copy (its timestamp may have been bumped by a concurrent update)
-        Entry c = v;
-        for (int tries = 0; tries < 16; ++tries) {
-          const Entry old = cas_entry_old(ab + s, c, empty);
-          if (same_entry(old, c) || old.key != v.key || old.row != v.row) break;
-          c = old;
-        }
-        changed = true;
-        break;
       }
+      // replace the marked original with `e` (copied) or take the mark back (alternate bucket full); nobody but a
+      // timestamp bump touches a marked entry, so the loop ends after a retry or two
+      Entry seen = marked;
+      bool done = false;
+      for (int tries = 0; tries < 64 && !done; ++tries) {
+        Entry want = e;
+        if (!copied) {
+          want = seen;
+          want.row &= kRowMask;
+        }
+        const Entry old = cas_entry_old(vp, seen, want);
+        if (same_entry(old, seen)) done = true;
+        else if (same_key_row(old, seen)) seen = old;   // its timestamp moved
+        else break;                                      // cannot happen while the mark is ours (structural ops are stream-ordered)
+      }
+      if (copied && done) return;              // placed; the victim lives on in its alternate bucket
+      if (copied) atomicOr(t->ctrs + kCtrError, 4u);  // lost a marked slot: table changed structurally under an insert
     }
-    if (changed) continue;  // the bucket changed under us: rescan it
-    // ---- every victim's alternate bucket is full: classic exchange step ----
+    if (rescan) continue;  // the bucket changed under us: rescan it
+    // ---- every victim is owned or its alternate bucket is full: classic step on an unmarked victim ----
     Entry* vp = buckets + (size_t)cur * kBucketSlots + v0;
+    Entry victim = ld_entry_cg(vp);
+    if (victim.row != kEmptyRow && (victim.row & kMovingBit)) continue;   // wait for its mover (costs an iteration)
     atomicAdd(t->ctrs + kCtrMoves, 1u);
     __threadfence();
-    Entry victim = exch_entry(vp, e);
-    if (victim.row == kEmptyRow) return;  // slot was freed meanwhile: we just filled it
+    if (!cas_entry(vp, victim, e)) continue;  // changed meanwhile: rescan
+    if (victim.row == kEmptyRow) return;      // slot was freed meanwhile: we just filled it
     e = victim;
     bucket_pair(e.key, nb, b1, b2);
     cur = (cur == b1) ? b2 : b1;
@@ -452,7 +475,7 @@ __device__ __forceinline__ void probe_keys(const TableDev* __restrict__ t, const
       const bool hit = pending[q] && gl < kBucketSlots && e[q].key == key[q] && e[q].row < kTombRow;
       const uint32_t bal = Group<G>::bits(__ballot_sync(0xffffffffu, hit));
       const int src = Group<G>::base() + (bal ? (__ffs(bal) - 1) : 0);
-      const uint32_t r = __shfl_sync(0xffffffffu, e[q].row, src);
+      const uint32_t r = __shfl_sync(0xffffffffu, e[q].row, src) & kRowMask;
       const unsigned long long pp = __shfl_sync(0xffffffffu, (unsigned long long)p[q], src);
       if (pending[q] && bal) {
         row[q] = r;
@@ -474,7 +497,7 @@ __device__ __forceinline__ void probe_keys(const TableDev* __restrict__ t, const
           Entry* pq = t->stash + ((s + i) & mask);
           Entry e = ld_entry_cg(pq);
           if (e.row == kEmptyRow) break;
-          if (e.key == key[q] && e.row < kTombRow) { r = e.row; sp = pq; break; }
+          if (e.key == key[q] && e.row < kTombRow) { r = e.row & kRowMask; sp = pq; break; }
         }
       }
       r = __shfl_sync(0xffffffffu, r, Group<G>::base());

@@ -540,10 +540,10 @@ lookup_pool_staged_kernel(const TableDev* __restrict__ t, const int64_t* __restr
       for (int s = 0; s < KPL; ++s) {
         const int k = s * G + gl;
         uint32_t row = kEmptyRow;
-        if (e0[s].key == key[s] && e0[s].row < kTombRow) row = e0[s].row;
-        if (e1[s].key == key[s] && e1[s].row < kTombRow) row = e1[s].row;
-        if (e2[s].key == key[s] && e2[s].row < kTombRow) row = e2[s].row;
-        if (e3[s].key == key[s] && e3[s].row < kTombRow) row = e3[s].row;
+        if (e0[s].key == key[s] && e0[s].row < kTombRow) row = e0[s].row & kRowMask;
+        if (e1[s].key == key[s] && e1[s].row < kTombRow) row = e1[s].row & kRowMask;
+        if (e2[s].key == key[s] && e2[s].row < kTombRow) row = e2[s].row & kRowMask;
+        if (e3[s].key == key[s] && e3[s].row < kTombRow) row = e3[s].row & kRowMask;
         const bool live = k < cnt && k < kStage;
         if (live && row == kEmptyRow) row = probe_lane(t, key[s]);  // second bucket / stash: the full probe
         if (live && row == kEmptyRow) row = probe_lane_confirm_miss(t, key[s]);  // inserts on another stream

@@ -132,10 +132,10 @@ __device__ __forceinline__ void opt_elem_more(const SegDev& s, int lc, float lr,
     double eta;
     if (s.opt_type == MONO_OPT_RMSPROP) {
       n1 = (float)__dadd_rn(__dmul_rn(mom, (double)n0), __dmul_rn(__dmul_rn(__dsub_rn(1.0, mom), dx), dx));
-      eta = __ddiv_rn((double)s.p[2], __dadd_rn((double)__fsqrt_rn(n1), 1.0));   // the CONFIG's learning rate
+      eta = __ddiv_rn((double)s.p[2], (double)__fadd_rn(__fsqrt_rn(n1), 1.0f));   // the CONFIG's learning rate; sqrt(n) + 1 is a FLOAT sum in the reference
     } else {
       n1 = (float)__dadd_rn(__dmul_rn(mom, (double)n0), __dmul_rn(dx, dx));
-      eta = __ddiv_rn((double)lr, __dadd_rn((double)__fsqrt_rn(n1), 1.0));
+      eta = __ddiv_rn((double)lr, (double)__fadd_rn(__fsqrt_rn(n1), 1.0f));
     }
     w = (float)__dsub_rn((double)w, __dmul_rn(eta, dx));
     sp[lc] = n1;
@@ -384,21 +384,21 @@ __device__ __forceinline__ uint32_t probe_lane(const TableDev* __restrict__ t, i
     const Entry* q = buckets + (size_t)b2 * kBucketSlots;
     Entry e0 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(p), e1 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(p + 1), e2 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(p + 2), e3 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(p + 3);
     Entry f0 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(q), f1 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(q + 1), f2 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(q + 2), f3 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(q + 3);
-    if (f0.key == key && f0.row < kTombRow) row = f0.row;
-    if (f1.key == key && f1.row < kTombRow) row = f1.row;
-    if (f2.key == key && f2.row < kTombRow) row = f2.row;
-    if (f3.key == key && f3.row < kTombRow) row = f3.row;
-    if (e0.key == key && e0.row < kTombRow) row = e0.row;
-    if (e1.key == key && e1.row < kTombRow) row = e1.row;
-    if (e2.key == key && e2.row < kTombRow) row = e2.row;
-    if (e3.key == key && e3.row < kTombRow) row = e3.row;
+    if (f0.key == key && f0.row < kTombRow) row = f0.row & kRowMask;
+    if (f1.key == key && f1.row < kTombRow) row = f1.row & kRowMask;
+    if (f2.key == key && f2.row < kTombRow) row = f2.row & kRowMask;
+    if (f3.key == key && f3.row < kTombRow) row = f3.row & kRowMask;
+    if (e0.key == key && e0.row < kTombRow) row = e0.row & kRowMask;
+    if (e1.key == key && e1.row < kTombRow) row = e1.row & kRowMask;
+    if (e2.key == key && e2.row < kTombRow) row = e2.row & kRowMask;
+    if (e3.key == key && e3.row < kTombRow) row = e3.row & kRowMask;
     if (row == kEmptyRow && t->ctrs[kCtrStash] != 0) {
       const uint32_t mask = t->stash_cap - 1;
       const uint32_t s = (uint32_t)(mix64((uint64_t)key) >> 17) & mask;
       for (uint32_t i = 0; i <= mask; ++i) {
         Entry e = ld_entry_cg(t->stash + ((s + i) & mask));
         if (e.row == kEmptyRow) break;
-        if (e.key == key && e.row < kTombRow) { row = e.row; break; }
+        if (e.key == key && e.row < kTombRow) { row = e.row & kRowMask; break; }
       }
     }
     return row;
@@ -406,25 +406,25 @@ __device__ __forceinline__ uint32_t probe_lane(const TableDev* __restrict__ t, i
   {
     const Entry* p = buckets + (size_t)b1 * kBucketSlots;
     Entry e0 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(p), e1 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(p + 1), e2 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(p + 2), e3 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(p + 3);
-    if (e0.key == key && e0.row < kTombRow) row = e0.row;
-    if (e1.key == key && e1.row < kTombRow) row = e1.row;
-    if (e2.key == key && e2.row < kTombRow) row = e2.row;
-    if (e3.key == key && e3.row < kTombRow) row = e3.row;
+    if (e0.key == key && e0.row < kTombRow) row = e0.row & kRowMask;
+    if (e1.key == key && e1.row < kTombRow) row = e1.row & kRowMask;
+    if (e2.key == key && e2.row < kTombRow) row = e2.row & kRowMask;
+    if (e3.key == key && e3.row < kTombRow) row = e3.row & kRowMask;
   }
   if (row == kEmptyRow) {
     const Entry* p = buckets + (size_t)b2 * kBucketSlots;
     Entry e0 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(p), e1 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(p + 1), e2 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(p + 2), e3 = (LD == 0 ? ld_entry_nc : ld_entry_cg)(p + 3);
-    if (e0.key == key && e0.row < kTombRow) row = e0.row;
-    if (e1.key == key && e1.row < kTombRow) row = e1.row;
-    if (e2.key == key && e2.row < kTombRow) row = e2.row;
-    if (e3.key == key && e3.row < kTombRow) row = e3.row;
+    if (e0.key == key && e0.row < kTombRow) row = e0.row & kRowMask;
+    if (e1.key == key && e1.row < kTombRow) row = e1.row & kRowMask;
+    if (e2.key == key && e2.row < kTombRow) row = e2.row & kRowMask;
+    if (e3.key == key && e3.row < kTombRow) row = e3.row & kRowMask;
     if (row == kEmptyRow && t->ctrs[kCtrStash] != 0) {
       const uint32_t mask = t->stash_cap - 1;
       const uint32_t s = (uint32_t)(mix64((uint64_t)key) >> 17) & mask;
       for (uint32_t i = 0; i <= mask; ++i) {
         Entry e = ld_entry_cg(t->stash + ((s + i) & mask));
         if (e.row == kEmptyRow) break;
-        if (e.key == key && e.row < kTombRow) { row = e.row; break; }
+        if (e.key == key && e.row < kTombRow) { row = e.row & kRowMask; break; }
       }
     }
   }
@@ -473,24 +473,24 @@ __device__ __forceinline__ uint32_t probe_lane_slot(const TableDev* __restrict__
     Entry* q = buckets + (size_t)b2 * kBucketSlots;
     Entry e0 = ld_entry(p), e1 = ld_entry(p + 1), e2 = ld_entry(p + 2), e3 = ld_entry(p + 3);
     Entry f0 = ld_entry(q), f1 = ld_entry(q + 1), f2 = ld_entry(q + 2), f3 = ld_entry(q + 3);
-    if (f0.key == key && f0.row < kTombRow) { row = f0.row; *slot = q; }
-    if (f1.key == key && f1.row < kTombRow) { row = f1.row; *slot = q + 1; }
-    if (f2.key == key && f2.row < kTombRow) { row = f2.row; *slot = q + 2; }
-    if (f3.key == key && f3.row < kTombRow) { row = f3.row; *slot = q + 3; }
-    if (e0.key == key && e0.row < kTombRow) { row = e0.row; *slot = p; }
-    if (e1.key == key && e1.row < kTombRow) { row = e1.row; *slot = p + 1; }
-    if (e2.key == key && e2.row < kTombRow) { row = e2.row; *slot = p + 2; }
-    if (e3.key == key && e3.row < kTombRow) { row = e3.row; *slot = p + 3; }
+    if (f0.key == key && f0.row < kTombRow) { row = f0.row & kRowMask; *slot = q; }
+    if (f1.key == key && f1.row < kTombRow) { row = f1.row & kRowMask; *slot = q + 1; }
+    if (f2.key == key && f2.row < kTombRow) { row = f2.row & kRowMask; *slot = q + 2; }
+    if (f3.key == key && f3.row < kTombRow) { row = f3.row & kRowMask; *slot = q + 3; }
+    if (e0.key == key && e0.row < kTombRow) { row = e0.row & kRowMask; *slot = p; }
+    if (e1.key == key && e1.row < kTombRow) { row = e1.row & kRowMask; *slot = p + 1; }
+    if (e2.key == key && e2.row < kTombRow) { row = e2.row & kRowMask; *slot = p + 2; }
+    if (e3.key == key && e3.row < kTombRow) { row = e3.row & kRowMask; *slot = p + 3; }
     if (row != kEmptyRow) return row;
   } else {
 #pragma unroll
     for (int round = 0; round < 2; ++round) {
       Entry* p = buckets + (size_t)(round == 0 ? b1 : b2) * kBucketSlots;
       Entry e0 = ld_entry(p), e1 = ld_entry(p + 1), e2 = ld_entry(p + 2), e3 = ld_entry(p + 3);
-      if (e0.key == key && e0.row < kTombRow) { row = e0.row; *slot = p; }
-      if (e1.key == key && e1.row < kTombRow) { row = e1.row; *slot = p + 1; }
-      if (e2.key == key && e2.row < kTombRow) { row = e2.row; *slot = p + 2; }
-      if (e3.key == key && e3.row < kTombRow) { row = e3.row; *slot = p + 3; }
+      if (e0.key == key && e0.row < kTombRow) { row = e0.row & kRowMask; *slot = p; }
+      if (e1.key == key && e1.row < kTombRow) { row = e1.row & kRowMask; *slot = p + 1; }
+      if (e2.key == key && e2.row < kTombRow) { row = e2.row & kRowMask; *slot = p + 2; }
+      if (e3.key == key && e3.row < kTombRow) { row = e3.row & kRowMask; *slot = p + 3; }
       if (row != kEmptyRow) return row;
     }
   }
@@ -501,7 +501,7 @@ __device__ __forceinline__ uint32_t probe_lane_slot(const TableDev* __restrict__
       Entry* p = t->stash + ((s + i) & mask);
       Entry e = ld_entry_cg(p);
       if (e.row == kEmptyRow) break;
-      if (e.key == key && e.row < kTombRow) { *slot = p; return e.row; }
+      if (e.key == key && e.row < kTombRow) { *slot = p; return e.row & kRowMask; }
     }
   }
   return kEmptyRow;

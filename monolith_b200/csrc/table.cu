@@ -99,7 +99,10 @@ rehash_kernel(const Entry* __restrict__ old_buckets, uint64_t old_slots,
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total;
        i += (uint64_t)gridDim.x * blockDim.x) {
     Entry e = i < old_slots ? ld_entry_nc(old_buckets + i) : ld_entry_nc(old_stash + (i - old_slots));
-    if (e.row < kTombRow) cuckoo_insert(nt, e);
+    if (e.row < kTombRow) {
+      e.row &= kRowMask;  // (no entry can be mid-move here: growth is stream-ordered with the inserts)
+      cuckoo_insert(nt, e);
+    }
   }
 }
 
@@ -129,7 +132,7 @@ evict_kernel(const TableDev* __restrict__ t, int64_t max_update_time) {
       if (i >= slots) dead.row = kTombRow;  // keep stash probe chains intact
       *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&dead);
       uint32_t idx = atomicAdd(t->ctrs + kCtrFree, 1u);
-      t->free_list[idx] = e.row;
+      t->free_list[idx] = e.row & kRowMask;
       atomicSub(t->ctrs + kCtrSize, 1u);
     }
   }
@@ -149,9 +152,9 @@ export_kernel(const TableDev* __restrict__ t, uint64_t slot0, uint64_t slot1, in
     uint32_t o = atomicAdd(n_out, 1u);
     ids_out[o] = e.key;
     float* dst = entry_out + (size_t)o * W;
-    const float* src = t->emb + (size_t)e.row * t->emb_stride;
+    const float* src = t->emb + (size_t)(e.row & kRowMask) * t->emb_stride;
     for (int j = 0; j < t->dim; ++j) dst[j] = src[j];
-    const float* st = t->state + (size_t)e.row * t->state_stride;
+    const float* st = t->state + (size_t)(e.row & kRowMask) * t->state_stride;
     for (int j = 0; j < t->state_dim; ++j) dst[t->dim + j] = st[j];
     dst[t->dim + t->state_dim] = __uint_as_float(1u);
     dst[t->dim + t->state_dim + 1] = __uint_as_float(e.ts);
@@ -228,7 +231,7 @@ void table_init(mono_mtable* mt, HostTable& t, const mono_table_cfg& cfg, cudaSt
     t.slot_expire_pairs.push_back(cfg.slot_expire_days[i]);
   }
   uint64_t rows = std::max<uint64_t>(cfg.initial_capacity, 1024);
-  if (rows > 0xFFFFFFF0ull) throw ArgError("initial_capacity too large");
+  if (rows > 0x7FFFFFF0ull) throw ArgError("initial_capacity too large (row indices are 31 bits)");
   d.row_cap = (uint32_t)rows;
   d.num_buckets = buckets_for(rows);
   d.stash_cap = 4096;
@@ -359,7 +362,10 @@ static void grow_rows(mono_mtable* mt, int k, uint64_t need_total, cudaStream_t 
   HostTable& t = mt->tables[k];
   TableDev& d = t.dev;
   uint64_t ncap = std::max<uint64_t>((uint64_t)d.row_cap * 2, need_total + need_total / 8);
-  if (ncap > 0xFFFFFFF0ull) throw ArgError("row capacity exceeds 32-bit row index");
+  if (ncap > 0x7FFFFFF0ull) {  // row indices are 31 bits (bit 31 of an entry's row marks a displacement in progress)
+    ncap = 0x7FFFFFF0ull;
+    if (ncap < need_total) throw ArgError("row capacity exceeds the 31-bit row index");
+  }
   float* nemb = nullptr;
   float* nstate = nullptr;
   uint32_t* nfree = nullptr;
