@@ -1334,3 +1334,61 @@ def test_lookup_never_misses_during_inserts_on_another_stream(dev):
   both = np.concatenate([a_ids, b_ids])
   np.testing.assert_array_equal(gpu_lookup(gpu, {"t": both}, dev)["t"].view(np.uint32), cpu.lookup({"t": both})["t"].view(np.uint32))
   assert gpu.size("t") == n_a + n_b
+
+
+def test_streaming_insert_evict_50_steps_vs_oracle(dev):
+  """The C4 stream in miniature (bench.py --workload c4): 50 steps of fused lookup+pool / fused backward on a table that is
+  small enough to GROW under load (capacity 1024 against ~30 K keys), every step 5 % never-seen FIDs, a TTL eviction scan
+  every 8 steps (one-day window, ref: CuckooEmbeddingHashTable::Evict via the bridge's eviction thread,
+  embedding_hash_table_tf_bridge.cc:73-104).  After every eviction and at the end: membership, rows, optimizer state and
+  timestamps equal the oracle's — bit for bit for every FID that never had more than 64 occurrences in a step (freed rows
+  are reused, the bucket array is rehashed several times), within the tree-sum tolerance for the hot ones."""
+  from monolith_b200 import entry
+  rng = np.random.default_rng(50)
+  D, M = 8, 4200
+  DAY, dt = 86400, 86400 // 20                       # the window is 20 steps
+  cfg = {"t": table([(D, "adagrad", {"initial_accumulator_value": 0.1})], [0.05], capacity=1024, default_expire_time=1,
+                    init=entry.RandomUniformInitializer(-0.05, 0.05), init_seed=4)}
+  gpu, cpu = pair(cfg, dev)
+  resident = 20_000
+  base = fid(1, np.arange(resident))
+  for c in range(20):                                 # prefill with last-update times spread over the window
+    sl = slice(c * resident // 20, (c + 1) * resident // 20)
+    z = np.zeros((base[sl].size, D), np.float32)
+    gpu.assign_add({"t": (T(base[sl], dev), T(z, dev))}, req_time=c * dt, ids_unique=True)
+    cpu.assign_add({"t": (base[sl], z)}, req_time=c * dt)
+  fresh = resident
+  hot_fids = set()
+  for step in range(50):
+    now = DAY + (step + 1) * dt
+    ranks = np.minimum((rng.pareto(1.05, M) * 50).astype(np.int64), resident - 1)
+    ids = fid(1, ranks)
+    n_new = M // 20
+    pos = rng.choice(M, n_new, replace=False)
+    ids[pos] = fid(1, fresh + np.arange(n_new))
+    fresh += n_new
+    u, inv = orc.dedup(ids)
+    cnt = np.bincount(inv, minlength=u.size)
+    hot_fids.update(u[cnt > 64].tolist())
+    cold = ~np.isin(ids, np.fromiter(hot_fids, np.int64, len(hot_fids)))
+    pooled = gpu.lookup_pool("t", T(ids, dev), None, "sum").cpu().numpy()
+    np.testing.assert_array_equal(pooled[cold].view(np.uint32), cpu.lookup({"t": ids})["t"][cold].view(np.uint32))
+    g = rng.standard_normal((M, D)).astype(np.float32)
+    gpu.pool_backward("t", T(ids, dev), T(g, dev), None, "sum", req_time=now)
+    ug = orc.gather_pool_grad(g, inv * D, D, u.size * D).reshape(-1, D)
+    cpu.apply_gradients({"t": (u, ug)}, req_time=now)
+    if (step + 1) % 8 == 0:
+      gpu.evict("t", now)
+      cpu.evict("t", now)
+      assert gpu.size("t") == cpu.size("t")
+  keys = cpu.keys("t")
+  assert gpu.size("t") == keys.size and 5_000 < keys.size < 15_000       # steady state: the window holds ~8 K live keys
+  probe = np.concatenate([keys, base])                             # live keys + every prefilled key (many evicted)
+  np.testing.assert_array_equal(gpu.contains("t", T(probe, dev)).cpu().numpy(), cpu.contains("t", probe))
+  eg = gpu.lookup_entry("t", T(keys, dev))["raw"].cpu().numpy()
+  ec = cpu.lookup_entry("t", keys)
+  hot = np.isin(keys, np.fromiter(hot_fids, np.int64, len(hot_fids)))
+  assert 0 < hot.sum() < 200
+  np.testing.assert_array_equal(eg[~hot].view(np.uint32), ec[~hot].view(np.uint32))
+  np.testing.assert_allclose(eg[hot][:, :-2], ec[hot][:, :-2], rtol=2e-3, atol=2e-4)
+  np.testing.assert_array_equal(eg[hot][:, -2:].view(np.uint32), ec[hot][:, -2:].view(np.uint32))
