@@ -52,6 +52,7 @@ enum Ctr {
   kCtrAux = 6,       // scratch
   kCtrMaxTs = 7,     // max update time seen (low 32 bits; ref tf_bridge.cc:202-206 truncates to int)
   kCtrMoves = 8,     // cuckoo displacements ever made (readers on other streams use it to confirm a miss)
+  kCtrInflight = 9,  // entries currently carried in a register by the exchange fallback of cuckoo_insert
   kNumCtrs = 16
 };
 
@@ -333,7 +334,8 @@ __device__ __forceinline__ bool same_entry(const Entry& a, const Entry& b) {
 // interleaving of movers can leave a key in the table twice: the original stays until ITS mover replaces it, and only
 // that mover creates a copy.  If the alternate bucket has no free slot the mark is taken back and the next victim is
 // tried; only when all four fail does the insert fall back to the classic step — swap `e` with an (unmarked) victim
-// and carry it to its alternate bucket, where it is briefly in a register only (at <= 60 % load a ~1e-5 event).
+// and carry it to its alternate bucket (at <= 60 % load a ~1e-5 event).  While an entry is carried it is in no bucket:
+// ctrs[kCtrInflight] counts such entries, and a reader that misses a key while the count is non-zero probes again.
 __device__ __forceinline__ bool same_key_row(const Entry& a, const Entry& b) {
   return a.key == b.key && ((a.row ^ b.row) & kRowMask) == 0;
 }
@@ -344,6 +346,13 @@ __device__ __forceinline__ void cuckoo_insert(const TableDev* __restrict__ t, En
   uint32_t b1, b2;
   bucket_pair(e.key, nb, b1, b2);
   uint32_t cur = b1;
+  bool carrying = false;   // `e` is a displaced RESIDENT entry held in this register (exchange fallback): readers must wait
+  auto placed = [&]() {
+    if (carrying) {
+      __threadfence();
+      atomicSub(t->ctrs + kCtrInflight, 1u);
+    }
+  };
   for (int it = 0; it < kMaxEvictions; ++it) {
     // try every empty slot of `cur`, and on the first iteration of the alternate bucket too
     for (int which = 0; which < (it == 0 ? 2 : 1); ++which) {
@@ -352,7 +361,7 @@ __device__ __forceinline__ void cuckoo_insert(const TableDev* __restrict__ t, En
 #pragma unroll
       for (int s = 0; s < kBucketSlots; ++s) {
         Entry o = ld_entry_cg(base + s);
-        if (o.row == kEmptyRow && cas_entry(base + s, empty, e)) return;
+        if (o.row == kEmptyRow && cas_entry(base + s, empty, e)) { placed(); return; }
       }
     }
     // ---- copy-first displacement of one entry of `cur` ----
@@ -362,7 +371,7 @@ __device__ __forceinline__ void cuckoo_insert(const TableDev* __restrict__ t, En
       Entry* vp = buckets + (size_t)cur * kBucketSlots + ((v0 + k) & (kBucketSlots - 1));
       const Entry v = ld_entry_cg(vp);
       if (v.row == kEmptyRow) {  // freed meanwhile
-        if (cas_entry(vp, empty, e)) return;
+        if (cas_entry(vp, empty, e)) { placed(); return; }
         rescan = true;
         break;
       }
@@ -402,7 +411,7 @@ __device__ __forceinline__ void cuckoo_insert(const TableDev* __restrict__ t, En
         else if (same_key_row(old, seen)) seen = old;   // its timestamp moved
         else break;                                      // cannot happen while the mark is ours (structural ops are stream-ordered)
       }
-      if (copied && done) return;              // placed; the victim lives on in its alternate bucket
+      if (copied && done) { placed(); return; }   // placed; the victim lives on in its alternate bucket
       if (copied) atomicOr(t->ctrs + kCtrError, 4u);  // lost a marked slot: table changed structurally under an insert
     }
     if (rescan) continue;  // the bucket changed under us: rescan it
@@ -410,10 +419,18 @@ __device__ __forceinline__ void cuckoo_insert(const TableDev* __restrict__ t, En
     Entry* vp = buckets + (size_t)cur * kBucketSlots + v0;
     Entry victim = ld_entry_cg(vp);
     if (victim.row != kEmptyRow && (victim.row & kMovingBit)) continue;   // wait for its mover (costs an iteration)
+    // the victim will be in this register only until it is placed again: announce it (a reader that misses a key while
+    // the in-flight count is non-zero probes again, rowops.cuh probe_lane_confirm_miss), then take it out
+    const bool first_carry = !carrying && victim.row != kEmptyRow;
+    if (first_carry) atomicAdd(t->ctrs + kCtrInflight, 1u);
     atomicAdd(t->ctrs + kCtrMoves, 1u);
     __threadfence();
-    if (!cas_entry(vp, victim, e)) continue;  // changed meanwhile: rescan
-    if (victim.row == kEmptyRow) return;      // slot was freed meanwhile: we just filled it
+    if (!cas_entry(vp, victim, e)) {          // changed meanwhile: rescan
+      if (first_carry) atomicSub(t->ctrs + kCtrInflight, 1u);
+      continue;
+    }
+    if (victim.row == kEmptyRow) { placed(); return; }   // slot was freed meanwhile: we just filled it
+    carrying = true;
     e = victim;
     bucket_pair(e.key, nb, b1, b2);
     cur = (cur == b1) ? b2 : b1;
@@ -426,10 +443,12 @@ __device__ __forceinline__ void cuckoo_insert(const TableDev* __restrict__ t, En
     Entry o = ld_entry_cg(p);
     if (o.row == kEmptyRow && cas_entry(p, empty, e)) {
       atomicAdd(t->ctrs + kCtrStash, 1u);
+      placed();
       return;
     }
   }
   atomicOr(t->ctrs + kCtrError, 1u);
+  placed();
 }
 
 // Batched probe: U independent keys per lane group.  All U bucket loads are issued back to back

@@ -443,16 +443,20 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
 // only miss a resident key if the counter changes between its two bucket reads.  The fast probe cannot be trusted for
 // that (its non-coherent loads may be served by an L1 line that is older than the move), so every miss is confirmed:
 // probe again with loads that are coherent at L2, bracketed by counter reads, until one probe runs with no move in
-// between.  Cost: two L2-hit loads and one extra probe per MISS (absent FIDs only; resident FIDs never come here).
+// between — and with no entry in flight: the rare exchange fallback of cuckoo_insert carries a resident entry in a
+// register, ctrs[kCtrInflight] counts those.  Cost: three L2-hit loads and one extra probe per MISS (absent FIDs only;
+// resident FIDs never come here).
 static __device__ __noinline__ uint32_t probe_lane_confirm_miss(const TableDev* __restrict__ t, int64_t key) {
   const uint32_t* mv = t->ctrs + kCtrMoves;
+  const uint32_t* fl = t->ctrs + kCtrInflight;
   uint32_t ma = ld_acquire_u32(mv);
-  for (int tries = 0; tries < 8; ++tries) {
+  for (int tries = 0; tries < 64; ++tries) {
     const uint32_t row = probe_lane<false, 1>(t, key);
     if (row != kEmptyRow) return row;
     __threadfence();
     const uint32_t mb = ld_acquire_u32(mv);
-    if (mb == ma) return kEmptyRow;
+    // absent for sure: no displacement completed during the probe and no entry is being carried between buckets
+    if (mb == ma && ld_acquire_u32(fl) == 0) return kEmptyRow;
     ma = mb;
   }
   return kEmptyRow;
