@@ -347,8 +347,10 @@ __device__ __forceinline__ void cuckoo_insert(const TableDev* __restrict__ t, En
   bucket_pair(e.key, nb, b1, b2);
   uint32_t cur = b1;
   bool carrying = false;   // `e` is a displaced RESIDENT entry held in this register (exchange fallback): readers must wait
-  auto placed = [&]() {
-    if (carrying) {
+  auto placed = [&]() {   // the carried entry is in the table again: bump the move counter FIRST, then leave the in-flight
+    if (carrying) {       // count — a reader that sees the count at zero then also sees the counter changed and probes again
+      __threadfence();
+      atomicAdd(t->ctrs + kCtrMoves, 1u);
       __threadfence();
       atomicSub(t->ctrs + kCtrInflight, 1u);
     }
@@ -435,14 +437,16 @@ __device__ __forceinline__ void cuckoo_insert(const TableDev* __restrict__ t, En
     bucket_pair(e.key, nb, b1, b2);
     cur = (cur == b1) ? b2 : b1;
   }
-  // stash
+  // stash.  The count goes up BEFORE the entry appears there: a reader that could see the entry must not skip the stash
+  // because it still read a zero count (the count is only ever used as "the stash may be non-empty").
+  atomicAdd(t->ctrs + kCtrStash, 1u);
+  __threadfence();
   uint32_t mask = t->stash_cap - 1;
   uint32_t s = (uint32_t)(mix64((uint64_t)e.key) >> 17) & mask;
   for (uint32_t i = 0; i <= mask; ++i) {
     Entry* p = t->stash + ((s + i) & mask);
     Entry o = ld_entry_cg(p);
     if (o.row == kEmptyRow && cas_entry(p, empty, e)) {
-      atomicAdd(t->ctrs + kCtrStash, 1u);
       placed();
       return;
     }

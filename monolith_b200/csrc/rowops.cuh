@@ -368,6 +368,12 @@ __device__ __forceinline__ void apply_row(const TableDev* __restrict__ t, uint32
   }
 }
 
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // lane-per-key probe of the bucketised table: the whole 64-byte bucket with 4 x LDG.128 per lane
 // DUAL: both candidate buckets are requested together (8 x LDG.128).  A warp-tile of 32 probes almost always holds a
 // key that lives in its second bucket, so the sequential form costs the WARP two dependent round trips; DUAL trades
@@ -392,7 +398,7 @@ __device__ __forceinline__ uint32_t probe_lane(const TableDev* __restrict__ t, i
     if (e1.key == key && e1.row < kTombRow) row = e1.row & kRowMask;
     if (e2.key == key && e2.row < kTombRow) row = e2.row & kRowMask;
     if (e3.key == key && e3.row < kTombRow) row = e3.row & kRowMask;
-    if (row == kEmptyRow && t->ctrs[kCtrStash] != 0) {
+    if (row == kEmptyRow && (LD == 0 ? t->ctrs[kCtrStash] : ld_acquire_u32(t->ctrs + kCtrStash)) != 0) {
       const uint32_t mask = t->stash_cap - 1;
       const uint32_t s = (uint32_t)(mix64((uint64_t)key) >> 17) & mask;
       for (uint32_t i = 0; i <= mask; ++i) {
@@ -418,7 +424,7 @@ __device__ __forceinline__ uint32_t probe_lane(const TableDev* __restrict__ t, i
     if (e1.key == key && e1.row < kTombRow) row = e1.row & kRowMask;
     if (e2.key == key && e2.row < kTombRow) row = e2.row & kRowMask;
     if (e3.key == key && e3.row < kTombRow) row = e3.row & kRowMask;
-    if (row == kEmptyRow && t->ctrs[kCtrStash] != 0) {
+    if (row == kEmptyRow && (LD == 0 ? t->ctrs[kCtrStash] : ld_acquire_u32(t->ctrs + kCtrStash)) != 0) {
       const uint32_t mask = t->stash_cap - 1;
       const uint32_t s = (uint32_t)(mix64((uint64_t)key) >> 17) & mask;
       for (uint32_t i = 0; i <= mask; ++i) {
@@ -431,12 +437,6 @@ __device__ __forceinline__ uint32_t probe_lane(const TableDev* __restrict__ t, i
   return row;
 }
 
-
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 
 // A lookup that missed while ANOTHER STREAM may be inserting.  cuckoo_insert moves a resident entry between its two
 // buckets copy-first and bumps ctrs[kCtrMoves] between the copy and the overwrite of the old slot, so a reader can
@@ -454,9 +454,12 @@ static __device__ __noinline__ uint32_t probe_lane_confirm_miss(const TableDev* 
     const uint32_t row = probe_lane<false, 1>(t, key);
     if (row != kEmptyRow) return row;
     __threadfence();
+    // the in-flight count is read BEFORE the move counter: an insert that re-places a carried entry bumps the counter
+    // and only then leaves the in-flight count, so "nothing in flight" + "counter unchanged" cannot both be observed
+    // around a probe that ran while the entry was in a register (tests/test_cuckoo_protocol_model.py found the other order)
+    const uint32_t in_flight = ld_acquire_u32(fl);
     const uint32_t mb = ld_acquire_u32(mv);
-    // absent for sure: no displacement completed during the probe and no entry is being carried between buckets
-    if (mb == ma && ld_acquire_u32(fl) == 0) return kEmptyRow;
+    if (mb == ma && in_flight == 0) return kEmptyRow;   // absent for sure
     ma = mb;
   }
   return kEmptyRow;
