@@ -95,3 +95,19 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
   subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
                          str(src), "-o", str(exe), "-L", libdir, "-lmono_emb", "-Wl,-rpath," + libdir])
   assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_tuning_knobs_set_get_without_a_gpu(lib):
+  """mono_set_option / mono_get_option are process-wide switches between implementations of the same result; they need
+  no device.  Unknown names are rejected."""
+  for name in (b"lookup_tma", b"claim_pf", b"apply_pf", b"lookup_pf", b"seg_vpl", b"seg_ahead", b"claim_dual", b"lookup_dual"):
+    old = lib.mono_get_option(name)
+    assert old >= 0
+    assert lib.mono_set_option(name, 1) == 0 and lib.mono_get_option(name) == 1
+    assert lib.mono_set_option(name, old) == 0 and lib.mono_get_option(name) == old
+  assert lib.mono_set_option(b"no_such_knob", 1) != 0
+  assert lib.mono_get_option(b"no_such_knob") == -1
+  # the measured defaults (profiles/r2_ab.txt): every L2-prefetch and dual-bucket variant off, look-ahead on
+  if not __import__("os").environ.get("MONO_KNOBS"):
+    assert [lib.mono_get_option(n) for n in (b"claim_pf", b"apply_pf", b"lookup_pf", b"claim_dual", b"lookup_dual")] == [0] * 5
+    assert lib.mono_get_option(b"seg_ahead") == 1 and lib.mono_get_option(b"seg_vpl") == 1
