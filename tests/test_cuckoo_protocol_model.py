@@ -271,6 +271,28 @@ def scenario(kind, reader_key, reader_home_swapped, vorders):
   return build
 
 
+def scenario_three_movers(reader_key, vorders):
+  """Three inserters and a reader on five buckets: x -> (B0, B1) and y -> (B1, B0) displace into B2, z -> (B2, B3) arrives in
+  B2 while the copies land there — the constellation in which a plain copy-then-overwrite displacement leaves a key twice
+  (two movers on one victim, a third moving the first copy)."""
+  def build():
+    homes = {"a": (0, 2), "b": (0, 2), "c": (1, 2), "d": (1, 2), "e": (2, 3), "f": (3, 4), "g": (3, 4),
+             "x": (0, 1), "y": (1, 0), "z": (2, 3)}
+    mem = Mem(5, dict(homes))
+    for i, k in enumerate(["a", "b", "c", "d", "e", None, "f", "g"]):
+      mem.slots[i] = (k, False) if k else EMPTY
+    resident = ["a", "b", "c", "d", "e", "f", "g"]
+    result = []
+    actors = [inserter(mem, "x", vorders[0]), inserter(mem, "y", vorders[1]), inserter(mem, "z", vorders[2]),
+              reader(mem, reader_key, result)]
+
+    def check(m):
+      final_invariants(m, resident + ["x", "y", "z"])
+      assert result and result[0] is not False, f"the reader missed resident key {reader_key}"
+    return mem, actors, check
+  return build
+
+
 def bounded_schedules(n_actors, max_preemptions, horizon):
   """All schedules that run one actor until it finishes (or until a chosen step), with <= max_preemptions switches at
   chosen steps: the classic context-bounded exploration.  Yields scheduler functions."""
@@ -309,6 +331,22 @@ def test_protocol_random_schedules(kind, reader_key, swapped):
       state["left"] -= 1
       return state["cur"]
     run(fn, scenario(kind, reader_key, swapped, vorders))
+
+
+@pytest.mark.parametrize("reader_key", ["a", "e"])
+def test_protocol_three_movers_random_schedules(reader_key):
+  rng = random.Random(zlib.crc32(reader_key.encode()) + 3)
+  for trial in range(3000):
+    vorders = tuple(rng.randrange(SLOTS) for _ in range(3))
+    state = {"cur": None, "left": 0}
+
+    def fn(step, ids, state=state):
+      if state["cur"] not in ids or state["left"] == 0:
+        state["cur"] = rng.choice(ids)
+        state["left"] = rng.choice((1, 1, 2, 3, 5, 8, 13))
+      state["left"] -= 1
+      return state["cur"]
+    run(fn, scenario_three_movers(reader_key, vorders))
 
 
 @pytest.mark.parametrize("kind", ["free", "tight"])
